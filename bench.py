@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py — hybrid-search throughput/latency of the retrieval hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl reference]
+
+One "step" = one hybrid search (cosine scoring of every chunk → top-k → min-cosine filter →
+RRF with the keyword list) of one query batch over the whole corpus.
+
+  value     queries/s with the batch already resident in HBM (device-timed with CUDA events on
+            the library stream, K steps back to back between barriers, max over ranks)
+  e2e       the same metric through the public call rag_hybrid_search with HOST buffers
+            (H2D of queries+keyword lists and D2H of results inside the timed region)
+  roofline  the dominant kernel (K1 stream scoring) against the measured HBM copy bandwidth
+  cpu_baseline  the oracle (a port of the reference's single-threaded JS algorithm) on host cores
+
+Workloads (BASELINE.json configs): c3 = 10M x 1536 fp32 batch 1 (default; the north-star
+target), c2 = 1M x 1536 fp32 batch 1, c1 = 10k x 1536 fp32 batch 1 (L2-resident).
+For N > 1 the SAME corpus is row-sharded over the ranks (strong scaling): every rank scores
+its shard, the exact local top-k lists are all-gathered over NCCL, and the merge + fusion
+runs on every rank.
+
+`--impl reference` times the reference's CPU algorithm (oracle port, all host threads, bounded
+row sample, linearly extrapolated — cost is exactly linear in rows) for the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: rows, dim, dtype, batch, vectorTopK, keywordLimit, minVectorScore, show
+    "c1": dict(rows=10_000, dim=1536, dtype="f32", batch=1, vector_top_k=5, keyword_limit=5, min_score=0.3, show=3,
+               desc="C1 search_knowledge: 10k x 1536 fp32, vectorTopK=5 keywordLimit=5 RRF(k=60) top-3, batch 1"),
+    "c2": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+               desc="C2 deep_search: 1M x 1536 fp32, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1"),
+    "c3": dict(rows=10_000_000, dim=1536, dtype="f32", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+               desc="C3: 10M x 1536 fp32, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1"),
+}
+SEEDS = dict(seed=0xC0FFEE, query_seed=0xBEEF, meta_seed=0xF00D)
+KW_SEED = 0xFACE
+METRIC, UNIT = "hybrid_search_qps", "queries/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def keyword_lists(top_ids: np.ndarray, rows: int, kl: int, rng: np.random.Generator):
+    """ceil(30%) of each list drawn from the true vector top-k (exercises 'both'),
+    the rest uniform random rows, in a seeded order. Key map = identity."""
+    out = []
+    for b in range(top_ids.shape[0]):
+        n_hit = min(kl, -(-3 * kl // 10))
+        hits = [int(x) for x in top_ids[b, :n_hit]]
+        hits += [int(x) for x in rng.integers(0, rows, kl - len(hits))]
+        rng.shuffle(hits)
+        out.append(hits)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons of one GPU sampled during the timed region (NVML)."""
+
+    def __init__(self, device: int):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self._stop_evt = device, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(2)
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s))
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py may execute oracle/)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_leg(w, steps, warmup, threads, sample_rows, faithful=True):
+    """The reference's algorithm (oracle port) over a bounded row sample of workload `w`.
+    Returns (qps_extrapolated, seconds_per_sample_query list, sample description)."""
+    import oracle
+
+    rows, d = w["rows"], w["dim"]
+    s_rows = min(rows, sample_rows)
+    g = oracle.make_gen(rows, **SEEDS)
+    X = oracle.gen_rows(g, 0, s_rows, d, threads=os.cpu_count() or 1)
+    Q = oracle.gen_queries(g, 0, steps + warmup, d)
+    rng = np.random.default_rng(KW_SEED)
+    cfg = oracle.RRFConfig()
+    times = []
+    for i in range(steps + warmup):
+        kw = [int(x) for x in rng.integers(0, s_rows, w["keyword_limit"])]
+        t0 = time.perf_counter()
+        ids, sc = oracle.topk(X, Q[i], w["vector_top_k"], faithful_sort=faithful, threads=threads)
+        ids, sc = oracle.filter_min_score(ids, sc, w["min_score"])
+        oracle.rrf(ids, kw, cfg)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    scale = rows / s_rows
+    per_query = float(np.mean(times)) * scale
+    sample = (f"{steps} queries x first {s_rows} of {rows} rows (fp64 left-to-right cosine, norms recomputed per row, "
+              f"score-all + full stable sort, filter, RRF); time scaled x{scale:g} (cost is linear in rows)")
+    return 1.0 / per_query, per_query, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    steps, warmup = args.steps or 5, args.warmup if args.warmup is not None else 1
+    t0 = time.perf_counter()
+    # bound the run to ~2 minutes: calibrate on 50k rows, then size the per-step row sample
+    _, cal, _ = cpu_reference_leg(dict(w, rows=50_000), 1, 1, threads, 50_000)
+    budget_rows = int(50_000 * 100.0 / max(cal * (steps + warmup), 1e-9))
+    sample_rows = max(20_000, min(w["rows"], 500_000, budget_rows))
+    qps, per_query, sample = cpu_reference_leg(w, steps, warmup, threads, sample_rows)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": per_query * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_of(w, args.workload, args.gpus),
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is TypeScript (no Node here; dense arithmetic in un-vendored llamaindex): oracle port, "
+                "row-parallel over all host threads (the reference itself is single-threaded)",
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_of(w, name, gpus):
+    return {"workload": w["desc"], "name": name, "rows": w["rows"], "dim": w["dim"], "corpus_dtype": w["dtype"],
+            "batch": w["batch"], "vector_top_k": w["vector_top_k"], "keyword_limit": w["keyword_limit"],
+            "min_vector_score": w["min_score"], "rrf": {"k": 60, "vector_weight": 1.0, "keyword_weight": 1.0, "both_bonus": 0.1},
+            "display_top": w["show"], "sharding": f"rows/{gpus}" if gpus > 1 else "none",
+            "cache": "corpus streamed per step is larger than L2 (126 MB); no flush needed" if w["rows"] * w["dim"] * 4 > 2.5e8
+            else "corpus is L2-resident (latency-bound case); reported as such"}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, do_cpu):
+    from rag_era_b200.sharded import create_sharded_index, shard_range
+
+    rows, d, B = w["rows"], w["dim"], w["batch"]
+    dt = N.F32 if w["dtype"] == "f32" else N.BF16
+    gen = N.GenDesc(SEEDS["seed"], SEEDS["query_seed"], SEEDS["meta_seed"], rows, 4096, 0.6, 0.5, 0, 0, 1_760_000_000_000)
+    if world > 1:
+        idx = create_sharded_index(dist, rows, d, dt, device)
+        base, n_local = shard_range(rows, world, rank)
+    else:
+        idx = rb.VectorIndex(d, rows, dtype=dt, device=device)
+        base, n_local = 0, rows
+    idx.generate(gen, n_local)
+    total = steps + warmup
+    Q = idx.generate_queries(gen, 0, total * B)
+    o = rb.hybrid_opts(w["vector_top_k"], w["keyword_limit"], w["min_score"], path=N.PATH_STREAM)
+
+    # setup (untimed): true vector top-k of every query → keyword lists with ~30% overlap
+    top = idx.query(Q, w["vector_top_k"], path=N.PATH_STREAM)
+    kw = keyword_lists(top.ids, rows, w["keyword_limit"], np.random.default_rng(KW_SEED))
+    certified_setup = int(top.certified.sum())
+
+    def barrier():
+        idx.sync()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-timed: batch resident in HBM ------------------------------------------------
+    idx.stage_batch(Q, kw, w["keyword_limit"])
+    for i in range(warmup):
+        idx.stage_window(i * B, B)
+        idx.hybrid_staged(B, o)
+    barrier()
+    idx.profile_enable(True)
+    idx.profile_read()
+    sampler = ClockSampler(device)
+    sampler.start()
+    l0 = idx.launch_count
+    barrier()
+    idx.timer_start()
+    for i in range(warmup, total):
+        idx.stage_window(i * B, B)
+        idx.hybrid_staged(B, o)
+    ms = idx.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = idx.launch_count - l0
+    prof = idx.profile_read()
+    idx.profile_enable(False)
+    last = idx.fetch_fused(B, o)
+    if world > 1:
+        import torch
+
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end to end: host buffers through rag_hybrid_search ---------------------------------
+    lat = []
+    for i in range(total):
+        q = Q[i * B:(i + 1) * B]
+        k = kw[i * B:(i + 1) * B]
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r = idx.hybrid(q, o, k)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            lat.append(t1 - t0)
+    e2e_s = float(np.sum(lat))
+    if world > 1:
+        import torch
+
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    cap = w["vector_top_k"] + w["keyword_limit"]
+    h2d = B * (d * 4 + w["keyword_limit"] * 8 + 4)
+    d2h = B * (4 + 1 + 4 + 1 + cap * (8 + 8 + 1 + 1) + w["vector_top_k"] * 16)
+
+    peak, peak_src = peaks()
+    k1_ms, k1_n = prof["stream"]
+    bytes_per_launch = n_local * idx_ld(d) * (4 if dt == N.F32 else 2) * B   # K1 streams the shard once per query
+    achieved = bytes_per_launch / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9 if k1_n else None
+    res = {
+        "value": steps * B / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": {"value": steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "latency_ms_p50": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
+                "timing": "host wall clock around the synchronous call"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "kernel": "k1_stream (fused cosine GEMV + top-K')", "algorithmic_bytes_per_launch": int(bytes_per_launch),
+                     "avg_launch_ms": k1_ms / max(k1_n, 1), "launches_timed": int(k1_n),
+                     "frac_of_nominal_8TBps": (achieved / 8000.0) if achieved else None},
+        "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]},
+        "certified": {"setup_queries": certified_setup, "of": total * B, "last_step": int(last.certified.sum())},
+    }
+    if do_cpu and rank == 0:
+        # reference-faithful: ONE thread (the reference is single-threaded JS), full stable sort
+        sample_rows = min(rows, 1_000_000)
+        n_q = 2 if sample_rows >= 500_000 else 20
+        qps, per_query, sample = cpu_reference_leg(w, n_q, 0, 1, sample_rows)
+        res["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                               "ms_per_query": per_query * 1e3}
+    idx.close()
+    return res
+
+
+def idx_ld(d):
+    return (d + 255) & ~255
+
+
+def run_ours(args):
+    import rag_era_b200 as rb
+    from rag_era_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N.load()
+    w = WORKLOADS[args.workload]
+    steps = args.steps or (200 if w["rows"] >= 1_000_000 else 1000)
+    warmup = args.warmup if args.warmup is not None else 10
+    warmup = max(3, warmup)
+    res = measure_workload(rb, N, w, args.workload, steps, warmup, dist, rank, world, local, do_cpu=(world == 1))
+    extra = {}
+    if world == 1 and not args.no_extra:
+        for name in ("c2", "c1"):
+            if name != args.workload:
+                e_steps = 200 if name == "c2" else 500
+                r = measure_workload(rb, N, WORKLOADS[name], name, e_steps, 5, None, 0, 1, local, do_cpu=False)
+                extra[name] = {"workload": WORKLOADS[name]["desc"], "value": r["value"], "unit": UNIT, "steps": e_steps,
+                               "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
+                               "kernel_ms_per_step": r["kernel_ms_per_step"]}
+    if rank == 0:
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_of(w, args.workload, world), "clocks": res["clocks"],
+                "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "roofline": res["roofline"],
+                "kernel_ms_per_step": res["kernel_ms_per_step"], "certified": res["certified"],
+                "arithmetic": "fp32 scoring selects K' candidates; fp64 reference-order rescoring decides ids/scores/ties"}
+        if "cpu_baseline" in res:
+            line["cpu_baseline"] = res["cpu_baseline"]
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the c2/c1 extra measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

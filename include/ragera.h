@@ -1,0 +1,253 @@
+/*
+ * ragera.h — C ABI of libragera.so, the B200-native (sm_100a) retrieval hot path
+ * of gong9/rag-era: dense cosine scoring → per-query top-k → min-cosine filter →
+ * Reciprocal Rank Fusion (+ memory freshness), behind hybridSearch().
+ *
+ * This is the drop-in boundary. The reference is TypeScript; the calls below are
+ * what an N-API addon / FFI shim binds (INTEGRATION.md shows the stub). Each
+ * entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ / torch types
+ *  - return 0 (RAG_OK) or a negative rag_status; rag_last_error() returns a
+ *    thread-local message for the last failing call on this thread
+ *  - the caller owns every host buffer (outputs are caller-allocated); the
+ *    library owns all device memory behind the opaque rag_index handle
+ *  - a handle may be used by one thread at a time; distinct handles concurrently
+ *  - calls are synchronous w.r.t. the host unless named *_async / *_staged
+ *  - there is NO CPU fallback: without a usable sm_100 device calls fail
+ *  - ids are uint64 chunk ids = id_base + local row (row order = insertion order
+ *    of the reference's embeddingDict, so "lower id wins ties" == its stable sort)
+ */
+#ifndef RAGERA_H
+#define RAGERA_H
+
+#include <stdint.h>
+#include "ragera_gen.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAGERA_VERSION 0x00010000 /* major<<16 | minor<<8 | patch */
+
+#define RAG_MAX_TOPK 64        /* similarityTopK; reference uses 2..29 */
+#define RAG_MAX_CANDIDATES 128 /* K' = k + slack candidates rescored exactly     */
+#define RAG_MAX_KEYWORDS 64    /* keywordLimit; reference uses 0..19             */
+#define RAG_MAX_FRESH 64
+
+typedef struct rag_index rag_index;
+
+typedef enum rag_status {
+  RAG_OK = 0,
+  RAG_ERR_INVALID = -1,     /* bad argument                                      */
+  RAG_ERR_CUDA = -2,        /* CUDA runtime / driver error (message has detail)   */
+  RAG_ERR_NOMEM = -3,
+  RAG_ERR_STATE = -4,       /* call order (e.g. search before any rows exist)     */
+  RAG_ERR_UNSUPPORTED = -5, /* e.g. tensor path requested without a bf16 shadow   */
+  RAG_ERR_NCCL = -6,
+  RAG_ERR_NO_DEVICE = -7    /* no sm_100 GPU: there is deliberately no fallback   */
+} rag_status;
+
+typedef enum rag_dtype { RAG_F32 = 0, RAG_BF16 = 1 } rag_dtype;
+
+/* HybridSearchResult.source — src/lib/hybrid-search.ts:24 (+ the N-c4 extension) */
+typedef enum rag_source { RAG_SRC_VECTOR = 0, RAG_SRC_KEYWORD = 1, RAG_SRC_BOTH = 2, RAG_SRC_FRESHNESS = 3 } rag_source;
+/* HybridSearchResult.contentType — src/lib/hybrid-search.ts:25,229-234 */
+typedef enum rag_content_type { RAG_CT_DOCUMENT = 0, RAG_CT_MEMORY = 1, RAG_CT_CODE = 2 } rag_content_type;
+
+/* which scoring kernel produces the candidates (results are identical) */
+typedef enum rag_path {
+  RAG_PATH_AUTO = 0,  /* B < gemm threshold → stream, else tensor (if shadow exists) */
+  RAG_PATH_STREAM = 1,/* K1: HBM-bound fused cosine GEMV + top-k, fp32 accumulate   */
+  RAG_PATH_TENSOR = 2,/* K2: tcgen05 bf16 GEMM + fused top-k epilogue               */
+  RAG_PATH_EXACT = 3  /* K1x: fp64 reference-order scan of every row (slow, exact)   */
+} rag_path;
+
+#define RAG_INDEX_BF16_SHADOW 1u /* keep a bf16 copy of an fp32 corpus for the tensor path */
+
+typedef struct rag_index_desc {
+  uint64_t capacity_rows; /* rows this handle (shard) can hold                      */
+  uint32_t dim;           /* embedding dimension D                                  */
+  uint32_t dtype;         /* rag_dtype of the stored corpus                         */
+  int32_t  device;        /* CUDA device ordinal                                    */
+  uint32_t flags;         /* RAG_INDEX_*                                            */
+  uint64_t id_base;       /* chunk id of local row 0 (row-sharded multi-GPU)        */
+} rag_index_desc;
+
+/* RRFConfig — src/lib/hybrid-search.ts:40-45; presets :77-105 */
+typedef struct rag_rrf_config {
+  double k;
+  double vector_weight;
+  double keyword_weight;
+  double both_bonus;
+} rag_rrf_config;
+
+typedef struct rag_search_opts {
+  uint32_t k;       /* similarityTopK (src/lib/hybrid-search.ts:223)                */
+  uint32_t path;    /* rag_path                                                     */
+  uint32_t slack;   /* K' = k + slack candidates; 0 → library default               */
+  uint32_t flags;   /* RAG_SEARCH_*                                                 */
+  double   epsilon; /* selection-error bound used for certification; 0 → default    */
+} rag_search_opts;
+
+#define RAG_SEARCH_NO_ESCALATE 1u /* do not re-run uncertified queries on a stronger path */
+
+/* result of SimpleVectorStore.query → {ids, similarities} (llamaindex, via
+ * src/lib/hybrid-search.ts:223-224); rank-ordered, scores are exact fp64 cosines */
+typedef struct rag_topk_out {
+  uint64_t* ids;       /* [B][k]                                                    */
+  double*   scores;    /* [B][k]                                                    */
+  uint32_t* counts;    /* [B]   results per query (<= k)                            */
+  uint8_t*  certified; /* [B]   optional (may be NULL): 1 = proven equal to an exact scan */
+} rag_topk_out;
+
+/* HybridSearchOptions + the engine's call (src/lib/hybrid-search.ts:51-58,275-295) */
+typedef struct rag_hybrid_opts {
+  uint32_t vector_top_k;     /* vectorTopK                                          */
+  uint32_t keyword_limit;    /* row stride of kw_keys (>= every kw_counts[b])       */
+  double   min_vector_score; /* minVectorScore, applied to raw cosine before fusion */
+  rag_rrf_config rrf;
+  uint32_t path;             /* rag_path                                            */
+  uint32_t slack;
+  uint32_t flags;
+  /* north-star extension (SURVEY N-c4 ii); fresh_limit = 0 → reference-faithful    */
+  uint32_t fresh_limit;      /* length of the freshness-ranked third list           */
+  double   fresh_weight;
+  int64_t  now_ms;
+  double   time_decay_factor; /* freshness.ts:20-23 defaults 0.05 / 0.1 when 0      */
+  double   frequency_bonus;
+  double   epsilon;
+} rag_hybrid_opts;
+
+/* HybridSearchResult[] per query (src/lib/hybrid-search.ts:18-27) as columns */
+typedef struct rag_fused_out {
+  uint32_t  capacity;     /* entries per query in the arrays below;
+                             must be >= vector_top_k + keyword_limit + fresh_limit */
+  uint64_t* keys;         /* [B][capacity] fusion key (RRF branch) or chunk id (vector-only branch) */
+  double*   scores;       /* [B][capacity] RRF score, or raw cosine in the vector-only branch (:346-354) */
+  uint8_t*  source;       /* [B][capacity] rag_source                               */
+  uint8_t*  content_type; /* [B][capacity] rag_content_type                         */
+  uint32_t* counts;       /* [B]                                                    */
+  uint8_t*  used_rrf;     /* [B] 1 = fused (:333), 0 = vector-only branch (:346)    */
+  /* the filtered vector stage (optional, may be NULL) */
+  uint64_t* vec_ids;      /* [B][vector_top_k]                                      */
+  double*   vec_scores;   /* [B][vector_top_k]                                      */
+  uint32_t* vec_counts;   /* [B]                                                    */
+  uint8_t*  certified;    /* [B] optional                                           */
+} rag_fused_out;
+
+/* MemoryStore.retrieve(query, limit, minRelevance) — src/lib/memory/store.ts:102-180 */
+typedef struct rag_memory_opts {
+  uint32_t limit;
+  uint32_t path;
+  double   min_relevance;     /* default 0.5 at the call site                       */
+  int64_t  now_ms;
+  double   time_decay_factor; /* 0 → 0.05                                           */
+  double   frequency_bonus;   /* 0 → 0.1                                            */
+} rag_memory_opts;
+
+typedef struct rag_memory_out {
+  uint64_t* ids;        /* [B][limit]                                               */
+  double*   scores;     /* [B][limit] 0.7·relevance + 0.3·freshness (store.ts:160)  */
+  double*   relevance;  /* [B][limit] cosine                                        */
+  double*   freshness;  /* [B][limit]                                               */
+  uint32_t* counts;     /* [B]                                                      */
+} rag_memory_out;
+
+/* ---- library ------------------------------------------------------------- */
+int rag_version(void);
+const char* rag_last_error(void);
+int rag_device_count(void);
+
+/* ---- index lifetime: replaces VectorStoreIndex.init / SimpleVectorStore
+ *      (src/lib/llm/index-manager.ts:218-227,264-270) -------------------------- */
+int rag_index_create(const rag_index_desc* desc, rag_index** out);
+void rag_index_destroy(rag_index* idx);
+/* copy host rows (dtype of the index, row-major [nrows][dim]) into rows
+ * [row0,row0+nrows); extends the row count; index.insert (memory/store.ts:67) appends */
+int rag_index_upload(rag_index* idx, uint64_t row0, uint64_t nrows, const void* host_rows);
+/* fill rows [0,nrows) with the synthetic corpus of include/ragera_gen.h on the device
+ * (global row = id_base + local row); also fills row meta from the generator */
+int rag_index_generate(rag_index* idx, const rag_gen_desc* gen, uint64_t nrows);
+/* per-row metadata: metadata.type (hybrid-search.ts:229-234) and the Memory columns
+ * confidence/accessCount/lastAccessedAt (prisma/schema.prisma:94-99). Any pointer may be NULL. */
+int rag_index_set_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, const uint8_t* content_type,
+                           const double* confidence, const int32_t* access_count,
+                           const int64_t* last_access_ms);
+/* optional row → fusion key map (key of content.substring(0,100), hybrid-search.ts:149);
+ * default key = chunk id */
+int rag_index_set_row_keys(rag_index* idx, uint64_t row0, uint64_t nrows, const uint64_t* keys);
+int rag_index_read_rows(rag_index* idx, uint64_t row0, uint64_t nrows, void* host_rows);
+uint64_t rag_index_rows(const rag_index* idx);
+/* synthetic queries of ragera_gen.h, generated on the device, copied to host_out [B][dim] */
+int rag_generate_queries(rag_index* idx, const rag_gen_desc* gen, uint64_t b0, uint32_t B, float* host_out);
+
+/* ---- search: replaces retriever.retrieve → SimpleVectorStore.query →
+ *      getTopKEmbeddings (src/lib/hybrid-search.ts:223-224) ---------------------- */
+int rag_search(rag_index* idx, const float* queries /*[B][dim] host*/, uint32_t B,
+               const rag_search_opts* opts, rag_topk_out* out);
+
+/* ---- hybrid search: replaces the body of hybridSearch() after the embedding and
+ *      Meilisearch round-trips (src/lib/hybrid-search.ts:303-354). kw_keys holds each
+ *      query's keyword hits as fusion keys in Meilisearch rank order (meilisearch.ts:
+ *      226-236); kw_counts[b] = 0 selects the vector-only branch for that query. */
+int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const rag_hybrid_opts* opts,
+                      const uint64_t* kw_keys /*[B][keyword_limit]*/, const uint32_t* kw_counts /*[B]*/,
+                      rag_fused_out* out);
+
+/* ---- fusion only: replaces reciprocalRankFusion() (src/lib/hybrid-search.ts:129-208)
+ *      for B independent (vector list, keyword list) pairs given as keys. */
+int rag_rrf_fuse(rag_index* idx, uint32_t B, const rag_rrf_config* cfg,
+                 const uint64_t* vec_keys /*[B][vec_stride]*/, const uint8_t* vec_ctype /*may be NULL*/,
+                 const uint32_t* vec_counts, uint32_t vec_stride,
+                 const uint64_t* kw_keys /*[B][kw_stride]*/, const uint32_t* kw_counts, uint32_t kw_stride,
+                 rag_fused_out* out);
+
+/* ---- memory: replaces MemoryStore.retrieve post-processing and
+ *      calculateFreshnessScore (src/lib/memory/store.ts:102-180, freshness.ts:37-56) */
+int rag_memory_retrieve(rag_index* idx, const float* queries, uint32_t B, const rag_memory_opts* opts,
+                        rag_memory_out* out);
+int rag_freshness_scores(rag_index* idx, uint64_t n, const double* confidence, const int32_t* access_count,
+                         const int64_t* last_access_ms, int64_t now_ms, double time_decay_factor,
+                         double frequency_bonus, double* out_scores);
+
+/* ---- staged (device-resident) form of rag_hybrid_search, for callers that keep
+ *      a batch in flight and for measurement: stage → run (async) → fetch. ------- */
+int rag_stage_batch(rag_index* idx, const float* queries, uint32_t B, const uint64_t* kw_keys,
+                    const uint32_t* kw_counts, uint32_t keyword_limit);
+/* select the window [first, first+count) of the staged pool as the batch of the following
+ * staged runs (default after rag_stage_batch: the whole pool) */
+int rag_stage_window(rag_index* idx, uint32_t first, uint32_t count);
+int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* opts); /* async */
+int rag_fetch_fused(rag_index* idx, uint32_t B, const rag_hybrid_opts* opts, rag_fused_out* out);
+int rag_sync(rag_index* idx);
+
+/* ---- measurement helpers (CUDA events on the library's own stream) ------------ */
+int rag_timer_start(rag_index* idx);
+int rag_timer_stop(rag_index* idx, float* elapsed_ms);           /* synchronises */
+uint64_t rag_launch_count(const rag_index* idx);                 /* kernels launched so far */
+/* per-kernel device time: when enabled, every pipeline kernel launch is bracketed by a
+ * pair of events on the library stream; rag_profile_read synchronises and returns the
+ * summed milliseconds and launch counts per kernel class since the last read. */
+enum { RAG_PROF_STREAM = 0, RAG_PROF_TENSOR = 1, RAG_PROF_MERGE = 2, RAG_PROF_RESCORE = 3,
+       RAG_PROF_FUSE = 4, RAG_PROF_COMM = 5, RAG_PROF_CLASSES = 6 };
+int rag_profile_enable(rag_index* idx, int on);
+int rag_profile_read(rag_index* idx, float ms[RAG_PROF_CLASSES], uint32_t counts[RAG_PROF_CLASSES]);
+/* pinned host memory for query / result buffers (what the N-API shim backs its
+ * Float32Array with, so H2D/D2H are true async DMA) */
+void* rag_host_alloc(uint64_t bytes);
+void rag_host_free(void* p);
+
+/* ---- row-sharded multi-GPU (one process per GPU; NCCL all-gather of each rank's
+ *      local top-k, final merge on every rank — rank 0 is the consumer) ---------- */
+#define RAG_COMM_ID_BYTES 128
+int rag_comm_unique_id(uint8_t id[RAG_COMM_ID_BYTES]);            /* rank 0 creates, host broadcasts */
+int rag_comm_init(rag_index* idx, int nranks, int rank, const uint8_t id[RAG_COMM_ID_BYTES]);
+int rag_comm_destroy(rag_index* idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAGERA_H */

@@ -1,0 +1,22 @@
+"""rag_era_b200 — B200-native (sm_100a) implementation of gong9/rag-era's retrieval hot path:
+dense cosine scoring → per-query top-k → min-cosine filter → Reciprocal Rank Fusion
+(+ memory freshness), behind the reference's ``hybridSearch`` signature.
+
+The product is ``libragera.so`` (CUDA kernels + C ABI, ``include/ragera.h``); this package is
+the host-side mirror of the reference's TypeScript interface used by tests and benchmarks.
+There is no CPU implementation: importing works anywhere, calling needs a B200.
+"""
+from . import _native
+from ._native import RagError
+from .index import VectorIndex, RRFConfig, TopK, Fused, hybrid_opts
+from .hybrid_search import (PRESET_CONFIGS, HybridSearchResult, KeywordHit, KnowledgeIndex, Node, format_search_results,
+                            get_preset_config, get_source_stats, hybrid_search, reciprocal_rank_fusion)
+from .memory import Memory, MemoryStore, ScoredMemory, batch_calculate_freshness, calculate_freshness_score
+from .sharded import create_sharded_index, shard_range
+
+__all__ = [
+    "RagError", "VectorIndex", "RRFConfig", "TopK", "Fused", "hybrid_opts", "PRESET_CONFIGS", "HybridSearchResult",
+    "KeywordHit", "KnowledgeIndex", "Node", "format_search_results", "get_preset_config", "get_source_stats",
+    "hybrid_search", "reciprocal_rank_fusion", "Memory", "MemoryStore", "ScoredMemory", "batch_calculate_freshness",
+    "calculate_freshness_score", "create_sharded_index", "shard_range",
+]

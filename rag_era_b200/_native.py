@@ -1,0 +1,169 @@
+"""ctypes binding of ``libragera.so`` — the C ABI declared in ``include/ragera.h``.
+
+This is the same boundary an N-API addon binds in the reference's Node process
+(INTEGRATION.md); Python is used here only because the container has no Node.
+There is no CPU fallback: if the shared library is missing ``load()`` raises, and
+without an sm_100 GPU ``rag_index_create`` returns ``RAG_ERR_NO_DEVICE``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libragera.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+RAGERA_VERSION = 0x00010000
+MAX_TOPK, MAX_CANDIDATES, MAX_KEYWORDS, MAX_FRESH = 64, 128, 64, 64
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6, -7
+F32, BF16 = 0, 1
+SRC_VECTOR, SRC_KEYWORD, SRC_BOTH, SRC_FRESHNESS = 0, 1, 2, 3
+CT_DOCUMENT, CT_MEMORY, CT_CODE = 0, 1, 2
+PATH_AUTO, PATH_STREAM, PATH_TENSOR, PATH_EXACT = 0, 1, 2, 3
+INDEX_BF16_SHADOW = 1
+SEARCH_NO_ESCALATE = 1
+PROF_CLASSES = 6
+PROF_NAMES = ("stream", "tensor", "merge", "rescore", "fuse", "comm")
+COMM_ID_BYTES = 128
+
+u8p, u32p, u64p, f64p, f32p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                               C.POINTER(C.c_double), C.POINTER(C.c_float))
+
+
+class RagError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libragera error {code}: {msg}")
+        self.code = code
+
+
+class GenDesc(C.Structure):
+    """rag_gen_desc (include/ragera_gen.h)."""
+    _fields_ = [("seed", C.c_uint64), ("query_seed", C.c_uint64), ("meta_seed", C.c_uint64),
+                ("total_rows", C.c_uint64), ("n_clusters", C.c_uint32), ("noise", C.c_float),
+                ("query_noise", C.c_float), ("dup_period", C.c_uint32), ("memory_rows", C.c_uint64),
+                ("now_ms", C.c_int64)]
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [("capacity_rows", C.c_uint64), ("dim", C.c_uint32), ("dtype", C.c_uint32),
+                ("device", C.c_int32), ("flags", C.c_uint32), ("id_base", C.c_uint64)]
+
+
+class RRFConfigC(C.Structure):
+    _fields_ = [("k", C.c_double), ("vector_weight", C.c_double), ("keyword_weight", C.c_double),
+                ("both_bonus", C.c_double)]
+
+
+class SearchOpts(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("path", C.c_uint32), ("slack", C.c_uint32), ("flags", C.c_uint32),
+                ("epsilon", C.c_double)]
+
+
+class TopkOut(C.Structure):
+    _fields_ = [("ids", C.c_void_p), ("scores", C.c_void_p), ("counts", C.c_void_p), ("certified", C.c_void_p)]
+
+
+class HybridOpts(C.Structure):
+    _fields_ = [("vector_top_k", C.c_uint32), ("keyword_limit", C.c_uint32), ("min_vector_score", C.c_double),
+                ("rrf", RRFConfigC), ("path", C.c_uint32), ("slack", C.c_uint32), ("flags", C.c_uint32),
+                ("fresh_limit", C.c_uint32), ("fresh_weight", C.c_double), ("now_ms", C.c_int64),
+                ("time_decay_factor", C.c_double), ("frequency_bonus", C.c_double), ("epsilon", C.c_double)]
+
+
+class FusedOut(C.Structure):
+    _fields_ = [("capacity", C.c_uint32), ("keys", C.c_void_p), ("scores", C.c_void_p), ("source", C.c_void_p),
+                ("content_type", C.c_void_p), ("counts", C.c_void_p), ("used_rrf", C.c_void_p),
+                ("vec_ids", C.c_void_p), ("vec_scores", C.c_void_p), ("vec_counts", C.c_void_p),
+                ("certified", C.c_void_p)]
+
+
+class MemoryOpts(C.Structure):
+    _fields_ = [("limit", C.c_uint32), ("path", C.c_uint32), ("min_relevance", C.c_double), ("now_ms", C.c_int64),
+                ("time_decay_factor", C.c_double), ("frequency_bonus", C.c_double)]
+
+
+class MemoryOut(C.Structure):
+    _fields_ = [("ids", C.c_void_p), ("scores", C.c_void_p), ("relevance", C.c_void_p), ("freshness", C.c_void_p),
+                ("counts", C.c_void_p)]
+
+
+# every symbol include/ragera.h declares: name -> (restype, argtypes)
+_vp = C.c_void_p
+SYMBOLS = {
+    "rag_version": (C.c_int, []),
+    "rag_last_error": (C.c_char_p, []),
+    "rag_device_count": (C.c_int, []),
+    "rag_index_create": (C.c_int, [C.POINTER(IndexDesc), C.POINTER(_vp)]),
+    "rag_index_destroy": (None, [_vp]),
+    "rag_index_upload": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "rag_index_generate": (C.c_int, [_vp, C.POINTER(GenDesc), C.c_uint64]),
+    "rag_index_set_row_meta": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "rag_index_set_row_keys": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "rag_index_read_rows": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "rag_index_rows": (C.c_uint64, [_vp]),
+    "rag_generate_queries": (C.c_int, [_vp, C.POINTER(GenDesc), C.c_uint64, C.c_uint32, _vp]),
+    "rag_search": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(SearchOpts), C.POINTER(TopkOut)]),
+    "rag_hybrid_search": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(HybridOpts), _vp, _vp, C.POINTER(FusedOut)]),
+    "rag_rrf_fuse": (C.c_int, [_vp, C.c_uint32, C.POINTER(RRFConfigC), _vp, _vp, _vp, C.c_uint32, _vp, _vp,
+                               C.c_uint32, C.POINTER(FusedOut)]),
+    "rag_memory_retrieve": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(MemoryOpts), C.POINTER(MemoryOut)]),
+    "rag_freshness_scores": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, C.c_int64, C.c_double, C.c_double, _vp]),
+    "rag_stage_batch": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, C.c_uint32]),
+    "rag_stage_window": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
+    "rag_hybrid_search_staged": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts)]),
+    "rag_fetch_fused": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts), C.POINTER(FusedOut)]),
+    "rag_sync": (C.c_int, [_vp]),
+    "rag_timer_start": (C.c_int, [_vp]),
+    "rag_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "rag_launch_count": (C.c_uint64, [_vp]),
+    "rag_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "rag_profile_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "rag_host_alloc": (_vp, [C.c_uint64]),
+    "rag_host_free": (None, [_vp]),
+    "rag_comm_unique_id": (C.c_int, [_vp]),
+    "rag_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "rag_comm_destroy": (C.c_int, [_vp]),
+}
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libragera.so for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("ragera.h", "ragera_gen.h")]
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.getmtime(p) > os.path.getmtime(LIB_PATH) for p in srcs if os.path.exists(p))
+    if force or stale:
+        cmd = ["make", "-C", CSRC, "-j", str(min(16, os.cpu_count() or 4))] + (["-B"] if force else [])
+        r = subprocess.run(cmd, capture_output=not verbose, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libragera.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libragera.so and type every entry point. Raises if it is not built — there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C rag_era_b200/csrc`). rag_era_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if lib.rag_version() != RAGERA_VERSION:
+            raise RuntimeError(f"libragera.so version {lib.rag_version():#x} != binding {RAGERA_VERSION:#x}")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise RagError(rc, load().rag_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,980 @@
+// api.cu — the C ABI of libragera.so (include/ragera.h): handle lifetime, staging, the
+// kernel pipeline  score+select (K1 | K2 | K1x) → merge (K3) → exact rescore (K4) →
+// [NCCL all-gather] → merge/filter/fuse (K5), certification-driven escalation, and the
+// measurement helpers. Host code only; every kernel lives in its own .cu.
+//
+// There is no CPU implementation of any step in this library: without an sm_100 device
+// rag_index_create fails with RAG_ERR_NO_DEVICE and nothing else can be called.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[1024] = "";
+
+constexpr uint32_t kProfSpans = 8192;
+constexpr uint32_t kTensorMinBatch = 16;  // RAG_PATH_AUTO: smaller batches stream (HBM-bound either way)
+
+size_t elem_size(const rag_index* idx) { return idx->desc.dtype == RAG_BF16 ? 2 : 4; }
+
+// grow a device buffer to at least `need` bytes (contents are not preserved)
+template <typename T>
+int grow_dev(T** p, size_t* cap, size_t need, bool zero) {
+  if (need <= *cap && *p) return RAG_OK;
+  if (*p) { RAG_CUDA(cudaFree(*p)); *p = nullptr; *cap = 0; }
+  if (need == 0) need = 16;
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, need);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return rag_set_error(RAG_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+  }
+  if (zero) RAG_CUDA(cudaMemset(q, 0, need));
+  *p = (T*)q;
+  *cap = need;
+  return RAG_OK;
+}
+
+int grow_pinned(uint8_t** p, size_t* cap, size_t need) {
+  if (need <= *cap && *p) return RAG_OK;
+  if (*p) { RAG_CUDA(cudaFreeHost(*p)); *p = nullptr; *cap = 0; }
+  if (need == 0) need = 16;
+  void* q = nullptr;
+  cudaError_t e = cudaHostAlloc(&q, need, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return rag_set_error(RAG_ERR_NOMEM, "cudaHostAlloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+  }
+  *p = (uint8_t*)q;
+  *cap = need;
+  return RAG_OK;
+}
+
+void free_batch(rag_batch* b) {
+  cudaFree(b->d_q); cudaFree(b->d_qb); cudaFree(b->d_in); cudaFree(b->d_sel); cudaFree(b->d_partial);
+  cudaFree(b->d_cand); cudaFree(b->d_local); cudaFree(b->d_gather); cudaFree(b->d_local_cnt); cudaFree(b->d_out);
+  if (b->h_in) cudaFreeHost(b->h_in);
+  if (b->h_out) cudaFreeHost(b->h_out);
+  *b = rag_batch();
+}
+
+// ---- carved per-call layouts ------------------------------------------------------
+struct out_layout {
+  size_t keys, scores, src, ct, cnt, rrf, vids, vscores, vcnt, cert, aux0, aux1, total, total_no_aux;
+};
+out_layout layout_out(uint32_t B, uint32_t cap, uint32_t k) {
+  out_layout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+  L.cnt = take((size_t)B * 4);
+  L.rrf = take(B);
+  L.vcnt = take((size_t)B * 4);
+  L.cert = take(B);
+  L.keys = take((size_t)B * cap * 8);
+  L.scores = take((size_t)B * cap * 8);
+  L.src = take((size_t)B * cap);
+  L.ct = take((size_t)B * cap);
+  L.vids = take((size_t)B * k * 8);
+  L.vscores = take((size_t)B * k * 8);
+  L.total_no_aux = o;
+  L.aux0 = take((size_t)B * cap * 8);
+  L.aux1 = take((size_t)B * cap * 8);
+  L.total = o;
+  return L;
+}
+void bind_out(rag_batch* b, const out_layout& L) {
+  b->d_out_cnt = (uint32_t*)(b->d_out + L.cnt);
+  b->d_out_rrf = b->d_out + L.rrf;
+  b->d_vec_cnt = (uint32_t*)(b->d_out + L.vcnt);
+  b->d_cert = b->d_out + L.cert;
+  b->d_out_keys = (uint64_t*)(b->d_out + L.keys);
+  b->d_out_scores = (double*)(b->d_out + L.scores);
+  b->d_out_src = b->d_out + L.src;
+  b->d_out_ct = b->d_out + L.ct;
+  b->d_vec_ids = (uint64_t*)(b->d_out + L.vids);
+  b->d_vec_scores = (double*)(b->d_out + L.vscores);
+  b->d_aux0 = (double*)(b->d_out + L.aux0);
+  b->d_aux1 = (double*)(b->d_out + L.aux1);
+}
+
+// ---- plan: which kernel scores, how many candidates, what error bound ---------------
+struct plan {
+  int path;          // rag_path (never AUTO)
+  uint32_t kp;       // K'
+  double eps;        // selection-error bound used by K4's certification
+  int key_has_qnorm; // K1x keys hold the cosine, K1/K2 keys hold dot/||x||
+};
+
+int make_plan(const rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_t slack, double eps,
+              plan* p) {
+  int path = (int)req_path;
+  if (path == RAG_PATH_AUTO)
+    path = (B >= kTensorMinBatch && idx->shadow && k2_available(idx)) ? RAG_PATH_TENSOR : RAG_PATH_STREAM;
+  if (path != RAG_PATH_STREAM && path != RAG_PATH_TENSOR && path != RAG_PATH_EXACT)
+    return rag_set_error(RAG_ERR_INVALID, "unknown rag_path %d", path);
+  if (path == RAG_PATH_TENSOR) {
+    if (!idx->shadow) return rag_set_error(RAG_ERR_UNSUPPORTED,
+                                           "tensor path needs a bf16 corpus or RAG_INDEX_BF16_SHADOW");
+    if (!k2_available(idx)) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path (K2) is not available");
+  }
+  uint32_t s = slack;
+  if (s == 0) s = path == RAG_PATH_TENSOR ? std::max(22u, k) : 6u;
+  uint32_t kp = std::min<uint32_t>(RAG_MAX_CANDIDATES, k + s);
+  p->path = path;
+  p->kp = kp;
+  p->key_has_qnorm = path == RAG_PATH_EXACT;
+  if (eps > 0.0) p->eps = eps;
+  else if (path == RAG_PATH_STREAM)
+    // fp32: <= ld/64 + 8 roundings per sum (2 accumulators per lane, 5 shuffle levels), twice
+    // (dot and norm), with a safety factor — 4.8e-6 at D = 1536
+    p->eps = 2.5 * ((double)idx->ld / 64.0 + 8.0) * 5.9604644775390625e-08;
+  else if (path == RAG_PATH_TENSOR)
+    p->eps = 1.0e-3;  // bf16 rounding of both operands: sigma ~ 4e-5 at D=1536
+  else
+    p->eps = 2.0e-7;  // one fp32 rounding of the exact cosine
+  return RAG_OK;
+}
+
+bool next_plan(const rag_index* idx, uint32_t k, const plan& cur, plan* nxt) {
+  *nxt = cur;
+  if (cur.path == RAG_PATH_TENSOR) {
+    make_plan(idx, 1, k, RAG_PATH_STREAM, 0, 0.0, nxt);
+    return true;
+  }
+  if (cur.path == RAG_PATH_STREAM) {
+    make_plan(idx, 1, k, RAG_PATH_EXACT, 0, 0.0, nxt);
+    return true;
+  }
+  if (cur.kp < RAG_MAX_CANDIDATES) {  // exact path, wider candidate window (long runs of exact ties)
+    nxt->kp = RAG_MAX_CANDIDATES;
+    return true;
+  }
+  return false;
+}
+
+struct fresh_cfg { int64_t now_ms; double decay, bonus; };
+
+// ---- buffers for one batch ----------------------------------------------------------
+int ensure_queries(rag_index* idx, rag_batch* bt, uint32_t B) {
+  return grow_dev(&bt->d_q, &bt->c_q, (size_t)B * idx->ld * sizeof(float), true);
+}
+
+int ensure_inputs(rag_index* idx, rag_batch* bt, uint32_t B, uint32_t kw_stride) {
+  (void)idx;
+  const size_t keys = ((size_t)B * kw_stride * 8 + 15) & ~(size_t)15;
+  const size_t need = keys + (size_t)B * 4;
+  RAG_CHECK(grow_dev(&bt->d_in, &bt->c_in, need, true));
+  RAG_CHECK(grow_pinned(&bt->h_in, &bt->c_hin, need));
+  bt->d_kw = (uint64_t*)bt->d_in;
+  bt->d_kwc = (uint32_t*)(bt->d_in + keys);
+  return RAG_OK;
+}
+
+int ensure_work(rag_index* idx, rag_batch* bt, uint32_t B, uint32_t k, uint32_t out_cap, out_layout* L) {
+  RAG_CHECK(grow_dev(&bt->d_cand, &bt->c_cand, (size_t)B * RAG_MAX_CANDIDATES * 8, false));
+  RAG_CHECK(grow_dev(&bt->d_local, &bt->c_local, (size_t)B * k * sizeof(rag_rec), false));
+  RAG_CHECK(grow_dev(&bt->d_local_cnt, &bt->c_lcnt, (size_t)B * 4, false));
+  if (idx->nranks > 1)
+    RAG_CHECK(grow_dev(&bt->d_gather, &bt->c_gather, (size_t)idx->nranks * B * k * sizeof(rag_rec), false));
+  *L = layout_out(B, out_cap, k);
+  RAG_CHECK(grow_dev(&bt->d_out, &bt->c_out, L->total, false));
+  RAG_CHECK(grow_pinned(&bt->h_out, &bt->c_hout, L->total));
+  bind_out(bt, *L);
+  return RAG_OK;
+}
+
+int stage_queries(rag_index* idx, rag_batch* bt, const float* queries, uint32_t B) {
+  RAG_CHECK(ensure_queries(idx, bt, B));
+  if (idx->ld == idx->dim)
+    RAG_CUDA(cudaMemcpyAsync(bt->d_q, queries, (size_t)B * idx->dim * 4, cudaMemcpyHostToDevice, idx->stream));
+  else
+    RAG_CUDA(cudaMemcpy2DAsync(bt->d_q, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4, (size_t)idx->dim * 4, B,
+                               cudaMemcpyHostToDevice, idx->stream));
+  return RAG_OK;
+}
+
+int stage_keywords(rag_index* idx, rag_batch* bt, uint32_t B, const uint64_t* kw_keys, const uint32_t* kw_counts,
+                   uint32_t kw_stride) {
+  RAG_CHECK(ensure_inputs(idx, bt, B, kw_stride));
+  const size_t keys = ((size_t)B * kw_stride * 8 + 15) & ~(size_t)15;
+  uint32_t* hc = (uint32_t*)(bt->h_in + keys);
+  if (kw_stride && kw_keys) memcpy(bt->h_in, kw_keys, (size_t)B * kw_stride * 8);
+  for (uint32_t b = 0; b < B; b++) {
+    uint32_t c = (kw_counts && kw_keys) ? kw_counts[b] : 0u;
+    if (c > kw_stride) return rag_set_error(RAG_ERR_INVALID, "kw_counts[%u]=%u exceeds keyword_limit=%u", b, c, kw_stride);
+    hc[b] = c;
+  }
+  RAG_CUDA(cudaMemcpyAsync(bt->d_in, bt->h_in, keys + (size_t)B * 4, cudaMemcpyHostToDevice, idx->stream));
+  bt->staged_kw_stride = kw_stride;
+  return RAG_OK;
+}
+
+// ---- the pipeline (asynchronous on idx->stream; operates on idx->cur) -----------------
+int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fresh_cfg& fc, rag_fuse_args fa) {
+  rag_batch* bt = idx->cur;
+  uint32_t parts = 0;
+  if (p.path == RAG_PATH_STREAM) RAG_CHECK(k1_plan(idx, B, p.kp, &parts));
+  else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_plan(idx, B, p.kp, &parts));
+  else RAG_CHECK(k1x_plan(idx, B, p.kp, &parts));
+  RAG_CHECK(grow_dev(&bt->d_partial, &bt->c_partial, (size_t)B * parts * p.kp * 8, false));
+  if (p.path == RAG_PATH_STREAM) RAG_CHECK(k1_launch(idx, B, p.kp, parts));
+  else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_launch(idx, B, p.kp, parts));
+  else RAG_CHECK(k1x_launch(idx, B, p.kp, parts));
+  RAG_CHECK(k3_launch(idx, B, p.kp, parts));
+  RAG_CHECK(k4_launch(idx, B, p.kp, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
+  RAG_CHECK(comm_allgather_local(idx, B, k));
+  fa.B = B;
+  fa.k = k;
+  fa.nranks = (uint32_t)idx->nranks;
+  RAG_CHECK(k5_launch(idx, &fa));
+  return RAG_OK;
+}
+
+int fetch_out(rag_index* idx, rag_batch* bt, const out_layout& L, bool with_aux) {
+  RAG_CUDA(cudaMemcpyAsync(bt->h_out, bt->d_out, with_aux ? L.total : L.total_no_aux, cudaMemcpyDeviceToHost,
+                           idx->stream));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+// writer(user_b, batch, layout, local_b): copy one query's result from the pinned mirror to the caller
+typedef std::function<void(uint32_t, const rag_batch*, const out_layout&, uint32_t)> writer_fn;
+
+// Re-run the queries whose result could not be certified on successively stronger paths.
+int escalate(rag_index* idx, std::vector<uint32_t> sel, uint32_t k, plan p, const fresh_cfg& fc,
+             const rag_fuse_args& fa, uint32_t out_cap, bool with_aux, const writer_fn& write) {
+  rag_batch* src = &idx->main;
+  rag_batch* bt = &idx->esc;
+  int rc = RAG_OK;
+  while (!sel.empty()) {
+    plan nxt;
+    if (!next_plan(idx, k, p, &nxt)) break;  // stays flagged as uncertified
+    p = nxt;
+    const uint32_t n = (uint32_t)sel.size();
+    idx->cur = bt;
+    out_layout L;
+    if ((rc = ensure_queries(idx, bt, n)) != RAG_OK) break;
+    if ((rc = ensure_inputs(idx, bt, n, fa.kw_stride)) != RAG_OK) break;
+    if ((rc = ensure_work(idx, bt, n, k, out_cap, &L)) != RAG_OK) break;
+    if ((rc = grow_dev(&bt->d_sel, &bt->c_sel, (size_t)n * 4, false)) != RAG_OK) break;
+    cudaError_t e = cudaMemcpyAsync(bt->d_sel, sel.data(), (size_t)n * 4, cudaMemcpyHostToDevice, idx->stream);
+    if (e != cudaSuccess) { rc = rag_set_error(RAG_ERR_CUDA, "escalation H2D failed: %s", cudaGetErrorString(e)); break; }
+    if ((rc = gather_batch_launch(idx, src, bt, n, fa.mode == 0 ? fa.kw_stride : 0)) != RAG_OK) break;
+    if ((rc = run_pipeline(idx, n, k, p, fc, fa)) != RAG_OK) break;
+    if ((rc = fetch_out(idx, bt, L, with_aux)) != RAG_OK) break;
+    const uint8_t* cert = bt->h_out + L.cert;
+    std::vector<uint32_t> still;
+    for (uint32_t i = 0; i < n; i++) {
+      write(sel[i], bt, L, i);
+      if (!cert[i]) still.push_back(sel[i]);
+    }
+    sel.swap(still);
+  }
+  idx->cur = &idx->main;
+  return rc;
+}
+
+int check_handle(const rag_index* idx) {
+  if (!idx) return rag_set_error(RAG_ERR_INVALID, "null index handle");
+  return RAG_OK;
+}
+
+int ensure_meta(rag_index* idx) {
+  if (idx->ctype) return RAG_OK;
+  const size_t cap = idx->desc.capacity_rows;
+  size_t dummy = 0;
+  RAG_CHECK(grow_dev(&idx->ctype, &dummy, cap, true)); dummy = 0;
+  RAG_CHECK(grow_dev(&idx->conf, &dummy, cap * 8, true)); dummy = 0;
+  RAG_CHECK(grow_dev(&idx->access, &dummy, cap * 4, true)); dummy = 0;
+  RAG_CHECK(grow_dev(&idx->last_ms, &dummy, cap * 8, true));
+  return RAG_OK;
+}
+
+void fresh_defaults(double* decay, double* bonus) {
+  if (*decay == 0.0) *decay = 0.05;  // DEFAULT_FRESHNESS_CONFIG, src/lib/memory/freshness.ts:20-23
+  if (*bonus == 0.0) *bonus = 0.1;
+}
+
+}  // namespace
+
+int rag_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ---- profiling spans -------------------------------------------------------------------
+static void prof_drain(rag_index* idx) {
+  if (idx->prof_used == 0) return;
+  cudaStreamSynchronize(idx->stream);
+  for (uint32_t i = 0; i < idx->prof_used; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, idx->prof_spans[i].a, idx->prof_spans[i].b) == cudaSuccess) {
+      idx->prof_ms[idx->prof_spans[i].cls] += ms;
+      idx->prof_cnt[idx->prof_spans[i].cls] += 1;
+    }
+  }
+  cudaGetLastError();
+  idx->prof_used = 0;
+}
+
+int rag_prof_begin(rag_index* idx, int cls) {
+  if (!idx->prof_spans) return -1;
+  if (idx->prof_used == idx->prof_cap) prof_drain(idx);
+  const int t = (int)idx->prof_used++;
+  idx->prof_spans[t].cls = cls;
+  cudaEventRecord(idx->prof_spans[t].a, idx->stream);
+  return t;
+}
+void rag_prof_end(rag_index* idx, int token) { cudaEventRecord(idx->prof_spans[token].b, idx->stream); }
+
+extern "C" {
+
+int rag_version(void) { return RAGERA_VERSION; }
+const char* rag_last_error(void) { return g_err; }
+
+int rag_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int rag_index_create(const rag_index_desc* d, rag_index** out) {
+  if (!d || !out) return rag_set_error(RAG_ERR_INVALID, "rag_index_create: null argument");
+  *out = nullptr;
+  if (d->dim == 0 || d->dim > 65536) return rag_set_error(RAG_ERR_INVALID, "dim must be in 1..65536");
+  if (d->capacity_rows == 0 || d->capacity_rows >= 0xFFFFFFFFull)
+    return rag_set_error(RAG_ERR_INVALID, "capacity_rows must be in 1..2^32-2 per shard");
+  if (d->dtype != RAG_F32 && d->dtype != RAG_BF16) return rag_set_error(RAG_ERR_INVALID, "unknown dtype %u", d->dtype);
+  const int ndev = rag_device_count();
+  if (ndev == 0) return rag_set_error(RAG_ERR_NO_DEVICE, "no CUDA device visible; libragera has no CPU fallback");
+  if (d->device < 0 || d->device >= ndev) return rag_set_error(RAG_ERR_INVALID, "device %d out of range (0..%d)", d->device, ndev - 1);
+  int major = 0;
+  RAG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d->device));
+  if (major != 10)
+    return rag_set_error(RAG_ERR_NO_DEVICE, "device %d is sm_%d0: libragera is built for sm_100a only (no fallback)",
+                         d->device, major);
+  RAG_CUDA(cudaSetDevice(d->device));
+
+  rag_index* idx = new (std::nothrow) rag_index();
+  if (!idx) return rag_set_error(RAG_ERR_NOMEM, "out of host memory");
+  idx->desc = *d;
+  idx->device = d->device;
+  idx->dim = d->dim;
+  idx->ld = (d->dim + 255u) & ~255u;
+  idx->cur = &idx->main;
+  int rc = RAG_OK;
+  do {
+    cudaError_t e;
+    if ((e = cudaDeviceGetAttribute(&idx->sm_count, cudaDevAttrMultiProcessorCount, d->device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&idx->ev0)) != cudaSuccess || (e = cudaEventCreate(&idx->ev1)) != cudaSuccess) {
+      rc = rag_set_error(RAG_ERR_CUDA, "rag_index_create: %s", cudaGetErrorString(e));
+      break;
+    }
+    size_t cap = 0;
+    const size_t bytes = (size_t)d->capacity_rows * idx->ld * elem_size(idx);
+    char* corpus = nullptr;
+    if ((rc = grow_dev(&corpus, &cap, bytes, false)) != RAG_OK) break;
+    idx->corpus = corpus;
+    if (idx->ld != idx->dim) {  // padding columns must read as zero
+      if ((e = cudaMemsetAsync(idx->corpus, 0, bytes, idx->stream)) != cudaSuccess) {
+        rc = rag_set_error(RAG_ERR_CUDA, "corpus memset: %s", cudaGetErrorString(e));
+        break;
+      }
+    }
+    if (d->dtype == RAG_BF16) {
+      idx->shadow = (__nv_bfloat16*)idx->corpus;
+    } else if (d->flags & RAG_INDEX_BF16_SHADOW) {
+      cap = 0;
+      if ((rc = grow_dev(&idx->shadow, &cap, (size_t)d->capacity_rows * idx->ld * 2, false)) != RAG_OK) break;
+    }
+    if (idx->shadow) {
+      cap = 0;
+      if ((rc = grow_dev(&idx->inv_norm, &cap, (size_t)d->capacity_rows * 4, true)) != RAG_OK) break;
+    }
+    if ((e = cudaStreamSynchronize(idx->stream)) != cudaSuccess) {
+      rc = rag_set_error(RAG_ERR_CUDA, "rag_index_create: %s", cudaGetErrorString(e));
+      break;
+    }
+  } while (0);
+  if (rc != RAG_OK) {
+    rag_index_destroy(idx);
+    return rc;
+  }
+  *out = idx;
+  return RAG_OK;
+}
+
+void rag_index_destroy(rag_index* idx) {
+  if (!idx) return;
+  cudaSetDevice(idx->device);
+  if (idx->stream) cudaStreamSynchronize(idx->stream);
+  rag_comm_destroy(idx);
+  k2_destroy(idx);
+  free_batch(&idx->main);
+  free_batch(&idx->esc);
+  if (idx->shadow && (void*)idx->shadow != idx->corpus) cudaFree(idx->shadow);
+  cudaFree(idx->corpus); cudaFree(idx->inv_norm); cudaFree(idx->ctype); cudaFree(idx->conf);
+  cudaFree(idx->access); cudaFree(idx->last_ms); cudaFree(idx->row_keys);
+  if (idx->prof_spans) {
+    for (uint32_t i = 0; i < idx->prof_cap; i++) { cudaEventDestroy(idx->prof_spans[i].a); cudaEventDestroy(idx->prof_spans[i].b); }
+    delete[] idx->prof_spans;
+  }
+  if (idx->ev0) cudaEventDestroy(idx->ev0);
+  if (idx->ev1) cudaEventDestroy(idx->ev1);
+  if (idx->stream) cudaStreamDestroy(idx->stream);
+  cudaGetLastError();
+  delete idx;
+}
+
+uint64_t rag_index_rows(const rag_index* idx) { return idx ? idx->rows : 0; }
+
+int rag_index_upload(rag_index* idx, uint64_t row0, uint64_t nrows, const void* host_rows) {
+  RAG_CHECK(check_handle(idx));
+  if (nrows == 0) return RAG_OK;
+  if (!host_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_upload: null rows");
+  if (row0 > idx->rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_upload: row0=%llu leaves a gap (rows=%llu)",
+                                             (unsigned long long)row0, (unsigned long long)idx->rows);
+  if (row0 + nrows > idx->desc.capacity_rows)
+    return rag_set_error(RAG_ERR_INVALID, "rag_index_upload: %llu rows exceed capacity %llu",
+                         (unsigned long long)(row0 + nrows), (unsigned long long)idx->desc.capacity_rows);
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const size_t es = elem_size(idx);
+  char* dst = (char*)idx->corpus + (size_t)row0 * idx->ld * es;
+  // 2-D copies are limited in height; upload in slabs
+  const uint64_t slab = 1u << 20;
+  for (uint64_t r = 0; r < nrows; r += slab) {
+    const uint64_t h = std::min(slab, nrows - r);
+    RAG_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * idx->ld * es, (size_t)idx->ld * es,
+                               (const char*)host_rows + (size_t)r * idx->dim * es, (size_t)idx->dim * es,
+                               (size_t)idx->dim * es, h, cudaMemcpyHostToDevice, idx->stream));
+  }
+  idx->rows = std::max(idx->rows, row0 + nrows);
+  if (idx->row_keys) RAG_CHECK(iota_u64_launch(idx, idx->row_keys + row0, nrows, idx->desc.id_base + row0));
+  RAG_CHECK(aux_build_launch(idx, row0, nrows));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+int rag_index_generate(rag_index* idx, const rag_gen_desc* gen, uint64_t nrows) {
+  RAG_CHECK(check_handle(idx));
+  if (!gen || gen->n_clusters == 0 || gen->total_rows == 0)
+    return rag_set_error(RAG_ERR_INVALID, "rag_index_generate: bad generator description");
+  if (nrows > idx->desc.capacity_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_generate: nrows exceeds capacity");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  RAG_CHECK(gen_corpus_launch(idx, gen, nrows));
+  idx->rows = nrows;
+  RAG_CHECK(ensure_meta(idx));
+  RAG_CHECK(gen_meta_launch(idx, gen, nrows));
+  if (idx->row_keys) RAG_CHECK(iota_u64_launch(idx, idx->row_keys, nrows, idx->desc.id_base));
+  RAG_CHECK(aux_build_launch(idx, 0, nrows));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+int rag_index_set_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, const uint8_t* content_type,
+                           const double* confidence, const int32_t* access_count, const int64_t* last_access_ms) {
+  RAG_CHECK(check_handle(idx));
+  if (row0 + nrows > idx->desc.capacity_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_set_row_meta: range exceeds capacity");
+  if (nrows == 0) return RAG_OK;
+  RAG_CUDA(cudaSetDevice(idx->device));
+  RAG_CHECK(ensure_meta(idx));
+  if (content_type) RAG_CUDA(cudaMemcpyAsync(idx->ctype + row0, content_type, nrows, cudaMemcpyHostToDevice, idx->stream));
+  if (confidence) RAG_CUDA(cudaMemcpyAsync(idx->conf + row0, confidence, nrows * 8, cudaMemcpyHostToDevice, idx->stream));
+  if (access_count) RAG_CUDA(cudaMemcpyAsync(idx->access + row0, access_count, nrows * 4, cudaMemcpyHostToDevice, idx->stream));
+  if (last_access_ms) RAG_CUDA(cudaMemcpyAsync(idx->last_ms + row0, last_access_ms, nrows * 8, cudaMemcpyHostToDevice, idx->stream));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+int rag_index_set_row_keys(rag_index* idx, uint64_t row0, uint64_t nrows, const uint64_t* keys) {
+  RAG_CHECK(check_handle(idx));
+  if (row0 + nrows > idx->desc.capacity_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_set_row_keys: range exceeds capacity");
+  if (nrows == 0) return RAG_OK;
+  if (!keys) return rag_set_error(RAG_ERR_INVALID, "rag_index_set_row_keys: null keys");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  if (!idx->row_keys) {
+    size_t cap = 0;
+    RAG_CHECK(grow_dev(&idx->row_keys, &cap, (size_t)idx->desc.capacity_rows * 8, false));
+    RAG_CHECK(iota_u64_launch(idx, idx->row_keys, idx->desc.capacity_rows, idx->desc.id_base));  // default key = chunk id
+  }
+  RAG_CUDA(cudaMemcpyAsync(idx->row_keys + row0, keys, nrows * 8, cudaMemcpyHostToDevice, idx->stream));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+int rag_index_read_rows(rag_index* idx, uint64_t row0, uint64_t nrows, void* host_rows) {
+  RAG_CHECK(check_handle(idx));
+  if (row0 + nrows > idx->rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_read_rows: range exceeds rows");
+  if (nrows == 0) return RAG_OK;
+  if (!host_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_read_rows: null buffer");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const size_t es = elem_size(idx);
+  const uint64_t slab = 1u << 20;
+  for (uint64_t r = 0; r < nrows; r += slab) {
+    const uint64_t h = std::min(slab, nrows - r);
+    RAG_CUDA(cudaMemcpy2DAsync((char*)host_rows + (size_t)r * idx->dim * es, (size_t)idx->dim * es,
+                               (const char*)idx->corpus + (size_t)(row0 + r) * idx->ld * es, (size_t)idx->ld * es,
+                               (size_t)idx->dim * es, h, cudaMemcpyDeviceToHost, idx->stream));
+  }
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+int rag_generate_queries(rag_index* idx, const rag_gen_desc* gen, uint64_t b0, uint32_t B, float* host_out) {
+  RAG_CHECK(check_handle(idx));
+  if (!gen || !host_out || B == 0 || gen->total_rows == 0 || gen->n_clusters == 0)
+    return rag_set_error(RAG_ERR_INVALID, "rag_generate_queries: bad argument");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  float* d = nullptr;
+  size_t cap = 0;
+  RAG_CHECK(grow_dev(&d, &cap, (size_t)B * idx->dim * 4, false));
+  int rc = gen_queries_launch(idx, gen, b0, B, d);
+  if (rc == RAG_OK) {
+    cudaError_t e = cudaMemcpyAsync(host_out, d, (size_t)B * idx->dim * 4, cudaMemcpyDeviceToHost, idx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+    if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "rag_generate_queries: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// ---- search --------------------------------------------------------------------------------
+int rag_search(rag_index* idx, const float* queries, uint32_t B, const rag_search_opts* o, rag_topk_out* out) {
+  RAG_CHECK(check_handle(idx));
+  if (!queries || !o || !out || !out->ids || !out->scores || !out->counts || B == 0)
+    return rag_set_error(RAG_ERR_INVALID, "rag_search: null argument or empty batch");
+  if (o->k == 0 || o->k > RAG_MAX_TOPK) return rag_set_error(RAG_ERR_INVALID, "k must be in 1..%d", RAG_MAX_TOPK);
+  if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const uint32_t k = o->k;
+  plan p;
+  RAG_CHECK(make_plan(idx, B, k, o->path, o->slack, o->epsilon, &p));
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  out_layout L;
+  RAG_CHECK(stage_queries(idx, bt, queries, B));
+  RAG_CHECK(ensure_work(idx, bt, B, k, k, &L));
+  rag_fuse_args fa = {};
+  fa.mode = 2;
+  fa.out_cap = k;
+  const fresh_cfg fc = {0, 0.05, 0.1};
+  RAG_CHECK(run_pipeline(idx, B, k, p, fc, fa));
+  RAG_CHECK(fetch_out(idx, bt, L, false));
+
+  writer_fn write = [&](uint32_t ub, const rag_batch* src, const out_layout& SL, uint32_t lb) {
+    const uint32_t cnt = ((const uint32_t*)(src->h_out + SL.cnt))[lb];
+    const uint64_t* keys = (const uint64_t*)(src->h_out + SL.keys) + (size_t)lb * k;
+    const double* sc = (const double*)(src->h_out + SL.scores) + (size_t)lb * k;
+    for (uint32_t i = 0; i < k; i++) {
+      out->ids[(size_t)ub * k + i] = i < cnt ? keys[i] : ~0ull;
+      out->scores[(size_t)ub * k + i] = i < cnt ? sc[i] : -INFINITY;
+    }
+    out->counts[ub] = cnt;
+    if (out->certified) out->certified[ub] = (src->h_out + SL.cert)[lb];
+  };
+  std::vector<uint32_t> sel;
+  const uint8_t* cert = bt->h_out + L.cert;
+  for (uint32_t b = 0; b < B; b++) {
+    write(b, bt, L, b);
+    if (!cert[b]) sel.push_back(b);
+  }
+  if (!sel.empty() && !(o->flags & RAG_SEARCH_NO_ESCALATE)) RAG_CHECK(escalate(idx, sel, k, p, fc, fa, k, false, write));
+  return RAG_OK;
+}
+
+// ---- hybrid search ---------------------------------------------------------------------------
+static int hybrid_args(const rag_index* idx, const rag_hybrid_opts* o, rag_fuse_args* fa, fresh_cfg* fc,
+                       uint32_t* out_cap) {
+  if (o->vector_top_k == 0 || o->vector_top_k > RAG_MAX_TOPK)
+    return rag_set_error(RAG_ERR_INVALID, "vector_top_k must be in 1..%d", RAG_MAX_TOPK);
+  if (o->keyword_limit > RAG_MAX_KEYWORDS) return rag_set_error(RAG_ERR_INVALID, "keyword_limit must be <= %d", RAG_MAX_KEYWORDS);
+  if (o->fresh_limit > RAG_MAX_FRESH) return rag_set_error(RAG_ERR_INVALID, "fresh_limit must be <= %d", RAG_MAX_FRESH);
+  if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
+  *fa = rag_fuse_args();
+  fa->mode = 0;
+  fa->kw_stride = o->keyword_limit;
+  fa->min_score = o->min_vector_score;
+  fa->rrf = o->rrf;
+  fa->fresh_limit = o->fresh_limit;
+  fa->fresh_weight = o->fresh_weight;
+  *out_cap = o->vector_top_k + o->keyword_limit + o->fresh_limit;
+  fa->out_cap = *out_cap;
+  fc->now_ms = o->now_ms;
+  fc->decay = o->time_decay_factor;
+  fc->bonus = o->frequency_bonus;
+  fresh_defaults(&fc->decay, &fc->bonus);
+  return RAG_OK;
+}
+
+static void write_fused(const rag_hybrid_opts* o, rag_fused_out* out, uint32_t out_cap, uint32_t ub, const rag_batch* src,
+                        const out_layout& SL, uint32_t lb) {
+  const uint32_t k = o->vector_top_k;
+  const uint32_t cnt = ((const uint32_t*)(src->h_out + SL.cnt))[lb];
+  const uint64_t* keys = (const uint64_t*)(src->h_out + SL.keys) + (size_t)lb * out_cap;
+  const double* sc = (const double*)(src->h_out + SL.scores) + (size_t)lb * out_cap;
+  const uint8_t* s8 = src->h_out + SL.src + (size_t)lb * out_cap;
+  const uint8_t* c8 = src->h_out + SL.ct + (size_t)lb * out_cap;
+  const size_t base = (size_t)ub * out->capacity;
+  for (uint32_t i = 0; i < out->capacity; i++) {
+    const bool live = i < cnt;
+    out->keys[base + i] = live ? keys[i] : ~0ull;
+    out->scores[base + i] = live ? sc[i] : -INFINITY;
+    if (out->source) out->source[base + i] = live ? s8[i] : 0;
+    if (out->content_type) out->content_type[base + i] = live ? c8[i] : 0;
+  }
+  out->counts[ub] = cnt;
+  if (out->used_rrf) out->used_rrf[ub] = (src->h_out + SL.rrf)[lb];
+  if (out->certified) out->certified[ub] = (src->h_out + SL.cert)[lb];
+  if (out->vec_ids && out->vec_scores && out->vec_counts) {
+    const uint32_t vc = ((const uint32_t*)(src->h_out + SL.vcnt))[lb];
+    const uint64_t* vi = (const uint64_t*)(src->h_out + SL.vids) + (size_t)lb * k;
+    const double* vs = (const double*)(src->h_out + SL.vscores) + (size_t)lb * k;
+    for (uint32_t i = 0; i < k; i++) {
+      out->vec_ids[(size_t)ub * k + i] = i < vc ? vi[i] : ~0ull;
+      out->vec_scores[(size_t)ub * k + i] = i < vc ? vs[i] : -INFINITY;
+    }
+    out->vec_counts[ub] = vc;
+  }
+}
+
+static int check_fused_out(const rag_hybrid_opts* o, const rag_fused_out* out, uint32_t out_cap) {
+  if (!out || !out->keys || !out->scores || !out->counts) return rag_set_error(RAG_ERR_INVALID, "rag_fused_out: null arrays");
+  if (out->capacity < out_cap)
+    return rag_set_error(RAG_ERR_INVALID, "rag_fused_out.capacity=%u < vector_top_k+keyword_limit+fresh_limit=%u",
+                         out->capacity, out_cap);
+  (void)o;
+  return RAG_OK;
+}
+
+int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const rag_hybrid_opts* o,
+                      const uint64_t* kw_keys, const uint32_t* kw_counts, rag_fused_out* out) {
+  RAG_CHECK(check_handle(idx));
+  if (!queries || !o || B == 0) return rag_set_error(RAG_ERR_INVALID, "rag_hybrid_search: null argument or empty batch");
+  rag_fuse_args fa;
+  fresh_cfg fc;
+  uint32_t out_cap = 0;
+  RAG_CHECK(hybrid_args(idx, o, &fa, &fc, &out_cap));
+  RAG_CHECK(check_fused_out(o, out, out_cap));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const uint32_t k = o->vector_top_k;
+  plan p;
+  RAG_CHECK(make_plan(idx, B, k, o->path, o->slack, o->epsilon, &p));
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  out_layout L;
+  RAG_CHECK(stage_queries(idx, bt, queries, B));
+  RAG_CHECK(stage_keywords(idx, bt, B, kw_keys, kw_counts, o->keyword_limit));
+  bt->staged_B = B;
+  bt->win_first = 0;
+  bt->win_count = B;
+  RAG_CHECK(ensure_work(idx, bt, B, k, out_cap, &L));
+  RAG_CHECK(run_pipeline(idx, B, k, p, fc, fa));
+  RAG_CHECK(fetch_out(idx, bt, L, false));
+  writer_fn write = [&](uint32_t ub, const rag_batch* src, const out_layout& SL, uint32_t lb) {
+    write_fused(o, out, out_cap, ub, src, SL, lb);
+  };
+  std::vector<uint32_t> sel;
+  const uint8_t* cert = bt->h_out + L.cert;
+  for (uint32_t b = 0; b < B; b++) {
+    write(b, bt, L, b);
+    if (!cert[b]) sel.push_back(b);
+  }
+  if (!sel.empty() && !(o->flags & RAG_SEARCH_NO_ESCALATE))
+    RAG_CHECK(escalate(idx, sel, k, p, fc, fa, out_cap, false, write));
+  return RAG_OK;
+}
+
+// ---- staged form -----------------------------------------------------------------------------
+int rag_stage_batch(rag_index* idx, const float* queries, uint32_t B, const uint64_t* kw_keys,
+                    const uint32_t* kw_counts, uint32_t keyword_limit) {
+  RAG_CHECK(check_handle(idx));
+  if (!queries || B == 0) return rag_set_error(RAG_ERR_INVALID, "rag_stage_batch: null queries or empty batch");
+  if (keyword_limit > RAG_MAX_KEYWORDS) return rag_set_error(RAG_ERR_INVALID, "keyword_limit must be <= %d", RAG_MAX_KEYWORDS);
+  RAG_CUDA(cudaSetDevice(idx->device));
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  RAG_CHECK(stage_queries(idx, bt, queries, B));
+  RAG_CHECK(stage_keywords(idx, bt, B, kw_keys, kw_counts, keyword_limit));
+  bt->staged_B = B;
+  bt->win_first = 0;
+  bt->win_count = B;
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+int rag_stage_window(rag_index* idx, uint32_t first, uint32_t count) {
+  RAG_CHECK(check_handle(idx));
+  rag_batch* bt = &idx->main;
+  if (count == 0 || (uint64_t)first + count > bt->staged_B)
+    return rag_set_error(RAG_ERR_INVALID, "rag_stage_window: [%u,%u) is outside the %u staged queries", first, first + count, bt->staged_B);
+  bt->win_first = first;
+  bt->win_count = count;
+  return RAG_OK;
+}
+
+int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* o) {
+  RAG_CHECK(check_handle(idx));
+  if (!o) return rag_set_error(RAG_ERR_INVALID, "rag_hybrid_search_staged: null options");
+  rag_batch* bt = &idx->main;
+  if (B == 0 || B != bt->win_count) return rag_set_error(RAG_ERR_STATE, "rag_hybrid_search_staged: B=%u but the staged window holds %u queries", B, bt->win_count);
+  if (o->keyword_limit != bt->staged_kw_stride)
+    return rag_set_error(RAG_ERR_STATE, "rag_hybrid_search_staged: keyword_limit=%u but staged with %u", o->keyword_limit, bt->staged_kw_stride);
+  rag_fuse_args fa;
+  fresh_cfg fc;
+  uint32_t out_cap = 0;
+  RAG_CHECK(hybrid_args(idx, o, &fa, &fc, &out_cap));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  plan p;
+  RAG_CHECK(make_plan(idx, B, o->vector_top_k, o->path, o->slack, o->epsilon, &p));
+  idx->cur = bt;
+  out_layout L;
+  RAG_CHECK(ensure_work(idx, bt, B, o->vector_top_k, out_cap, &L));
+  // view of the window: inputs shifted, work/output buffers shared
+  rag_batch view = *bt;
+  view.d_q = bt->d_q + (size_t)bt->win_first * idx->ld;
+  view.d_kw = bt->d_kw + (size_t)bt->win_first * bt->staged_kw_stride;
+  view.d_kwc = bt->d_kwc + bt->win_first;
+  idx->cur = &view;
+  int rc = run_pipeline(idx, B, o->vector_top_k, p, fc, fa);
+  bt->d_partial = view.d_partial;  // run_pipeline may have grown the partial buffer through the view
+  bt->c_partial = view.c_partial;
+  idx->cur = bt;
+  return rc;
+}
+
+int rag_fetch_fused(rag_index* idx, uint32_t B, const rag_hybrid_opts* o, rag_fused_out* out) {
+  RAG_CHECK(check_handle(idx));
+  if (!o) return rag_set_error(RAG_ERR_INVALID, "rag_fetch_fused: null options");
+  rag_batch* bt = &idx->main;
+  if (B == 0 || B != bt->win_count) return rag_set_error(RAG_ERR_STATE, "rag_fetch_fused: B does not match the staged window");
+  const uint32_t out_cap = o->vector_top_k + o->keyword_limit + o->fresh_limit;
+  RAG_CHECK(check_fused_out(o, out, out_cap));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const out_layout L = layout_out(B, out_cap, o->vector_top_k);
+  if (!bt->d_out || L.total > bt->c_out) return rag_set_error(RAG_ERR_STATE, "rag_fetch_fused: no staged search has run");
+  RAG_CHECK(fetch_out(idx, bt, L, false));
+  for (uint32_t b = 0; b < B; b++) write_fused(o, out, out_cap, b, bt, L, b);
+  return RAG_OK;
+}
+
+int rag_sync(rag_index* idx) {
+  RAG_CHECK(check_handle(idx));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
+// ---- fusion only ---------------------------------------------------------------------------------
+int rag_rrf_fuse(rag_index* idx, uint32_t B, const rag_rrf_config* cfg, const uint64_t* vec_keys,
+                 const uint8_t* vec_ctype, const uint32_t* vec_counts, uint32_t vec_stride, const uint64_t* kw_keys,
+                 const uint32_t* kw_counts, uint32_t kw_stride, rag_fused_out* out) {
+  RAG_CHECK(check_handle(idx));
+  if (!cfg || !out || !out->keys || !out->scores || !out->counts || B == 0 || !vec_counts || !kw_counts)
+    return rag_set_error(RAG_ERR_INVALID, "rag_rrf_fuse: null argument or empty batch");
+  if (vec_stride > RAG_MAX_TOPK || kw_stride > RAG_MAX_KEYWORDS)
+    return rag_set_error(RAG_ERR_INVALID, "rag_rrf_fuse: list strides exceed %d / %d", RAG_MAX_TOPK, RAG_MAX_KEYWORDS);
+  const uint32_t out_cap = std::max(1u, vec_stride + kw_stride);
+  if (out->capacity < out_cap) return rag_set_error(RAG_ERR_INVALID, "rag_fused_out.capacity=%u < %u", out->capacity, out_cap);
+  for (uint32_t b = 0; b < B; b++)
+    if (vec_counts[b] > vec_stride || kw_counts[b] > kw_stride)
+      return rag_set_error(RAG_ERR_INVALID, "rag_rrf_fuse: counts[%u] exceed the list stride", b);
+  RAG_CUDA(cudaSetDevice(idx->device));
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  bt->staged_B = bt->win_count = 0;  // the input block is re-carved below
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+  const size_t o_vk = take((size_t)B * vec_stride * 8), o_kk = take((size_t)B * kw_stride * 8);
+  const size_t o_vc = take((size_t)B * 4), o_kc = take((size_t)B * 4), o_vt = take((size_t)B * vec_stride);
+  RAG_CHECK(grow_dev(&bt->d_in, &bt->c_in, o, true));
+  RAG_CHECK(grow_pinned(&bt->h_in, &bt->c_hin, o));
+  if (vec_stride && vec_keys) memcpy(bt->h_in + o_vk, vec_keys, (size_t)B * vec_stride * 8);
+  if (kw_stride && kw_keys) memcpy(bt->h_in + o_kk, kw_keys, (size_t)B * kw_stride * 8);
+  memcpy(bt->h_in + o_vc, vec_counts, (size_t)B * 4);
+  memcpy(bt->h_in + o_kc, kw_counts, (size_t)B * 4);
+  if (vec_ctype && vec_stride) memcpy(bt->h_in + o_vt, vec_ctype, (size_t)B * vec_stride);
+  RAG_CUDA(cudaMemcpyAsync(bt->d_in, bt->h_in, o, cudaMemcpyHostToDevice, idx->stream));
+  const out_layout L = layout_out(B, out_cap, 1);
+  RAG_CHECK(grow_dev(&bt->d_out, &bt->c_out, L.total, false));
+  RAG_CHECK(grow_pinned(&bt->h_out, &bt->c_hout, L.total));
+  bind_out(bt, L);
+  RAG_CHECK(k5_rrf_only_launch(idx, B, cfg, (const uint64_t*)(bt->d_in + o_vk), vec_ctype ? bt->d_in + o_vt : nullptr,
+                               (const uint32_t*)(bt->d_in + o_vc), vec_stride, (const uint64_t*)(bt->d_in + o_kk),
+                               (const uint32_t*)(bt->d_in + o_kc), kw_stride, out_cap));
+  RAG_CHECK(fetch_out(idx, bt, L, false));
+  for (uint32_t b = 0; b < B; b++) {
+    const uint32_t cnt = ((const uint32_t*)(bt->h_out + L.cnt))[b];
+    const size_t base = (size_t)b * out->capacity, sb = (size_t)b * out_cap;
+    for (uint32_t i = 0; i < out->capacity; i++) {
+      const bool live = i < cnt;
+      out->keys[base + i] = live ? ((const uint64_t*)(bt->h_out + L.keys))[sb + i] : ~0ull;
+      out->scores[base + i] = live ? ((const double*)(bt->h_out + L.scores))[sb + i] : -INFINITY;
+      if (out->source) out->source[base + i] = live ? (bt->h_out + L.src)[sb + i] : 0;
+      if (out->content_type) out->content_type[base + i] = live ? (bt->h_out + L.ct)[sb + i] : 0;
+    }
+    out->counts[b] = cnt;
+    if (out->used_rrf) out->used_rrf[b] = 1;
+    if (out->certified) out->certified[b] = 1;
+  }
+  return RAG_OK;
+}
+
+// ---- memory ------------------------------------------------------------------------------------
+int rag_memory_retrieve(rag_index* idx, const float* queries, uint32_t B, const rag_memory_opts* o, rag_memory_out* out) {
+  RAG_CHECK(check_handle(idx));
+  if (!queries || !o || !out || !out->ids || !out->scores || !out->counts || B == 0)
+    return rag_set_error(RAG_ERR_INVALID, "rag_memory_retrieve: null argument or empty batch");
+  if (o->limit == 0 || o->limit * 2 > RAG_MAX_TOPK) return rag_set_error(RAG_ERR_INVALID, "limit must be in 1..%d", RAG_MAX_TOPK / 2);
+  if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const uint32_t k = o->limit * 2;  // similarityTopK: limit * 2 — src/lib/memory/store.ts:112
+  const uint32_t out_cap = o->limit;
+  plan p;
+  RAG_CHECK(make_plan(idx, B, k, o->path, 0, 0.0, &p));
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  bt->staged_B = bt->win_count = 0;
+  out_layout L;
+  RAG_CHECK(stage_queries(idx, bt, queries, B));
+  RAG_CHECK(ensure_work(idx, bt, B, k, out_cap, &L));
+  rag_fuse_args fa = {};
+  fa.mode = 1;
+  fa.out_cap = out_cap;
+  fa.mem_limit = o->limit;
+  fa.mem_min_relevance = o->min_relevance;
+  fresh_cfg fc = {o->now_ms, o->time_decay_factor, o->frequency_bonus};
+  fresh_defaults(&fc.decay, &fc.bonus);
+  RAG_CHECK(run_pipeline(idx, B, k, p, fc, fa));
+  RAG_CHECK(fetch_out(idx, bt, L, true));
+  writer_fn write = [&](uint32_t ub, const rag_batch* src, const out_layout& SL, uint32_t lb) {
+    const uint32_t cnt = ((const uint32_t*)(src->h_out + SL.cnt))[lb];
+    const size_t sb = (size_t)lb * out_cap, base = (size_t)ub * o->limit;
+    for (uint32_t i = 0; i < o->limit; i++) {
+      const bool live = i < cnt;
+      out->ids[base + i] = live ? ((const uint64_t*)(src->h_out + SL.keys))[sb + i] : ~0ull;
+      out->scores[base + i] = live ? ((const double*)(src->h_out + SL.scores))[sb + i] : -INFINITY;
+      if (out->relevance) out->relevance[base + i] = live ? ((const double*)(src->h_out + SL.aux0))[sb + i] : -INFINITY;
+      if (out->freshness) out->freshness[base + i] = live ? ((const double*)(src->h_out + SL.aux1))[sb + i] : 0.0;
+    }
+    out->counts[ub] = cnt;
+  };
+  std::vector<uint32_t> sel;
+  const uint8_t* cert = bt->h_out + L.cert;
+  for (uint32_t b = 0; b < B; b++) {
+    write(b, bt, L, b);
+    if (!cert[b]) sel.push_back(b);
+  }
+  if (!sel.empty()) RAG_CHECK(escalate(idx, sel, k, p, fc, fa, out_cap, true, write));
+  return RAG_OK;
+}
+
+int rag_freshness_scores(rag_index* idx, uint64_t n, const double* confidence, const int32_t* access_count,
+                         const int64_t* last_access_ms, int64_t now_ms, double decay, double bonus, double* out_scores) {
+  RAG_CHECK(check_handle(idx));
+  if (n == 0) return RAG_OK;
+  if (!confidence || !access_count || !last_access_ms || !out_scores)
+    return rag_set_error(RAG_ERR_INVALID, "rag_freshness_scores: null argument");
+  fresh_defaults(&decay, &bonus);
+  RAG_CUDA(cudaSetDevice(idx->device));
+  uint8_t* d = nullptr;
+  size_t cap = 0;
+  RAG_CHECK(grow_dev(&d, &cap, n * 28, false));
+  double* d_conf = (double*)d;
+  int64_t* d_last = (int64_t*)(d + n * 8);
+  double* d_out = (double*)(d + n * 16);
+  int32_t* d_acc = (int32_t*)(d + n * 24);
+  int rc = RAG_OK;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(d_conf, confidence, n * 8, cudaMemcpyHostToDevice, idx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(d_last, last_access_ms, n * 8, cudaMemcpyHostToDevice, idx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(d_acc, access_count, n * 4, cudaMemcpyHostToDevice, idx->stream)) != cudaSuccess)
+    rc = rag_set_error(RAG_ERR_CUDA, "rag_freshness_scores H2D: %s", cudaGetErrorString(e));
+  if (rc == RAG_OK) rc = k5_freshness_launch(idx, n, d_conf, d_acc, d_last, now_ms, decay, bonus, d_out);
+  if (rc == RAG_OK) {
+    e = cudaMemcpyAsync(out_scores, d_out, n * 8, cudaMemcpyDeviceToHost, idx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+    if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "rag_freshness_scores D2H: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+int rag_timer_start(rag_index* idx) {
+  RAG_CHECK(check_handle(idx));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  RAG_CUDA(cudaEventRecord(idx->ev0, idx->stream));
+  return RAG_OK;
+}
+
+int rag_timer_stop(rag_index* idx, float* elapsed_ms) {
+  RAG_CHECK(check_handle(idx));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  RAG_CUDA(cudaEventRecord(idx->ev1, idx->stream));
+  RAG_CUDA(cudaEventSynchronize(idx->ev1));
+  float ms = 0.f;
+  RAG_CUDA(cudaEventElapsedTime(&ms, idx->ev0, idx->ev1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return RAG_OK;
+}
+
+uint64_t rag_launch_count(const rag_index* idx) { return idx ? idx->launches : 0; }
+
+int rag_profile_enable(rag_index* idx, int on) {
+  RAG_CHECK(check_handle(idx));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  if (on && !idx->prof_spans) {
+    idx->prof_spans = new (std::nothrow) rag_prof_span[kProfSpans];
+    if (!idx->prof_spans) return rag_set_error(RAG_ERR_NOMEM, "out of host memory");
+    idx->prof_cap = 0;
+    for (uint32_t i = 0; i < kProfSpans; i++) {
+      RAG_CUDA(cudaEventCreate(&idx->prof_spans[i].a));
+      RAG_CUDA(cudaEventCreate(&idx->prof_spans[i].b));
+      idx->prof_cap = i + 1;
+    }
+  }
+  if (!on) prof_drain(idx);
+  idx->prof_on = on != 0;
+  return RAG_OK;
+}
+
+int rag_profile_read(rag_index* idx, float ms[RAG_PROF_CLASSES], uint32_t counts[RAG_PROF_CLASSES]) {
+  RAG_CHECK(check_handle(idx));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  prof_drain(idx);
+  for (int i = 0; i < RAG_PROF_CLASSES; i++) {
+    if (ms) ms[i] = idx->prof_ms[i];
+    if (counts) counts[i] = idx->prof_cnt[i];
+    idx->prof_ms[i] = 0.f;
+    idx->prof_cnt[i] = 0;
+  }
+  return RAG_OK;
+}
+
+void* rag_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    rag_set_error(RAG_ERR_NOMEM, "cudaHostAlloc(%llu) failed", (unsigned long long)bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void rag_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

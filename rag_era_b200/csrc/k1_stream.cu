@@ -1,0 +1,239 @@
+// k1_stream.cu — K1: batch-1 (small-batch) cosine scoring fused with top-K' selection.
+//
+// Replaces the hot loops of getTopKEmbeddings / similarity(cosine) (llamaindex,
+// reached from src/lib/hybrid-search.ts:223-224): score every row, keep the best.
+//
+// Roofline: HBM. Algorithmic bytes per launch = rows * ld * sizeof(elem) (the corpus is
+// streamed exactly once per query); everything else (query, candidate lists) is o(1%).
+//   - every warp owns whole rows (row = global warp id + i * total warps), so a warp
+//     reads 6 KB (fp32, D=1536) of contiguous memory per row with 128-bit loads that
+//     bypass L1 (ld.global.nc.L1::no_allocate); all of a row's loads are issued before
+//     the first FMA so each warp keeps a full row in flight
+//   - dot(q,x) and ||x||^2 are accumulated from the same registers: the cosine
+//     normalisation costs no extra HBM traffic (the reference recomputes both norms
+//     per row; ||q|| is a positive per-query constant and cannot change the order)
+//   - the query lives in shared memory, read as conflict-free 128-bit LDS
+//   - selection: per-warp sorted list of K' packed keys in shared memory guarded by a
+//     register threshold, so the common case is one 64-bit compare per row
+//   - output: one sorted K' list per CTA; K3 merges them
+//
+// fp32 accumulation decides only WHICH K' rows survive; K4 rescored them exactly.
+#include "common.cuh"
+
+namespace {
+
+constexpr int K1_THREADS = 512;
+constexpr int K1_WARPS = K1_THREADS / 32;
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float finish_score(float dot, float nrm) {
+  float s = dot * rsqrtf(nrm);
+  // zero-norm / non-finite rows: the reference yields NaN; defined here as never selected
+  return (nrm > 0.0f && s == s) ? s : -INFINITY;
+}
+
+// ---- fp32 corpus: U float4 per lane per sub-chunk, nsub sub-chunks per row ----------
+template <int U>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_stream_f32(const float* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsub,
+              const float* __restrict__ Q, uint32_t kp, uint32_t parts, uint64_t* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* qs = reinterpret_cast<float4*>(smem_raw);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ld * sizeof(float));
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b = blockIdx.y;
+  const float4* q4 = reinterpret_cast<const float4*>(Q + (size_t)b * ld);
+  for (uint32_t i = threadIdx.x; i < ld / 4; i += K1_THREADS) qs[i] = q4[i];
+  uint64_t* mylist = lists + (size_t)warp * kp;
+  for (uint32_t i = lane; i < kp; i += 32) mylist[i] = 0ull;
+  __syncthreads();
+
+  uint64_t thresh = 0ull;
+  const uint32_t stride = gridDim.x * K1_WARPS;
+  for (uint32_t row = blockIdx.x * K1_WARPS + warp; row < n_rows; row += stride) {
+    const float4* xr = reinterpret_cast<const float4*>(X + (size_t)row * ld);
+    float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+    for (int s = 0; s < nsub; s++) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = ldg_stream_f4(xr + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float4 qq = qs[(s * U + u) * 32 + lane];
+        d0 = fmaf(v[u].x, qq.x, d0); d1 = fmaf(v[u].y, qq.y, d1);
+        d0 = fmaf(v[u].z, qq.z, d0); d1 = fmaf(v[u].w, qq.w, d1);
+        n0 = fmaf(v[u].x, v[u].x, n0); n1 = fmaf(v[u].y, v[u].y, n1);
+        n0 = fmaf(v[u].z, v[u].z, n0); n1 = fmaf(v[u].w, v[u].w, n1);
+      }
+    }
+    const float dot = warp_sum(d0 + d1), nrm = warp_sum(n0 + n1);
+    const uint64_t key = rag_pack_key(finish_score(dot, nrm), row);
+    if (key > thresh) warp_list_insert(mylist, kp, key, lane, thresh);
+  }
+  __syncthreads();
+  if (warp == 0)
+    warp_merge_lists(lists, K1_WARPS, kp, kp, partial + ((size_t)b * parts + blockIdx.x) * kp, lane);
+}
+
+// ---- bf16 corpus: U 16-byte loads (8 elements) per lane per sub-chunk, 2 rows in flight ----
+__device__ __forceinline__ void bf16x8_fma(const uint4 v, const float4 qa, const float4 qb, float& d0,
+                                           float& d1, float& n0, float& n1) {
+  float x0 = __uint_as_float(v.x << 16), x1 = __uint_as_float(v.x & 0xFFFF0000u);
+  float x2 = __uint_as_float(v.y << 16), x3 = __uint_as_float(v.y & 0xFFFF0000u);
+  float x4 = __uint_as_float(v.z << 16), x5 = __uint_as_float(v.z & 0xFFFF0000u);
+  float x6 = __uint_as_float(v.w << 16), x7 = __uint_as_float(v.w & 0xFFFF0000u);
+  d0 = fmaf(x0, qa.x, d0); d1 = fmaf(x1, qa.y, d1); d0 = fmaf(x2, qa.z, d0); d1 = fmaf(x3, qa.w, d1);
+  d0 = fmaf(x4, qb.x, d0); d1 = fmaf(x5, qb.y, d1); d0 = fmaf(x6, qb.z, d0); d1 = fmaf(x7, qb.w, d1);
+  n0 = fmaf(x0, x0, n0); n1 = fmaf(x1, x1, n1); n0 = fmaf(x2, x2, n0); n1 = fmaf(x3, x3, n1);
+  n0 = fmaf(x4, x4, n0); n1 = fmaf(x5, x5, n1); n0 = fmaf(x6, x6, n0); n1 = fmaf(x7, x7, n1);
+}
+
+template <int U>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_stream_bf16(const __nv_bfloat16* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsub,
+               const float* __restrict__ Q, uint32_t kp, uint32_t parts, uint64_t* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // query split into two planes so each 128-bit LDS has a 16-byte lane stride:
+  // qa[i] = q[8i..8i+3], qb[i] = q[8i+4..8i+7]
+  float4* qa = reinterpret_cast<float4*>(smem_raw);
+  float4* qb = qa + ld / 8;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ld * sizeof(float));
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b = blockIdx.y;
+  const float4* q4 = reinterpret_cast<const float4*>(Q + (size_t)b * ld);
+  for (uint32_t i = threadIdx.x; i < ld / 4; i += K1_THREADS) {
+    if (i & 1) qb[i >> 1] = q4[i]; else qa[i >> 1] = q4[i];
+  }
+  uint64_t* mylist = lists + (size_t)warp * kp;
+  for (uint32_t i = lane; i < kp; i += 32) mylist[i] = 0ull;
+  __syncthreads();
+
+  uint64_t thresh = 0ull;
+  const uint32_t stride = gridDim.x * K1_WARPS;
+  const uint32_t first = blockIdx.x * K1_WARPS + warp;
+  for (uint32_t row = first; row < n_rows; row += 2 * stride) {
+    const uint32_t row2 = row + stride;
+    const bool has2 = row2 < n_rows;
+    const uint4* xr0 = reinterpret_cast<const uint4*>(X + (size_t)row * ld);
+    const uint4* xr1 = reinterpret_cast<const uint4*>(X + (size_t)(has2 ? row2 : row) * ld);
+    float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f, e0 = 0.f, e1 = 0.f, m0 = 0.f, m1 = 0.f;
+    for (int s = 0; s < nsub; s++) {
+      uint4 v[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = ldg_stream_u4(xr0 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) w[u] = ldg_stream_u4(xr1 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = (s * U + u) * 32 + lane;
+        const float4 a = qa[i], c = qb[i];
+        bf16x8_fma(v[u], a, c, d0, d1, n0, n1);
+        bf16x8_fma(w[u], a, c, e0, e1, m0, m1);
+      }
+    }
+    const float dotA = warp_sum(d0 + d1), nrmA = warp_sum(n0 + n1);
+    const float dotB = warp_sum(e0 + e1), nrmB = warp_sum(m0 + m1);
+    const uint64_t keyA = rag_pack_key(finish_score(dotA, nrmA), row);
+    if (keyA > thresh) warp_list_insert(mylist, kp, keyA, lane, thresh);
+    if (has2) {
+      const uint64_t keyB = rag_pack_key(finish_score(dotB, nrmB), row2);
+      if (keyB > thresh) warp_list_insert(mylist, kp, keyB, lane, thresh);
+    }
+  }
+  __syncthreads();
+  if (warp == 0)
+    warp_merge_lists(lists, K1_WARPS, kp, kp, partial + ((size_t)b * parts + blockIdx.x) * kp, lane);
+}
+
+template <typename F>
+int launch_cfg(F kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return rag_set_error(RAG_ERR_CUDA, "K1 smem opt-in failed: %s", cudaGetErrorString(e));
+  }
+  return RAG_OK;
+}
+
+// largest supported unroll that divides the per-lane vector count of a row
+int pick_unroll(uint32_t per_lane, const int* opts, int nopts) {
+  for (int i = 0; i < nopts; i++)
+    if (per_lane % opts[i] == 0) return opts[i];
+  return 1;
+}
+
+}  // namespace
+
+int k1_plan(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
+  (void)kp;
+  // one CTA per SM per query plane; with several queries in flight the planes share L2
+  uint32_t p = (uint32_t)idx->sm_count;
+  if (B > 1 && B <= 8) p = (uint32_t)idx->sm_count;
+  *parts = p;
+  return RAG_OK;
+}
+
+int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
+  rag_prof_scope ps(idx, RAG_PROF_STREAM);
+  if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
+  if (idx->rows >= 0xFFFFFFFFull) return rag_set_error(RAG_ERR_UNSUPPORTED, "more than 2^32-2 rows per shard");
+  const uint32_t n = (uint32_t)idx->rows, ld = idx->ld;
+  const size_t smem = (size_t)ld * sizeof(float) + (size_t)K1_WARPS * kp * sizeof(uint64_t);
+  dim3 grid(parts, B), block(K1_THREADS);
+#define K1_GO(KERNEL, TYPE)                                                                     \
+  do {                                                                                          \
+    RAG_CHECK(launch_cfg(KERNEL, smem));                                                        \
+    KERNEL<<<grid, block, smem, idx->stream>>>((const TYPE*)idx->corpus, n, ld, nsub, idx->cur->d_q, \
+                                               kp, parts, idx->cur->d_partial);                      \
+  } while (0)
+  if (idx->desc.dtype == RAG_F32) {
+    static const int opts[] = {12, 8, 6, 4, 2};
+    const uint32_t per_lane = ld / 128;  // float4 per lane per row
+    const int U = pick_unroll(per_lane, opts, 5);
+    const int nsub = (int)(per_lane / U);
+    switch (U) {
+      case 12: K1_GO(k1_stream_f32<12>, float); break;
+      case 8: K1_GO(k1_stream_f32<8>, float); break;
+      case 6: K1_GO(k1_stream_f32<6>, float); break;
+      case 4: K1_GO(k1_stream_f32<4>, float); break;
+      default: K1_GO(k1_stream_f32<2>, float); break;
+    }
+  } else {
+    static const int opts[] = {6, 4, 3, 2, 1};
+    const uint32_t per_lane = ld / 256;  // 16-byte loads per lane per row
+    const int U = pick_unroll(per_lane, opts, 5);
+    const int nsub = (int)(per_lane / U);
+    switch (U) {
+      case 6: K1_GO(k1_stream_bf16<6>, __nv_bfloat16); break;
+      case 4: K1_GO(k1_stream_bf16<4>, __nv_bfloat16); break;
+      case 3: K1_GO(k1_stream_bf16<3>, __nv_bfloat16); break;
+      case 2: K1_GO(k1_stream_bf16<2>, __nv_bfloat16); break;
+      default: K1_GO(k1_stream_bf16<1>, __nv_bfloat16); break;
+    }
+  }
+#undef K1_GO
+  RAG_CUDA(cudaGetLastError());
+  idx->launches++;
+  return RAG_OK;
+}

@@ -1,0 +1,66 @@
+"""Host-side mirror of the reference interface: pieces that need no GPU."""
+import numpy as np
+
+import importlib
+
+hs = importlib.import_module("rag_era_b200.hybrid_search")
+from rag_era_b200 import shard_range
+from rag_era_b200.sharded import merge_reference_order
+
+
+def test_js_substring_counts_utf16_units():
+    s = "a😀b" * 60                       # the emoji is 2 UTF-16 code units
+    k = hs.js_substring(s, 0, 100)
+    assert len(k.encode("utf-16-le", "surrogatepass")) == 200
+    assert hs.js_substring("【文档: x】\n\nhello", 0, 100) == "【文档: x】\n\nhello"
+    assert hs.js_substring("x" * 300, 0, 100) == "x" * 100
+
+
+def test_key_interner_is_prefix_equality():
+    ki = hs.KeyInterner()
+    a = ki.key("p" * 100 + "tail one")
+    b = ki.key("p" * 100 + "another tail")
+    c = ki.key("q" + "p" * 99)
+    assert a == b != c and ki.string(a) == "p" * 100
+
+
+def test_presets_match_reference():
+    d, c = hs.get_preset_config("document"), hs.get_preset_config("code")
+    assert (d["rrf"].k, d["rrf"].vector_weight, d["rrf"].keyword_weight, d["rrf"].both_bonus) == (60, 1.0, 1.0, 0.1)
+    assert (d["vectorTopK"], d["keywordLimit"], d["minVectorScore"]) == (8, 8, 0.3)
+    assert (c["rrf"].k, c["rrf"].keyword_weight, c["rrf"].both_bonus) == (40, 1.3, 0.15)
+    assert (c["vectorTopK"], c["keywordLimit"], c["minVectorScore"]) == (6, 5, 0.25)
+
+
+def test_content_type_rule():
+    assert hs.classify_content_type({"type": "memory", "language": "ts"}, True) == "memory"
+    assert hs.classify_content_type({"language": "ts"}, False) == "code"
+    assert hs.classify_content_type({}, True) == "code"
+    assert hs.classify_content_type({}, False) == "document"
+
+
+def test_format_and_stats():
+    r = [hs.HybridSearchResult("k1", "doc.md", "alpha", 0.03, "both", "document"),
+         hs.HybridSearchResult("k2", "用户记忆", "beta", 0.02, "vector", "memory"),
+         hs.HybridSearchResult("k3", "a.ts", "gamma", 0.01, "keyword", "code")]
+    txt = hs.format_search_results(r, 2)
+    assert txt == "[来源1: doc.md] 🎯📄\nalpha\n\n[来源2: 用户记忆] 📊🧠\nbeta"
+    st = hs.get_source_stats(r)
+    assert st == dict(total=3, vector=1, keyword=1, both=1, byType={"document": 1, "memory": 1, "code": 1})
+
+
+def test_shard_ranges_partition_rows():
+    for total in (1, 7, 10_000, 50_000_000):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(total, w, r) for r in range(w)]
+            assert sum(n for _, n in spans) == total
+            pos = 0
+            for base, n in spans:
+                if n:
+                    assert base == pos
+                pos += n
+
+
+def test_merge_reference_order_ties_by_id():
+    ids, sc = merge_reference_order([[5, 9], [2, 7]], [[0.9, 0.5], [0.9, 0.5]], 3)
+    assert ids.tolist() == [2, 5, 7] and sc.tolist() == [0.9, 0.9, 0.5]
