@@ -18,6 +18,6 @@ timeout 300 $BENCH_SHORT > $OUT/${TAG}_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $BENCH_SHORT > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches exit $?"
 timeout 300 $BENCH_SHORT > $OUT/${TAG}_plain2.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_stream -s 20 -c 2 -o $OUT/${TAG}_k1_full $BENCH_SHORT > $OUT/${TAG}_ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_stream -s 5 -c 2 -o $OUT/${TAG}_k1_full $BENCH_SHORT > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT
