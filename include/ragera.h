@@ -224,6 +224,10 @@ int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* 
 int rag_fetch_fused(rag_index* idx, uint32_t B, const rag_hybrid_opts* opts, rag_fused_out* out);
 int rag_sync(rag_index* idx);
 
+/* ---- diagnostics: the raw scaled scores (dot_bf16 * 1/||x||, no 1/||q||) the tensor path (K2)
+ *      computes, written as out_scores[B][rows]; for validating the tcgen05 pipeline on small inputs */
+int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, float* out_scores);
+
 /* ---- measurement helpers (CUDA events on the library's own stream) ------------ */
 int rag_timer_start(rag_index* idx);
 int rag_timer_stop(rag_index* idx, float* elapsed_ms);           /* synchronises */

@@ -115,6 +115,7 @@ SYMBOLS = {
     "rag_hybrid_search_staged": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts)]),
     "rag_fetch_fused": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts), C.POINTER(FusedOut)]),
     "rag_sync": (C.c_int, [_vp]),
+    "rag_debug_tensor_scores": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "rag_timer_start": (C.c_int, [_vp]),
     "rag_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rag_launch_count": (C.c_uint64, [_vp]),

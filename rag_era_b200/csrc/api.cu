@@ -128,7 +128,7 @@ int make_plan(const rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, u
   }
   uint32_t s = slack;
   if (s == 0) s = path == RAG_PATH_TENSOR ? std::max(22u, k) : 6u;
-  uint32_t kp = std::min<uint32_t>(RAG_MAX_CANDIDATES, k + s);
+  uint32_t kp = std::min<uint32_t>(path == RAG_PATH_TENSOR ? 64u : (uint32_t)RAG_MAX_CANDIDATES, k + s);
   p->path = path;
   p->kp = kp;
   p->key_has_qnorm = path == RAG_PATH_EXACT;
@@ -749,8 +749,10 @@ int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* 
   view.d_kwc = bt->d_kwc + bt->win_first;
   idx->cur = &view;
   int rc = run_pipeline(idx, B, o->vector_top_k, p, fc, fa);
-  bt->d_partial = view.d_partial;  // run_pipeline may have grown the partial buffer through the view
+  bt->d_partial = view.d_partial;  // run_pipeline may have grown these through the view
   bt->c_partial = view.c_partial;
+  bt->d_qb = view.d_qb;
+  bt->c_qb = view.c_qb;
   idx->cur = bt;
   return rc;
 }
@@ -907,6 +909,38 @@ int rag_freshness_scores(rag_index* idx, uint64_t n, const double* confidence, c
     e = cudaMemcpyAsync(out_scores, d_out, n * 8, cudaMemcpyDeviceToHost, idx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
     if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "rag_freshness_scores D2H: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// ---- diagnostics -----------------------------------------------------------------------------------
+int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, float* out_scores) {
+  RAG_CHECK(check_handle(idx));
+  if (!queries || !out_scores || B == 0) return rag_set_error(RAG_ERR_INVALID, "rag_debug_tensor_scores: null argument");
+  if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  plan p;
+  RAG_CHECK(make_plan(idx, B, 8, RAG_PATH_TENSOR, 0, 0.0, &p));
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  bt->staged_B = bt->win_count = 0;
+  RAG_CHECK(stage_queries(idx, bt, queries, B));
+  float* d = nullptr;
+  size_t cap = 0;
+  RAG_CHECK(grow_dev(&d, &cap, (size_t)B * idx->rows * 4, true));
+  uint32_t parts = 0;
+  int rc = k2_plan(idx, B, p.kp, &parts);
+  if (rc == RAG_OK) rc = grow_dev(&bt->d_partial, &bt->c_partial, (size_t)B * parts * p.kp * 8, false);
+  if (rc == RAG_OK) {
+    k2_set_debug(idx, d);
+    rc = k2_launch(idx, B, p.kp, parts);
+    k2_set_debug(idx, nullptr);
+  }
+  if (rc == RAG_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_scores, d, (size_t)B * idx->rows * 4, cudaMemcpyDeviceToHost, idx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+    if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "rag_debug_tensor_scores: %s", cudaGetErrorString(e));
   }
   cudaFree(d);
   return rc;

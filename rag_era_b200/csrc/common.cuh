@@ -213,6 +213,7 @@ int k2_available(const rag_index* idx);
 int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
 int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 void k2_destroy(rag_index* idx);
+void k2_set_debug(rag_index* idx, float* d_scores);  // diagnostics: dump the scaled score matrix of the next launch
 // K3 — merge partial lists → K' candidates per query (k3_merge.cu)
 int k3_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // K4 — exact fp64 rescoring in reference order + local top-k + certification (k4_rescore.cu)

@@ -264,6 +264,12 @@ class VectorIndex:
         N.check(self._lib.rag_fetch_fused(self._h, B, C.byref(opts), C.byref(out._c)))
         return out
 
+    def debug_tensor_scores(self, queries) -> np.ndarray:
+        q = self._queries(queries)
+        out = np.empty((q.shape[0], self.rows), dtype=np.float32)
+        N.check(self._lib.rag_debug_tensor_scores(self._h, _ptr(q), q.shape[0], _ptr(out)))
+        return out
+
     def sync(self):
         N.check(self._lib.rag_sync(self._h))
 

@@ -1,0 +1,77 @@
+"""K2 (tcgen05 tensor path) against numpy / the oracle. Run on a B200: ``pytest -m gpu``."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb(native):
+    import rag_era_b200
+
+    assert native.load().rag_device_count() > 0
+    return rag_era_b200
+
+
+def bf16_round(oracle, a):
+    return oracle.bf16_to_f32(oracle.f32_to_bf16(a))
+
+
+@pytest.mark.parametrize("n,d,B", [(256, 256, 1), (300, 64, 5), (1000, 1536, 128), (777, 512, 129), (5000, 256, 256),
+                                   (2049, 1024, 300), (70000, 128, 600)])
+def test_tensor_scores_match_numpy(rb, native, oracle, n, d, B):
+    """The raw K2 scores = <bf16(q), x_bf16> / ||x_bf16|| in fp32 accumulation."""
+    rng = np.random.default_rng(n + d + B)
+    X = oracle.f32_to_bf16(rng.standard_normal((n, d)).astype(np.float32))
+    Q = rng.standard_normal((B, d)).astype(np.float32)
+    with rb.VectorIndex(d, n, dtype=native.BF16) as idx:
+        idx.upload(X)
+        S = idx.debug_tensor_scores(Q)
+    Xf = oracle.bf16_to_f32(X).astype(np.float64)
+    Qf = bf16_round(oracle, Q).astype(np.float64)
+    E = (Qf @ Xf.T) / np.sqrt((Xf * Xf).sum(1))[None, :]
+    scale = np.sqrt((Qf * Qf).sum(1))[:, None]
+    assert np.abs(S - E).max() <= 2e-5 * scale.max(), float(np.abs(S - E).max())
+
+
+@pytest.mark.parametrize("dtype_name", ["bf16", "f32+shadow"])
+@pytest.mark.parametrize("B,k", [(16, 10), (130, 5), (256, 10), (700, 23)])
+def test_tensor_topk_matches_oracle(rb, native, oracle, dtype_name, B, k):
+    n, d = 30000, 512
+    go = oracle.make_gen(n, n_clusters=64, dup_period=17)
+    gn = native.GenDesc.from_buffer_copy(bytes(go))
+    bf = dtype_name == "bf16"
+    X = oracle.gen_rows(go, 0, n, d, dtype=oracle.BF16 if bf else oracle.F32)
+    with rb.VectorIndex(d, n, dtype=native.BF16 if bf else native.F32, bf16_shadow=not bf) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, B)
+        r = idx.query(Q, k, path=native.PATH_TENSOR)
+        raw = idx.query(Q, k, path=native.PATH_TENSOR, flags=native.SEARCH_NO_ESCALATE)
+        for b in range(0, B, max(1, B // 40)):
+            ei, es = oracle.topk(X, Q[b], k)
+            gi, gs = r.row(b)
+            assert np.array_equal(gi, ei), (b, gi, ei)
+            assert np.array_equal(gs, es)
+        assert r.certified.all()
+        # the tensor path alone certifies nearly everything on this data; the rest was escalated
+        assert raw.certified.mean() > 0.9
+
+
+def test_tensor_hybrid_batch(rb, native, oracle):
+    n, d, B = 20000, 1536, 96
+    go = oracle.make_gen(n, n_clusters=32)
+    gn = native.GenDesc.from_buffer_copy(bytes(go))
+    X = oracle.gen_rows(go, 0, n, d)
+    with rb.VectorIndex(d, n, bf16_shadow=True) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, B)
+        kw = [[int(x) for x in oracle.topk(X, Q[b], 3)[0]] + [n - 1 - b] for b in range(B)]
+        o = rb.hybrid_opts(10, 4, 0.3, path=native.PATH_TENSOR)
+        res = idx.hybrid(Q, o, kw)
+        auto = idx.hybrid(Q, rb.hybrid_opts(10, 4, 0.3), kw)          # AUTO picks the tensor path at B >= 16
+        for b in range(B):
+            e = oracle.hybrid_search(X, Q[b], 10, 0.3, kw[b])
+            g = res.row(b)
+            assert np.array_equal(g["keys"], e["keys"]) and np.array_equal(g["scores"], e["scores"])
+            assert np.array_equal(g["vec_ids"], e["vec_ids"]) and np.array_equal(g["vec_scores"], e["vec_scores"])
+            assert np.array_equal(auto.row(b)["keys"], e["keys"])
