@@ -44,6 +44,15 @@ WORKLOADS = {
                desc="C2 deep_search: 1M x 1536 fp32, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1"),
     "c3": dict(rows=10_000_000, dim=1536, dtype="f32", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                desc="C3: 10M x 1536 fp32, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1"),
+    "c2b": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+                path="tensor", shadow=True,
+                desc="C2 deep_search batched: 1M x 1536 fp32 (+bf16 shadow), vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 path"),
+    "c4": dict(rows=7_000_000, dim=1536, dtype="f32", batch=256, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+               path="tensor", shadow=True, memory_rows=2_000_000, fresh_limit=10,
+               desc="C4 memory+RAG unified: 2M memory + 5M doc rows x 1536 fp32 (+bf16 shadow), vector+keyword+freshness lists fused by RRF, batch 256, tcgen05 path"),
+    "c5": dict(rows=50_000_000, dim=1536, dtype="bf16", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+               path="tensor",
+               desc="C5: 50M x 1536 bf16 row-sharded, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 path + NCCL all-gather"),
 }
 SEEDS = dict(seed=0xC0FFEE, query_seed=0xBEEF, meta_seed=0xF00D)
 KW_SEED = 0xFACE
@@ -51,13 +60,16 @@ METRIC, UNIT = "hybrid_search_qps", "queries/s"
 
 
 def peaks():
+    """(hbm GB/s, bf16 TFLOP/s sustained, bf16 TFLOP/s burst, source)"""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            j = json.load(open(p))
+            return (float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), float(j["bf16_tflops"]),
+                    "measured (MEASURED_PEAKS.json)")
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    return 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s burst / ~1.4 sustained)"
 
 
 def keyword_lists(top_ids: np.ndarray, rows: int, kl: int, rng: np.random.Generator):
@@ -195,20 +207,27 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
 
     rows, d, B = w["rows"], w["dim"], w["batch"]
     dt = N.F32 if w["dtype"] == "f32" else N.BF16
-    gen = N.GenDesc(SEEDS["seed"], SEEDS["query_seed"], SEEDS["meta_seed"], rows, 4096, 0.6, 0.5, 0, 0, 1_760_000_000_000)
+    now_ms = 1_760_000_000_000
+    gen = N.GenDesc(SEEDS["seed"], SEEDS["query_seed"], SEEDS["meta_seed"], rows, 4096, 0.6, 0.5, 0,
+                    w.get("memory_rows", 0), now_ms)
+    tensor = w.get("path") == "tensor"
+    path = N.PATH_TENSOR if tensor else N.PATH_STREAM
+    shadow = bool(w.get("shadow")) and dt == N.F32
     if world > 1:
-        idx = create_sharded_index(dist, rows, d, dt, device)
+        idx = create_sharded_index(dist, rows, d, dt, device, bf16_shadow=shadow)
         base, n_local = shard_range(rows, world, rank)
     else:
-        idx = rb.VectorIndex(d, rows, dtype=dt, device=device)
+        idx = rb.VectorIndex(d, rows, dtype=dt, device=device, bf16_shadow=shadow)
         base, n_local = 0, rows
     idx.generate(gen, n_local)
     total = steps + warmup
-    Q = idx.generate_queries(gen, 0, total * B)
-    o = rb.hybrid_opts(w["vector_top_k"], w["keyword_limit"], w["min_score"], path=N.PATH_STREAM)
+    n_pool = min(total, 8) if B >= 64 else total       # big batches cycle through a pool of distinct batches
+    Q = idx.generate_queries(gen, 0, n_pool * B)
+    o = rb.hybrid_opts(w["vector_top_k"], w["keyword_limit"], w["min_score"], path=path,
+                       fresh_limit=w.get("fresh_limit", 0), fresh_weight=1.0, now_ms=now_ms)
 
     # setup (untimed): true vector top-k of every query → keyword lists with ~30% overlap
-    top = idx.query(Q, w["vector_top_k"], path=N.PATH_STREAM)
+    top = idx.query(Q, w["vector_top_k"], path=path)
     kw = keyword_lists(top.ids, rows, w["keyword_limit"], np.random.default_rng(KW_SEED))
     certified_setup = int(top.certified.sum())
 
@@ -220,7 +239,7 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     # ---- device-timed: batch resident in HBM ------------------------------------------------
     idx.stage_batch(Q, kw, w["keyword_limit"])
     for i in range(warmup):
-        idx.stage_window(i * B, B)
+        idx.stage_window((i % n_pool) * B, B)
         idx.hybrid_staged(B, o)
     barrier()
     idx.profile_enable(True)
@@ -231,7 +250,7 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     barrier()
     idx.timer_start()
     for i in range(warmup, total):
-        idx.stage_window(i * B, B)
+        idx.stage_window((i % n_pool) * B, B)
         idx.hybrid_staged(B, o)
     ms = idx.timer_stop()
     barrier()
@@ -250,8 +269,8 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     # ---- end to end: host buffers through rag_hybrid_search ---------------------------------
     lat = []
     for i in range(total):
-        q = Q[i * B:(i + 1) * B]
-        k = kw[i * B:(i + 1) * B]
+        q = Q[(i % n_pool) * B:(i % n_pool + 1) * B]
+        k = kw[(i % n_pool) * B:(i % n_pool + 1) * B]
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -266,32 +285,44 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{device}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    cap = w["vector_top_k"] + w["keyword_limit"]
+    cap = w["vector_top_k"] + w["keyword_limit"] + w.get("fresh_limit", 0)
     h2d = B * (d * 4 + w["keyword_limit"] * 8 + 4)
     d2h = B * (4 + 1 + 4 + 1 + cap * (8 + 8 + 1 + 1) + w["vector_top_k"] * 16)
 
-    peak, peak_src = peaks()
-    k1_ms, k1_n = prof["stream"]
-    bytes_per_launch = n_local * idx_ld(d) * (4 if dt == N.F32 else 2) * B   # K1 streams the shard once per query
-    achieved = bytes_per_launch / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9 if k1_n else None
+    hbm_peak, tf_sus, tf_burst, peak_src = peaks()
+    if tensor:
+        k_ms, k_n = prof["tensor"]
+        flops = 2.0 * n_local * idx_ld(d) * B                                 # dot products only
+        ach = flops / (k_ms / max(k_n, 1) * 1e-3) / 1e12 if k_n else None
+        roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": (ach / tf_sus) if ach else None,
+                "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "frac_of_burst_peak": (ach / tf_burst) if ach else None,
+                "kernel": "k2_tensor (tcgen05 bf16 GEMM + fused top-K' epilogue)", "algorithmic_flops_per_launch": flops,
+                "algorithmic_bytes_per_launch": int(n_local * idx_ld(d) * 2), "avg_launch_ms": k_ms / max(k_n, 1),
+                "launches_timed": int(k_n)}
+    else:
+        k1_ms, k1_n = prof["stream"]
+        bytes_per_launch = n_local * idx_ld(d) * (4 if dt == N.F32 else 2) * B   # K1 streams the shard once per query
+        achieved = bytes_per_launch / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9 if k1_n else None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src + " hbm_gbs",
+                "kernel": "k1_stream (fused cosine GEMV + top-K')", "algorithmic_bytes_per_launch": int(bytes_per_launch),
+                "avg_launch_ms": k1_ms / max(k1_n, 1), "launches_timed": int(k1_n),
+                "frac_of_nominal_8TBps": (achieved / 8000.0) if achieved else None}
     res = {
         "value": steps * B / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches), "clocks": clocks,
         "e2e": {"value": steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "latency_ms_p50": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
                 "timing": "host wall clock around the synchronous call"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                     "kernel": "k1_stream (fused cosine GEMV + top-K')", "algorithmic_bytes_per_launch": int(bytes_per_launch),
-                     "avg_launch_ms": k1_ms / max(k1_n, 1), "launches_timed": int(k1_n),
-                     "frac_of_nominal_8TBps": (achieved / 8000.0) if achieved else None},
+        "roofline": roof,
         "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]},
-        "certified": {"setup_queries": certified_setup, "of": total * B, "last_step": int(last.certified.sum())},
+        "certified": {"setup_queries": certified_setup, "of": n_pool * B, "last_step": int(last.certified.sum()), "last_step_of": B},
     }
     if do_cpu and rank == 0:
         # reference-faithful: ONE thread (the reference is single-threaded JS), full stable sort
         sample_rows = min(rows, 1_000_000)
         n_q = 2 if sample_rows >= 500_000 else 20
-        qps, per_query, sample = cpu_reference_leg(w, n_q, 0, 1, sample_rows)
+        qps, per_query, sample = cpu_reference_leg(w, n_q, 0, 1, sample_rows)   # queries/s (batching does not help a scalar loop)
         res["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                "ms_per_query": per_query * 1e3}
     idx.close()
@@ -324,13 +355,13 @@ def run_ours(args):
     res = measure_workload(rb, N, w, args.workload, steps, warmup, dist, rank, world, local, do_cpu=(world == 1))
     extra = {}
     if world == 1 and not args.no_extra:
-        for name in ("c2", "c1"):
+        for name in ("c2", "c2b", "c1"):
             if name != args.workload:
-                e_steps = 200 if name == "c2" else 500
+                e_steps = {"c2": 200, "c2b": 30, "c1": 500}[name]
                 r = measure_workload(rb, N, WORKLOADS[name], name, e_steps, 5, None, 0, 1, local, do_cpu=False)
                 extra[name] = {"workload": WORKLOADS[name]["desc"], "value": r["value"], "unit": UNIT, "steps": e_steps,
                                "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
-                               "kernel_ms_per_step": r["kernel_ms_per_step"]}
+                               "kernel_ms_per_step": r["kernel_ms_per_step"], "certified": r["certified"]}
     if rank == 0:
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
