@@ -171,8 +171,9 @@ struct rag_index {
   float prof_ms[RAG_PROF_CLASSES] = {0};
   uint32_t prof_cnt[RAG_PROF_CLASSES] = {0};
 
-  // tensor path (K2) state
+  // tensor path (K2) state: single-CTA kernel / CTA-pair kernel
   void* k2_state = nullptr;
+  void* k2p_state = nullptr;
 };
 
 // error plumbing (api.cu)
@@ -213,7 +214,12 @@ int k2_available(const rag_index* idx);
 int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
 int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 void k2_destroy(rag_index* idx);
-void k2_set_debug(rag_index* idx, float* d_scores);  // diagnostics: dump the scaled score matrix of the next launch
+void k2_set_debug(rag_index* idx, float* d_scores);
+// K2 on CTA pairs (k2_pair.cu, cta_group::2) — what k2_* dispatch to by default
+int k2p_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
+int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
+void k2p_set_debug(rag_index* idx, float* d_scores);
+void k2p_destroy(rag_index* idx);  // diagnostics: dump the scaled score matrix of the next launch
 // K3 — merge partial lists → K' candidates per query (k3_merge.cu)
 int k3_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // K4 — exact fp64 rescoring in reference order + local top-k + certification (k4_rescore.cu)

@@ -44,7 +44,10 @@ k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restri
   const uint32_t j = threadIdx.x;  // candidate index
   const uint64_t key = j < kp ? cand[(size_t)b * RAG_MAX_CANDIDATES + j] : 0ull;
   const bool valid = key != 0ull;
-  const uint32_t row = valid ? rag_key_row(key) : 0u;
+  // empty slots re-read the query's best candidate (a row this CTA fetches anyway) instead of all
+  // hammering row 0 — thousands of CTAs on one L2 line set is a measurable hot spot
+  const uint64_t key0 = cand[(size_t)b * RAG_MAX_CANDIDATES];
+  const uint32_t row = valid ? rag_key_row(key) : (key0 != 0ull ? rag_key_row(key0) : 0u);
 
   unsigned char* wsm = smem + (size_t)warp * K4_WARP_BYTES;
   const chains c = warp_exact_sums<BF16>(X, ld, Q + (size_t)b * ld, row, wsm, lane);
