@@ -267,17 +267,30 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         ms = float(t.item())
 
     # ---- end to end: host buffers through rag_hybrid_search ---------------------------------
+    # inputs live in pinned host memory (what the N-API shim backs its typed arrays with); every call
+    # copies them H2D, runs the pipeline, copies the packed result block D2H and unpacks it
+    kl = w["keyword_limit"]
+    Qp = idx.pinned_array((n_pool * B, d), np.float32)
+    Qp[:] = Q
+    kwk = np.zeros((n_pool * B, max(kl, 1)), dtype=np.uint64)
+    kwc = np.zeros(n_pool * B, dtype=np.uint32)
+    for b, lst in enumerate(kw):
+        kwk[b, :len(lst)] = lst
+        kwc[b] = len(lst)
+    kwk = np.ascontiguousarray(kwk[:, :kl]) if kl else kwk[:, :0].copy()
+    out = idx.alloc_fused(B, o)
     lat = []
+    uncert = 0
     for i in range(total):
-        q = Q[(i % n_pool) * B:(i % n_pool + 1) * B]
-        k = kw[(i % n_pool) * B:(i % n_pool + 1) * B]
+        lo = (i % n_pool) * B
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        r = idx.hybrid(q, o, k)
+        r = idx.hybrid_raw(Qp[lo:lo + B], o, kwk[lo:lo + B], kwc[lo:lo + B], out)
         t1 = time.perf_counter()
         if i >= warmup:
             lat.append(t1 - t0)
+            uncert += int(B - r.certified.sum())
     e2e_s = float(np.sum(lat))
     if world > 1:
         import torch
@@ -313,7 +326,8 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         "value": steps * B / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches), "clocks": clocks,
         "e2e": {"value": steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "latency_ms_p50": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
-                "timing": "host wall clock around the synchronous call"},
+                "timing": "host wall clock around the synchronous call (pinned host buffers; escalations included)",
+                "uncertified_after_escalation": uncert},
         "roofline": roof,
         "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]},
         "certified": {"setup_queries": certified_setup, "of": n_pool * B, "last_step": int(last.certified.sum()), "last_step_of": B},

@@ -38,7 +38,12 @@ int grow_dev(T** p, size_t* cap, size_t need, bool zero) {
     cudaGetLastError();
     return rag_set_error(RAG_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
   }
-  if (zero) RAG_CUDA(cudaMemset(q, 0, need));
+  if (zero) {
+    // cudaMemset runs on the legacy default stream, which the library's non-blocking stream does NOT
+    // wait for: finish it here, or a later async copy into this buffer can be overwritten by the zeros
+    RAG_CUDA(cudaMemset(q, 0, need));
+    RAG_CUDA(cudaDeviceSynchronize());
+  }
   *p = (T*)q;
   *cap = need;
   return RAG_OK;

@@ -167,6 +167,87 @@ k1_stream_bf16(const __nv_bfloat16* __restrict__ X, uint32_t n_rows, uint32_t ld
     warp_merge_lists(lists, K1_WARPS, kp, kp, partial + ((size_t)b * parts + blockIdx.x) * kp, lane);
 }
 
+// ---- fp32 corpus, several queries per corpus pass (small batches, escalated queries) -----------
+// Same streaming pattern as k1_stream_f32, but every row a warp loads is scored against QB
+// queries held in shared memory, and a warp keeps TWO rows in flight so each 128-bit query
+// read from shared memory is used twice. HBM traffic stays rows*ld*4 bytes per PASS of QB
+// queries (LDS traffic QB/2 x the row bytes: within the shared-memory budget up to QB = 8).
+constexpr int K1M_THREADS = 512;
+constexpr int K1M_WARPS = K1M_THREADS / 32;
+
+template <int QB, int U>
+__global__ void __launch_bounds__(K1M_THREADS, 1)
+k1_multi_f32(const float* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsub, const float* __restrict__ Q,
+             uint32_t B, uint32_t kp, uint32_t parts, uint64_t* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* qs = reinterpret_cast<float4*>(smem_raw);  // [QB][ld/4]
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (size_t)QB * ld * sizeof(float));  // [warps][QB][kp]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b0 = blockIdx.y * QB;
+  const uint32_t ld4 = ld / 4;
+  for (uint32_t i = threadIdx.x; i < QB * ld4; i += K1M_THREADS) {
+    const uint32_t b = i / ld4, c = i % ld4;
+    qs[i] = b0 + b < B ? reinterpret_cast<const float4*>(Q + (size_t)(b0 + b) * ld)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint64_t* mylists = lists + (size_t)warp * QB * kp;
+  for (uint32_t i = lane; i < QB * kp; i += 32) mylists[i] = 0ull;
+  __syncthreads();
+
+  uint64_t thresh[QB];
+#pragma unroll
+  for (int b = 0; b < QB; b++) thresh[b] = 0ull;
+
+  const uint32_t stride = gridDim.x * K1M_WARPS;
+  for (uint32_t row = blockIdx.x * K1M_WARPS + warp; row < n_rows; row += 2 * stride) {
+    const uint32_t row2 = row + stride;
+    const bool has2 = row2 < n_rows;
+    const float4* x0 = reinterpret_cast<const float4*>(X + (size_t)row * ld);
+    const float4* x1 = reinterpret_cast<const float4*>(X + (size_t)(has2 ? row2 : row) * ld);
+    float d0[QB], d1[QB], n0 = 0.f, n1 = 0.f;
+#pragma unroll
+    for (int b = 0; b < QB; b++) { d0[b] = 0.f; d1[b] = 0.f; }
+    for (int s = 0; s < nsub; s++) {
+      float4 v[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = ldg_stream_f4(x0 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) w[u] = ldg_stream_f4(x1 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        n0 = fmaf(v[u].x, v[u].x, n0); n0 = fmaf(v[u].y, v[u].y, n0); n0 = fmaf(v[u].z, v[u].z, n0); n0 = fmaf(v[u].w, v[u].w, n0);
+        n1 = fmaf(w[u].x, w[u].x, n1); n1 = fmaf(w[u].y, w[u].y, n1); n1 = fmaf(w[u].z, w[u].z, n1); n1 = fmaf(w[u].w, w[u].w, n1);
+#pragma unroll
+        for (int b = 0; b < QB; b++) {
+          const float4 qq = qs[b * ld4 + (s * U + u) * 32 + lane];
+          d0[b] = fmaf(v[u].x, qq.x, d0[b]); d0[b] = fmaf(v[u].y, qq.y, d0[b]);
+          d0[b] = fmaf(v[u].z, qq.z, d0[b]); d0[b] = fmaf(v[u].w, qq.w, d0[b]);
+          d1[b] = fmaf(w[u].x, qq.x, d1[b]); d1[b] = fmaf(w[u].y, qq.y, d1[b]);
+          d1[b] = fmaf(w[u].z, qq.z, d1[b]); d1[b] = fmaf(w[u].w, qq.w, d1[b]);
+        }
+      }
+    }
+    const float nrm0 = warp_sum(n0), nrm1 = warp_sum(n1);
+#pragma unroll
+    for (int b = 0; b < QB; b++) {
+      const float dot0 = warp_sum(d0[b]), dot1 = warp_sum(d1[b]);
+      if (b0 + b < B) {  // warp-uniform
+        const uint64_t key0 = rag_pack_key(finish_score(dot0, nrm0), row);
+        if (key0 > thresh[b]) warp_list_insert(mylists + (size_t)b * kp, kp, key0, lane, thresh[b]);
+        if (has2) {
+          const uint64_t key1 = rag_pack_key(finish_score(dot1, nrm1), row2);
+          if (key1 > thresh[b]) warp_list_insert(mylists + (size_t)b * kp, kp, key1, lane, thresh[b]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // one warp per query merges the 16 per-warp lists of that query
+  for (uint32_t b = warp; b < QB; b += K1M_WARPS)
+    if (b0 + b < B)
+      warp_merge_lists(lists + (size_t)b * kp, K1M_WARPS, QB * kp, kp, partial + ((size_t)(b0 + b) * parts + blockIdx.x) * kp, lane);
+}
+
 template <typename F>
 int launch_cfg(F kernel, size_t smem) {
   if (smem > 48 * 1024) {
@@ -207,7 +288,25 @@ int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     KERNEL<<<grid, block, smem, idx->stream>>>((const TYPE*)idx->corpus, n, ld, nsub, idx->cur->d_q, \
                                                kp, parts, idx->cur->d_partial);                      \
   } while (0)
-  if (idx->desc.dtype == RAG_F32) {
+  if (idx->desc.dtype == RAG_F32 && B > 1) {
+    // several queries per corpus pass: 8 (or 4) queries share every row a warp streams
+    const uint32_t per_lane = ld / 128;
+    const int U = per_lane % 6 == 0 ? 6 : (per_lane % 4 == 0 ? 4 : 2);
+    const int nsub = (int)(per_lane / U);
+    const uint32_t QB = B > 4 ? 8 : 4;
+    const size_t msmem = (size_t)QB * ld * sizeof(float) + (size_t)K1M_WARPS * QB * kp * sizeof(uint64_t);
+    dim3 mgrid(parts, (B + QB - 1) / QB);
+#define K1M_GO(QBv, Uv)                                                                                        \
+  do {                                                                                                         \
+    RAG_CHECK(launch_cfg(k1_multi_f32<QBv, Uv>, msmem));                                                       \
+    k1_multi_f32<QBv, Uv><<<mgrid, K1M_THREADS, msmem, idx->stream>>>((const float*)idx->corpus, n, ld, nsub, \
+                                                                      idx->cur->d_q, B, kp, parts, idx->cur->d_partial); \
+  } while (0)
+    if (msmem > 200 * 1024) return rag_set_error(RAG_ERR_UNSUPPORTED, "stream path: dim too large for the multi-query kernel");
+    if (QB == 8) { if (U == 6) K1M_GO(8, 6); else if (U == 4) K1M_GO(8, 4); else K1M_GO(8, 2); }
+    else         { if (U == 6) K1M_GO(4, 6); else if (U == 4) K1M_GO(4, 4); else K1M_GO(4, 2); }
+#undef K1M_GO
+  } else if (idx->desc.dtype == RAG_F32) {
     static const int opts[] = {12, 8, 6, 4, 2};
     const uint32_t per_lane = ld / 128;  // float4 per lane per row
     const int U = pick_unroll(per_lane, opts, 5);

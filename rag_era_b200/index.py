@@ -106,6 +106,9 @@ class VectorIndex:
         if getattr(self, "_h", None):
             self._lib.rag_index_destroy(self._h)
             self._h = None
+        for p in getattr(self, "_pinned", []):
+            self._lib.rag_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -203,6 +206,32 @@ class VectorIndex:
         out = _alloc_fused(B, max(1, opts.vector_top_k + opts.keyword_limit + opts.fresh_limit), opts.vector_top_k)
         N.check(self._lib.rag_hybrid_search(self._h, _ptr(q), B, C.byref(opts), _ptr(keys), _ptr(counts), C.byref(out._c)))
         return out
+
+    def hybrid_raw(self, q: np.ndarray, opts: N.HybridOpts, kw_keys: np.ndarray, kw_counts: np.ndarray,
+                   out: Fused | None = None) -> Fused:
+        """rag_hybrid_search on caller-prepared arrays (no per-call list handling): q float32 [B, dim],
+        kw_keys uint64 [B, keyword_limit], kw_counts uint32 [B]; ``out`` may be reused across calls."""
+        B = q.shape[0]
+        if out is None:
+            out = _alloc_fused(B, max(1, opts.vector_top_k + opts.keyword_limit + opts.fresh_limit), opts.vector_top_k)
+        N.check(self._lib.rag_hybrid_search(self._h, _ptr(q), B, C.byref(opts), _ptr(kw_keys), _ptr(kw_counts), C.byref(out._c)))
+        return out
+
+    def alloc_fused(self, B: int, opts: N.HybridOpts) -> Fused:
+        return _alloc_fused(B, max(1, opts.vector_top_k + opts.keyword_limit + opts.fresh_limit), opts.vector_top_k)
+
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """A numpy array over page-locked host memory (rag_host_alloc): H2D/D2H of it are true async DMA.
+        The memory lives until the process exits or ``free_pinned`` is called with the array."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self._lib.rag_host_alloc(max(n, 16))
+        if not p:
+            raise N.RagError(N.ERR_NOMEM, "rag_host_alloc failed")
+        buf = (C.c_uint8 * max(n, 16)).from_address(p)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return arr
 
     def rrf_fuse(self, vec_lists, kw_lists, cfg: RRFConfig = RRFConfig(), vec_ctypes=None) -> Fused:
         """reciprocalRankFusion on integer keys for B independent list pairs (hybrid-search.ts:129-208)."""

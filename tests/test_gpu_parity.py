@@ -455,3 +455,22 @@ def oracle_planted(g, b):
         return z ^ (z >> 31)
 
     return mix(g.query_seed ^ 0x9A17 ^ mix(b)) % g.total_rows
+
+
+@pytest.mark.parametrize("B", [2, 4, 5, 8, 9, 17])
+@pytest.mark.parametrize("d", [1536, 100])
+def test_multi_query_stream_kernel(rb, native, oracle, B, d):
+    """K1m: several queries share one corpus pass; results must not depend on how queries are grouped."""
+    n = 7000
+    go, gn = gen(oracle, native, n, n_clusters=16, dup_period=6)
+    X = oracle.gen_rows(go, 0, n, d)
+    with rb.VectorIndex(d, n) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, B)
+        r = idx.query(Q, 10, path=native.PATH_STREAM)
+        single = [idx.query(Q[b:b + 1], 10, path=native.PATH_STREAM) for b in range(B)]
+        for b in range(B):
+            ei, es = oracle.topk(X, Q[b], 10)
+            assert np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es)
+            assert np.array_equal(single[b].row(0)[0], ei)
+        assert r.certified.all()
