@@ -72,6 +72,17 @@ def peaks():
     return 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s burst / ~1.4 sustained)"
 
 
+def traffic_ratio(kernel: str, name: str):
+    """DRAM traffic / algorithmic bytes of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json); None if this workload has not been captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        e = t.get(name) or t.get({"c3": "c2", "c2": "c3"}.get(name, ""))   # same kernel, same access pattern
+        return float(e.get("ratio", e.get("traffic_over_algorithmic")))
+    except Exception:
+        return None
+
+
 def keyword_lists(top_ids: np.ndarray, rows: int, kl: int, rng: np.random.Generator):
     """ceil(30%) of each list drawn from the true vector top-k (exercises 'both'),
     the rest uniform random rows, in a seeded order. Key map = identity."""
@@ -310,9 +321,13 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": (ach / tf_sus) if ach else None,
                 "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": (ach / tf_burst) if ach else None,
-                "kernel": "k2_tensor (tcgen05 bf16 GEMM + fused top-K' epilogue)", "algorithmic_flops_per_launch": flops,
+                "kernel": "k2_pair (tcgen05 cta_group::2 bf16 GEMM + fused top-K' epilogue)", "algorithmic_flops_per_launch": flops,
                 "algorithmic_bytes_per_launch": int(n_local * idx_ld(d) * 2), "avg_launch_ms": k_ms / max(k_n, 1),
                 "launches_timed": int(k_n)}
+        tr = traffic_ratio("k2_pair", name)
+        if tr:
+            roof["traffic"] = int(tr * n_local * idx_ld(d) * 2)
+            roof["traffic_source"] = "profiles/traffic.json (ncu --set full dram bytes / algorithmic, scaled to this launch)"
     else:
         k1_ms, k1_n = prof["stream"]
         bytes_per_launch = n_local * idx_ld(d) * (4 if dt == N.F32 else 2) * B   # K1 streams the shard once per query
@@ -322,6 +337,10 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
                 "kernel": "k1_stream (fused cosine GEMV + top-K')", "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "avg_launch_ms": k1_ms / max(k1_n, 1), "launches_timed": int(k1_n),
                 "frac_of_nominal_8TBps": (achieved / 8000.0) if achieved else None}
+        tr = traffic_ratio("k1_stream", name)
+        if tr:
+            roof["traffic"] = int(tr * bytes_per_launch)
+            roof["traffic_source"] = "profiles/traffic.json (ncu --set full dram bytes / algorithmic, scaled to this launch)"
     res = {
         "value": steps * B / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches), "clocks": clocks,
         "e2e": {"value": steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -355,6 +374,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         import torch
         import torch.distributed as dist
