@@ -67,6 +67,7 @@ int grow_pinned(uint8_t** p, size_t* cap, size_t need) {
 void free_batch(rag_batch* b) {
   cudaFree(b->d_q); cudaFree(b->d_qb); cudaFree(b->d_in); cudaFree(b->d_sel); cudaFree(b->d_partial);
   cudaFree(b->d_cand); cudaFree(b->d_local); cudaFree(b->d_gather); cudaFree(b->d_local_cnt); cudaFree(b->d_out);
+  cudaFree(b->d_k4s); cudaFree(b->d_ticket);
   if (b->h_in) cudaFreeHost(b->h_in);
   if (b->h_out) cudaFreeHost(b->h_out);
   *b = rag_batch();
@@ -194,6 +195,10 @@ int ensure_work(rag_index* idx, rag_batch* bt, uint32_t B, uint32_t k, uint32_t 
   RAG_CHECK(grow_dev(&bt->d_cand, &bt->c_cand, (size_t)B * RAG_MAX_CANDIDATES * 8, false));
   RAG_CHECK(grow_dev(&bt->d_local, &bt->c_local, (size_t)B * k * sizeof(rag_rec), false));
   RAG_CHECK(grow_dev(&bt->d_local_cnt, &bt->c_lcnt, (size_t)B * 4, false));
+  if (B <= 32) {
+    RAG_CHECK(grow_dev(&bt->d_k4s, &bt->c_k4s, (size_t)B * (2 * RAG_MAX_CANDIDATES + 2) * 8, false));
+    RAG_CHECK(grow_dev(&bt->d_ticket, &bt->c_ticket, (size_t)32 * 4, true));
+  }
   if (idx->nranks > 1)
     RAG_CHECK(grow_dev(&bt->d_gather, &bt->c_gather, (size_t)idx->nranks * B * k * sizeof(rag_rec), false));
   *L = layout_out(B, out_cap, k);
@@ -240,8 +245,12 @@ int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fr
   if (p.path == RAG_PATH_STREAM) RAG_CHECK(k1_launch(idx, B, p.kp, parts));
   else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_launch(idx, B, p.kp, parts));
   else RAG_CHECK(k1x_launch(idx, B, p.kp, parts));
-  RAG_CHECK(k3_launch(idx, B, p.kp, parts));
-  RAG_CHECK(k4_launch(idx, B, p.kp, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
+  if (k34_small_ok(idx, B, p.kp, parts)) {
+    RAG_CHECK(k34_small_launch(idx, B, p.kp, parts, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
+  } else {
+    RAG_CHECK(k3_launch(idx, B, p.kp, parts));
+    RAG_CHECK(k4_launch(idx, B, p.kp, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
+  }
   RAG_CHECK(comm_allgather_local(idx, B, k));
   fa.B = B;
   fa.k = k;

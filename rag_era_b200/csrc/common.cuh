@@ -124,6 +124,8 @@ struct rag_batch {
   rag_rec* d_local = nullptr;       size_t c_local = 0;    // [B][k] this rank's exact top-k
   rag_rec* d_gather = nullptr;      size_t c_gather = 0;   // [G][B][k]
   uint32_t* d_local_cnt = nullptr;  size_t c_lcnt = 0;     // [B]
+  double* d_k4s = nullptr;          size_t c_k4s = 0;      // [B][2*128+2] exact sums of the small-batch K3+K4 kernel
+  unsigned int* d_ticket = nullptr; size_t c_ticket = 0;   // [B] arrival tickets (zero between launches)
   // fused outputs: one device block + pinned host mirror, carved per call (out_layout in api.cu)
   uint8_t* d_out = nullptr;         size_t c_out = 0;
   uint8_t* h_out = nullptr;         size_t c_hout = 0;
@@ -225,6 +227,10 @@ int k3_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // K4 — exact fp64 rescoring in reference order + local top-k + certification (k4_rescore.cu)
 int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, double eps, int key_has_qnorm,
               int64_t now_ms, double decay, double bonus);
+// K3+K4 fused, latency variant for small batches (k4_rescore.cu)
+bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
+int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, double eps, int key_has_qnorm,
+                     int64_t now_ms, double decay, double bonus);
 // K5 — cross-rank merge, min-cosine filter, RRF / freshness fusion, memory blend (k5_fuse.cu)
 struct rag_fuse_args {
   uint32_t B, k, nranks;

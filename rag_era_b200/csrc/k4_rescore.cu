@@ -26,38 +26,30 @@ namespace {
 using namespace rag_exact;
 constexpr int K4_WARP_BYTES = WARP_BYTES;
 
-template <bool BF16>
-__global__ void __launch_bounds__(RAG_MAX_CANDIDATES)
-k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restrict__ Q,
-                  const uint64_t* __restrict__ cand, uint32_t kp, uint32_t k, double eps,
-                  int key_has_qnorm, uint64_t id_base, const uint8_t* __restrict__ ctype, const double* __restrict__ conf,
-                  const int32_t* __restrict__ access, const int64_t* __restrict__ last_ms,
-                  const uint64_t* __restrict__ row_keys, int64_t now_ms, double decay, double bonus,
-                  rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double s_score[RAG_MAX_CANDIDATES];
-  __shared__ uint32_t s_row[RAG_MAX_CANDIDATES];
-  __shared__ double s_nq;
+struct k4_meta {
+  uint64_t id_base;
+  const uint8_t* ctype;
+  const double* conf;
+  const int32_t* access;
+  const int64_t* last_ms;
+  const uint64_t* row_keys;
+  int64_t now_ms;
+  double decay, bonus;
+};
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t b = blockIdx.x;
-  const uint32_t j = threadIdx.x;  // candidate index
-  const uint64_t key = j < kp ? cand[(size_t)b * RAG_MAX_CANDIDATES + j] : 0ull;
-  const bool valid = key != 0ull;
-  // empty slots re-read the query's best candidate (a row this CTA fetches anyway) instead of all
-  // hammering row 0 — thousands of CTAs on one L2 line set is a measurable hot spot
-  const uint64_t key0 = cand[(size_t)b * RAG_MAX_CANDIDATES];
-  const uint32_t row = valid ? rag_key_row(key) : (key0 != 0ull ? rag_key_row(key0) : 0u);
-
-  unsigned char* wsm = smem + (size_t)warp * K4_WARP_BYTES;
-  const chains c = warp_exact_sums<BF16>(X, ld, Q + (size_t)b * ld, row, wsm, lane);
-
+// Shared tail of both K4 kernels, executed by one thread per candidate (j < blockDim.x, all threads
+// of the CTA must call): exact rank, certification, record write. s_score/s_row/s_tmp are shared
+// arrays of >= kp entries that this function fills.
+__device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k, bool valid, uint32_t row, double score,
+                                            double nq, uint64_t last_key, double eps, int key_has_qnorm,
+                                            const k4_meta& M, double* s_score, uint32_t* s_row, double* s_kth,
+                                            rag_rec* __restrict__ out, uint32_t* __restrict__ out_cnt) {
   // similarity = dot / (norm(q) * norm(x)); NaN (zero norm) is defined as never selected
-  double score = finish(c);
   const bool good = valid && score == score;
-  s_score[j] = good ? score : -INFINITY;
-  s_row[j] = row;
-  if (j == 0) s_nq = c.nq;
+  if (j < kp) {
+    s_score[j] = good ? score : -INFINITY;
+    s_row[j] = row;
+  }
   __syncthreads();
 
   // exact order: score desc, chunk id asc (== the reference's stable sort over insertion order)
@@ -72,46 +64,255 @@ k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restri
   const uint32_t cnt = n_good < k ? n_good : k;
 
   // certification of the local top-k against rows that were never candidates
-  __shared__ double s_kth;
-  if (good && rank + 1 == cnt) s_kth = score;
+  if (good && rank + 1 == cnt) *s_kth = score;
   __syncthreads();
   bool certified = true;
-  const uint64_t last_key = cand[(size_t)b * RAG_MAX_CANDIDATES + kp - 1];
   if (last_key != 0ull && cnt > 0) {  // list full: rows outside the candidate set exist
     // K1/K2 keys hold dot/||x|| (||q|| cannot change the order); K1x keys hold the cosine itself
-    const double t = key_has_qnorm ? (double)rag_key_score(last_key)
-                                   : (double)rag_key_score(last_key) / sqrt(s_nq);
-    certified = cnt == k && s_kth > t + eps;
+    const double t = key_has_qnorm ? (double)rag_key_score(last_key) : (double)rag_key_score(last_key) / sqrt(nq);
+    certified = cnt == k && *s_kth > t + eps;
   }
   const uint32_t flags = certified ? 0u : 1u;
 
-  rag_rec* out = local + (size_t)b * k;
   if (good && rank < k) {
     rag_rec r;
     r.score = score;
-    r.id = id_base + row;
-    r.key = row_keys ? row_keys[row] : r.id;
-    r.ctype = ctype ? ctype[row] : (uint32_t)RAG_CT_DOCUMENT;
+    r.id = M.id_base + row;
+    r.key = M.row_keys ? M.row_keys[row] : r.id;
+    r.ctype = M.ctype ? M.ctype[row] : (uint32_t)RAG_CT_DOCUMENT;
     r.flags = flags;
     r.fresh = 0.0;
     r.conf_pad = 0.0;
-    if (r.ctype == RAG_CT_MEMORY && conf && access && last_ms) {
+    if (r.ctype == RAG_CT_MEMORY && M.conf && M.access && M.last_ms) {
       // calculateFreshnessScore — src/lib/memory/freshness.ts:43-55 (exp/log: <=1 ulp libm variance)
-      const double hours = (double)(now_ms - last_ms[row]) / 3600000.0;
-      const double dec = exp(__dmul_rn(-decay, hours));
-      const double fb = __dmul_rn(log((double)access[row] + 1.0), bonus);
-      const double sc = __dmul_rn(__dmul_rn(conf[row], dec), __dadd_rn(1.0, fb));
+      const double hours = (double)(M.now_ms - M.last_ms[row]) / 3600000.0;
+      const double dec = exp(__dmul_rn(-M.decay, hours));
+      const double fb = __dmul_rn(log((double)M.access[row] + 1.0), M.bonus);
+      const double sc = __dmul_rn(__dmul_rn(M.conf[row], dec), __dadd_rn(1.0, fb));
       r.fresh = fmax(0.0, fmin(1.0, sc));
     }
     out[rank] = r;
   }
   // empty tail + flags on every slot so the merge sees them even for empty shards
-  for (uint32_t i = cnt + threadIdx.x; i < k; i += blockDim.x) {
+  for (uint32_t i = cnt + j; i < k; i += blockDim.x) {
     rag_rec e;
     e.score = -INFINITY; e.id = ~0ull; e.key = ~0ull; e.fresh = 0.0; e.ctype = 0; e.flags = flags; e.conf_pad = 0.0;
     out[i] = e;
   }
-  if (threadIdx.x == 0) local_cnt[b] = cnt;
+  if (j == 0) *out_cnt = cnt;
+}
+
+// ---- throughput variant (large batches): one CTA per query, one LANE per candidate ---------------
+template <bool BF16>
+__global__ void __launch_bounds__(RAG_MAX_CANDIDATES)
+k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restrict__ Q,
+                  const uint64_t* __restrict__ cand, uint32_t kp, uint32_t k, double eps,
+                  int key_has_qnorm, k4_meta M, rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double s_score[RAG_MAX_CANDIDATES];
+  __shared__ uint32_t s_row[RAG_MAX_CANDIDATES];
+  __shared__ double s_nq, s_kth;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b = blockIdx.x;
+  const uint32_t j = threadIdx.x;  // candidate index
+  const uint64_t key = j < kp ? cand[(size_t)b * RAG_MAX_CANDIDATES + j] : 0ull;
+  const bool valid = key != 0ull;
+  // empty slots re-read the query's best candidate (a row this CTA fetches anyway) instead of all
+  // hammering row 0 — thousands of CTAs on one L2 line set is a measurable hot spot
+  const uint64_t key0 = cand[(size_t)b * RAG_MAX_CANDIDATES];
+  const uint32_t row = valid ? rag_key_row(key) : (key0 != 0ull ? rag_key_row(key0) : 0u);
+
+  unsigned char* wsm = smem + (size_t)warp * K4_WARP_BYTES;
+  const chains c = warp_exact_sums<BF16>(X, ld, Q + (size_t)b * ld, row, wsm, lane);
+  if (j == 0) s_nq = c.nq;
+  __syncthreads();
+  k4_finalize(j, kp, k, valid, row, finish(c), s_nq, cand[(size_t)b * RAG_MAX_CANDIDATES + kp - 1], eps, key_has_qnorm, M,
+              s_score, s_row, &s_kth, local + (size_t)b * k, local_cnt + b);
+}
+
+// ---- latency variant (small batches): K3 + K4 fused, one WARP per candidate, several CTAs per query --
+// The three sums of a row are strictly sequential (the reference adds left to right), so one
+// candidate is a dependent chain of `ld` fp64 adds no matter how it is mapped. Here the 32 lanes
+// of a warp compute the products of 32 consecutive elements in parallel (exact: one rounding
+// each, same as the reference's q[i]*x[i]) and then every lane replays the adds in order, fetching
+// product i from lane i%32 with a shuffle — 2 SHFL + 1 DADD per element per sum, no shared
+// memory, nothing but the add latency on the critical path. A query's K' candidates are spread
+// over K'/4 CTAs (4 candidate warps + 1 warp for ||q||^2 each), so a batch-1 search uses 4-8 SMs
+// instead of one warp of one SM. Every CTA first merges the per-CTA candidate lists of K1/K2
+// itself (sorted lists, k-way merge from shared memory — this is K3, fused); the last CTA of a
+// query to finish (atomic ticket) ranks, certifies and writes the records.
+constexpr int K4S_CW = 4;                       // candidate warps per CTA
+constexpr int K4S_WARPS = K4S_CW + 1;           // + the ||q||^2 warp
+constexpr int K4S_THREADS = K4S_WARPS * 32;
+constexpr size_t K4S_MAX_STAGE = 96 * 1024;     // staged candidate keys (parts * K' * 8 bytes)
+
+template <bool BF16>
+__device__ __forceinline__ void load_block(const void* __restrict__ X, size_t row_off, const float* __restrict__ q,
+                                           int blk, int lane, float (&xr)[8], float (&qr)[8]) {
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const int e = blk * 256 + t * 32 + lane;
+    qr[t] = q ? q[e] : 0.f;
+    if (X) {
+      if (BF16) xr[t] = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(X)[row_off + e] << 16);
+      else xr[t] = reinterpret_cast<const float*>(X)[row_off + e];
+    } else {
+      xr[t] = 0.f;
+    }
+  }
+}
+
+// dot = sum q[i]*x[i], nx = sum x[i]*x[i] in reference order (X != null), or nq = sum q[i]*q[i] (X == null).
+// The 32 lanes compute the (exact) products of a 256-element block in parallel and park them in the
+// warp's shared-memory scratch `sp` [2 buffers][2 sums][256]; the adds are then replayed in order from
+// broadcast 128-bit shared loads, so the only thing on the critical path is the fp64 add latency.
+// Products of block b+1 are computed while the global loads of block b+2 are in flight.
+template <bool BF16>
+__device__ __forceinline__ void warp_chain(const void* __restrict__ X, uint32_t row, uint32_t ld,
+                                           const float* __restrict__ q, int lane, double* sp, double& s0, double& s1) {
+  s0 = 0.0;
+  s1 = 0.0;
+  const int nblk = (int)(ld / 256);
+  const size_t row_off = (size_t)row * ld;
+  float xr[8], qr[8];
+  auto park = [&](int buf) {
+    double* p0 = sp + buf * 512;
+    double* p1 = p0 + 256;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const double qd = (double)qr[t], xd = (double)xr[t];
+      p0[t * 32 + lane] = X ? __dmul_rn(qd, xd) : __dmul_rn(qd, qd);
+      if (X) p1[t * 32 + lane] = __dmul_rn(xd, xd);
+    }
+  };
+  load_block<BF16>(X, row_off, q, 0, lane, xr, qr);
+  park(0);
+  __syncwarp();
+  for (int blk = 0; blk < nblk; blk++) {
+    if (blk + 1 < nblk) load_block<BF16>(X, row_off, q, blk + 1, lane, xr, qr);
+    const double2* a0 = reinterpret_cast<const double2*>(sp + (blk & 1) * 512);
+    const double2* a1 = a0 + 128;
+    if (X) {
+#pragma unroll 8
+      for (int i = 0; i < 128; i++) {
+        const double2 u = a0[i], v = a1[i];
+        s0 = __dadd_rn(__dadd_rn(s0, u.x), u.y);
+        s1 = __dadd_rn(__dadd_rn(s1, v.x), v.y);
+      }
+    } else {
+#pragma unroll 8
+      for (int i = 0; i < 128; i++) {
+        const double2 u = a0[i];
+        s0 = __dadd_rn(__dadd_rn(s0, u.x), u.y);
+      }
+    }
+    if (blk + 1 < nblk) {
+      park((blk + 1) & 1);
+      __syncwarp();
+    }
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(K4S_THREADS)
+k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restrict__ Q,
+                 const uint64_t* __restrict__ partial, uint32_t parts, uint32_t kp, uint32_t k, double eps,
+                 int key_has_qnorm, k4_meta M, double* __restrict__ scratch /*[B][2*128+2]*/,
+                 unsigned int* __restrict__ ticket /*[B]*/, uint64_t* __restrict__ cand_out /*[B][128]*/,
+                 rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* stg = reinterpret_cast<uint64_t*>(smem);               // [parts][kp] staged lists
+  uint64_t* wl = stg + (size_t)parts * kp;                         // [2][K4S_WARPS][kp] per-warp merged lists
+  __shared__ __align__(16) double s_prod[K4S_WARPS][2 * 2 * 256];  // per-warp product scratch of warp_chain
+  __shared__ uint64_t s_cand[RAG_MAX_CANDIDATES];
+  __shared__ double s_score[RAG_MAX_CANDIDATES];
+  __shared__ uint32_t s_row[RAG_MAX_CANDIDATES];
+  __shared__ double s_kth;
+  __shared__ int s_last;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b = blockIdx.x, slice = blockIdx.y, nslices = gridDim.y;
+
+  // ---- K3: merge the sorted per-CTA lists of the scoring kernel (every slice does it: ~1 us) ----
+  const uint64_t* in = partial + (size_t)b * parts * kp;
+  for (uint32_t i = threadIdx.x; i < parts * kp; i += K4S_THREADS) stg[i] = in[i];
+  __syncthreads();
+  // warp w merges lists w, w+W, w+2W, ... at most 31 at a time, together with its running result
+  // (ping-pong between two per-warp buffers; every warp runs the same number of rounds)
+  uint64_t* wl2 = wl + (size_t)K4S_WARPS * kp;
+  uint64_t* res = wl;  // where the per-warp results end up
+  {
+    uint64_t* cur_l = wl + (size_t)warp * kp;
+    uint64_t* nxt_l = wl2 + (size_t)warp * kp;
+    for (uint32_t i = lane; i < kp; i += 32) cur_l[i] = 0ull;
+    __syncwarp();
+    for (uint32_t base = 0; base < parts; base += K4S_WARPS * 31) {
+      // lane 0 walks the running list, lane l >= 1 walks list base + warp + (l-1)*W
+      const uint32_t li = base + warp + (uint32_t)(lane - 1) * K4S_WARPS;
+      const uint64_t* lst = lane == 0 ? cur_l : (li < parts ? stg + (size_t)li * kp : nullptr);
+      uint32_t head = 0;
+      uint64_t cur = lst ? lst[0] : 0ull;
+      for (uint32_t r = 0; r < kp; r++) {
+        const uint64_t m = warp_max_u64(cur);
+        if (lane == 0) nxt_l[r] = m;
+        if (m != 0ull && cur == m) {  // keys are unique (the row is part of the key)
+          head++;
+          cur = head < kp ? lst[head] : 0ull;
+        }
+      }
+      __syncwarp();
+      uint64_t* t = cur_l; cur_l = nxt_l; nxt_l = t;
+      res = res == wl ? wl2 : wl;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    warp_merge_lists(res, K4S_WARPS, (int)kp, (int)kp, s_cand, lane);
+    if (slice == 0)
+      for (uint32_t i = lane; i < RAG_MAX_CANDIDATES; i += 32) cand_out[(size_t)b * RAG_MAX_CANDIDATES + i] = i < kp ? s_cand[i] : 0ull;
+  }
+  __syncthreads();
+
+  // ---- K4: exact sums, one warp per candidate -----------------------------------------------------
+  double* my_scratch = scratch + (size_t)b * (2 * RAG_MAX_CANDIDATES + 2);
+  const float* q = Q + (size_t)b * ld;
+  if (warp < K4S_CW) {
+    for (uint32_t j = slice * K4S_CW + warp; j < kp; j += nslices * K4S_CW) {
+      const uint64_t key = s_cand[j];
+      if (key == 0ull) continue;  // warp-uniform
+      double dot, nx;
+      warp_chain<BF16>(X, rag_key_row(key), ld, q, lane, s_prod[warp], dot, nx);
+      if (lane == 0) { my_scratch[2 * j] = dot; my_scratch[2 * j + 1] = nx; }
+    }
+  } else if (slice == 0) {
+    double nq, unused;
+    warp_chain<BF16>(nullptr, 0, ld, q, lane, s_prod[warp], nq, unused);
+    if (lane == 0) my_scratch[2 * RAG_MAX_CANDIDATES] = nq;
+  }
+
+  // ---- the last slice of this query to arrive finishes it ------------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&ticket[b], 1u);
+    s_last = (t == nslices - 1) ? 1 : 0;
+    if (s_last) ticket[b] = 0u;  // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile double* vs = my_scratch;
+  const double nq = vs[2 * RAG_MAX_CANDIDATES];
+  for (uint32_t j0 = 0; j0 < kp || j0 == 0; j0 += K4S_THREADS) {  // kp <= 128 <= K4S_THREADS: one pass
+    const uint32_t j = j0 + threadIdx.x;
+    const uint64_t key = j < kp ? s_cand[j] : 0ull;
+    const bool valid = key != 0ull;
+    const uint32_t row = valid ? rag_key_row(key) : 0u;
+    const double score = valid ? __ddiv_rn(vs[2 * j], __dmul_rn(__dsqrt_rn(nq), __dsqrt_rn(vs[2 * j + 1]))) : 0.0;
+    k4_finalize(j, kp, k, valid, row, score, nq, s_cand[kp - 1], eps, key_has_qnorm, M, s_score, s_row, &s_kth,
+                local + (size_t)b * k, local_cnt + b);
+  }
 }
 
 }  // namespace
@@ -122,13 +323,36 @@ int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, double eps, i
   const uint32_t nw = (kp + 31) / 32;
   const size_t smem = (size_t)nw * K4_WARP_BYTES;
   const bool bf16 = idx->desc.dtype == RAG_BF16;
+  const k4_meta M = {idx->desc.id_base, idx->ctype, idx->conf, idx->access, idx->last_ms, idx->row_keys, now_ms, decay, bonus};
   auto kern = bf16 ? k4_rescore_kernel<true> : k4_rescore_kernel<false>;
   RAG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * K4_WARP_BYTES)));
-  kern<<<B, nw * 32, smem, idx->stream>>>(idx->corpus, idx->ld, idx->cur->d_q, idx->cur->d_cand, kp, k, eps,
-                                           key_has_qnorm,
-                                           idx->desc.id_base, idx->ctype, idx->conf, idx->access,
-                                           idx->last_ms, idx->row_keys, now_ms, decay, bonus,
-                                           idx->cur->d_local, idx->cur->d_local_cnt);
+  kern<<<B, nw * 32, smem, idx->stream>>>(idx->corpus, idx->ld, idx->cur->d_q, idx->cur->d_cand, kp, k, eps, key_has_qnorm,
+                                           M, idx->cur->d_local, idx->cur->d_local_cnt);
+  RAG_CUDA(cudaGetLastError());
+  idx->launches++;
+  return RAG_OK;
+}
+
+// K3 + K4 in one launch for small batches (see k34_small_kernel). Returns RAG_ERR_UNSUPPORTED-free:
+// the caller asks k34_small_ok() first.
+bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
+  (void)idx;
+  return B <= 32 && (size_t)parts * kp * 8 <= K4S_MAX_STAGE && kp <= RAG_MAX_CANDIDATES;
+}
+
+int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, double eps, int key_has_qnorm,
+                     int64_t now_ms, double decay, double bonus) {
+  rag_prof_scope ps(idx, RAG_PROF_RESCORE);
+  rag_batch* bt = idx->cur;
+  const bool bf16 = idx->desc.dtype == RAG_BF16;
+  const k4_meta M = {idx->desc.id_base, idx->ctype, idx->conf, idx->access, idx->last_ms, idx->row_keys, now_ms, decay, bonus};
+  const size_t smem = ((size_t)parts * kp + 2 * (size_t)K4S_WARPS * kp) * 8;
+  auto kern = bf16 ? k34_small_kernel<true> : k34_small_kernel<false>;
+  RAG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K4S_MAX_STAGE + 2 * K4S_WARPS * RAG_MAX_CANDIDATES * 8)));
+  const uint32_t slices = (kp + K4S_CW - 1) / K4S_CW;
+  kern<<<dim3(B, slices), K4S_THREADS, smem, idx->stream>>>(idx->corpus, idx->ld, bt->d_q, bt->d_partial, parts, kp, k, eps,
+                                                             key_has_qnorm, M, bt->d_k4s, bt->d_ticket, bt->d_cand, bt->d_local,
+                                                             bt->d_local_cnt);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   return RAG_OK;
