@@ -184,6 +184,18 @@ uint64_t rag_index_rows(const rag_index* idx);
 /* synthetic queries of ragera_gen.h, generated on the device, copied to host_out [B][dim] */
 int rag_generate_queries(rag_index* idx, const rag_gen_desc* gen, uint64_t b0, uint32_t B, float* host_out);
 
+/* ---- the reference's persisted index: llamaindex `vector_store.json` under
+ *      ./storage/kb_<id>/ (src/lib/llm/index-manager.ts:218-220,264-270). Rows are appended in file
+ *      order (= the insertion order the reference scans). `ids`, if non-NULL, receives the node ids
+ *      as a '\0'-separated blob allocated by the library — release it with rag_free(). ------------- */
+int rag_index_load_vector_store(rag_index* idx, const char* vector_store_json, uint64_t* rows_loaded,
+                                char** ids, uint64_t* ids_bytes);
+/* the host-side parser on its own (no GPU needed): calls on_rows for every slab of <= slab_rows rows */
+int rag_parse_vector_store_json(const char* path, uint32_t dim, uint64_t slab_rows,
+                                int (*on_rows)(void* user, uint64_t first_row, uint64_t nrows, const float* rows),
+                                void* user, uint64_t* rows_out, char** ids, uint64_t* ids_bytes);
+void rag_free(void* p);
+
 /* ---- search: replaces retriever.retrieve → SimpleVectorStore.query →
  *      getTopKEmbeddings (src/lib/hybrid-search.ts:223-224) ---------------------- */
 int rag_search(rag_index* idx, const float* queries /*[B][dim] host*/, uint32_t B,

@@ -104,6 +104,10 @@ SYMBOLS = {
     "rag_index_read_rows": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "rag_index_rows": (C.c_uint64, [_vp]),
     "rag_generate_queries": (C.c_int, [_vp, C.POINTER(GenDesc), C.c_uint64, C.c_uint32, _vp]),
+    "rag_index_load_vector_store": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
+    "rag_parse_vector_store_json": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint64),
+                                              C.POINTER(_vp), C.POINTER(C.c_uint64)]),
+    "rag_free": (None, [_vp]),
     "rag_search": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(SearchOpts), C.POINTER(TopkOut)]),
     "rag_hybrid_search": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(HybridOpts), _vp, _vp, C.POINTER(FusedOut)]),
     "rag_rrf_fuse": (C.c_int, [_vp, C.c_uint32, C.POINTER(RRFConfigC), _vp, _vp, _vp, C.c_uint32, _vp, _vp,
@@ -163,6 +167,30 @@ def load() -> C.CDLL:
             raise RuntimeError(f"libragera.so version {lib.rag_version():#x} != binding {RAGERA_VERSION:#x}")
         _lib = lib
     return _lib
+
+
+ON_ROWS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_float))
+
+
+def parse_vector_store_json(path: str, dim: int, slab_rows: int = 4096):
+    """Host-only parse of a llamaindex vector_store.json → (ids, rows float32 [n, dim]). No GPU needed."""
+    import numpy as np
+
+    lib = load()
+    chunks = []
+
+    def on_rows(_user, first, n, ptr):
+        chunks.append(np.ctypeslib.as_array(ptr, shape=(n * dim,)).reshape(n, dim).copy())
+        return OK
+
+    cb = ON_ROWS(on_rows)
+    rows, blob, nbytes = C.c_uint64(0), C.c_void_p(), C.c_uint64(0)
+    check(lib.rag_parse_vector_store_json(path.encode(), dim, slab_rows, C.cast(cb, C.c_void_p), None, C.byref(rows),
+                                          C.byref(blob), C.byref(nbytes)))
+    ids = C.string_at(blob, nbytes.value).decode("utf-8").split("\0")[:-1] if nbytes.value else []
+    lib.rag_free(blob)
+    X = np.vstack(chunks) if chunks else np.zeros((0, dim), np.float32)
+    return ids, X
 
 
 def check(rc: int) -> None:

@@ -139,6 +139,15 @@ class VectorIndex:
         N.check(self._lib.rag_index_upload(self._h, r0, rows.shape[0], _ptr(rows)))
         return r0
 
+    def load_vector_store(self, path: str) -> list:
+        """Append every embedding of a llamaindex ``vector_store.json`` (the reference's persisted index,
+        index-manager.ts:218-220) in file order; returns the node ids, row by row."""
+        rows, blob, nbytes = C.c_uint64(0), C.c_void_p(), C.c_uint64(0)
+        N.check(self._lib.rag_index_load_vector_store(self._h, path.encode(), C.byref(rows), C.byref(blob), C.byref(nbytes)))
+        ids = C.string_at(blob, nbytes.value).decode("utf-8").split("\0")[:-1] if nbytes.value else []
+        self._lib.rag_free(blob)
+        return ids
+
     def generate(self, gen: N.GenDesc, nrows: int):
         N.check(self._lib.rag_index_generate(self._h, C.byref(gen), nrows))
 
