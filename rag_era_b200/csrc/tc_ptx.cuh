@@ -109,6 +109,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
+// same, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), layout SWIZZLE_128B=2
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // instruction descriptor kind::f16: D=f32 (1<<4) · A=bf16 (1<<7) · B=bf16 (1<<10) · both K-major ·
 // N>>3 at [17,23) · M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
