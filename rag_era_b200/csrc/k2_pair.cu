@@ -48,6 +48,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int CAP = 64;
 constexpr int SETS = 2;
+constexpr int KP_PREFETCH = 8;         // k-slices of L2 prefetch ahead of the TMA loads
 constexpr int KP_MAX_KP = CAP - 16;   // keep a useful append window above K'
 constexpr uint32_t kIdescPair = idesc_bf16(PAIR_M, TILE_N);
 
@@ -177,8 +178,19 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       long long w_empty = 0;
       const long long t_begin = clk();
+      // L2 prefetch runs KP_PREFETCH k-slices ahead of the loads: a corpus slice is new to L2 for the first
+      // query group that reaches it, and three stages of shared memory cannot hide an HBM miss
+      uint32_t pf_tile = pair, pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile < P.n_tiles) {
+          tma_prefetch_2d(&map_x, (int)(pf_kb * BK), (int)(pf_tile * TILE_N + rank * HALF_N));
+          if (++pf_kb == nkb) { pf_kb = 0; pf_tile += P.pairs; }
+        }
+      };
+      for (int i = 0; i < KP_PREFETCH; i++) prefetch_next();
       for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs) {
         for (uint32_t kb = 0; kb < nkb; kb++) {
+          prefetch_next();
           const long long t0 = clk();
           mbar_wait(&empty[stage], phase ^ 1);
           w_empty += clk() - t0;
@@ -266,6 +278,27 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     long long c_wait = 0, c_ld = 0, c_sel = 0, c_prune = 0, n_prune = 0, n_app = 0;
     const long long t_begin = clk();
 
+    // trim the buffer of lane `src` to its K' best and raise that lane's threshold (whole warp helps)
+    auto prune_lane = [&](int src) {
+      n_prune++;
+      const int c = __shfl_sync(0xFFFFFFFFu, cnt, src);
+      if (fast_prune) {
+        const int was_sorted = __shfl_sync(0xFFFFFFFFu, sorted, src);
+        const uint64_t t = warp_prune_sort(warp_bufs + (size_t)src * CAP, c, kp, src, lane, was_sorted);
+        if (lane == src) {
+          cnt = 32;  // K' best in the lower half (zero padded), appends continue in the upper half
+          sorted = 1;
+          if (t != 0ull) thr = rag_key_score(t);
+        }
+      } else {
+        const uint64_t t = warp_prune(warp_bufs + (size_t)src * CAP, c, kp, src, lane);
+        if (lane == src) {
+          cnt = min(c, kp);
+          if (t != 0ull) thr = rag_key_score(t);
+        }
+      }
+    };
+
     auto process16 = [&](const uint32_t (&v)[16], const float* inv, uint32_t row) {
       float s[16];
 #pragma unroll
@@ -292,34 +325,26 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (__any_sync(0xFFFFFFFFu, pm != 0u)) {
         // straight-line predicated appends; the slot of hit i is cnt + (hits below i), so the sixteen
         // stores are independent of each other (no serial dependence through cnt)
+        // (inline PTX keeps the sixteen stores predicated instead of sixteen divergent branches)
+        const uint32_t buf_addr = smem_u32(mybuf);
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-          if (pm & (1u << i))
-            mybuf[(cnt + __popc(pm & ((1u << i) - 1u)) + lane) & (CAP - 1)] = rag_pack_key(s[i], row + i);
+          const uint64_t key = rag_pack_key(s[i], row + i);
+          const uint32_t slot = (uint32_t)(cnt + __popc(pm & ((1u << i) - 1u)) + lane) & (CAP - 1);
+          asm volatile(
+              "{\n\t.reg .pred q;\n\t"
+              "setp.ne.b32 q, %0, 0;\n\t"
+              "@q st.shared.b64 [%1], %2;\n\t}"
+              ::"r"(pm & (1u << i)), "r"(buf_addr + slot * 8u), "l"(key)
+              : "memory");
         }
         cnt += __popc(pm);
         __syncwarp();  // the appends above are visible to the lanes that help prune
-        unsigned need = __ballot_sync(0xFFFFFFFFu, cnt > CAP - 16);
+        unsigned need = __ballot_sync(0xFFFFFFFFu, cnt > CAP - 16);  // must make room now
         while (need) {
-          n_prune++;
           const int src = __ffs(need) - 1;
           need &= need - 1;
-          const int c = __shfl_sync(0xFFFFFFFFu, cnt, src);
-          if (fast_prune) {
-            const int was_sorted = __shfl_sync(0xFFFFFFFFu, sorted, src);
-            const uint64_t t = warp_prune_sort(warp_bufs + (size_t)src * CAP, c, kp, src, lane, was_sorted);
-            if (lane == src) {
-              cnt = 32;  // K' best in the lower half (zero padded), appends continue in the upper half
-              sorted = 1;
-              if (t != 0ull) thr = rag_key_score(t);
-            }
-          } else {
-            const uint64_t t = warp_prune(warp_bufs + (size_t)src * CAP, c, kp, src, lane);
-            if (lane == src) {
-              cnt = min(c, kp);
-              if (t != 0ull) thr = rag_key_score(t);
-            }
-          }
+          prune_lane(src);
         }
       }
       c_prune += clk() - tp;
@@ -355,6 +380,18 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (lane == 0) {
         mbar_arrive_cluster(bar_tmem_empty);  // the leader's barrier (also from the leader itself)
         mbar_arrive(&inv_empty[set]);
+      }
+      // Off the critical path (the accumulator is already released): trim buffers that are getting
+      // full, so that the next tile rarely has to stop and prune while it holds TMEM.
+      if (P.mode == 0) {
+        const long long tq = clk();
+        unsigned need = __ballot_sync(0xFFFFFFFFu, cnt > CAP - 24);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          prune_lane(src);
+        }
+        c_prune += clk() - tq;
       }
     }
     if (P.cyc && lane == 0) {
