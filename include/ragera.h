@@ -236,6 +236,22 @@ int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* 
 int rag_fetch_fused(rag_index* idx, uint32_t B, const rag_hybrid_opts* opts, rag_fused_out* out);
 int rag_sync(rag_index* idx);
 
+/* ---- micro-batching front end: concurrent batch-1 callers (one per request thread,
+ *      like the reference's per-request hybridSearch) share one corpus pass. One batcher per call-site
+ *      class (fixed options). submit() blocks until the caller's own result is ready; results are
+ *      identical to a direct batch-1 call. The worker thread is the only user of the index handle. */
+typedef struct rag_batcher rag_batcher;
+typedef struct rag_batcher_desc {
+  uint32_t max_batch;    /* 1..4096 queries per pass                                    */
+  uint32_t max_wait_us;  /* how long the first request of a batch waits for company     */
+  rag_hybrid_opts opts;  /* HybridSearchOptions of this call site (keyword_limit = row stride) */
+} rag_batcher_desc;
+int rag_batcher_create(rag_index* idx, const rag_batcher_desc* desc, rag_batcher** out);
+int rag_batcher_submit(rag_batcher* b, const float* query /*[dim]*/, const uint64_t* kw_keys, uint32_t kw_count,
+                       rag_fused_out* out /* shaped for one query */);
+int rag_batcher_stats(rag_batcher* b, uint64_t* batches, uint64_t* queries, uint64_t* largest_batch);
+void rag_batcher_destroy(rag_batcher* b);
+
 /* ---- diagnostics: the raw scaled scores (dot_bf16 * 1/||x||, no 1/||q||) the tensor path (K2)
  *      computes, written as out_scores[B][rows]; for validating the tcgen05 pipeline on small inputs */
 int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, float* out_scores);

@@ -8,14 +8,14 @@ There is no CPU implementation: importing works anywhere, calling needs a B200.
 """
 from . import _native
 from ._native import RagError
-from .index import VectorIndex, RRFConfig, TopK, Fused, hybrid_opts
+from .index import Batcher, VectorIndex, RRFConfig, TopK, Fused, hybrid_opts
 from .hybrid_search import (PRESET_CONFIGS, HybridSearchResult, KeywordHit, KnowledgeIndex, Node, format_search_results,
                             get_preset_config, get_source_stats, hybrid_search, reciprocal_rank_fusion)
 from .memory import Memory, MemoryStore, ScoredMemory, batch_calculate_freshness, calculate_freshness_score
 from .sharded import create_sharded_index, shard_range
 
 __all__ = [
-    "RagError", "VectorIndex", "RRFConfig", "TopK", "Fused", "hybrid_opts", "PRESET_CONFIGS", "HybridSearchResult",
+    "RagError", "Batcher", "VectorIndex", "RRFConfig", "TopK", "Fused", "hybrid_opts", "PRESET_CONFIGS", "HybridSearchResult",
     "KeywordHit", "KnowledgeIndex", "Node", "format_search_results", "get_preset_config", "get_source_stats",
     "hybrid_search", "reciprocal_rank_fusion", "Memory", "MemoryStore", "ScoredMemory", "batch_calculate_freshness",
     "calculate_freshness_score", "create_sharded_index", "shard_range",

@@ -79,6 +79,10 @@ class FusedOut(C.Structure):
                 ("certified", C.c_void_p)]
 
 
+class BatcherDesc(C.Structure):
+    _fields_ = [("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32), ("opts", HybridOpts)]
+
+
 class MemoryOpts(C.Structure):
     _fields_ = [("limit", C.c_uint32), ("path", C.c_uint32), ("min_relevance", C.c_double), ("now_ms", C.c_int64),
                 ("time_decay_factor", C.c_double), ("frequency_bonus", C.c_double)]
@@ -119,6 +123,10 @@ SYMBOLS = {
     "rag_hybrid_search_staged": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts)]),
     "rag_fetch_fused": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts), C.POINTER(FusedOut)]),
     "rag_sync": (C.c_int, [_vp]),
+    "rag_batcher_create": (C.c_int, [_vp, C.POINTER(BatcherDesc), C.POINTER(_vp)]),
+    "rag_batcher_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.POINTER(FusedOut)]),
+    "rag_batcher_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rag_batcher_destroy": (None, [_vp]),
     "rag_debug_tensor_scores": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "rag_timer_start": (C.c_int, [_vp]),
     "rag_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),

@@ -345,3 +345,41 @@ class VectorIndex:
 
     def comm_destroy(self):
         N.check(self._lib.rag_comm_destroy(self._h))
+
+
+class Batcher:
+    """Micro-batching front end (``rag_batcher_*``): many threads call ``submit`` with one query each; the
+    library groups what arrives within ``max_wait_us`` into one corpus pass. ctypes releases the GIL during
+    the call, so Python request threads really do overlap."""
+
+    def __init__(self, index: VectorIndex, opts: N.HybridOpts, max_batch: int = 1024, max_wait_us: int = 200):
+        self._lib = N.load()
+        self.index, self.opts = index, opts
+        d = N.BatcherDesc(max_batch, max_wait_us, opts)
+        h = C.c_void_p()
+        N.check(self._lib.rag_batcher_create(index._h, C.byref(d), C.byref(h)))
+        self._h = h
+
+    def submit(self, query, kw_keys=()) -> dict:
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        kw = np.ascontiguousarray(kw_keys, dtype=np.uint64)
+        out = _alloc_fused(1, max(1, self.opts.vector_top_k + self.opts.keyword_limit + self.opts.fresh_limit),
+                           self.opts.vector_top_k)
+        N.check(self._lib.rag_batcher_submit(self._h, _ptr(q), _ptr(kw), len(kw), C.byref(out._c)))
+        return out.row(0)
+
+    def stats(self) -> dict:
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        N.check(self._lib.rag_batcher_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(batches=a.value, queries=b.value, largest_batch=c.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rag_batcher_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -48,6 +48,7 @@ int main(void) {
   printf("rag_fused_out %zu\n", sizeof(rag_fused_out));
   printf("rag_memory_opts %zu\n", sizeof(rag_memory_opts));
   printf("rag_memory_out %zu\n", sizeof(rag_memory_out));
+  printf("rag_batcher_desc %zu\n", sizeof(rag_batcher_desc));
   printf("off_hybrid_now_ms %zu\n", offsetof(rag_hybrid_opts, now_ms));
   printf("off_hybrid_epsilon %zu\n", offsetof(rag_hybrid_opts, epsilon));
   printf("off_fused_certified %zu\n", offsetof(rag_fused_out, certified));
@@ -71,6 +72,7 @@ int main(void) {
     assert int(got["rag_fused_out"]) == C.sizeof(N.FusedOut)
     assert int(got["rag_memory_opts"]) == C.sizeof(N.MemoryOpts)
     assert int(got["rag_memory_out"]) == C.sizeof(N.MemoryOut)
+    assert int(got["rag_batcher_desc"]) == C.sizeof(N.BatcherDesc)
     assert int(got["off_hybrid_now_ms"]) == N.HybridOpts.now_ms.offset
     assert int(got["off_hybrid_epsilon"]) == N.HybridOpts.epsilon.offset
     assert int(got["off_fused_certified"]) == N.FusedOut.certified.offset

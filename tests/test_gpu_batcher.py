@@ -1,0 +1,53 @@
+"""§8f N4 — the micro-batcher: concurrent batch-1 callers share corpus passes and every caller gets exactly
+the result of a direct call."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batcher_results_equal_direct_calls(native, oracle):
+    import rag_era_b200 as rb
+
+    n, d, nq, nthreads = 40000, 512, 256, 32
+    go = oracle.make_gen(n, n_clusters=64, dup_period=19)
+    gn = native.GenDesc.from_buffer_copy(bytes(go))
+    with rb.VectorIndex(d, n, bf16_shadow=True) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, nq)
+        rng = np.random.default_rng(3)
+        kw = [rng.integers(0, n, int(rng.integers(0, 6))).tolist() for _ in range(nq)]
+        o = rb.hybrid_opts(10, 5, 0.3)
+        direct = [idx.hybrid(Q[i], o, [kw[i]]).row(0) for i in range(nq)]     # batch-1 calls, one by one
+        results = [None] * nq
+        with rb.Batcher(idx, o, max_batch=64, max_wait_us=2000) as bt:
+            def work(t):
+                for i in range(t, nq, nthreads):
+                    results[i] = bt.submit(Q[i], kw[i])
+            th = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+            [x.start() for x in th]
+            [x.join() for x in th]
+            st = bt.stats()
+        assert st["queries"] == nq and st["batches"] < nq and st["largest_batch"] > 1      # requests were grouped
+        for i in range(nq):
+            for key in ("keys", "scores", "source", "ctype", "vec_ids", "vec_scores", "used_rrf"):
+                assert np.array_equal(results[i][key], direct[i][key]), (i, key)
+            e = oracle.hybrid_search(oracle.gen_rows(go, 0, n, d), Q[i], 10, 0.3, kw[i]) if i < 4 else None
+            if e is not None:
+                assert np.array_equal(results[i]["keys"], e["keys"]) and np.array_equal(results[i]["scores"], e["scores"])
+
+
+def test_batcher_errors(native):
+    import rag_era_b200 as rb
+
+    with rb.VectorIndex(64, 100) as idx:
+        idx.upload(np.ones((10, 64), np.float32))
+        with pytest.raises(rb.RagError):
+            rb.Batcher(idx, rb.hybrid_opts(0, 5, 0.3))
+        with rb.Batcher(idx, rb.hybrid_opts(5, 2, 0.0), max_batch=8, max_wait_us=100) as bt:
+            with pytest.raises(rb.RagError):
+                bt.submit(np.ones(64, np.float32), [1, 2, 3])          # more keyword hits than keyword_limit
+            r = bt.submit(np.ones(64, np.float32), [1])
+            assert len(r["vec_ids"]) == 5
