@@ -44,6 +44,8 @@ WORKLOADS = {
                desc="C2 deep_search: 1M x 1536 fp32, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1"),
     "c3": dict(rows=10_000_000, dim=1536, dtype="f32", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                desc="C3: 10M x 1536 fp32, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1"),
+    "c3h": dict(rows=10_000_000, dim=1536, dtype="bf16", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+                desc="C3 with a bf16 corpus: 10M x 1536 bf16, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1 (stream path)"),
     "c2b": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                 path="tensor", shadow=True,
                 desc="C2 deep_search batched: 1M x 1536 fp32 (+bf16 shadow), vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 path"),

@@ -373,7 +373,7 @@ int rag_device_count(void) {
 int rag_index_create(const rag_index_desc* d, rag_index** out) {
   if (!d || !out) return rag_set_error(RAG_ERR_INVALID, "rag_index_create: null argument");
   *out = nullptr;
-  if (d->dim == 0 || d->dim > 65536) return rag_set_error(RAG_ERR_INVALID, "dim must be in 1..65536");
+  if (d->dim == 0 || d->dim > 8192) return rag_set_error(RAG_ERR_INVALID, "dim must be in 1..8192");
   if (d->capacity_rows == 0 || d->capacity_rows >= 0xFFFFFFFFull)
     return rag_set_error(RAG_ERR_INVALID, "capacity_rows must be in 1..2^32-2 per shard");
   if (d->dtype != RAG_F32 && d->dtype != RAG_BF16) return rag_set_error(RAG_ERR_INVALID, "unknown dtype %u", d->dtype);

@@ -288,12 +288,19 @@ int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     KERNEL<<<grid, block, smem, idx->stream>>>((const TYPE*)idx->corpus, n, ld, nsub, idx->cur->d_q, \
                                                kp, parts, idx->cur->d_partial);                      \
   } while (0)
+  // several queries per corpus pass when they fit in shared memory: 8 (or 4) queries share every row a
+  // warp streams; otherwise (very wide rows, very long candidate lists) one query per pass, grid.y = B
+  uint32_t QB = 0;
   if (idx->desc.dtype == RAG_F32 && B > 1) {
-    // several queries per corpus pass: 8 (or 4) queries share every row a warp streams
+    const size_t budget = 200 * 1024;
+    auto need = [&](uint32_t qb) { return (size_t)qb * ld * sizeof(float) + (size_t)K1M_WARPS * qb * kp * sizeof(uint64_t); };
+    if (B > 4 && need(8) <= budget) QB = 8;
+    else if (need(4) <= budget) QB = 4;
+  }
+  if (QB != 0) {
     const uint32_t per_lane = ld / 128;
     const int U = per_lane % 6 == 0 ? 6 : (per_lane % 4 == 0 ? 4 : 2);
     const int nsub = (int)(per_lane / U);
-    const uint32_t QB = B > 4 ? 8 : 4;
     const size_t msmem = (size_t)QB * ld * sizeof(float) + (size_t)K1M_WARPS * QB * kp * sizeof(uint64_t);
     dim3 mgrid(parts, (B + QB - 1) / QB);
 #define K1M_GO(QBv, Uv)                                                                                        \
@@ -302,7 +309,6 @@ int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     k1_multi_f32<QBv, Uv><<<mgrid, K1M_THREADS, msmem, idx->stream>>>((const float*)idx->corpus, n, ld, nsub, \
                                                                       idx->cur->d_q, B, kp, parts, idx->cur->d_partial); \
   } while (0)
-    if (msmem > 200 * 1024) return rag_set_error(RAG_ERR_UNSUPPORTED, "stream path: dim too large for the multi-query kernel");
     if (QB == 8) { if (U == 6) K1M_GO(8, 6); else if (U == 4) K1M_GO(8, 4); else K1M_GO(8, 2); }
     else         { if (U == 6) K1M_GO(4, 6); else if (U == 4) K1M_GO(4, 4); else K1M_GO(4, 2); }
 #undef K1M_GO

@@ -536,3 +536,20 @@ def test_c4_memory_rag_three_lists_full_size(rb, native, oracle):
             assert np.array_equal(g3["keys"], ek3) and np.array_equal(g3["scores"], es3) and np.array_equal(g3["source"], esrc3)
             n_fresh_both += len(mem)
         assert n_fresh_both > 0                                                  # the freshness list was exercised
+
+
+def test_wide_rows_and_long_lists_fall_back_gracefully(rb, native, oracle):
+    """dim 4096 with K'=70: the 8-query kernel does not fit in shared memory; the library picks a smaller
+    grouping instead of failing, and results stay exact."""
+    rng = np.random.default_rng(12)
+    n, d = 600, 4096
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = (X[[3, 77, 500, 12, 13, 14]] + 0.3 * rng.standard_normal((6, d))).astype(np.float32)
+    with rb.VectorIndex(d, n) as idx:
+        idx.upload(X)
+        r = idx.query(Q, 64, path=native.PATH_STREAM)
+        for b in range(6):
+            ei, es = oracle.topk(X, Q[b], 64)
+            assert np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es)
+    with pytest.raises(rb.RagError):
+        rb.VectorIndex(8193, 10)
