@@ -376,8 +376,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    # keep NCCL's version banner / debug lines off stdout: rank 0 prints exactly one JSON line there
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # rank 0 prints exactly ONE JSON line on stdout: anything native code prints meanwhile (NCCL's version
+    # banner, for one) is sent to stderr by pointing fd 1 at fd 2 until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -410,7 +413,10 @@ def run_ours(args):
             line["cpu_baseline"] = res["cpu_baseline"]
         if extra:
             line["extra"] = extra
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
