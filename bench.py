@@ -49,6 +49,9 @@ WORKLOADS = {
     "c2b": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                 path="tensor", shadow=True,
                 desc="C2 deep_search batched: 1M x 1536 fp32 (+bf16 shadow), vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 path"),
+    "c4f": dict(rows=7_000_000, dim=1536, dtype="f32", batch=256, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+                path="tensor", shadow=False, memory_rows=2_000_000, fresh_limit=10,
+                desc="C4 memory+RAG unified, fp32 operand: 2M memory + 5M doc rows x 1536 fp32 scored as tf32 (no shadow), vector+keyword+freshness lists fused by RRF, batch 256, tcgen05 kind::tf32"),
     "c4": dict(rows=7_000_000, dim=1536, dtype="f32", batch=256, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                path="tensor", shadow=True, memory_rows=2_000_000, fresh_limit=10,
                desc="C4 memory+RAG unified: 2M memory + 5M doc rows x 1536 fp32 (+bf16 shadow), vector+keyword+freshness lists fused by RRF, batch 256, tcgen05 path"),
@@ -320,12 +323,20 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         k_ms, k_n = prof["tensor"]
         flops = 2.0 * n_local * idx_ld(d) * B                                 # dot products only
         ach = flops / (k_ms / max(k_n, 1) * 1e-3) / 1e12 if k_n else None
+        op_bytes = 2 if (dt == N.BF16 or shadow) else 4                       # bf16 operand, or fp32 rows read as tf32
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": (ach / tf_sus) if ach else None,
                 "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": (ach / tf_burst) if ach else None,
                 "kernel": "k2_pair (tcgen05 cta_group::2 bf16 GEMM + fused top-K' epilogue)", "algorithmic_flops_per_launch": flops,
-                "algorithmic_bytes_per_launch": int(n_local * idx_ld(d) * 2), "avg_launch_ms": k_ms / max(k_n, 1),
+                "algorithmic_bytes_per_launch": int(n_local * idx_ld(d) * op_bytes), "avg_launch_ms": k_ms / max(k_n, 1),
                 "launches_timed": int(k_n)}
+        if op_bytes == 4:
+            # tf32 runs at half the bf16 tensor rate and streams 4 B/element: report the HBM side as well
+            roof["operand"] = "fp32 corpus read as tf32 (kind::tf32, peak = half of the bf16 figure)"
+            roof["peak"] = tf_sus / 2
+            roof["frac"] = (ach / (tf_sus / 2)) if ach else None
+            roof["hbm_achieved_GBps"] = (n_local * idx_ld(d) * 4) / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_n else None
+            roof["hbm_frac_of_measured"] = roof["hbm_achieved_GBps"] / hbm_peak if k_n else None
         tr = traffic_ratio("k2_pair", name)
         if tr:
             roof["traffic"] = int(tr * n_local * idx_ld(d) * 2)

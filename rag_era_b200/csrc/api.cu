@@ -124,14 +124,11 @@ int make_plan(const rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, u
               plan* p) {
   int path = (int)req_path;
   if (path == RAG_PATH_AUTO)
-    path = (B >= kTensorMinBatch && idx->shadow && k2_available(idx)) ? RAG_PATH_TENSOR : RAG_PATH_STREAM;
+    path = (B >= kTensorMinBatch && k2_available(idx)) ? RAG_PATH_TENSOR : RAG_PATH_STREAM;
   if (path != RAG_PATH_STREAM && path != RAG_PATH_TENSOR && path != RAG_PATH_EXACT)
     return rag_set_error(RAG_ERR_INVALID, "unknown rag_path %d", path);
-  if (path == RAG_PATH_TENSOR) {
-    if (!idx->shadow) return rag_set_error(RAG_ERR_UNSUPPORTED,
-                                           "tensor path needs a bf16 corpus or RAG_INDEX_BF16_SHADOW");
-    if (!k2_available(idx)) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path (K2) is not available");
-  }
+  if (path == RAG_PATH_TENSOR && !k2_available(idx))
+    return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path (K2) is not available for this index");
   uint32_t s = slack;
   // the tensor path selects on bf16 scores: a wider window keeps (nearly) every query certifiable in one
   // pass — an uncertified query costs a whole extra corpus pass on the stream path
@@ -150,7 +147,9 @@ int make_plan(const rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, u
     // bf16 rounding of both operands: measured per-score error sigma ~ 0.0022/sqrt(D) (5.6e-5 at
     // D=1536, max 2.8e-4 over 5e5 pairs — tests/test_gpu_tensor.py). The bound is ~11 sigma:
     // statistical, not a proof; callers can pass their own epsilon
-    p->eps = 0.024 / sqrt((double)idx->ld);
+    // An fp32 index without a shadow is scored as tf32 (TMA rounds both operands to 10 mantissa bits):
+    // 4x finer than bf16, bound 0.006/sqrt(ld).
+    p->eps = (idx->shadow ? 0.024 : 0.006) / sqrt((double)idx->ld);
   else
     p->eps = 2.0e-7;  // one fp32 rounding of the exact cosine
   return RAG_OK;
@@ -420,10 +419,9 @@ int rag_index_create(const rag_index_desc* d, rag_index** out) {
       cap = 0;
       if ((rc = grow_dev(&idx->shadow, &cap, (size_t)d->capacity_rows * idx->ld * 2, false)) != RAG_OK) break;
     }
-    if (idx->shadow) {
-      cap = 0;
-      if ((rc = grow_dev(&idx->inv_norm, &cap, (size_t)d->capacity_rows * 4, true)) != RAG_OK) break;
-    }
+    // 1/||x|| per row of the tensor-path operand (the bf16 rows, or the fp32 rows read as tf32)
+    cap = 0;
+    if ((rc = grow_dev(&idx->inv_norm, &cap, (size_t)d->capacity_rows * 4, true)) != RAG_OK) break;
     if ((e = cudaStreamSynchronize(idx->stream)) != cudaSuccess) {
       rc = rag_set_error(RAG_ERR_CUDA, "rag_index_create: %s", cudaGetErrorString(e));
       break;

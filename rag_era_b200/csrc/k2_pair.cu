@@ -35,13 +35,14 @@
 namespace {
 using namespace tc;
 
-constexpr int BK = 64;                 // k elements per stage (128 B rows = whole L2 lines, SWIZZLE_128B)
+constexpr int ROW_BYTES = 128;         // bytes of one operand row per stage = one whole L2 line, SWIZZLE_128B:
+                                       // 64 bf16 elements, or 32 fp32 elements read as tf32
 constexpr int TILE_N = 256;            // corpus rows per tile (UMMA N)
 constexpr int HALF_N = TILE_N / 2;     // rows each CTA of the pair loads
 constexpr int CTA_M = 128;             // queries per CTA (TMEM lanes)
 constexpr int PAIR_M = 2 * CTA_M;      // UMMA M
-constexpr int A_BYTES = CTA_M * BK * 2;    // 16 KB
-constexpr int B_BYTES = HALF_N * BK * 2;   // 16 KB
+constexpr int A_BYTES = CTA_M * ROW_BYTES;    // 16 KB
+constexpr int B_BYTES = HALF_N * ROW_BYTES;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int KP_THREADS = 384;        // w0 TMA · w1 MMA · w2 TMEM alloc · w3 inv-norm loader · w4..11 epilogue
 constexpr int MAX_STAGES = 8;
@@ -50,7 +51,8 @@ constexpr int CAP = 64;
 constexpr int SETS = 2;
 constexpr int KP_PREFETCH = 8;         // k-slices of L2 prefetch ahead of the TMA loads
 constexpr int KP_MAX_KP = CAP - 16;   // keep a useful append window above K'
-constexpr uint32_t kIdescPair = idesc_bf16(PAIR_M, TILE_N);
+constexpr uint32_t kIdescBf16 = idesc_bf16(PAIR_M, TILE_N);
+constexpr uint32_t kIdescTf32 = idesc_tf32(PAIR_M, TILE_N);
 
 struct kp_params {
   uint32_t n_rows, ld, B, kp, parts, stages, n_tiles, pairs;
@@ -126,6 +128,11 @@ __device__ __noinline__ uint64_t warp_prune_sort(uint64_t* buf, int cnt, int kp,
   return shfl_u64(c, kp - 1);
 }
 
+// TF32 = false: bf16 operands (bf16 corpus or bf16 shadow, queries rounded to bf16), UMMA K = 16.
+// TF32 = true : the fp32 corpus and the fp32 queries themselves, rounded to tf32 by TMA on the way into
+//               shared memory (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), kind::tf32 UMMA K = 8 — batched scoring
+//               of an fp32 index without the extra memory of a bf16 shadow (HBM streams 4 B/element).
+template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KP_THREADS, 1)
 k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const kp_params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -147,6 +154,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const bool leader = rank == 0;
   const uint32_t pair = blockIdx.x >> 1;
   const uint32_t q0 = blockIdx.y * PAIR_M + rank * CTA_M;  // first query of this CTA
+  constexpr int BK = TF32 ? ROW_BYTES / 4 : ROW_BYTES / 2;  // k elements per stage
   const uint32_t nkb = P.ld / BK;
 
   for (uint32_t i = threadIdx.x; i < SETS * CTA_M * CAP; i += KP_THREADS) lists[i] = 0ull;
@@ -227,9 +235,14 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           const uint32_t sa = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-          for (uint32_t k16 = 0; k16 < BK / 16; k16++)
-            tcgen05_mma_f16_pair(tmem_base + buf * TILE_N, umma_desc_sw128(sa + k16 * 32), umma_desc_sw128(sb + k16 * 32),
-                                 kIdescPair, (kb | k16) != 0 ? 1u : 0u);
+          for (uint32_t ks = 0; ks < ROW_BYTES / 32; ks++) {  // one UMMA consumes 32 bytes of K per row
+            if (TF32)
+              tcgen05_mma_tf32_pair(tmem_base + buf * TILE_N, umma_desc_sw128(sa + ks * 32), umma_desc_sw128(sb + ks * 32),
+                                    kIdescTf32, (kb | ks) != 0 ? 1u : 0u);
+            else
+              tcgen05_mma_f16_pair(tmem_base + buf * TILE_N, umma_desc_sw128(sa + ks * 32), umma_desc_sw128(sb + ks * 32),
+                                   kIdescBf16, (kb | ks) != 0 ? 1u : 0u);
+          }
           tcgen05_commit_pair(&empty[stage], 3);  // both CTAs may refill this stage once the MMAs have read it
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
@@ -460,12 +473,13 @@ int kp_init(rag_index* idx) {
   return RAG_OK;
 }
 
-int kp_make_map(kp_state* st, CUtensorMap* m, const void* base, uint64_t rows, uint32_t ld, uint32_t box_rows) {
+int kp_make_map(kp_state* st, CUtensorMap* m, const void* base, uint64_t rows, uint32_t ld, uint32_t box_rows, bool tf32) {
+  const uint32_t es = tf32 ? 4 : 2;
   cuuint64_t dims[2] = {ld, rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {BK, box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {ROW_BYTES / es, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = st->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = st->encode(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return rag_set_error(RAG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -497,21 +511,29 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   RAG_CHECK(kp_init(idx));
   kp_state* st = (kp_state*)idx->k2p_state;
   rag_batch* bt = idx->cur;
-  const uint32_t Bpad = (B + CTA_M - 1) / CTA_M * CTA_M;
-  const size_t need = (size_t)Bpad * idx->ld * 2;
-  if (need > bt->c_qb || !bt->d_qb) {
-    if (bt->d_qb) RAG_CUDA(cudaFree(bt->d_qb));
-    bt->d_qb = nullptr;
-    bt->c_qb = 0;
-    RAG_CUDA(cudaMalloc((void**)&bt->d_qb, need));
-    bt->c_qb = need;
+  const bool tf32 = idx->shadow == nullptr;  // fp32 index without a bf16 shadow: score the fp32 rows as tf32
+  if (tf32 && idx->desc.dtype != RAG_F32) return rag_set_error(RAG_ERR_STATE, "tensor path: no bf16 operand");
+  CUtensorMap map_q, map_x;
+  if (!tf32) {
+    const uint32_t Bpad = (B + CTA_M - 1) / CTA_M * CTA_M;
+    const size_t need = (size_t)Bpad * idx->ld * 2;
+    if (need > bt->c_qb || !bt->d_qb) {
+      if (bt->d_qb) RAG_CUDA(cudaFree(bt->d_qb));
+      bt->d_qb = nullptr;
+      bt->c_qb = 0;
+      RAG_CUDA(cudaMalloc((void**)&bt->d_qb, need));
+      bt->c_qb = need;
+    }
+    RAG_CHECK(q_to_bf16_launch(idx, B, Bpad));
+    RAG_CHECK(kp_make_map(st, &map_q, bt->d_qb, Bpad, idx->ld, CTA_M, false));
+    RAG_CHECK(kp_make_map(st, &map_x, idx->shadow, idx->rows, idx->ld, HALF_N, false));
+  } else {
+    // the fp32 queries as staged ([B][ld], zero padded columns); rows past B read as zeros (TMA OOB fill)
+    RAG_CHECK(kp_make_map(st, &map_q, bt->d_q, B, idx->ld, CTA_M, true));
+    RAG_CHECK(kp_make_map(st, &map_x, idx->corpus, idx->rows, idx->ld, HALF_N, true));
   }
-  RAG_CHECK(q_to_bf16_launch(idx, B, Bpad));
 
   rag_prof_scope ps(idx, RAG_PROF_TENSOR);
-  CUtensorMap map_q, map_x;
-  RAG_CHECK(kp_make_map(st, &map_q, bt->d_qb, Bpad, idx->ld, CTA_M));
-  RAG_CHECK(kp_make_map(st, &map_x, idx->shadow, idx->rows, idx->ld, HALF_N));
   kp_params P;
   P.n_rows = (uint32_t)idx->rows;
   P.ld = idx->ld;
@@ -535,11 +557,13 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   }
   const size_t smem = kp_smem_bytes(P.stages);
   if (!st->attr_set) {
-    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
     st->attr_set = true;
   }
   const uint32_t groups = (B + PAIR_M - 1) / PAIR_M;
-  k2_pair_kernel<<<dim3(P.pairs * 2, groups), KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
+  if (tf32) k2_pair_kernel<true><<<dim3(P.pairs * 2, groups), KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
+  else k2_pair_kernel<false><<<dim3(P.pairs * 2, groups), KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   if (st->prof) {

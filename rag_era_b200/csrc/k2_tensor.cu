@@ -405,7 +405,12 @@ int k2_impl() {
 }
 }  // namespace
 
-int k2_available(const rag_index* idx) { return idx->shadow != nullptr && idx->inv_norm != nullptr; }
+// bf16 operand (bf16 corpus / bf16 shadow) on either kernel, or the fp32 corpus as tf32 on the pair kernel
+int k2_available(const rag_index* idx) {
+  if (!idx->inv_norm) return 0;
+  if (idx->shadow) return 1;
+  return idx->desc.dtype == RAG_F32 && k2_impl() != 1;
+}
 
 static int k2s_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   RAG_CHECK(k2_init(idx));

@@ -94,3 +94,32 @@ def test_bf16_selection_error_is_within_the_stated_tolerance(rb, native, oracle)
     eps = 0.024 / np.sqrt(d)
     assert np.abs(err).max() < 0.6 * eps, (float(np.abs(err).max()), eps)
     assert err.std() < 0.0022 / np.sqrt(d) * 1.25, float(err.std())
+
+
+def test_tf32_path_on_fp32_index_without_shadow(rb, native, oracle):
+    """An fp32 index without a bf16 shadow is scored by the same tcgen05 kernel in kind::tf32 (TMA rounds the
+    fp32 rows and queries to tf32): stated tolerance 0.006/sqrt(ld), ids and scores still the oracle's."""
+    n, d, B = 30000, 1536, 200
+    go = oracle.make_gen(n, n_clusters=64, dup_period=23)
+    gn = native.GenDesc.from_buffer_copy(bytes(go))
+    X = oracle.gen_rows(go, 0, n, d)
+    with rb.VectorIndex(d, n) as idx:                       # no shadow
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, B)
+        S = idx.debug_tensor_scores(Q[:64]).astype(np.float64)
+        Xd, Qd = X.astype(np.float64), Q[:64].astype(np.float64)
+        exact = (Qd @ Xd.T) / (np.sqrt((Qd * Qd).sum(1))[:, None] * np.sqrt((Xd * Xd).sum(1))[None, :])
+        err = S / np.sqrt((Qd * Qd).sum(1))[:, None] - exact
+        eps = 0.006 / np.sqrt(d)
+        assert np.abs(err).max() < 0.6 * eps, (float(np.abs(err).max()), eps)
+        r = idx.query(Q, 10, path=native.PATH_TENSOR)
+        auto = idx.query(Q, 10)                              # AUTO: B >= 16 → tensor (tf32) path
+        for b in range(0, B, 5):
+            ei, es = oracle.topk(X, Q[b], 10)
+            assert np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es)
+            assert np.array_equal(auto.row(b)[0], ei)
+        assert r.certified.all()
+        small = idx.query(Q[:16], 5, path=native.PATH_TENSOR)   # fewer queries than one 128-row TMA box
+        for b in range(16):
+            ei, es = oracle.topk(X, Q[b], 5)
+            assert np.array_equal(small.row(b)[0], ei) and np.array_equal(small.row(b)[1], es)
