@@ -22,7 +22,11 @@ namespace {
 thread_local char g_err[1024] = "";
 
 constexpr uint32_t kProfSpans = 8192;
-constexpr uint32_t kTensorMinBatch = 16;  // RAG_PATH_AUTO: smaller batches stream (HBM-bound either way)
+// RAG_PATH_AUTO (measured on 1M x 1536, tools/k2_small_probe.py): the tensor kernel is HBM-bound at small
+// batches too, and a bf16 operand halves the bytes — it wins from 4 queries (0.61 vs 0.93 ms); fp32 rows
+// read as tf32 win from 8 (1.3 vs 1.5 ms). Below that the stream kernels (K1 / K1m) keep fp32 selection.
+constexpr uint32_t kTensorMinBatchBf16 = 4;
+constexpr uint32_t kTensorMinBatchTf32 = 8;
 
 size_t elem_size(const rag_index* idx) { return idx->desc.dtype == RAG_BF16 ? 2 : 4; }
 
@@ -124,7 +128,8 @@ int make_plan(const rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, u
               plan* p) {
   int path = (int)req_path;
   if (path == RAG_PATH_AUTO)
-    path = (B >= kTensorMinBatch && k2_available(idx)) ? RAG_PATH_TENSOR : RAG_PATH_STREAM;
+    path = (k2_available(idx) && B >= (idx->shadow ? kTensorMinBatchBf16 : kTensorMinBatchTf32)) ? RAG_PATH_TENSOR
+                                                                                              : RAG_PATH_STREAM;
   if (path != RAG_PATH_STREAM && path != RAG_PATH_TENSOR && path != RAG_PATH_EXACT)
     return rag_set_error(RAG_ERR_INVALID, "unknown rag_path %d", path);
   if (path == RAG_PATH_TENSOR && !k2_available(idx))

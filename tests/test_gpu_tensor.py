@@ -68,7 +68,7 @@ def test_tensor_hybrid_batch(rb, native, oracle):
         kw = [[int(x) for x in oracle.topk(X, Q[b], 3)[0]] + [n - 1 - b] for b in range(B)]
         o = rb.hybrid_opts(10, 4, 0.3, path=native.PATH_TENSOR)
         res = idx.hybrid(Q, o, kw)
-        auto = idx.hybrid(Q, rb.hybrid_opts(10, 4, 0.3), kw)          # AUTO picks the tensor path at B >= 16
+        auto = idx.hybrid(Q, rb.hybrid_opts(10, 4, 0.3), kw)          # AUTO picks the tensor path for batches
         for b in range(B):
             e = oracle.hybrid_search(X, Q[b], 10, 0.3, kw[b])
             g = res.row(b)
@@ -113,7 +113,7 @@ def test_tf32_path_on_fp32_index_without_shadow(rb, native, oracle):
         eps = 0.006 / np.sqrt(d)
         assert np.abs(err).max() < 0.6 * eps, (float(np.abs(err).max()), eps)
         r = idx.query(Q, 10, path=native.PATH_TENSOR)
-        auto = idx.query(Q, 10)                              # AUTO: B >= 16 → tensor (tf32) path
+        auto = idx.query(Q, 10)                              # AUTO: batches of 8+ → tensor (tf32) path
         for b in range(0, B, 5):
             ei, es = oracle.topk(X, Q[b], 10)
             assert np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es)
