@@ -28,10 +28,6 @@ PROF_CLASSES = 6
 PROF_NAMES = ("stream", "tensor", "merge", "rescore", "fuse", "comm")
 COMM_ID_BYTES = 128
 
-u8p, u32p, u64p, f64p, f32p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
-                               C.POINTER(C.c_double), C.POINTER(C.c_float))
-
-
 class RagError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libragera error {code}: {msg}")

@@ -268,10 +268,8 @@ int pick_unroll(uint32_t per_lane, const int* opts, int nopts) {
 
 int k1_plan(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   (void)kp;
-  // one CTA per SM per query plane; with several queries in flight the planes share L2
-  uint32_t p = (uint32_t)idx->sm_count;
-  if (B > 1 && B <= 8) p = (uint32_t)idx->sm_count;
-  *parts = p;
+  (void)B;
+  *parts = (uint32_t)idx->sm_count;  // persistent: one CTA per SM (per group of queries), one candidate list each
   return RAG_OK;
 }
 

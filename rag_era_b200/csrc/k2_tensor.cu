@@ -1,5 +1,9 @@
-// k2_tensor.cu — K2: batched cosine scoring on the 5th-gen tensor cores (tcgen05) with the
-// top-K' selection fused into the epilogue, so the [B x N] score matrix never leaves the SM.
+// k2_tensor.cu — K2, single-CTA variant (cta_group::1) + the dispatch between the K2 variants.
+// The default tensor-path kernel is the CTA-pair kernel of k2_pair.cu (cta_group::2, double-buffered
+// TMEM, tf32 mode); this predecessor stays selectable with RAGERA_K2_IMPL=1 and is kept under test.
+//
+// K2: batched cosine scoring on the 5th-gen tensor cores (tcgen05) with the top-K' selection
+// fused into the epilogue, so the [B x N] score matrix never leaves the SM.
 //
 // Replaces the same reference loop as K1 (getTopKEmbeddings, reached from
 // src/lib/hybrid-search.ts:223-224) when many queries are in flight: only then is the path a
