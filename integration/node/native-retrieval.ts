@@ -1,0 +1,129 @@
+/**
+ * native-retrieval.ts — drop into the reference as src/lib/native-retrieval.ts.
+ *
+ * Keeps `hybridSearch(index, knowledgeBaseId, query, options)` (src/lib/hybrid-search.ts:275-280) and its
+ * result type unchanged; the dense scoring, top-k, min-cosine filter, RRF arithmetic and final stable sort
+ * run on the GPU through the N-API addon (ragera_addon.cc → libragera.so). The host keeps what the
+ * reference's host does: embedding the query and asking Meilisearch (both network calls), and re-attaching
+ * strings to the integer fusion keys.
+ *
+ * Wiring in src/lib/hybrid-search.ts (the only edit to existing reference code):
+ *
+ *   import { NativeKnowledgeIndex, hybridSearchNative } from './native-retrieval';
+ *   export async function hybridSearch(index, knowledgeBaseId, query, options = {}) {
+ *     if (index instanceof NativeKnowledgeIndex) return hybridSearchNative(index, knowledgeBaseId, query, options);
+ *     ... existing body ...
+ *   }
+ *
+ * and in src/lib/llm/index-manager.ts `loadIndex` returns a NativeKnowledgeIndex built with
+ * `NativeKnowledgeIndex.fromPersistDir(storageDir, dim)` when RAGERA_NATIVE=1.
+ */
+import * as fs from 'fs';
+import * as path from 'path';
+// eslint-disable-next-line @typescript-eslint/no-var-requires
+const native = require('../../integration/node/build/Release/ragera_addon.node');
+import { meilisearchService } from './meilisearch';
+import type { HybridSearchResult, HybridSearchOptions, RRFConfig, SearchPreset } from './hybrid-search';
+
+const SOURCE = ['vector', 'keyword', 'both'] as const;
+const CTYPE = ['document', 'memory', 'code'] as const;
+
+// PRESET_CONFIGS — src/lib/hybrid-search.ts:77-105
+const PRESETS: Record<SearchPreset, { rrf: RRFConfig; vectorTopK: number; keywordLimit: number; minVectorScore: number }> = {
+  document: { rrf: { k: 60, vectorWeight: 1.0, keywordWeight: 1.0, bothBonus: 0.1 }, vectorTopK: 8, keywordLimit: 8, minVectorScore: 0.3 },
+  code: { rrf: { k: 40, vectorWeight: 1.0, keywordWeight: 1.3, bothBonus: 0.15 }, vectorTopK: 6, keywordLimit: 5, minVectorScore: 0.25 },
+};
+
+interface NodeRow { id: string; text: string; metadata: Record<string, any> }
+
+export class NativeKnowledgeIndex {
+  /** row r of the device matrix ↔ nodes[r] (insertion order of embeddingDict). */
+  nodes: NodeRow[] = [];
+  private keyIds = new Map<string, bigint>();
+  private keyStrs: string[] = [];
+
+  constructor(readonly handle: unknown, readonly dim: number, private embed: (q: string) => Promise<Float32Array>) {}
+
+  /** Load ./storage/kb_<id>/ as written by storageContextFromDefaults (index-manager.ts:218-220,264-270). */
+  static fromPersistDir(dir: string, dim: number, capacityRows: number, embed: (q: string) => Promise<Float32Array>,
+                        isCodebase = false): NativeKnowledgeIndex {
+    const handle = native.createIndex({ rows: capacityRows, dim, device: 0, bf16Shadow: 1 });
+    const idx = new NativeKnowledgeIndex(handle, dim, embed);
+    const ids: string[] = native.loadVectorStore(handle, path.join(dir, 'vector_store.json'));
+    const docstore = JSON.parse(fs.readFileSync(path.join(dir, 'doc_store.json'), 'utf8'));
+    const docs = docstore['docstore/data'] ?? {};
+    const ctype = new Uint8Array(ids.length);
+    const keys = new BigUint64Array(ids.length);
+    ids.forEach((id, r) => {
+      const d = docs[id]?.__data__ ?? {};
+      const metadata = d.metadata ?? {};
+      const text: string = d.text ?? '';
+      idx.nodes.push({ id, text, metadata });
+      // contentType rule — hybrid-search.ts:229-234
+      ctype[r] = metadata.type === 'memory' ? 1 : (isCodebase || metadata.language !== undefined) ? 2 : 0;
+      keys[r] = idx.keyOf(text);
+    });
+    native.setRowMeta(handle, 0, ctype);
+    native.setRowKeys(handle, 0, keys);
+    return idx;
+  }
+
+  /** content.substring(0,100) de-dup key (hybrid-search.ts:149,171) interned to an integer. */
+  keyOf(content: string): bigint {
+    const k = content.substring(0, 100);
+    let id = this.keyIds.get(k);
+    if (id === undefined) { id = BigInt(this.keyStrs.length); this.keyIds.set(k, id); this.keyStrs.push(k); }
+    return id;
+  }
+  keyString(id: bigint): string { return this.keyStrs[Number(id)]; }
+  embedQuery(q: string): Promise<Float32Array> { return this.embed(q); }
+}
+
+const docName = (m: any) => (m?.type === 'memory' ? '用户记忆' : m?.documentName || m?.relativePath || m?.filePath || '未知文档'); // :238-240
+
+export async function hybridSearchNative(index: NativeKnowledgeIndex, knowledgeBaseId: string, query: string,
+                                         options: HybridSearchOptions = {}): Promise<HybridSearchResult[]> {
+  const presetConfig = PRESETS[options.preset || 'document'];
+  const vectorTopK = options.vectorTopK ?? presetConfig.vectorTopK;             // :286-289 (?? keeps 0)
+  const keywordLimit = options.keywordLimit ?? presetConfig.keywordLimit;
+  const useKeyword = options.useKeyword ?? true;
+  const minVectorScore = options.minVectorScore ?? presetConfig.minVectorScore;
+  const rrf: RRFConfig = { ...presetConfig.rrf, ...options.rrfConfig };          // :292-295
+
+  const [q, hits] = await Promise.all([
+    index.embedQuery(query),                                                      // network, as today
+    useKeyword && keywordLimit > 0 && (await meilisearchService.isAvailable())    // :321-330
+      ? meilisearchService.search(knowledgeBaseId, query, keywordLimit) : Promise.resolve([]),
+  ]);
+  const kwKeys = BigUint64Array.from(hits.map(h => index.keyOf(h.content)));
+  const r = await native.hybridSearch(index.handle, q, 1,
+    { vectorTopK, keywordLimit: hits.length, minVectorScore, rrf }, kwKeys, Uint32Array.of(hits.length));
+
+  // re-attach strings: the first occurrence of a key wins, vector hits first, then keyword hits (:147-188)
+  const first = new Map<bigint, { n?: NodeRow; h?: (typeof hits)[number] }>();
+  for (let i = 0; i < r.vecCounts[0]; i++) {
+    const n = index.nodes[Number(r.vecIds[i])];
+    const k = index.keyOf(n.text);
+    if (!first.has(k)) first.set(k, { n });
+  }
+  hits.forEach(h => { const k = index.keyOf(h.content); if (!first.has(k)) first.set(k, { h }); });
+
+  const out: HybridSearchResult[] = [];
+  for (let i = 0; i < r.counts[0]; i++) {
+    if (!r.usedRrf[0]) {                                                          // vector-only branch :346-354
+      const n = index.nodes[Number(r.keys[i])];
+      out.push({ id: n.id, documentName: docName(n.metadata), content: n.text, score: r.scores[i], source: 'vector',
+                 contentType: CTYPE[r.contentType[i]], metadata: n.metadata });
+      continue;
+    }
+    const e = first.get(r.keys[i])!;
+    if (e.n) {
+      out.push({ id: index.keyString(r.keys[i]), documentName: docName(e.n.metadata), content: e.n.text, score: r.scores[i],
+                 source: SOURCE[r.source[i]], contentType: CTYPE[r.contentType[i]], metadata: e.n.metadata });
+    } else {
+      out.push({ id: index.keyString(r.keys[i]), documentId: e.h!.documentId, documentName: e.h!.documentName, content: e.h!.content,
+                 score: r.scores[i], source: SOURCE[r.source[i]], contentType: 'document' });
+    }
+  }
+  return out;
+}

@@ -1,0 +1,373 @@
+// ragera_addon.cc — N-API binding of include/ragera.h for the reference's Node process.
+//
+// NOT compiled in the build container (no Node toolchain there); the same C ABI is exercised end to end
+// from Python (rag_era_b200/_native.py) and from C (tests/c/abi_demo.c). Build in the reference repo with
+//     cd integration/node && npx node-gyp rebuild
+// Pure C N-API (node_api.h), no C++ wrapper dependency. Every GPU call runs on a libuv worker thread
+// (napi_create_async_work) so the event loop never blocks; a handle is used by one worker at a time
+// because JS callers await each call (or go through the batcher, which has its own worker thread).
+//
+// JS surface (see native-retrieval.ts):
+//   createIndex({rows, dim, dtype:'f32'|'bf16', device, bf16Shadow}) -> handle (External)
+//   uploadRows(handle, Float32Array rows, nrows, row0 = append) -> first row
+//   loadVectorStore(handle, path) -> string[] node ids          (llamaindex vector_store.json)
+//   setRowMeta(handle, row0, Uint8Array contentType, Float64Array confidence, Int32Array accessCount, BigInt64Array lastAccessMs)
+//   setRowKeys(handle, row0, BigUint64Array keys)
+//   hybridSearch(handle, Float32Array queries, B, opts, BigUint64Array kwKeys, Uint32Array kwCounts) -> Promise<result>
+//   createBatcher(handle, opts, maxBatch, maxWaitUs) -> batcher; submit(batcher, Float32Array q, BigUint64Array kwKeys) -> Promise<result>
+//   destroy(handle) / destroyBatcher(batcher)
+#include <node_api.h>
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ragera.h"
+
+#define NAPI_OK(env, call)                                                   \
+  do {                                                                       \
+    if ((call) != napi_ok) {                                                 \
+      napi_throw_error((env), nullptr, "N-API call failed: " #call);         \
+      return nullptr;                                                        \
+    }                                                                        \
+  } while (0)
+
+namespace {
+
+napi_value throw_rag(napi_env env, int rc) {
+  std::string msg = "libragera error " + std::to_string(rc) + ": " + rag_last_error();
+  napi_throw_error(env, nullptr, msg.c_str());
+  return nullptr;
+}
+
+bool get_u32(napi_env env, napi_value obj, const char* name, uint32_t* out) {
+  napi_value v;
+  bool has = false;
+  if (napi_has_named_property(env, obj, name, &has) != napi_ok || !has) return false;
+  return napi_get_named_property(env, obj, name, &v) == napi_ok && napi_get_value_uint32(env, v, out) == napi_ok;
+}
+bool get_f64(napi_env env, napi_value obj, const char* name, double* out) {
+  napi_value v;
+  bool has = false;
+  if (napi_has_named_property(env, obj, name, &has) != napi_ok || !has) return false;
+  return napi_get_named_property(env, obj, name, &v) == napi_ok && napi_get_value_double(env, v, out) == napi_ok;
+}
+
+// HybridSearchOptions + RRFConfig (src/lib/hybrid-search.ts:40-58) -> rag_hybrid_opts
+bool read_opts(napi_env env, napi_value o, rag_hybrid_opts* out) {
+  memset(out, 0, sizeof *out);
+  out->rrf = rag_rrf_config{60.0, 1.0, 1.0, 0.1};  // PRESET_CONFIGS.document.rrf (:83-88)
+  out->vector_top_k = 8;
+  out->keyword_limit = 8;
+  out->min_vector_score = 0.3;
+  get_u32(env, o, "vectorTopK", &out->vector_top_k);
+  get_u32(env, o, "keywordLimit", &out->keyword_limit);
+  get_f64(env, o, "minVectorScore", &out->min_vector_score);
+  napi_value rrf;
+  bool has = false;
+  if (napi_has_named_property(env, o, "rrf", &has) == napi_ok && has && napi_get_named_property(env, o, "rrf", &rrf) == napi_ok) {
+    get_f64(env, rrf, "k", &out->rrf.k);
+    get_f64(env, rrf, "vectorWeight", &out->rrf.vector_weight);
+    get_f64(env, rrf, "keywordWeight", &out->rrf.keyword_weight);
+    get_f64(env, rrf, "bothBonus", &out->rrf.both_bonus);
+  }
+  return true;
+}
+
+template <typename T>
+bool typed(napi_env env, napi_value v, napi_typedarray_type want, const T** data, size_t* len) {
+  napi_typedarray_type t;
+  void* p = nullptr;
+  if (napi_get_typedarray_info(env, v, &t, len, &p, nullptr, nullptr) != napi_ok || t != want) return false;
+  *data = static_cast<const T*>(p);
+  return true;
+}
+
+// ---- one hybrid search (direct or through a batcher) as async work --------------------------------
+struct SearchWork {
+  napi_async_work work = nullptr;
+  napi_deferred deferred = nullptr;
+  rag_index* idx = nullptr;
+  rag_batcher* batcher = nullptr;
+  std::vector<float> q;
+  uint32_t B = 1;
+  rag_hybrid_opts opts;
+  std::vector<uint64_t> kw_keys;
+  std::vector<uint32_t> kw_counts;
+  uint32_t cap = 0;
+  std::vector<uint64_t> keys, vec_ids;
+  std::vector<double> scores, vec_scores;
+  std::vector<uint8_t> source, ctype, used_rrf, certified;
+  std::vector<uint32_t> counts, vec_counts;
+  int rc = RAG_OK;
+  std::string err;
+};
+
+void search_execute(napi_env, void* data) {  // worker thread: the only place that touches CUDA
+  auto* w = static_cast<SearchWork*>(data);
+  const uint32_t k = w->opts.vector_top_k;
+  w->cap = k + w->opts.keyword_limit + w->opts.fresh_limit;
+  w->keys.resize((size_t)w->B * w->cap); w->scores.resize((size_t)w->B * w->cap);
+  w->source.resize((size_t)w->B * w->cap); w->ctype.resize((size_t)w->B * w->cap);
+  w->counts.resize(w->B); w->used_rrf.resize(w->B); w->certified.resize(w->B);
+  w->vec_ids.resize((size_t)w->B * k); w->vec_scores.resize((size_t)w->B * k); w->vec_counts.resize(w->B);
+  rag_fused_out out = {w->cap, w->keys.data(), w->scores.data(), w->source.data(), w->ctype.data(), w->counts.data(),
+                       w->used_rrf.data(), w->vec_ids.data(), w->vec_scores.data(), w->vec_counts.data(), w->certified.data()};
+  if (w->batcher)
+    w->rc = rag_batcher_submit(w->batcher, w->q.data(), w->kw_keys.data(), w->kw_counts.empty() ? 0 : w->kw_counts[0], &out);
+  else
+    w->rc = rag_hybrid_search(w->idx, w->q.data(), w->B, &w->opts, w->kw_keys.data(), w->kw_counts.data(), &out);
+  if (w->rc != RAG_OK) w->err = rag_last_error();
+}
+
+template <typename T>
+napi_value make_typed(napi_env env, napi_typedarray_type t, const std::vector<T>& v) {
+  napi_value ab, ta;
+  void* p = nullptr;
+  napi_create_arraybuffer(env, v.size() * sizeof(T), &p, &ab);
+  if (!v.empty()) memcpy(p, v.data(), v.size() * sizeof(T));
+  napi_create_typedarray(env, t, v.size(), ab, 0, &ta);
+  return ta;
+}
+
+void search_complete(napi_env env, napi_status, void* data) {  // main thread: build the JS result
+  auto* w = static_cast<SearchWork*>(data);
+  if (w->rc != RAG_OK) {
+    napi_value msg, e;
+    std::string m = "libragera error " + std::to_string(w->rc) + ": " + w->err;
+    napi_create_string_utf8(env, m.c_str(), NAPI_AUTO_LENGTH, &msg);
+    napi_create_error(env, nullptr, msg, &e);
+    napi_reject_deferred(env, w->deferred, e);  // hybridSearch does not catch; its callers do (engine.ts:295)
+  } else {
+    napi_value r, v;
+    napi_create_object(env, &r);
+    napi_create_uint32(env, w->cap, &v);                                         napi_set_named_property(env, r, "capacity", v);
+    napi_set_named_property(env, r, "keys", make_typed(env, napi_biguint64_array, w->keys));
+    napi_set_named_property(env, r, "scores", make_typed(env, napi_float64_array, w->scores));
+    napi_set_named_property(env, r, "source", make_typed(env, napi_uint8_array, w->source));
+    napi_set_named_property(env, r, "contentType", make_typed(env, napi_uint8_array, w->ctype));
+    napi_set_named_property(env, r, "counts", make_typed(env, napi_uint32_array, w->counts));
+    napi_set_named_property(env, r, "usedRrf", make_typed(env, napi_uint8_array, w->used_rrf));
+    napi_set_named_property(env, r, "certified", make_typed(env, napi_uint8_array, w->certified));
+    napi_set_named_property(env, r, "vecIds", make_typed(env, napi_biguint64_array, w->vec_ids));
+    napi_set_named_property(env, r, "vecScores", make_typed(env, napi_float64_array, w->vec_scores));
+    napi_set_named_property(env, r, "vecCounts", make_typed(env, napi_uint32_array, w->vec_counts));
+    napi_resolve_deferred(env, w->deferred, r);
+  }
+  napi_delete_async_work(env, w->work);
+  delete w;
+}
+
+napi_value queue_search(napi_env env, SearchWork* w) {
+  napi_value promise, name;
+  NAPI_OK(env, napi_create_promise(env, &w->deferred, &promise));
+  NAPI_OK(env, napi_create_string_utf8(env, "ragera.hybridSearch", NAPI_AUTO_LENGTH, &name));
+  NAPI_OK(env, napi_create_async_work(env, nullptr, name, search_execute, search_complete, w, &w->work));
+  NAPI_OK(env, napi_queue_async_work(env, w->work));
+  return promise;
+}
+
+// ---- exported functions ------------------------------------------------------------------------------
+napi_value CreateIndex(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index_desc d;
+  memset(&d, 0, sizeof d);
+  uint32_t rows = 0, dev = 0, shadow = 0;
+  get_u32(env, argv[0], "rows", &rows);
+  get_u32(env, argv[0], "dim", &d.dim);
+  get_u32(env, argv[0], "device", &dev);
+  get_u32(env, argv[0], "bf16Shadow", &shadow);
+  d.capacity_rows = rows;
+  d.device = (int32_t)dev;
+  d.dtype = RAG_F32;
+  d.flags = shadow ? RAG_INDEX_BF16_SHADOW : 0;
+  rag_index* idx = nullptr;
+  const int rc = rag_index_create(&d, &idx);
+  if (rc != RAG_OK) return throw_rag(env, rc);
+  napi_value ext;
+  NAPI_OK(env, napi_create_external(env, idx, nullptr, nullptr, &ext));
+  return ext;
+}
+
+napi_value UploadRows(napi_env env, napi_callback_info info) {  // uploadRows(handle, Float32Array rows, nrows, row0?)
+  size_t argc = 4;
+  napi_value argv[4];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  const float* rows = nullptr;
+  size_t n = 0;
+  if (!typed(env, argv[1], napi_float32_array, &rows, &n)) { napi_throw_type_error(env, nullptr, "rows must be a Float32Array"); return nullptr; }
+  uint32_t nrows = 0, r0 = 0;
+  NAPI_OK(env, napi_get_value_uint32(env, argv[2], &nrows));
+  uint64_t row0 = rag_index_rows(idx);  // index.insert appends (src/lib/memory/store.ts:67)
+  if (argc > 3 && napi_get_value_uint32(env, argv[3], &r0) == napi_ok) row0 = r0;
+  const int rc = rag_index_upload(idx, row0, nrows, rows);
+  if (rc != RAG_OK) return throw_rag(env, rc);
+  napi_value out;
+  NAPI_OK(env, napi_create_double(env, (double)row0, &out));
+  return out;
+}
+
+napi_value LoadVectorStore(napi_env env, napi_callback_info info) {  // loadVectorStore(handle, path) -> string[]
+  size_t argc = 2;
+  napi_value argv[2];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  char path[4096];
+  size_t len = 0;
+  NAPI_OK(env, napi_get_value_string_utf8(env, argv[1], path, sizeof path, &len));
+  uint64_t rows = 0, bytes = 0;
+  char* ids = nullptr;
+  const int rc = rag_index_load_vector_store(idx, path, &rows, &ids, &bytes);
+  if (rc != RAG_OK) return throw_rag(env, rc);
+  napi_value arr;
+  NAPI_OK(env, napi_create_array_with_length(env, (size_t)rows, &arr));
+  const char* p = ids;
+  for (uint64_t i = 0; i < rows; i++) {
+    napi_value s;
+    napi_create_string_utf8(env, p, NAPI_AUTO_LENGTH, &s);
+    napi_set_element(env, arr, (uint32_t)i, s);
+    p += strlen(p) + 1;
+  }
+  rag_free(ids);
+  return arr;
+}
+
+napi_value SetRowMeta(napi_env env, napi_callback_info info) {
+  size_t argc = 6;
+  napi_value argv[6];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  uint32_t row0 = 0;
+  NAPI_OK(env, napi_get_value_uint32(env, argv[1], &row0));
+  const uint8_t* ct = nullptr; const double* conf = nullptr; const int32_t* acc = nullptr; const int64_t* last = nullptr;
+  size_t n = 0, m = 0;
+  if (!typed(env, argv[2], napi_uint8_array, &ct, &n)) { napi_throw_type_error(env, nullptr, "contentType must be a Uint8Array"); return nullptr; }
+  if (argc > 3) typed(env, argv[3], napi_float64_array, &conf, &m);
+  if (argc > 4) typed(env, argv[4], napi_int32_array, &acc, &m);
+  if (argc > 5) typed(env, argv[5], napi_bigint64_array, &last, &m);
+  const int rc = rag_index_set_row_meta(idx, row0, n, ct, conf, acc, last);
+  return rc == RAG_OK ? nullptr : throw_rag(env, rc);
+}
+
+napi_value SetRowKeys(napi_env env, napi_callback_info info) {
+  size_t argc = 3;
+  napi_value argv[3];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  uint32_t row0 = 0;
+  NAPI_OK(env, napi_get_value_uint32(env, argv[1], &row0));
+  const uint64_t* keys = nullptr;
+  size_t n = 0;
+  if (!typed(env, argv[2], napi_biguint64_array, &keys, &n)) { napi_throw_type_error(env, nullptr, "keys must be a BigUint64Array"); return nullptr; }
+  const int rc = rag_index_set_row_keys(idx, row0, n, keys);
+  return rc == RAG_OK ? nullptr : throw_rag(env, rc);
+}
+
+napi_value HybridSearch(napi_env env, napi_callback_info info) {
+  size_t argc = 6;
+  napi_value argv[6];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  auto* w = new SearchWork();
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&w->idx));
+  const float* q = nullptr;
+  size_t nq = 0;
+  if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { delete w; napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
+  NAPI_OK(env, napi_get_value_uint32(env, argv[2], &w->B));
+  read_opts(env, argv[3], &w->opts);
+  w->q.assign(q, q + nq);  // copied: the JS buffer may be reused before the worker runs
+  const uint64_t* kk = nullptr; const uint32_t* kc = nullptr;
+  size_t nk = 0, nc = 0;
+  if (argc > 4 && typed(env, argv[4], napi_biguint64_array, &kk, &nk)) w->kw_keys.assign(kk, kk + nk);
+  if (argc > 5 && typed(env, argv[5], napi_uint32_array, &kc, &nc)) w->kw_counts.assign(kc, kc + nc);
+  w->kw_counts.resize(w->B, 0);
+  w->kw_keys.resize((size_t)w->B * w->opts.keyword_limit + 1, 0);
+  return queue_search(env, w);
+}
+
+napi_value CreateBatcher(napi_env env, napi_callback_info info) {  // createBatcher(handle, opts, maxBatch, maxWaitUs)
+  size_t argc = 4;
+  napi_value argv[4];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  rag_batcher_desc d;
+  read_opts(env, argv[1], &d.opts);
+  d.max_batch = 1024;
+  d.max_wait_us = 200;
+  if (argc > 2) napi_get_value_uint32(env, argv[2], &d.max_batch);
+  if (argc > 3) napi_get_value_uint32(env, argv[3], &d.max_wait_us);
+  rag_batcher* b = nullptr;
+  const int rc = rag_batcher_create(idx, &d, &b);
+  if (rc != RAG_OK) return throw_rag(env, rc);
+  napi_value ext;
+  NAPI_OK(env, napi_create_external(env, b, nullptr, nullptr, &ext));
+  return ext;
+}
+
+napi_value Submit(napi_env env, napi_callback_info info) {  // submit(batcher, opts, Float32Array q, BigUint64Array kwKeys)
+  size_t argc = 4;
+  napi_value argv[4];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  auto* w = new SearchWork();
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&w->batcher));
+  read_opts(env, argv[1], &w->opts);  // must equal the batcher's options (sizes the result arrays)
+  const float* q = nullptr;
+  size_t nq = 0;
+  if (!typed(env, argv[2], napi_float32_array, &q, &nq)) { delete w; napi_throw_type_error(env, nullptr, "query must be a Float32Array"); return nullptr; }
+  w->q.assign(q, q + nq);
+  const uint64_t* kk = nullptr;
+  size_t nk = 0;
+  if (argc > 3 && typed(env, argv[3], napi_biguint64_array, &kk, &nk)) w->kw_keys.assign(kk, kk + nk);
+  w->kw_counts.assign(1, (uint32_t)nk);
+  w->kw_keys.resize(nk + 1, 0);
+  w->B = 1;
+  return queue_search(env, w);
+}
+
+napi_value Destroy(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  rag_index_destroy(idx);
+  return nullptr;
+}
+
+napi_value DestroyBatcher(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_batcher* b = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&b));
+  rag_batcher_destroy(b);
+  return nullptr;
+}
+
+}  // namespace
+
+NAPI_MODULE_INIT() {
+  napi_property_descriptor props[] = {
+      {"createIndex", nullptr, CreateIndex, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"uploadRows", nullptr, UploadRows, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"loadVectorStore", nullptr, LoadVectorStore, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"setRowMeta", nullptr, SetRowMeta, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"setRowKeys", nullptr, SetRowKeys, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"hybridSearch", nullptr, HybridSearch, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"createBatcher", nullptr, CreateBatcher, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"submit", nullptr, Submit, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"destroy", nullptr, Destroy, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"destroyBatcher", nullptr, DestroyBatcher, nullptr, nullptr, nullptr, napi_default, nullptr},
+  };
+  napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
+  return exports;
+}

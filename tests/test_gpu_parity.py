@@ -552,3 +552,24 @@ def test_wide_rows_and_long_lists_fall_back_gracefully(rb, native, oracle):
             assert np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es)
     with pytest.raises(rb.RagError):
         rb.VectorIndex(8193, 10)
+
+
+def test_c_abi_from_plain_c(rb, native, oracle, tmp_path):
+    """tests/c/abi_demo.c: the boundary used from C (what the N-API shim does), checked against the oracle."""
+    import subprocess
+
+    exe = str(tmp_path / "abi_demo")
+    lib_dir = os.path.join(ROOT, "rag_era_b200")
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_demo.c"), "-o", exe,
+                    "-L", lib_dir, "-lragera", f"-Wl,-rpath,{lib_dir}"], check=True)
+    n = 20000
+    lines = subprocess.run([exe, str(n)], capture_output=True, text=True, check=True).stdout.split("\n")[:3]
+    go = oracle.make_gen(n, n_clusters=32)
+    X = oracle.gen_rows(go, 0, n, 256)
+    Q = oracle.gen_queries(go, 0, 3, 256)
+    kws = [[1, 2, 3, 4], [], [n - 1, 7]]
+    for b, line in enumerate(lines):
+        _, used, cnt, key0, score0, cert = line.split()
+        e = oracle.hybrid_search(X, Q[b], 10, 0.3, kws[b])
+        assert int(used) == int(e["used_rrf"]) and int(cnt) == len(e["keys"]) and int(cert) == 1
+        assert int(key0) == int(e["keys"][0]) and float.fromhex(score0) == float(e["scores"][0])
