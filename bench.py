@@ -239,7 +239,7 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     total = steps + warmup
     n_pool = min(total, 8) if B >= 64 else total       # big batches cycle through a pool of distinct batches
     Q = idx.generate_queries(gen, 0, n_pool * B)
-    o = rb.hybrid_opts(w["vector_top_k"], w["keyword_limit"], w["min_score"], path=path,
+    o = rb.hybrid_opts(w["vector_top_k"], w["keyword_limit"], w["min_score"], path=path, slack=int(os.environ.get("RAGERA_BENCH_SLACK", "0")),
                        fresh_limit=w.get("fresh_limit", 0), fresh_weight=1.0, now_ms=now_ms)
 
     # setup (untimed): true vector top-k of every query → keyword lists with ~30% overlap

@@ -236,6 +236,29 @@ int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* 
 int rag_fetch_fused(rag_index* idx, uint32_t B, const rag_hybrid_opts* opts, rag_fused_out* out);
 int rag_sync(rag_index* idx);
 
+/* ---- host-side post-filter: processResults of src/lib/context/rag/dedup-filter.ts:193-247,
+ *      the step ContextEngine.buildContext applies to the fused list (engine.ts:289). Strings are UTF-16
+ *      code units (what a JS string is); no GPU involved. opts == NULL → the reference's defaults. -------- */
+typedef struct rag_text { const uint16_t* units; uint32_t len; } rag_text;
+typedef struct rag_process_opts {
+  double   similarity_threshold; /* 0.85  DEFAULT_CONFIG, dedup-filter.ts:16-20 */
+  uint32_t min_content_length;   /* 20                                          */
+  uint32_t max_results;          /* 10                                          */
+  uint32_t enable_noise_filter;  /* 1     (enableNoiseFiltler)                  */
+  uint32_t enable_rerank;        /* 1                                           */
+} rag_process_opts;
+typedef struct rag_processed_out {
+  uint32_t  capacity;      /* entries in the arrays below (>= min(n, max_results))      */
+  uint32_t* index;         /* [capacity] index of the surviving input result            */
+  double*   fusion_score;  /* [capacity] FusedResult.fusionScore                        */
+  uint8_t*  deduplicated;  /* [capacity] optional                                       */
+  uint32_t* source_mask;   /* [capacity] optional: bit s set if a merged result had source s */
+  uint32_t* n_sources;     /* [capacity] optional: FusedResult.sources.length           */
+  uint32_t  count;         /* out: number of results                                    */
+} rag_processed_out;
+int rag_process_results(const rag_text* contents, const double* scores, const uint8_t* sources, uint32_t n,
+                        rag_text query, const rag_process_opts* opts, rag_processed_out* out);
+
 /* ---- micro-batching front end: concurrent batch-1 callers (one per request thread,
  *      like the reference's per-request hybridSearch) share one corpus pass. One batcher per call-site
  *      class (fixed options). submit() blocks until the caller's own result is ready; results are

@@ -75,6 +75,20 @@ class FusedOut(C.Structure):
                 ("certified", C.c_void_p)]
 
 
+class Text(C.Structure):
+    _fields_ = [("units", C.c_void_p), ("len", C.c_uint32)]
+
+
+class ProcessOpts(C.Structure):
+    _fields_ = [("similarity_threshold", C.c_double), ("min_content_length", C.c_uint32), ("max_results", C.c_uint32),
+                ("enable_noise_filter", C.c_uint32), ("enable_rerank", C.c_uint32)]
+
+
+class ProcessedOut(C.Structure):
+    _fields_ = [("capacity", C.c_uint32), ("index", C.c_void_p), ("fusion_score", C.c_void_p), ("deduplicated", C.c_void_p),
+                ("source_mask", C.c_void_p), ("n_sources", C.c_void_p), ("count", C.c_uint32)]
+
+
 class BatcherDesc(C.Structure):
     _fields_ = [("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32), ("opts", HybridOpts)]
 
@@ -119,6 +133,7 @@ SYMBOLS = {
     "rag_hybrid_search_staged": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts)]),
     "rag_fetch_fused": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts), C.POINTER(FusedOut)]),
     "rag_sync": (C.c_int, [_vp]),
+    "rag_process_results": (C.c_int, [C.POINTER(Text), _vp, _vp, C.c_uint32, Text, C.POINTER(ProcessOpts), C.POINTER(ProcessedOut)]),
     "rag_batcher_create": (C.c_int, [_vp, C.POINTER(BatcherDesc), C.POINTER(_vp)]),
     "rag_batcher_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.POINTER(FusedOut)]),
     "rag_batcher_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

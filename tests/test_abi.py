@@ -49,6 +49,9 @@ int main(void) {
   printf("rag_memory_opts %zu\n", sizeof(rag_memory_opts));
   printf("rag_memory_out %zu\n", sizeof(rag_memory_out));
   printf("rag_batcher_desc %zu\n", sizeof(rag_batcher_desc));
+  printf("rag_text %zu\n", sizeof(rag_text));
+  printf("rag_process_opts %zu\n", sizeof(rag_process_opts));
+  printf("rag_processed_out %zu\n", sizeof(rag_processed_out));
   printf("off_hybrid_now_ms %zu\n", offsetof(rag_hybrid_opts, now_ms));
   printf("off_hybrid_epsilon %zu\n", offsetof(rag_hybrid_opts, epsilon));
   printf("off_fused_certified %zu\n", offsetof(rag_fused_out, certified));
@@ -73,6 +76,9 @@ int main(void) {
     assert int(got["rag_memory_opts"]) == C.sizeof(N.MemoryOpts)
     assert int(got["rag_memory_out"]) == C.sizeof(N.MemoryOut)
     assert int(got["rag_batcher_desc"]) == C.sizeof(N.BatcherDesc)
+    assert int(got["rag_text"]) == C.sizeof(N.Text)
+    assert int(got["rag_process_opts"]) == C.sizeof(N.ProcessOpts)
+    assert int(got["rag_processed_out"]) == C.sizeof(N.ProcessedOut)
     assert int(got["off_hybrid_now_ms"]) == N.HybridOpts.now_ms.offset
     assert int(got["off_hybrid_epsilon"]) == N.HybridOpts.epsilon.offset
     assert int(got["off_fused_certified"]) == N.FusedOut.certified.offset
