@@ -278,6 +278,11 @@ void rag_batcher_destroy(rag_batcher* b);
 /* ---- diagnostics: the raw scaled scores (dot_bf16 * 1/||x||, no 1/||q||) the tensor path (K2)
  *      computes, written as out_scores[B][rows]; for validating the tcgen05 pipeline on small inputs */
 int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, float* out_scores);
+/*      the same launch followed by the K3 merge: out_keys[B][kp] = the K' packed candidate keys per query
+ *      (ordered score bits << 32 | ~row, best first, 0 = empty) next to the scores they were selected from,
+ *      so the fused tcgen05 selection can be checked exactly (ties included) on small inputs */
+int rag_debug_tensor_candidates(rag_index* idx, const float* queries, uint32_t B, uint32_t kp, float* out_scores,
+                                uint64_t* out_keys);
 
 /* ---- measurement helpers (CUDA events on the library's own stream) ------------ */
 int rag_timer_start(rag_index* idx);

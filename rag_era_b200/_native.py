@@ -139,6 +139,7 @@ SYMBOLS = {
     "rag_batcher_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rag_batcher_destroy": (None, [_vp]),
     "rag_debug_tensor_scores": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "rag_debug_tensor_candidates": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "rag_timer_start": (C.c_int, [_vp]),
     "rag_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rag_launch_count": (C.c_uint64, [_vp]),

@@ -969,6 +969,46 @@ int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, fl
   return rc;
 }
 
+// K2 + K3 only: the K' packed candidate keys per query next to the score matrix they were selected from
+// (one launch, so both views come from the same accumulators) — lets a test check the fused selection
+// exactly, ties included, without going through the fp64 rescoring
+int rag_debug_tensor_candidates(rag_index* idx, const float* queries, uint32_t B, uint32_t kp, float* out_scores,
+                                uint64_t* out_keys) {
+  RAG_CHECK(check_handle(idx));
+  if (!queries || !out_scores || !out_keys || B == 0 || kp == 0 || kp > RAG_MAX_CANDIDATES)
+    return rag_set_error(RAG_ERR_INVALID, "rag_debug_tensor_candidates: bad argument");
+  if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
+  if (!k2_available(idx)) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path (K2) is not available for this index");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  bt->staged_B = bt->win_count = 0;
+  RAG_CHECK(stage_queries(idx, bt, queries, B));
+  float* d = nullptr;
+  size_t cap = 0;
+  RAG_CHECK(grow_dev(&d, &cap, (size_t)B * idx->rows * 4, true));
+  uint32_t parts = 0;
+  int rc = k2_plan(idx, B, kp, &parts);
+  if (rc == RAG_OK) rc = grow_dev(&bt->d_partial, &bt->c_partial, (size_t)B * parts * kp * 8, false);
+  if (rc == RAG_OK) rc = grow_dev(&bt->d_cand, &bt->c_cand, (size_t)B * RAG_MAX_CANDIDATES * 8, false);
+  if (rc == RAG_OK) {
+    k2_set_debug(idx, d);
+    rc = k2_launch(idx, B, kp, parts);
+    k2_set_debug(idx, nullptr);
+  }
+  if (rc == RAG_OK) rc = k3_launch(idx, B, kp, parts);
+  if (rc == RAG_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_scores, d, (size_t)B * idx->rows * 4, cudaMemcpyDeviceToHost, idx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(out_keys, (size_t)kp * 8, bt->d_cand, (size_t)RAG_MAX_CANDIDATES * 8, (size_t)kp * 8, B,
+                            cudaMemcpyDeviceToHost, idx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+    if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "rag_debug_tensor_candidates: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d);
+  return rc;
+}
+
 // ---- measurement ---------------------------------------------------------------------------------
 int rag_timer_start(rag_index* idx) {
   RAG_CHECK(check_handle(idx));

@@ -7,19 +7,24 @@
 //   cluster = 2 CTAs (one TPC). The pair owns 256 queries (128 TMEM lanes in each CTA) and walks
 //   corpus tiles of 256 rows. Per 64-element k-slice each CTA TMA-loads only its own 128 queries
 //   (16 KB) and its own HALF of the corpus tile (128 rows, 16 KB); UMMAs 256x256x16 issued by the
-//   leader reads both CTAs' shared memory and writes 128 lanes x 256 columns of fp32 into EACH
+//   leader read both CTAs' shared memory and write 128 lanes x 256 columns of fp32 into EACH
 //   CTA's TMEM. A 256-column accumulator is half of TMEM, so there are two: tile t+1 accumulates
-//   into one while the epilogue drains tile t from the other. L2->smem traffic per MMA cycle is
-//   the same as the single-CTA kernel's (16 KB per 2 MMAs); the ring holds 3 stages of 32 KB.
+//   into one while the epilogue drains tile t from the other. The ring holds 6 stages of 32 KB
+//   (3 stages left the MMA waiting for TMA 13% of the time).
 //
-//   Epilogue warps come in two sets of four (set = tile parity): one LANE per query, 256 scores per
-//   tile each; scale by 1/||x||, threshold test, rare survivors appended to the query's 64-slot
-//   buffer, warp-pruned to the K' best when it fills (see k2_tensor.cu). Each set keeps its own
-//   buffers, so a (pair, query) publishes two lists: partial[B][2*pairs][K'].
+//   Epilogue = 4 warps, one LANE per query, 256 scores per tile each. The common case is branch-free:
+//   scale 32 scores by 1/||x||, take their maximum, one vote against the per-query threshold
+//   (~2 instructions per score). Survivors (rare once the threshold has risen) are appended to the
+//   query's 32-slot WINDOW in shared memory; a full window is bitonic-sorted by the warp and merged into
+//   the query's sorted K' best, which live directly in their output slot partial[q][pair][K'] (lane l
+//   owns rank l, so a lane only ever reads back what it wrote itself). The first tile of a CTA has no
+//   threshold yet: instead of appending all 256 scores, every lane first finds its exact K'-th largest
+//   score of the tile with a register sorting network (branch-free, all 32 queries at once) and starts
+//   from that threshold — the start-up transient used to stall the tensor pipe for ~10% of the kernel.
 //
 // Barriers: full[s] lives in the leader (it counts both CTAs' TMA bytes), empty[s] and
 // tmem_full[b] are signalled in both CTAs by multicast tcgen05.commit, tmem_empty[b] lives in the
-// leader and collects the 8 epilogue warps of both CTAs (remote mbarrier.arrive via mapa).
+// leader and collects the 4 epilogue warps of both CTAs (remote mbarrier.arrive via mapa).
 //
 // Roofline: tensor pipe for B >= ~64: 2*rows*ld*B flop per launch; HBM below (rows*ld*2 bytes).
 #include "common.cuh"
@@ -27,6 +32,7 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <math_constants.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -44,13 +50,13 @@ constexpr int PAIR_M = 2 * CTA_M;      // UMMA M
 constexpr int A_BYTES = CTA_M * ROW_BYTES;    // 16 KB
 constexpr int B_BYTES = HALF_N * ROW_BYTES;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int KP_THREADS = 384;        // w0 TMA · w1 MMA · w2 TMEM alloc · w3 inv-norm loader · w4..11 epilogue
-constexpr int MAX_STAGES = 8;
+constexpr int KP_THREADS = 256;        // w0 TMA · w1 MMA · w2 TMEM alloc · w3 inv-norm loader · w4..7 epilogue
+constexpr int KP_WARPS = KP_THREADS / 32;
+constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
-constexpr int CAP = 64;
-constexpr int SETS = 2;
+constexpr int WIN = 32;                // append window per query (shared memory), entries
 constexpr int KP_PREFETCH = 8;         // k-slices of L2 prefetch ahead of the TMA loads
-constexpr int KP_MAX_KP = CAP - 16;   // keep a useful append window above K'
+constexpr int KP_MAX_KP = 64;          // two ranks per lane
 constexpr uint32_t kIdescBf16 = idesc_bf16(PAIR_M, TILE_N);
 constexpr uint32_t kIdescTf32 = idesc_tf32(PAIR_M, TILE_N);
 
@@ -58,45 +64,20 @@ struct kp_params {
   uint32_t n_rows, ld, B, kp, parts, stages, n_tiles, pairs;
   const float* inv_norm;
   uint64_t* partial;
+  uint32_t* pub;       // [pairs][Bpub] ordered score of each (pair, query)'s pub_rank-th best so far (0 = none yet)
+  uint32_t Bpub, pub_rank, pub_every;
   float* dbg_scores;
   uint32_t mode;
-  unsigned long long* cyc;  // diagnostics (RAGERA_K2_PROF): [ctas][12 warps][8] cycle counters
+  unsigned long long* cyc;  // diagnostics (RAGERA_K2_PROF): [ctas][8 warps][8] cycle counters
 };
 __device__ __forceinline__ long long clk() { return clock64(); }
 
-// see k2_tensor.cu::warp_prune
-__device__ __noinline__ uint64_t warp_prune(uint64_t* buf, int cnt, int kp, int rot, int lane) {
-  const uint64_t k0 = lane < cnt ? buf[(lane + rot) & (CAP - 1)] : 0ull;
-  const uint64_t k1 = lane + 32 < cnt ? buf[(lane + 32 + rot) & (CAP - 1)] : 0ull;
-  int r0 = 0, r1 = 0;
-#pragma unroll
-  for (int j = 0; j < 32; j++) {
-    const uint64_t a = shfl_u64(k0, j), b = shfl_u64(k1, j);
-    r0 += (a > k0 ? 1 : 0) + (b > k0 ? 1 : 0);
-    r1 += (a > k1 ? 1 : 0) + (b > k1 ? 1 : 0);
-  }
-  __syncwarp();
-  buf[lane] = 0ull;
-  buf[lane + 32] = 0ull;
-  __syncwarp();
-  if (k0 != 0ull && r0 < kp) buf[(r0 + rot) & (CAP - 1)] = k0;
-  if (k1 != 0ull && r1 < kp) buf[(r1 + rot) & (CAP - 1)] = k1;
-  __syncwarp();
-  return cnt >= kp ? buf[(kp - 1 + rot) & (CAP - 1)] : 0ull;
-}
-
-// Sorting-network prune for K' <= 32 (the default window): lane l holds logical entries l (lower half)
-// and 32+l (upper half) of one query's buffer. Each half is bitonic-sorted across the lanes
-// (descending; the lower half is skipped when it is still the sorted result of the previous prune),
-// the upper half is reversed so that max(lower[l], upper[31-l]) is the bitonic sequence of the 32
-// largest keys, and one bitonic merge sorts it: ~3x fewer instructions than rank-by-counting.
-// On return the lower half holds the K' best in rank order (zeros after), the upper half is empty;
-// the caller sets the entry count to 32 so new keys are appended to the upper half.
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
   const uint32_t hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), m);
   const uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)v, m);
   return ((uint64_t)hi << 32) | lo;
 }
+// 32 keys, one per lane, sorted descending across the lanes
 __device__ __forceinline__ uint64_t bitonic_sort32_desc(uint64_t key, int lane) {
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
@@ -109,23 +90,252 @@ __device__ __forceinline__ uint64_t bitonic_sort32_desc(uint64_t key, int lane) 
   }
   return key;
 }
-__device__ __noinline__ uint64_t warp_prune_sort(uint64_t* buf, int cnt, int kp, int rot, int lane, int lower_sorted) {
-  uint64_t lo = lane < cnt ? buf[(lane + rot) & (CAP - 1)] : 0ull;
-  uint64_t hi = lane + 32 < cnt ? buf[(lane + 32 + rot) & (CAP - 1)] : 0ull;
-  if (!lower_sorted) lo = bitonic_sort32_desc(lo, lane);
-  hi = bitonic_sort32_desc(hi, lane);
-  const uint64_t hr = shfl_u64(hi, 31 - lane);
-  uint64_t c = max(lo, hr);
+// a bitonic sequence of 32 keys (one per lane) -> sorted descending
+__device__ __forceinline__ uint64_t bitonic_merge32_desc(uint64_t c, int lane) {
 #pragma unroll
   for (int j = 16; j > 0; j >>= 1) {
     const uint64_t other = shfl_xor_u64(c, j);
     c = ((lane & j) == 0) ? max(c, other) : min(c, other);
   }
+  return c;
+}
+
+// Fold up to FOLD_N queries' windows (unsorted raw entries in shared memory) into their sorted best lists
+// (global memory, lane l owns ranks l and 32+l) and return, to the lane that owns the query, the K'-th best
+// key (0 while fewer than K' candidates exist). Whole warp. The FOLD_N bitonic networks are independent and
+// interleaved instruction by instruction: a single network is a chain of ~20 dependent shuffle steps and
+// the epilogue has one warp per scheduler, so folding one query at a time is pure latency.
+// `srcs` packs the lanes to fold, one per byte, 0xFF = none. Half-cleaner identities: with B0 and W sorted
+// descending, max(B0[l], W[31-l]) is a bitonic sequence of the 32 largest of B0 u W, min(...) of the rest.
+constexpr int FOLD_N = 4;
+__device__ __forceinline__ void bitonic_sort32_desc_n(uint64_t (&key)[FOLD_N], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const bool take_max = ((lane & j) == 0) == ((lane & k) == 0);
+#pragma unroll
+      for (int q = 0; q < FOLD_N; q++) {
+        const uint64_t other = shfl_xor_u64(key[q], j);
+        key[q] = take_max ? max(key[q], other) : min(key[q], other);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void bitonic_merge32_desc_n(uint64_t (&c)[FOLD_N], int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const bool take_max = (lane & j) == 0;
+#pragma unroll
+    for (int q = 0; q < FOLD_N; q++) {
+      const uint64_t other = shfl_xor_u64(c[q], j);
+      c[q] = take_max ? max(c[q], other) : min(c[q], other);
+    }
+  }
+}
+__device__ __noinline__ uint64_t k2p_fold_windows(const uint64_t* warp_win, uint64_t* warp_best, size_t best_stride, int kp, int lane,
+                                                  uint32_t srcs, uint32_t my_cnt, int my_nbest) {
+  uint64_t w[FOLD_N], b0[FOLD_N], b1[FOLD_N];
+  uint64_t* bptr[FOLD_N];
+  bool on[FOLD_N];
+#pragma unroll
+  for (int q = 0; q < FOLD_N; q++) {
+    const int src = (int)((srcs >> (8 * q)) & 0xFFu);
+    on[q] = src != 0xFF;
+    const int sl = on[q] ? src : 0;
+    const int c = on[q] ? (int)__shfl_sync(0xFFFFFFFFu, my_cnt, sl) : 0;
+    const int nb = on[q] ? __shfl_sync(0xFFFFFFFFu, my_nbest, sl) : 0;
+    bptr[q] = warp_best + (size_t)sl * best_stride;
+    b0[q] = lane < nb ? bptr[q][lane] : 0ull;
+    b1[q] = lane + 32 < nb ? bptr[q][lane + 32] : 0ull;
+    // window entry j of lane sl sits at slot j ^ sl; raw entry = score bits << 32 | row
+    const uint64_t raw = warp_win[(size_t)sl * WIN + (lane ^ sl)];
+    w[q] = lane < c ? rag_pack_key(__uint_as_float((uint32_t)(raw >> 32)), (uint32_t)raw) : 0ull;
+  }
+  bitonic_sort32_desc_n(w, lane);
+  uint64_t x[FOLD_N], y[FOLD_N];
+#pragma unroll
+  for (int q = 0; q < FOLD_N; q++) {
+    const uint64_t wr = shfl_u64(w[q], 31 - lane);
+    x[q] = max(b0[q], wr);
+    y[q] = min(b0[q], wr);
+  }
+  bitonic_merge32_desc_n(x, lane);
+  uint64_t ret = 0ull;
+  if (kp <= 32) {
+#pragma unroll
+    for (int q = 0; q < FOLD_N; q++) {
+      if (on[q] && lane < kp) bptr[q][lane] = x[q];
+      const uint64_t kth = shfl_u64(x[q], kp - 1);
+      if (on[q] && lane == (int)((srcs >> (8 * q)) & 0xFFu)) ret = kth;
+    }
+    return ret;
+  }
+  bitonic_merge32_desc_n(y, lane);
+#pragma unroll
+  for (int q = 0; q < FOLD_N; q++) y[q] = max(b1[q], shfl_u64(y[q], 31 - lane));
+  bitonic_merge32_desc_n(y, lane);
+#pragma unroll
+  for (int q = 0; q < FOLD_N; q++) {
+    if (on[q]) {
+      bptr[q][lane] = x[q];
+      if (lane + 32 < kp) bptr[q][lane + 32] = y[q];
+    }
+    const uint64_t kth = shfl_u64(y[q], kp - 33);
+    if (on[q] && lane == (int)((srcs >> (8 * q)) & 0xFFu)) ret = kth;
+  }
+  return ret;
+}
+
+// Fold ONE query's window into its best list by rank counting — the steady-state case (windows fill one at
+// a time once the thresholds have risen). Every key's final rank = how many keys of the union beat it: the
+// window keys are broadcast from shared memory (independent loads and compares, no dependent shuffle chain —
+// this warp is alone on its scheduler, so latency is what costs), the sorted best list is binary-searched
+// with indexed shuffles. Keys are distinct (they contain the row), so the ranks are a permutation; a key
+// whose rank is < K' is stored at best[rank]. Same result as k2p_fold_windows for one lane.
+__device__ __noinline__ uint64_t k2p_fold_one(uint64_t* wsrc, uint64_t* bsrc, int c, int nb, int kp, int src, int lane) {
+  const uint64_t b0 = lane < nb ? bsrc[lane] : 0ull;
+  const uint64_t b1 = lane + 32 < nb ? bsrc[lane + 32] : 0ull;
+  uint64_t w = 0ull;
+  if (lane < c) {
+    const uint64_t raw = wsrc[lane ^ src];
+    w = rag_pack_key(__uint_as_float((uint32_t)(raw >> 32)), (uint32_t)raw);
+    wsrc[lane ^ src] = w;
+  }
   __syncwarp();
-  buf[(lane + rot) & (CAP - 1)] = lane < kp ? c : 0ull;
-  buf[(lane + 32 + rot) & (CAP - 1)] = 0ull;
-  __syncwarp();
-  return shfl_u64(c, kp - 1);
+  int rw = 0, r0 = 0, r1 = 0;
+#pragma unroll 4
+  for (int j = 0; j < c; j++) {
+    const uint64_t wj = wsrc[j ^ src];  // uniform address: one broadcast load
+    rw += wj > w ? 1 : 0;
+    r0 += wj > b0 ? 1 : 0;
+    r1 += wj > b1 ? 1 : 0;
+  }
+  // how many of the nb sorted best keys beat w: invariant best[0..lo) > w > best[hi..)
+  int lo = 0, hi = nb;
+  const int steps = nb > 32 ? 7 : 6;
+  for (int t = 0; t < steps; t++) {
+    const int mid = min((lo + hi) >> 1, 63);
+    uint64_t bm = shfl_u64(b0, mid & 31);
+    if (nb > 32) {
+      const uint64_t bm1 = shfl_u64(b1, mid & 31);
+      if (mid >= 32) bm = bm1;
+    }
+    if (lo < hi) {
+      if (bm > w) lo = mid + 1;
+      else hi = mid;
+    }
+  }
+  rw += lo;
+  const int p0 = lane + r0, p1 = 32 + lane + r1;
+  const bool has_w = lane < c, has0 = lane < nb, has1 = lane + 32 < nb;
+  if (has_w && rw < kp) bsrc[rw] = w;
+  if (has0 && r0 != 0 && p0 < kp) bsrc[p0] = b0;
+  if (has1 && r1 != 0 && p1 < kp) bsrc[p1] = b1;
+  uint64_t kth = 0ull;
+  if (nb + c >= kp) {  // uniform
+    const unsigned mw = __ballot_sync(0xFFFFFFFFu, has_w && rw == kp - 1);
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, has0 && p0 == kp - 1);
+    const unsigned m1 = __ballot_sync(0xFFFFFFFFu, has1 && p1 == kp - 1);
+    const uint64_t kw = shfl_u64(w, mw ? __ffs(mw) - 1 : 0);
+    const uint64_t k0 = shfl_u64(b0, m0 ? __ffs(m0) - 1 : 0);
+    const uint64_t k1 = shfl_u64(b1, m1 ? __ffs(m1) - 1 : 0);
+    kth = mw ? kw : (m0 ? k0 : k1);
+  }
+  __syncwarp();  // the stores above are ordered before the next fold's loads of the same list
+  return kth;
+}
+
+// ---- register sorting networks (one query per lane, static indices only) -------------------
+__device__ __forceinline__ void ce_desc(float& a, float& b) {  // a >= b afterwards
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  a = hi;
+  b = lo;
+}
+__device__ __forceinline__ void reg_sort32_desc(float (&v)[32]) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const int l = i ^ j;
+        if (l > i) {
+          if ((i & k) == 0) ce_desc(v[i], v[l]);
+          else ce_desc(v[l], v[i]);
+        }
+      }
+    }
+  }
+}
+__device__ __forceinline__ void reg_merge32_desc(float (&v)[32]) {  // bitonic -> sorted descending
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      const int l = i ^ j;
+      if (l > i) ce_desc(v[i], v[l]);
+    }
+  }
+}
+// 32 accumulator columns of this lane's query, scaled by 1/||x||; rows that must never be selected
+// (inverse norm = NaN) read as -inf
+__device__ __forceinline__ void load32_scaled(uint32_t taddr, const float* inv, float (&s)[32]) {
+  uint32_t va[16], vb[16];
+  tmem_ld16(taddr, va);
+  tmem_ld16(taddr + 16, vb);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 wa = *reinterpret_cast<const float4*>(inv + i);
+    const float4 wb = *reinterpret_cast<const float4*>(inv + 16 + i);
+    s[i] = __uint_as_float(va[i]) * wa.x;
+    s[i + 1] = __uint_as_float(va[i + 1]) * wa.y;
+    s[i + 2] = __uint_as_float(va[i + 2]) * wa.z;
+    s[i + 3] = __uint_as_float(va[i + 3]) * wa.w;
+    s[16 + i] = __uint_as_float(vb[i]) * wb.x;
+    s[16 + i + 1] = __uint_as_float(vb[i + 1]) * wb.y;
+    s[16 + i + 2] = __uint_as_float(vb[i + 2]) * wb.z;
+    s[16 + i + 3] = __uint_as_float(vb[i + 3]) * wb.w;
+  }
+}
+// First tile of a CTA: a score T such that at least K' of this lane's 256 scores are >= T, found without
+// touching the candidate lists. K' <= 32: the exact K'-th largest — a running sorted top-32 in registers,
+// each new group of 32 scores is sorted by a network and merged (half-cleaner + bitonic merge).
+// 32 < K' <= 64: the same over the 128 minima of adjacent score pairs — the ceil(K'/2)-th largest minimum
+// has that many PAIRS, so at least K' scores, at or above it. Branch-free: ~5k instructions per warp, once.
+__device__ __noinline__ float k2p_first_tile_threshold(uint32_t taddr, const float* inv, int kp) {
+  float R[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) R[i] = -CUDART_INF_F;
+  const bool by_pairs = kp > 32;
+#pragma unroll 1
+  for (uint32_t c0 = 0; c0 < TILE_N; c0 += by_pairs ? 64u : 32u) {
+    float C[32];
+    if (!by_pairs) {
+      load32_scaled(taddr + c0, inv + c0, C);
+#pragma unroll
+      for (int i = 0; i < 32; i++) C[i] = fmaxf(C[i], -CUDART_INF_F);  // NaN -> -inf
+    } else {
+      float s[32];
+      load32_scaled(taddr + c0, inv + c0, s);
+#pragma unroll
+      for (int i = 0; i < 16; i++) C[i] = fminf(fmaxf(s[2 * i], -CUDART_INF_F), fmaxf(s[2 * i + 1], -CUDART_INF_F));
+      load32_scaled(taddr + c0 + 32, inv + c0 + 32, s);
+#pragma unroll
+      for (int i = 0; i < 16; i++) C[16 + i] = fminf(fmaxf(s[2 * i], -CUDART_INF_F), fmaxf(s[2 * i + 1], -CUDART_INF_F));
+    }
+    reg_sort32_desc(C);
+#pragma unroll
+    for (int i = 0; i < 32; i++) R[i] = fmaxf(R[i], C[31 - i]);
+    reg_merge32_desc(R);
+  }
+  const int want = (by_pairs ? (kp + 1) / 2 : kp) - 1;
+  float T = R[31];
+#pragma unroll
+  for (int i = 0; i < 31; i++)
+    if (i == want) T = R[i];
+  return T;
 }
 
 // TF32 = false: bf16 operands (bf16 corpus or bf16 shadow, queries rounded to bf16), UMMA K = 16.
@@ -136,10 +346,13 @@ template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KP_THREADS, 1)
 k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const kp_params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  // layout (identical in both CTAs): [stages][A | B] · lists [SETS][128][CAP] u64 · inv [2][256] f32 · barriers · tmem ptr
+  // layout (identical in both CTAs): [stages][A | B] · windows [128][WIN] u64 · best [128][32 or 64] u64 ·
+  // inv [2][256] f32 · barriers · tmem ptr
   unsigned char* stage_base = smem;
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * STAGE_BYTES);
-  float* s_inv = reinterpret_cast<float*>(lists + (size_t)SETS * CTA_M * CAP);
+  uint64_t* win = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * STAGE_BYTES);
+  uint64_t* best = win + (size_t)CTA_M * WIN;
+  const uint32_t best_stride = P.kp > 32 ? 64u : 32u;  // sorted K' best per query, lane l owns ranks l and 32+l
+  float* s_inv = reinterpret_cast<float*>(best + (size_t)CTA_M * best_stride);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 2 * TILE_N);
   uint64_t* full = bars;                        // [stages]  (the leader's are used)
   uint64_t* empty = bars + MAX_STAGES;          // [stages]  (local)
@@ -156,8 +369,8 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   const uint32_t q0 = blockIdx.y * PAIR_M + rank * CTA_M;  // first query of this CTA
   constexpr int BK = TF32 ? ROW_BYTES / 4 : ROW_BYTES / 2;  // k elements per stage
   const uint32_t nkb = P.ld / BK;
+  unsigned long long* cyc = P.cyc ? P.cyc + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * KP_WARPS + warp) * 8 : nullptr;
 
-  for (uint32_t i = threadIdx.x; i < SETS * CTA_M * CAP; i += KP_THREADS) lists[i] = 0ull;
   if (threadIdx.x == 0) {
     // full[s]: one arrival (the leader's expect_tx of BOTH CTAs' bytes). The peer's TMA completes on the
     // leader's barrier without an arrival of its own; its bytes can only land in the phase they belong
@@ -165,7 +378,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     for (uint32_t s = 0; s < P.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; b++) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 8);  // 4 epilogue warps of the set x 2 CTAs
+      mbar_init(&tmem_empty[b], 8);  // 4 epilogue warps x 2 CTAs
       mbar_init(&inv_full[b], 1);
       mbar_init(&inv_empty[b], 4);
     }
@@ -187,7 +400,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       long long w_empty = 0;
       const long long t_begin = clk();
       // L2 prefetch runs KP_PREFETCH k-slices ahead of the loads: a corpus slice is new to L2 for the first
-      // query group that reaches it, and three stages of shared memory cannot hide an HBM miss
+      // query group that reaches it
       uint32_t pf_tile = pair, pf_kb = 0;
       auto prefetch_next = [&]() {
         if (pf_tile < P.n_tiles) {
@@ -199,9 +412,9 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs) {
         for (uint32_t kb = 0; kb < nkb; kb++) {
           prefetch_next();
-          const long long t0 = clk();
+          const long long t0 = cyc ? clk() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
-          w_empty += clk() - t0;
+          if (cyc) w_empty += clk() - t0;
           unsigned char* sa = stage_base + (size_t)stage * STAGE_BYTES;
           const uint32_t bar = mapa(smem_u32(&full[stage]), 0);  // the leader's full barrier
           if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
@@ -210,10 +423,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (P.cyc) {
-        unsigned long long* c = P.cyc + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 12 + warp) * 8;
-        c[0] = (unsigned long long)(clk() - t_begin); c[1] = (unsigned long long)w_empty;
-      }
+      if (cyc) { cyc[0] = (unsigned long long)(clk() - t_begin); cyc[1] = (unsigned long long)w_empty; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
@@ -223,14 +433,14 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const long long t_begin = clk();
       for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
         const uint32_t buf = it & 1;
-        long long t0 = clk();
+        long long t0 = cyc ? clk() : 0;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
-        w_tmem += clk() - t0;
+        if (cyc) w_tmem += clk() - t0;
         tcgen05_fence_after();
         for (uint32_t kb = 0; kb < nkb; kb++) {
-          t0 = clk();
+          t0 = cyc ? clk() : 0;
           mbar_wait(&full[stage], phase);
-          w_full += clk() - t0;
+          if (cyc) w_full += clk() - t0;
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -248,9 +458,8 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         tcgen05_commit_pair(&tmem_full[buf], 3);  // accumulator complete in both CTAs
       }
-      if (P.cyc) {
-        unsigned long long* c = P.cyc + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 12 + warp) * 8;
-        c[0] = (unsigned long long)(clk() - t_begin); c[1] = (unsigned long long)w_tmem; c[2] = (unsigned long long)w_full;
+      if (cyc) {
+        cyc[0] = (unsigned long long)(clk() - t_begin); cyc[1] = (unsigned long long)w_tmem; cyc[2] = (unsigned long long)w_full;
       }
     }
   } else if (warp == 3) {
@@ -274,153 +483,184 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (lane == 0) mbar_arrive(&inv_full[buf]);
     }
   } else if (warp >= 4) {
-    // ===== epilogue: set = tile parity, one lane per query =====
-    const uint32_t set = (uint32_t)(warp - 4) >> 2, quarter = warp & 3;
+    // ===== epilogue: one lane per query =====
+    const uint32_t quarter = warp & 3;
     const uint32_t ql = quarter * 32 + lane;  // query within the CTA
     const uint32_t qg = q0 + ql;              // query in the batch
     const bool live = qg < P.B;
-    uint64_t* warp_bufs = lists + ((size_t)set * CTA_M + quarter * 32) * CAP;
-    uint64_t* mybuf = warp_bufs + (size_t)lane * CAP;
-    float thr = live ? -INFINITY : INFINITY;
-    int cnt = 0;
-    int sorted = 0;  // the lower half of this lane's buffer is the sorted result of a previous prune
     const int kp = (int)P.kp;
-    const bool fast_prune = kp <= 32;
-    const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + set * TILE_N;
-    const uint32_t bar_tmem_empty = mapa(smem_u32(&tmem_empty[set]), 0);
-    long long c_wait = 0, c_ld = 0, c_sel = 0, c_prune = 0, n_prune = 0, n_app = 0;
+    uint64_t* warp_win = win + (size_t)quarter * 32 * WIN;
+    uint64_t* mywin = warp_win + (size_t)lane * WIN;
+    uint64_t* warp_best = best + (size_t)quarter * 32 * best_stride;
+    float thr = live ? -CUDART_INF_F : CUDART_INF_F;  // a score must beat it to be a candidate
+    uint32_t off = 0;  // bytes used in this lane's window (8 per entry)
+    int nbest = 0;     // keys in this lane's sorted best list
+    const uint32_t win_addr = smem_u32(mywin);  // 256-byte aligned; entry j lives at (j*8) ^ (lane*8)
+    const uint32_t lane8 = (uint32_t)lane << 3;
+    const uint32_t taddr_q = tmem_base + ((quarter * 32u) << 16);
+    const uint32_t bar_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t bar_tmem_empty1 = mapa(smem_u32(&tmem_empty[1]), 0);
+    // Cooperative threshold: the P.pairs CTA pairs that share this query each publish their pub_rank-th best
+    // score so far (pairs * pub_rank >= K'). At least K' scored rows are >= the MINIMUM of the published values,
+    // so that minimum is a lower bound of the final K'-th best score and nothing below it can be a candidate.
+    // The local threshold only knows this CTA's 1/pairs of the corpus; the shared one cuts the survivors (and
+    // the window folds) several times. Published values only grow, so any snapshot is valid; ties with the
+    // bound are admitted (>=), which keeps the merged top-K' independent of timing.
+    uint32_t* my_pub = P.pub + (size_t)pair * P.Bpub + qg;
+    const uint32_t* q_pub = P.pub + qg;
+    uint32_t last_pub = 0;
+    long long c_wait = 0, c_first = 0, n_fold = 0, n_fold4 = 0, c_fold = 0, n_slow = 0, c_ld = 0;
     const long long t_begin = clk();
 
-    // trim the buffer of lane `src` to its K' best and raise that lane's threshold (whole warp helps)
-    auto prune_lane = [&](int src) {
-      n_prune++;
-      const int c = __shfl_sync(0xFFFFFFFFu, cnt, src);
-      if (fast_prune) {
-        const int was_sorted = __shfl_sync(0xFFFFFFFFu, sorted, src);
-        const uint64_t t = warp_prune_sort(warp_bufs + (size_t)src * CAP, c, kp, src, lane, was_sorted);
-        if (lane == src) {
-          cnt = 32;  // K' best in the lower half (zero padded), appends continue in the upper half
-          sorted = 1;
-          if (t != 0ull) thr = rag_key_score(t);
-        }
-      } else {
-        const uint64_t t = warp_prune(warp_bufs + (size_t)src * CAP, c, kp, src, lane);
-        if (lane == src) {
-          cnt = min(c, kp);
-          if (t != 0ull) thr = rag_key_score(t);
+    // fold the windows of the lanes in `need` into their best lists and raise those lanes' thresholds
+    // called by a lane whose best list just changed
+    auto publish = [&]() {
+      if (nbest >= (int)P.pub_rank) {
+        const uint32_t v = (uint32_t)(warp_best[(size_t)lane * best_stride + P.pub_rank - 1] >> 32);
+        if (v > last_pub) {
+          last_pub = v;
+          __stcg(my_pub, v);
         }
       }
     };
-
-    auto process16 = [&](const uint32_t (&v)[16], const float* inv, uint32_t row) {
-      float s[16];
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(inv + i);
-        s[i] = __uint_as_float(v[i]) * w.x;
-        s[i + 1] = __uint_as_float(v[i + 1]) * w.y;
-        s[i + 2] = __uint_as_float(v[i + 2]) * w.z;
-        s[i + 3] = __uint_as_float(v[i + 3]) * w.w;
-      }
-      if (P.dbg_scores && live) {
-#pragma unroll
-        for (int i = 0; i < 16; i++)
-          if (row + i < P.n_rows) P.dbg_scores[(size_t)qg * P.n_rows + row + i] = s[i];
-      }
-      if (P.mode != 0) return;
-      const long long ts = clk();
-      // rows arrive in increasing order within a set, so a later equal score can never displace an
-      // earlier one: the strict float compare against the K'-th best is exact. NaN never passes.
-      const long long tp = clk();
-      unsigned pm = 0;
-#pragma unroll
-      for (int i = 0; i < 16; i++) pm |= s[i] > thr ? (1u << i) : 0u;
-      if (__any_sync(0xFFFFFFFFu, pm != 0u)) {
-        // straight-line predicated appends; the slot of hit i is cnt + (hits below i), so the sixteen
-        // stores are independent of each other (no serial dependence through cnt)
-        // (inline PTX keeps the sixteen stores predicated instead of sixteen divergent branches)
-        const uint32_t buf_addr = smem_u32(mybuf);
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const uint64_t key = rag_pack_key(s[i], row + i);
-          const uint32_t slot = (uint32_t)(cnt + __popc(pm & ((1u << i) - 1u)) + lane) & (CAP - 1);
-          asm volatile(
-              "{\n\t.reg .pred q;\n\t"
-              "setp.ne.b32 q, %0, 0;\n\t"
-              "@q st.shared.b64 [%1], %2;\n\t}"
-              ::"r"(pm & (1u << i)), "r"(buf_addr + slot * 8u), "l"(key)
-              : "memory");
-        }
-        cnt += __popc(pm);
-        __syncwarp();  // the appends above are visible to the lanes that help prune
-        unsigned need = __ballot_sync(0xFFFFFFFFu, cnt > CAP - 16);  // must make room now
+    auto fold_lanes = [&](unsigned need) {
+      const long long tf0 = cyc ? clk() : 0;
+      if (__popc(need) <= 2) {
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
-          prune_lane(src);
+          n_fold++;
+          const int c = (int)(__shfl_sync(0xFFFFFFFFu, off, src) >> 3), nb = __shfl_sync(0xFFFFFFFFu, nbest, src);
+          const uint64_t t = k2p_fold_one(warp_win + (size_t)src * WIN, warp_best + (size_t)src * best_stride, c, nb, kp, src, lane);
+          if (lane == src) {
+            nbest = min(kp, nb + c);
+            off = 0;
+            // rows arrive in increasing order, so a later equal score can never displace an earlier one: the
+            // strict float compare against the K'-th best is exact
+            if (t != 0ull) thr = fmaxf(thr, rag_key_score(t));
+            publish();
+          }
+        }
+      } else {
+        while (need) {  // bursts (the first tiles of a CTA): FOLD_N interleaved sorting networks per call
+          uint32_t srcs = 0xFFFFFFFFu;
+          bool mine = false;
+#pragma unroll
+          for (int q = 0; q < FOLD_N; q++) {
+            if (need) {
+              const int src = __ffs(need) - 1;
+              need &= need - 1;
+              srcs = (srcs & ~(0xFFu << (8 * q))) | ((uint32_t)src << (8 * q));
+              mine |= src == lane;
+            }
+          }
+          n_fold4++;
+          const uint64_t t = k2p_fold_windows(warp_win, warp_best, best_stride, kp, lane, srcs, off >> 3, nbest);
+          if (mine) {
+            nbest = min(kp, nbest + (int)(off >> 3));
+            off = 0;
+            if (t != 0ull) thr = fmaxf(thr, rag_key_score(t));
+            publish();
+          }
         }
       }
-      c_prune += clk() - tp;
-      c_sel += clk() - ts;
+      if (cyc) c_fold += clk() - tf0;
+    };
+    // 16 columns: branch-free predicated appends (raw entry = score bits << 32 | row), then make room.
+    // Precondition: every lane has at least 16 free entries.
+    auto scan16 = [&](const float* sc, uint32_t row) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint32_t addr = win_addr | (off ^ lane8);
+        asm volatile(
+            "{\n\t.reg .pred q;\n\t"
+            "setp.gt.f32 q, %1, %2;\n\t"
+            "@q st.shared.v2.b32 [%3], {%4, %5};\n\t"
+            "@q add.u32 %0, %0, 8;\n\t}"
+            : "+r"(off)
+            : "f"(sc[i]), "f"(thr), "r"(addr), "r"(row + i), "r"(__float_as_uint(sc[i]))
+            : "memory");
+      }
+      __syncwarp();  // the appends are visible to the lanes that help fold
+      const unsigned need = __ballot_sync(0xFFFFFFFFu, off > (WIN - 16) * 8);
+      if (need) fold_lanes(need);
     };
 
     uint32_t it = 0;
     for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
-      if ((it & 1) != set) continue;
-      const uint32_t use = it >> 1;  // how many times this set's buffers have been used before
-      const long long tw = clk();
-      mbar_wait(&inv_full[set], use & 1);
-      mbar_wait(&tmem_full[set], use & 1);
-      c_wait += clk() - tw;
+      const uint32_t buf = it & 1, par = (it >> 1) & 1;
+      const long long tw = cyc ? clk() : 0;
+      // refresh the shared bound while the tile is still being accumulated (the loads fly during the wait)
+      if (live && it != 0 && it % P.pub_every == 0 && P.mode == 0) {
+        uint32_t g = 0xFFFFFFFFu;
+#pragma unroll 6
+        for (uint32_t p = 0; p < P.pairs; p++) g = min(g, __ldcg(q_pub + (size_t)p * P.Bpub));
+        if (g > 1u) thr = fmaxf(thr, rag_unorder_f32(g - 1u));  // admit scores >= the bound
+      }
+      mbar_wait(&inv_full[buf], par);
+      mbar_wait(&tmem_full[buf], par);
+      if (cyc) c_wait += clk() - tw;
       tcgen05_fence_after();
-      const float* inv = s_inv + set * TILE_N;
+      const float* inv = s_inv + buf * TILE_N;
+      const uint32_t taddr = taddr_q + buf * TILE_N;
       const uint32_t row0 = tile * TILE_N;
       if (P.mode != 2) {
+        if (it == 0 && P.mode == 0) {
+          const long long tf = cyc ? clk() : 0;
+          const float T = k2p_first_tile_threshold(taddr, inv, kp);
+          // admit scores >= T: the threshold is the next float below T
+          if (live && T > -CUDART_INF_F) thr = rag_unorder_f32(rag_order_f32(T) - 1u);
+          if (cyc) c_first = clk() - tf;
+        }
 #pragma unroll 1
         for (uint32_t c0 = 0; c0 < TILE_N; c0 += 32) {
-          uint32_t va[16], vb[16];
-          const long long tl = clk();
-          tmem_ld16(taddr0 + c0, va);
-          tmem_ld16(taddr0 + c0 + 16, vb);
-          tmem_ld_wait();
-          c_ld += clk() - tl;
-          process16(va, inv + c0, row0 + c0);
-          process16(vb, inv + c0 + 16, row0 + c0 + 16);
+          float s[32];
+          const long long tl0 = cyc ? clk() : 0;
+          load32_scaled(taddr + c0, inv + c0, s);
+          if (cyc) c_ld += clk() - tl0;
+          const uint32_t row = row0 + c0;
+          if (P.dbg_scores && live) {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (row + i < P.n_rows) P.dbg_scores[(size_t)qg * P.n_rows + row + i] = s[i];
+          }
+          if (P.mode != 0) continue;
+          // common case once the thresholds have risen: nothing in these 32 columns beats any query's
+          // threshold (fmaxf drops NaN)
+          float m0 = fmaxf(s[0], s[1]), m1 = fmaxf(s[2], s[3]), m2 = fmaxf(s[4], s[5]), m3 = fmaxf(s[6], s[7]);
+#pragma unroll
+          for (int i = 8; i < 32; i += 4) {
+            m0 = fmaxf(m0, s[i]);
+            m1 = fmaxf(m1, s[i + 1]);
+            m2 = fmaxf(m2, s[i + 2]);
+            m3 = fmaxf(m3, s[i + 3]);
+          }
+          if (!__any_sync(0xFFFFFFFFu, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > thr)) continue;
+          n_slow++;
+          scan16(s, row);
+          scan16(s + 16, row + 16);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_cluster(bar_tmem_empty);  // the leader's barrier (also from the leader itself)
-        mbar_arrive(&inv_empty[set]);
-      }
-      // Off the critical path (the accumulator is already released): trim buffers that are getting
-      // full, so that the next tile rarely has to stop and prune while it holds TMEM.
-      if (P.mode == 0) {
-        const long long tq = clk();
-        unsigned need = __ballot_sync(0xFFFFFFFFu, cnt > CAP - 24);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          prune_lane(src);
-        }
-        c_prune += clk() - tq;
+        mbar_arrive_cluster(buf ? bar_tmem_empty1 : bar_tmem_empty0);  // the leader's barrier (also from the leader itself)
+        mbar_arrive(&inv_empty[buf]);
       }
     }
-    if (P.cyc && lane == 0) {
-      unsigned long long* c = P.cyc + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 12 + warp) * 8;
-      c[0] = (unsigned long long)(clk() - t_begin); c[1] = (unsigned long long)c_wait; c[2] = (unsigned long long)c_ld;
-      c[3] = (unsigned long long)c_sel; c[4] = (unsigned long long)c_prune; c[5] = (unsigned long long)n_app;
-      c[6] = (unsigned long long)n_prune;
+    if (cyc && lane == 0) {
+      cyc[0] = (unsigned long long)(clk() - t_begin); cyc[1] = (unsigned long long)c_wait; cyc[2] = (unsigned long long)c_first;
+      cyc[3] = (unsigned long long)n_fold; cyc[4] = (unsigned long long)c_fold; cyc[5] = (unsigned long long)n_slow; cyc[6] = (unsigned long long)c_ld; cyc[7] = (unsigned long long)n_fold4;
     }
-    // final prune of every query of this warp, then publish the K' best (sorted) of this (pair, set)
+    // fold what is left in the windows
+    fold_lanes(__ballot_sync(0xFFFFFFFFu, live && off != 0));
+    __syncwarp();
+    // publish partial[q][pair][K']: sorted, zero padded when fewer than K' candidates exist
     for (int src = 0; src < 32; src++) {
-      const int c = __shfl_sync(0xFFFFFFFFu, cnt, src);
-      warp_prune(warp_bufs + (size_t)src * CAP, c, kp, src, lane);
-    }
-    if (live) {
-      uint64_t* out = P.partial + ((size_t)qg * P.parts + pair * SETS + set) * P.kp;
-      for (int j = 0; j < kp; j++) out[j] = mybuf[(j + lane) & (CAP - 1)];
+      if (q0 + quarter * 32 + src >= P.B) break;
+      const int nb = __shfl_sync(0xFFFFFFFFu, nbest, src);
+      uint64_t* out = P.partial + ((size_t)(q0 + quarter * 32 + src) * P.parts + pair) * P.kp;
+      for (int r = lane; r < kp; r += 32) out[r] = r < nb ? warp_best[(size_t)src * best_stride + r] : 0ull;
     }
   }
 
@@ -442,15 +682,18 @@ struct kp_state {
   uint32_t mode = 0;
   bool prof = false;
   unsigned long long* d_cyc = nullptr;
+  uint32_t* d_pub = nullptr;  // cooperative-threshold board [pairs][Bpub]
+  size_t c_pub = 0;
 };
 
-size_t kp_smem_bytes(uint32_t stages) {
-  return (size_t)stages * STAGE_BYTES + (size_t)SETS * CTA_M * CAP * 8 + 2 * TILE_N * 4 + (2 * MAX_STAGES + 8) * 8 + 16;
+size_t kp_smem_bytes(uint32_t stages, uint32_t kp) {
+  return (size_t)stages * STAGE_BYTES + (size_t)CTA_M * WIN * 8 + (size_t)CTA_M * (kp > 32 ? 64 : 32) * 8 + 2 * TILE_N * 4 +
+         (2 * MAX_STAGES + 8) * 8 + 16;
 }
 
-uint32_t kp_pick_stages(const kp_state* st) {
+uint32_t kp_pick_stages(const kp_state* st, uint32_t kp) {
   uint32_t s = MAX_STAGES;
-  while (s > 0 && kp_smem_bytes(s) > (size_t)st->max_smem) s--;
+  while (s > 0 && kp_smem_bytes(s, kp) > (size_t)st->max_smem) s--;
   return s;
 }
 
@@ -492,7 +735,7 @@ int k2p_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   RAG_CHECK(kp_init(idx));
   kp_state* st = (kp_state*)idx->k2p_state;
   if (kp > KP_MAX_KP) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path keeps at most %d candidates per query (K'=%u)", KP_MAX_KP, kp);
-  if (kp_pick_stages(st) < 3) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path: not enough shared memory");
+  if (kp_pick_stages(st, kp) < 3) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path: not enough shared memory");
   const uint32_t groups = (B + PAIR_M - 1) / PAIR_M;
   const uint32_t all_pairs = (uint32_t)idx->sm_count / 2;
   if (groups > all_pairs)
@@ -501,7 +744,7 @@ int k2p_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   uint64_t pairs = all_pairs / groups;
   if (pairs > n_tiles) pairs = n_tiles;
   if (pairs < 1) pairs = 1;
-  *parts = (uint32_t)pairs * SETS;
+  *parts = (uint32_t)pairs;
   return RAG_OK;
 }
 
@@ -540,22 +783,38 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   P.B = B;
   P.kp = kp;
   P.parts = parts;
-  P.pairs = parts / SETS;
-  P.stages = kp_pick_stages(st);
+  P.pairs = parts;
+  P.stages = kp_pick_stages(st, kp);
   P.n_tiles = (uint32_t)((idx->rows + TILE_N - 1) / TILE_N);
   P.inv_norm = idx->inv_norm;
   P.partial = bt->d_partial;
+  {
+    const uint32_t groups_ = (B + PAIR_M - 1) / PAIR_M;
+    P.Bpub = groups_ * PAIR_M;
+    P.pub_rank = (kp + P.pairs - 1) / P.pairs;  // pairs * pub_rank >= K'
+    P.pub_every = P.pairs <= 24 ? 1 : 4;
+    const size_t need = (size_t)P.pairs * P.Bpub * sizeof(uint32_t);
+    if (need > st->c_pub) {
+      if (st->d_pub) RAG_CUDA(cudaFree(st->d_pub));
+      st->d_pub = nullptr;
+      st->c_pub = 0;
+      RAG_CUDA(cudaMalloc((void**)&st->d_pub, need));
+      st->c_pub = need;
+    }
+    RAG_CUDA(cudaMemsetAsync(st->d_pub, 0, need, idx->stream));
+    P.pub = st->d_pub;
+  }
   P.dbg_scores = st->dbg;
   P.mode = st->mode;
   P.cyc = nullptr;
-  const size_t n_cyc = (size_t)P.pairs * 2 * ((B + PAIR_M - 1) / PAIR_M) * 12 * 8;
+  const size_t n_cyc = (size_t)P.pairs * 2 * ((B + PAIR_M - 1) / PAIR_M) * KP_WARPS * 8;
   if (st->prof) {
     if (st->d_cyc) cudaFree(st->d_cyc);
     RAG_CUDA(cudaMalloc((void**)&st->d_cyc, n_cyc * 8));
     RAG_CUDA(cudaMemsetAsync(st->d_cyc, 0, n_cyc * 8, idx->stream));
     P.cyc = st->d_cyc;
   }
-  const size_t smem = kp_smem_bytes(P.stages);
+  const size_t smem = kp_smem_bytes(P.stages, kp);
   if (!st->attr_set) {
     RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
     RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
@@ -572,17 +831,17 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     RAG_CUDA(cudaMemcpyAsync(h.data(), st->d_cyc, n_cyc * 8, cudaMemcpyDeviceToHost, idx->stream));
     RAG_CUDA(cudaStreamSynchronize(idx->stream));
     if (printed++ % 16 == 8) {
-      const size_t nct = n_cyc / 96;
-      double acc[2][12][8] = {{{0}}};
+      const size_t nct = n_cyc / (KP_WARPS * 8);
+      double acc[2][KP_WARPS][8] = {{{0}}};
       for (size_t c = 0; c < nct; c++)
-        for (int w = 0; w < 12; w++)
-          for (int j = 0; j < 8; j++) acc[c & 1][w][j] += (double)h[(c * 12 + w) * 8 + j] / (nct / 2);
+        for (int w = 0; w < KP_WARPS; w++)
+          for (int j = 0; j < 8; j++) acc[c & 1][w][j] += (double)h[(c * KP_WARPS + w) * 8 + j] / (nct / 2);
       fprintf(stderr, "[k2 pair prof] B=%u rows=%u kp=%u stages=%u ctas=%zu (avg cycles per CTA; rank0 | rank1)\n", B, P.n_rows, kp, P.stages, nct);
       fprintf(stderr, "  producer: total %.0f wait_empty %.0f | total %.0f wait_empty %.0f\n", acc[0][0][0], acc[0][0][1], acc[1][0][0], acc[1][0][1]);
       fprintf(stderr, "  mma     : total %.0f wait_tmem_empty %.0f wait_full %.0f\n", acc[0][1][0], acc[0][1][1], acc[0][1][2]);
-      for (int w = 4; w < 12; w++)
-        fprintf(stderr, "  epi w%-2d : total %.0f wait %.0f ld %.0f select %.0f (prune %.0f) appends(lane0) %.0f prunes %.0f | wait %.0f ld %.0f select %.0f\n", w,
-                acc[0][w][0], acc[0][w][1], acc[0][w][2], acc[0][w][3], acc[0][w][4], acc[0][w][5], acc[0][w][6], acc[1][w][1], acc[1][w][2], acc[1][w][3]);
+      for (int w = 4; w < KP_WARPS; w++)
+        fprintf(stderr, "  epi w%-2d : total %.0f wait %.0f first-tile %.0f fold1 %.0f fold4 %.0f fold cycles %.0f slow chunks %.0f ld cycles %.0f | wait %.0f fold cycles %.0f\n", w,
+                acc[0][w][0], acc[0][w][1], acc[0][w][2], acc[0][w][3], acc[0][w][7], acc[0][w][4], acc[0][w][5], acc[0][w][6], acc[1][w][1], acc[1][w][4]);
     }
   }
   return RAG_OK;
@@ -594,6 +853,7 @@ void k2p_set_debug(rag_index* idx, float* d_scores) {
 
 void k2p_destroy(rag_index* idx) {
   if (idx->k2p_state && ((kp_state*)idx->k2p_state)->d_cyc) cudaFree(((kp_state*)idx->k2p_state)->d_cyc);
+  if (idx->k2p_state && ((kp_state*)idx->k2p_state)->d_pub) cudaFree(((kp_state*)idx->k2p_state)->d_pub);
   delete (kp_state*)idx->k2p_state;
   idx->k2p_state = nullptr;
 }

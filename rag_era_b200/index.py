@@ -308,6 +308,17 @@ class VectorIndex:
         N.check(self._lib.rag_debug_tensor_scores(self._h, _ptr(q), q.shape[0], _ptr(out)))
         return out
 
+    def debug_tensor_candidates(self, queries, kp: int):
+        """(scores [B][rows] f32, rows [B][kp] int64 (-1 = empty), cand_scores [B][kp] f32) of one K2+K3 pass."""
+        q = self._queries(queries)
+        scores = np.empty((q.shape[0], self.rows), dtype=np.float32)
+        keys = np.zeros((q.shape[0], kp), dtype=np.uint64)
+        N.check(self._lib.rag_debug_tensor_candidates(self._h, _ptr(q), q.shape[0], kp, _ptr(scores), _ptr(keys)))
+        rows = np.where(keys != 0, (0xFFFFFFFF - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64), -1)
+        o = (keys >> np.uint64(32)).astype(np.uint32)
+        bits = np.where(o & np.uint32(0x80000000), o ^ np.uint32(0x80000000), ~o).astype(np.uint32)
+        return scores, rows, bits.view(np.float32)
+
     def sync(self):
         N.check(self._lib.rag_sync(self._h))
 

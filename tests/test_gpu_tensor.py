@@ -123,3 +123,47 @@ def test_tf32_path_on_fp32_index_without_shadow(rb, native, oracle):
         for b in range(16):
             ei, es = oracle.topk(X, Q[b], 5)
             assert np.array_equal(small.row(b)[0], ei) and np.array_equal(small.row(b)[1], es)
+
+
+def _expected_candidates(scores_row, kp):
+    """Top-K' rows of one query by (score desc, row asc); NaN (zero-norm rows) never selected."""
+    valid = np.flatnonzero(~np.isnan(scores_row))
+    order = valid[np.lexsort((valid, -scores_row[valid].astype(np.float64)))]
+    return order[:kp]
+
+
+@pytest.mark.parametrize("n,d,B,kp", [(70000, 64, 600, 32), (70000, 64, 600, 48), (70000, 64, 256, 8), (5000, 128, 130, 33),
+                                      (200, 64, 40, 32), (20, 64, 3, 32), (40000, 64, 1100, 17)])
+def test_tensor_candidate_lists_are_the_exact_topk_of_the_scores(rb, native, oracle, n, d, B, kp):
+    """The fused selection (register-network first tile, threshold votes, window folds, K3 merge) returns
+    exactly the K' best (score desc, row asc) of the scores the same launch computed."""
+    rng = np.random.default_rng(n * 31 + B + kp)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[rng.integers(0, n, size=max(1, n // 50))] = 0.0                       # zero-norm rows are never candidates
+    X = oracle.f32_to_bf16(X)
+    Q = rng.standard_normal((B, d)).astype(np.float32)
+    with rb.VectorIndex(d, n, dtype=native.BF16) as idx:
+        idx.upload(X)
+        S, rows, cs = idx.debug_tensor_candidates(Q, kp)
+    for b in range(B):
+        e = _expected_candidates(S[b], kp)
+        assert np.array_equal(rows[b, :len(e)], e), (b, rows[b], e)
+        assert (rows[b, len(e):] == -1).all()
+        assert np.array_equal(cs[b, :len(e)], S[b, e])
+
+
+@pytest.mark.parametrize("distinct,kp", [(16, 32), (3, 48), (1, 10), (300, 32)])
+def test_tensor_candidate_ties_go_to_the_lower_row(rb, native, oracle, distinct, kp):
+    """A corpus of a few distinct rows repeated over and over: every score is tied many times; the K' candidates
+    are the lowest row ids of the best score classes (the reference's stable sort keeps insertion order)."""
+    n, d, B = 30000, 64, 300
+    rng = np.random.default_rng(distinct)
+    base = oracle.f32_to_bf16(rng.standard_normal((distinct, d)).astype(np.float32))
+    X = base[rng.integers(0, distinct, size=n)]
+    Q = rng.standard_normal((B, d)).astype(np.float32)
+    with rb.VectorIndex(d, n, dtype=native.BF16) as idx:
+        idx.upload(X)
+        S, rows, cs = idx.debug_tensor_candidates(Q, kp)
+    for b in range(0, B, 7):
+        e = _expected_candidates(S[b], kp)
+        assert np.array_equal(rows[b], e), (b, rows[b], e)
