@@ -66,125 +66,95 @@ struct kp_params {
   uint64_t* partial;
   uint32_t* pub;       // [pairs][Bpub] ordered score of each (pair, query)'s pub_rank-th best so far (0 = none yet)
   uint32_t Bpub, pub_rank, pub_every;
+  uint32_t prefetch;   // k-slices of L2 prefetch ahead of the TMA loads
   float* dbg_scores;
   uint32_t mode;
   unsigned long long* cyc;  // diagnostics (RAGERA_K2_PROF): [ctas][8 warps][8] cycle counters
 };
 __device__ __forceinline__ long long clk() { return clock64(); }
 
-__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
-  const uint32_t hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), m);
-  const uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)v, m);
-  return ((uint64_t)hi << 32) | lo;
+// ---- lane-local fold: every lane folds ITS OWN query's window into its own best list ---------------
+// Used when several queries of the warp need folding at once (the first tiles of a CTA, before the
+// thresholds have risen): 32 register sorting networks run side by side in the 32 lanes, instead of one
+// warp-wide network per query. Window and best list are XOR-swizzled by the lane (entry j of lane l sits
+// at slot j ^ l), so lane-local and warp-cooperative accesses are both bank-conflict free.
+__device__ __forceinline__ void ce64_desc(uint64_t& a, uint64_t& b) {  // a >= b afterwards
+  const uint64_t hi = max(a, b), lo = min(a, b);
+  a = hi;
+  b = lo;
 }
-// 32 keys, one per lane, sorted descending across the lanes
-__device__ __forceinline__ uint64_t bitonic_sort32_desc(uint64_t key, int lane) {
+__device__ __forceinline__ void reg_sort32_desc_u64(uint64_t (&v)[32]) {
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      const uint64_t other = shfl_xor_u64(key, j);
-      const bool take_max = ((lane & j) == 0) == ((lane & k) == 0);
-      key = take_max ? max(key, other) : min(key, other);
-    }
-  }
-  return key;
-}
-// a bitonic sequence of 32 keys (one per lane) -> sorted descending
-__device__ __forceinline__ uint64_t bitonic_merge32_desc(uint64_t c, int lane) {
 #pragma unroll
-  for (int j = 16; j > 0; j >>= 1) {
-    const uint64_t other = shfl_xor_u64(c, j);
-    c = ((lane & j) == 0) ? max(c, other) : min(c, other);
-  }
-  return c;
-}
-
-// Fold up to FOLD_N queries' windows (unsorted raw entries in shared memory) into their sorted best lists
-// (global memory, lane l owns ranks l and 32+l) and return, to the lane that owns the query, the K'-th best
-// key (0 while fewer than K' candidates exist). Whole warp. The FOLD_N bitonic networks are independent and
-// interleaved instruction by instruction: a single network is a chain of ~20 dependent shuffle steps and
-// the epilogue has one warp per scheduler, so folding one query at a time is pure latency.
-// `srcs` packs the lanes to fold, one per byte, 0xFF = none. Half-cleaner identities: with B0 and W sorted
-// descending, max(B0[l], W[31-l]) is a bitonic sequence of the 32 largest of B0 u W, min(...) of the rest.
-constexpr int FOLD_N = 4;
-__device__ __forceinline__ void bitonic_sort32_desc_n(uint64_t (&key)[FOLD_N], int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const bool take_max = ((lane & j) == 0) == ((lane & k) == 0);
-#pragma unroll
-      for (int q = 0; q < FOLD_N; q++) {
-        const uint64_t other = shfl_xor_u64(key[q], j);
-        key[q] = take_max ? max(key[q], other) : min(key[q], other);
+      for (int i = 0; i < 32; i++) {
+        const int l = i ^ j;
+        if (l > i) {
+          if ((i & k) == 0) ce64_desc(v[i], v[l]);
+          else ce64_desc(v[l], v[i]);
+        }
       }
     }
   }
 }
-__device__ __forceinline__ void bitonic_merge32_desc_n(uint64_t (&c)[FOLD_N], int lane) {
+__device__ __forceinline__ void reg_merge32_desc_u64(uint64_t (&v)[32]) {  // bitonic -> sorted descending
 #pragma unroll
   for (int j = 16; j > 0; j >>= 1) {
-    const bool take_max = (lane & j) == 0;
 #pragma unroll
-    for (int q = 0; q < FOLD_N; q++) {
-      const uint64_t other = shfl_xor_u64(c[q], j);
-      c[q] = take_max ? max(c[q], other) : min(c[q], other);
+    for (int i = 0; i < 32; i++) {
+      const int l = i ^ j;
+      if (l > i) ce64_desc(v[i], v[l]);
     }
   }
 }
-__device__ __noinline__ uint64_t k2p_fold_windows(const uint64_t* warp_win, uint64_t* warp_best, size_t best_stride, int kp, int lane,
-                                                  uint32_t srcs, uint32_t my_cnt, int my_nbest) {
-  uint64_t w[FOLD_N], b0[FOLD_N], b1[FOLD_N];
-  uint64_t* bptr[FOLD_N];
-  bool on[FOLD_N];
+// mywin/mybest: this lane's window (raw entries) and best list; c, nb: their entry counts. Returns the K'-th
+// best key afterwards (0 while fewer than K' exist). Half-cleaner identities: with B and W sorted descending,
+// max(B[i], W[31-i]) is a bitonic sequence of the 32 largest of B u W, min(...) of the other 32.
+__device__ __noinline__ uint64_t k2p_fold_local(const uint64_t* mywin, uint64_t* mybest, int c, int nb, int kp, int lane) {
+  uint64_t W[32], B[32];
 #pragma unroll
-  for (int q = 0; q < FOLD_N; q++) {
-    const int src = (int)((srcs >> (8 * q)) & 0xFFu);
-    on[q] = src != 0xFF;
-    const int sl = on[q] ? src : 0;
-    const int c = on[q] ? (int)__shfl_sync(0xFFFFFFFFu, my_cnt, sl) : 0;
-    const int nb = on[q] ? __shfl_sync(0xFFFFFFFFu, my_nbest, sl) : 0;
-    bptr[q] = warp_best + (size_t)sl * best_stride;
-    b0[q] = lane < nb ? bptr[q][lane] : 0ull;
-    b1[q] = lane + 32 < nb ? bptr[q][lane + 32] : 0ull;
-    // window entry j of lane sl sits at slot j ^ sl; raw entry = score bits << 32 | row
-    const uint64_t raw = warp_win[(size_t)sl * WIN + (lane ^ sl)];
-    w[q] = lane < c ? rag_pack_key(__uint_as_float((uint32_t)(raw >> 32)), (uint32_t)raw) : 0ull;
+  for (int i = 0; i < 32; i++) {
+    const uint64_t raw = mywin[i ^ lane];
+    W[i] = i < c ? rag_pack_key(__uint_as_float((uint32_t)(raw >> 32)), (uint32_t)raw) : 0ull;
   }
-  bitonic_sort32_desc_n(w, lane);
-  uint64_t x[FOLD_N], y[FOLD_N];
+  reg_sort32_desc_u64(W);
 #pragma unroll
-  for (int q = 0; q < FOLD_N; q++) {
-    const uint64_t wr = shfl_u64(w[q], 31 - lane);
-    x[q] = max(b0[q], wr);
-    y[q] = min(b0[q], wr);
+  for (int i = 0; i < 32; i++) B[i] = i < nb ? mybest[i ^ lane] : 0ull;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {  // half-cleaner: B <- the 32 largest, W <- the rest (both bitonic)
+    const uint64_t wa = W[i], wb = W[31 - i];
+    W[i] = min(B[i], wb);
+    B[i] = max(B[i], wb);
+    W[31 - i] = min(B[31 - i], wa);
+    B[31 - i] = max(B[31 - i], wa);
   }
-  bitonic_merge32_desc_n(x, lane);
-  uint64_t ret = 0ull;
+  reg_merge32_desc_u64(B);
+#pragma unroll
+  for (int i = 0; i < 32; i++) mybest[i ^ lane] = B[i];
   if (kp <= 32) {
+    uint64_t kth = B[31];
 #pragma unroll
-    for (int q = 0; q < FOLD_N; q++) {
-      if (on[q] && lane < kp) bptr[q][lane] = x[q];
-      const uint64_t kth = shfl_u64(x[q], kp - 1);
-      if (on[q] && lane == (int)((srcs >> (8 * q)) & 0xFFu)) ret = kth;
-    }
-    return ret;
+    for (int i = 0; i < 31; i++)
+      if (i == kp - 1) kth = B[i];
+    return kth;
   }
-  bitonic_merge32_desc_n(y, lane);
+  // ranks 32..63: the 32 largest of (the displaced half W) u (the old ranks 32..63)
+  reg_merge32_desc_u64(W);
 #pragma unroll
-  for (int q = 0; q < FOLD_N; q++) y[q] = max(b1[q], shfl_u64(y[q], 31 - lane));
-  bitonic_merge32_desc_n(y, lane);
-#pragma unroll
-  for (int q = 0; q < FOLD_N; q++) {
-    if (on[q]) {
-      bptr[q][lane] = x[q];
-      if (lane + 32 < kp) bptr[q][lane + 32] = y[q];
-    }
-    const uint64_t kth = shfl_u64(y[q], kp - 33);
-    if (on[q] && lane == (int)((srcs >> (8 * q)) & 0xFFu)) ret = kth;
+  for (int i = 0; i < 32; i++) {
+    const uint64_t b1 = 32 + (31 - i) < nb ? mybest[32 + ((31 - i) ^ lane)] : 0ull;
+    W[i] = max(W[i], b1);
   }
-  return ret;
+  reg_merge32_desc_u64(W);
+#pragma unroll
+  for (int i = 0; i < 32; i++) mybest[32 + (i ^ lane)] = W[i];
+  uint64_t kth = W[31];
+#pragma unroll
+  for (int i = 0; i < 31; i++)
+    if (i == kp - 33) kth = W[i];
+  return kth;
 }
 
 // Fold ONE query's window into its best list by rank counting — the steady-state case (windows fill one at
@@ -192,10 +162,10 @@ __device__ __noinline__ uint64_t k2p_fold_windows(const uint64_t* warp_win, uint
 // window keys are broadcast from shared memory (independent loads and compares, no dependent shuffle chain —
 // this warp is alone on its scheduler, so latency is what costs), the sorted best list is binary-searched
 // with indexed shuffles. Keys are distinct (they contain the row), so the ranks are a permutation; a key
-// whose rank is < K' is stored at best[rank]. Same result as k2p_fold_windows for one lane.
+// whose rank is < K' is stored at best[rank]. Same result as k2p_fold_local for that lane.
 __device__ __noinline__ uint64_t k2p_fold_one(uint64_t* wsrc, uint64_t* bsrc, int c, int nb, int kp, int src, int lane) {
-  const uint64_t b0 = lane < nb ? bsrc[lane] : 0ull;
-  const uint64_t b1 = lane + 32 < nb ? bsrc[lane + 32] : 0ull;
+  const uint64_t b0 = lane < nb ? bsrc[lane ^ src] : 0ull;  // rank r of query src sits at slot (r & 32) | ((r ^ src) & 31)
+  const uint64_t b1 = lane + 32 < nb ? bsrc[32 + (lane ^ src)] : 0ull;
   uint64_t w = 0ull;
   if (lane < c) {
     const uint64_t raw = wsrc[lane ^ src];
@@ -229,9 +199,9 @@ __device__ __noinline__ uint64_t k2p_fold_one(uint64_t* wsrc, uint64_t* bsrc, in
   rw += lo;
   const int p0 = lane + r0, p1 = 32 + lane + r1;
   const bool has_w = lane < c, has0 = lane < nb, has1 = lane + 32 < nb;
-  if (has_w && rw < kp) bsrc[rw] = w;
-  if (has0 && r0 != 0 && p0 < kp) bsrc[p0] = b0;
-  if (has1 && r1 != 0 && p1 < kp) bsrc[p1] = b1;
+  if (has_w && rw < kp) bsrc[(rw & 32) | ((rw ^ src) & 31)] = w;
+  if (has0 && r0 != 0 && p0 < kp) bsrc[(p0 & 32) | ((p0 ^ src) & 31)] = b0;
+  if (has1 && r1 != 0 && p1 < kp) bsrc[(p1 & 32) | ((p1 ^ src) & 31)] = b1;
   uint64_t kth = 0ull;
   if (nb + c >= kp) {  // uniform
     const unsigned mw = __ballot_sync(0xFFFFFFFFu, has_w && rw == kp - 1);
@@ -408,7 +378,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           if (++pf_kb == nkb) { pf_kb = 0; pf_tile += P.pairs; }
         }
       };
-      for (int i = 0; i < KP_PREFETCH; i++) prefetch_next();
+      for (uint32_t i = 0; i < P.prefetch; i++) prefetch_next();
       for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs) {
         for (uint32_t kb = 0; kb < nkb; kb++) {
           prefetch_next();
@@ -516,7 +486,8 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // called by a lane whose best list just changed
     auto publish = [&]() {
       if (nbest >= (int)P.pub_rank) {
-        const uint32_t v = (uint32_t)(warp_best[(size_t)lane * best_stride + P.pub_rank - 1] >> 32);
+        const uint32_t r = P.pub_rank - 1;
+        const uint32_t v = (uint32_t)(warp_best[(size_t)lane * best_stride + ((r & 32) | ((r ^ lane) & 31))] >> 32);
         if (v > last_pub) {
           last_pub = v;
           __stcg(my_pub, v);
@@ -542,27 +513,19 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
         }
       } else {
-        while (need) {  // bursts (the first tiles of a CTA): FOLD_N interleaved sorting networks per call
-          uint32_t srcs = 0xFFFFFFFFu;
-          bool mine = false;
-#pragma unroll
-          for (int q = 0; q < FOLD_N; q++) {
-            if (need) {
-              const int src = __ffs(need) - 1;
-              need &= need - 1;
-              srcs = (srcs & ~(0xFFu << (8 * q))) | ((uint32_t)src << (8 * q));
-              mine |= src == lane;
-            }
-          }
-          n_fold4++;
-          const uint64_t t = k2p_fold_windows(warp_win, warp_best, best_stride, kp, lane, srcs, off >> 3, nbest);
-          if (mine) {
-            nbest = min(kp, nbest + (int)(off >> 3));
+        // several at once (the first tiles of a CTA): every lane folds its own window, side by side
+        n_fold4++;
+        const int c = (int)(off >> 3);
+        if (__any_sync(0xFFFFFFFFu, c != 0)) {
+          const uint64_t t = k2p_fold_local(mywin, warp_best + (size_t)lane * best_stride, c, nbest, kp, lane);
+          if (c != 0) {
+            nbest = min(kp, nbest + c);
             off = 0;
-            if (t != 0ull) thr = fmaxf(thr, rag_key_score(t));
+            if (t != 0ull && nbest >= kp) thr = fmaxf(thr, rag_key_score(t));
             publish();
           }
         }
+        __syncwarp();
       }
       if (cyc) c_fold += clk() - tf0;
     };
@@ -660,7 +623,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (q0 + quarter * 32 + src >= P.B) break;
       const int nb = __shfl_sync(0xFFFFFFFFu, nbest, src);
       uint64_t* out = P.partial + ((size_t)(q0 + quarter * 32 + src) * P.parts + pair) * P.kp;
-      for (int r = lane; r < kp; r += 32) out[r] = r < nb ? warp_best[(size_t)src * best_stride + r] : 0ull;
+      for (int r = lane; r < kp; r += 32) out[r] = r < nb ? warp_best[(size_t)src * best_stride + ((r & 32) | ((r ^ src) & 31))] : 0ull;
     }
   }
 
@@ -680,6 +643,7 @@ struct kp_state {
   bool attr_set = false;
   float* dbg = nullptr;
   uint32_t mode = 0;
+  uint32_t prefetch = KP_PREFETCH;
   bool prof = false;
   unsigned long long* d_cyc = nullptr;
   uint32_t* d_pub = nullptr;  // cooperative-threshold board [pairs][Bpub]
@@ -711,6 +675,7 @@ int kp_init(rag_index* idx) {
   st->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   if (const char* m = getenv("RAGERA_K2_MODE")) st->mode = (uint32_t)atoi(m);
   if (const char* m = getenv("RAGERA_K2_PROF")) st->prof = atoi(m) != 0;
+  if (const char* m = getenv("RAGERA_K2_PREFETCH")) st->prefetch = (uint32_t)atoi(m);
   cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, idx->device);
   idx->k2p_state = st;
   return RAG_OK;
@@ -806,6 +771,7 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   }
   P.dbg_scores = st->dbg;
   P.mode = st->mode;
+  P.prefetch = st->prefetch;
   P.cyc = nullptr;
   const size_t n_cyc = (size_t)P.pairs * 2 * ((B + PAIR_M - 1) / PAIR_M) * KP_WARPS * 8;
   if (st->prof) {
@@ -840,7 +806,7 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
       fprintf(stderr, "  producer: total %.0f wait_empty %.0f | total %.0f wait_empty %.0f\n", acc[0][0][0], acc[0][0][1], acc[1][0][0], acc[1][0][1]);
       fprintf(stderr, "  mma     : total %.0f wait_tmem_empty %.0f wait_full %.0f\n", acc[0][1][0], acc[0][1][1], acc[0][1][2]);
       for (int w = 4; w < KP_WARPS; w++)
-        fprintf(stderr, "  epi w%-2d : total %.0f wait %.0f first-tile %.0f fold1 %.0f fold4 %.0f fold cycles %.0f slow chunks %.0f ld cycles %.0f | wait %.0f fold cycles %.0f\n", w,
+        fprintf(stderr, "  epi w%-2d : total %.0f wait %.0f first-tile %.0f fold1 %.0f fold-local %.0f fold cycles %.0f slow chunks %.0f ld cycles %.0f | wait %.0f fold cycles %.0f\n", w,
                 acc[0][w][0], acc[0][w][1], acc[0][w][2], acc[0][w][3], acc[0][w][7], acc[0][w][4], acc[0][w][5], acc[0][w][6], acc[1][w][1], acc[1][w][4]);
     }
   }
