@@ -67,6 +67,7 @@ struct kp_params {
   uint32_t* pub;       // [pairs][Bpub] ordered score of each (pair, query)'s pub_rank-th best so far (0 = none yet)
   uint32_t Bpub, pub_rank, pub_every;
   uint32_t prefetch;   // k-slices of L2 prefetch ahead of the TMA loads
+  uint32_t local_min;  // fold lane-locally (all 32 queries at once) when at least this many windows are full
   float* dbg_scores;
   uint32_t mode;
   unsigned long long* cyc;  // diagnostics (RAGERA_K2_PROF): [ctas][8 warps][8] cycle counters
@@ -496,7 +497,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     };
     auto fold_lanes = [&](unsigned need) {
       const long long tf0 = cyc ? clk() : 0;
-      if (__popc(need) <= 2) {
+      if (__popc(need) < (int)P.local_min) {
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
@@ -644,6 +645,7 @@ struct kp_state {
   float* dbg = nullptr;
   uint32_t mode = 0;
   uint32_t prefetch = KP_PREFETCH;
+  uint32_t local_min = 3;
   bool prof = false;
   unsigned long long* d_cyc = nullptr;
   uint32_t* d_pub = nullptr;  // cooperative-threshold board [pairs][Bpub]
@@ -676,6 +678,7 @@ int kp_init(rag_index* idx) {
   if (const char* m = getenv("RAGERA_K2_MODE")) st->mode = (uint32_t)atoi(m);
   if (const char* m = getenv("RAGERA_K2_PROF")) st->prof = atoi(m) != 0;
   if (const char* m = getenv("RAGERA_K2_PREFETCH")) st->prefetch = (uint32_t)atoi(m);
+  if (const char* m = getenv("RAGERA_K2_LOCAL_MIN")) st->local_min = (uint32_t)atoi(m);
   cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, idx->device);
   idx->k2p_state = st;
   return RAG_OK;
@@ -772,6 +775,7 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   P.dbg_scores = st->dbg;
   P.mode = st->mode;
   P.prefetch = st->prefetch;
+  P.local_min = st->local_min;
   P.cyc = nullptr;
   const size_t n_cyc = (size_t)P.pairs * 2 * ((B + PAIR_M - 1) / PAIR_M) * KP_WARPS * 8;
   if (st->prof) {

@@ -69,6 +69,16 @@ def check_topk(rb, native, oracle, X, Q, k, path, id_base=0, dtype=None, slack=0
         return r
 
 
+@pytest.mark.parametrize("B,k", [(40, 10), (70, 29)])
+def test_stream_path_batches_above_32_go_through_the_k3_merge(rb, native, oracle, B, k):
+    """B > 32 on the stream path: per-CTA lists -> K3 tournament merge -> K4 (throughput variant)."""
+    rng = np.random.default_rng(B)
+    X = rng.standard_normal((6000, 96)).astype(np.float32)
+    X[100] = X[7]                                                # an exact tie across CTAs
+    Q = rng.standard_normal((B, 96)).astype(np.float32)
+    check_topk(rb, native, oracle, X, Q, k, native.PATH_STREAM)
+
+
 @pytest.mark.parametrize("path", ["stream", "exact"])
 @pytest.mark.parametrize("n,d,k", [(1, 64, 5), (3, 64, 10), (31, 128, 29), (33, 96, 64), (1000, 1536, 10),
                                    (5000, 1024, 5), (4097, 100, 12), (20000, 256, 23), (257, 1536, 2)])

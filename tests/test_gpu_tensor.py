@@ -133,7 +133,7 @@ def _expected_candidates(scores_row, kp):
 
 
 @pytest.mark.parametrize("n,d,B,kp", [(70000, 64, 600, 32), (70000, 64, 600, 48), (70000, 64, 256, 8), (5000, 128, 130, 33),
-                                      (200, 64, 40, 32), (20, 64, 3, 32), (40000, 64, 1100, 17)])
+                                      (200, 64, 40, 32), (20, 64, 3, 32), (40000, 64, 1100, 17), (120000, 64, 2050, 32)])
 def test_tensor_candidate_lists_are_the_exact_topk_of_the_scores(rb, native, oracle, n, d, B, kp):
     """The fused selection (register-network first tile, threshold votes, window folds, K3 merge) returns
     exactly the K' best (score desc, row asc) of the scores the same launch computed."""
@@ -145,7 +145,7 @@ def test_tensor_candidate_lists_are_the_exact_topk_of_the_scores(rb, native, ora
     with rb.VectorIndex(d, n, dtype=native.BF16) as idx:
         idx.upload(X)
         S, rows, cs = idx.debug_tensor_candidates(Q, kp)
-    for b in range(B):
+    for b in range(0, B, 1 if B <= 1100 else 9):   # the largest case (52 tiles per CTA pair) is sampled
         e = _expected_candidates(S[b], kp)
         assert np.array_equal(rows[b, :len(e)], e), (b, rows[b], e)
         assert (rows[b, len(e):] == -1).all()
