@@ -364,6 +364,13 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]},
         "certified": {"setup_queries": certified_setup, "of": n_pool * B, "last_step": int(last.certified.sum()), "last_step_of": B},
     }
+    if world > 1:
+        # every rank's own kernel times: the step ends when the SLOWEST rank's scoring kernel does (K5 waits for
+        # every rank's records), so the spread between ranks is what the exchange wait in "fuse" is made of
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {k: round(v, 4) for k, v in res["kernel_ms_per_step"].items()})
+        res["per_rank_kernel_ms"] = per_rank
+        res["exchange"] = os.environ.get("RAGERA_COMM", "p2p")
     if do_cpu and rank == 0:
         # reference-faithful: ONE thread (the reference is single-threaded JS), full stable sort
         sample_rows = min(rows, 1_000_000)
@@ -420,6 +427,12 @@ def run_ours(args):
                 "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "roofline": res["roofline"],
                 "kernel_ms_per_step": res["kernel_ms_per_step"], "certified": res["certified"],
                 "arithmetic": "fp32 scoring selects K' candidates; fp64 reference-order rescoring decides ids/scores/ties"}
+        if res["roofline"].get("bound") == "tensor":
+            # the batched path selects on tcgen05 products of bf16 (or tf32) operands; ids and scores are still decided in fp64
+            line["dtype"] = "tf32" if "operand" in res["roofline"] else "bf16"
+        for key in ("per_rank_kernel_ms", "exchange"):
+            if key in res:
+                line[key] = res[key]
         if "cpu_baseline" in res:
             line["cpu_baseline"] = res["cpu_baseline"]
         if extra:

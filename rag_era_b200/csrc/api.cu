@@ -203,8 +203,11 @@ int ensure_work(rag_index* idx, rag_batch* bt, uint32_t B, uint32_t k, uint32_t 
     RAG_CHECK(grow_dev(&bt->d_k4s, &bt->c_k4s, (size_t)B * (2 * RAG_MAX_CANDIDATES + 2) * 8, false));
     RAG_CHECK(grow_dev(&bt->d_ticket, &bt->c_ticket, (size_t)32 * 4, true));
   }
-  if (idx->nranks > 1)
-    RAG_CHECK(grow_dev(&bt->d_gather, &bt->c_gather, (size_t)idx->nranks * B * k * sizeof(rag_rec), false));
+  if (idx->nranks > 1) {
+    RAG_CHECK(comm_p2p_ensure(idx, B, k));  // collective when the mailboxes grow; may fall back to NCCL
+    if (!comm_uses_p2p(idx))
+      RAG_CHECK(grow_dev(&bt->d_gather, &bt->c_gather, (size_t)idx->nranks * B * k * sizeof(rag_rec), false));
+  }
   *L = layout_out(B, out_cap, k);
   RAG_CHECK(grow_dev(&bt->d_out, &bt->c_out, L->total, false));
   RAG_CHECK(grow_pinned(&bt->h_out, &bt->c_hout, L->total));

@@ -257,5 +257,20 @@ int aux_build_launch(rag_index* idx, uint64_t row0, uint64_t nrows);  // shadow 
 int q_to_bf16_launch(rag_index* idx, uint32_t B, uint32_t Bpad);
 int gather_batch_launch(rag_index* idx, const rag_batch* src, rag_batch* dst, uint32_t n, uint32_t kw_stride);
 int iota_u64_launch(rag_index* idx, uint64_t* d, uint64_t n, uint64_t base);
-// comm (comm.cu): all-gather of cur->d_local → cur->d_gather
+// comm (comm.cu): exchange of the ranks' local top-k records.
+// Default: peer-to-peer mailboxes over NVLink, fused into K5 — each rank's K5 stores its [B][k] records straight
+// into every peer's mailbox (CUDA IPC mapping), raises a per-query flag, waits for the peers' flags and merges;
+// no collective call on the hot path. Fallback (RAGERA_COMM=nccl, or no peer access): ncclAllGather of
+// cur->d_local → cur->d_gather before K5.
+struct rag_p2p_view {
+  unsigned char* base[8];  // rank g's mailbox as mapped into this process (base[rank] is the local allocation)
+  uint32_t nranks, rank;   // nranks <= 1: no exchange (single GPU, or the NCCL fallback already gathered)
+  uint32_t step;           // exchange number (parity selects the mailbox half, the value is the flag)
+  uint64_t half_bytes;     // bytes of one parity half: [records | flags]
+  uint64_t flags_off;      // offset of the flag words inside a half: [src rank][flag_stride] u32
+  uint32_t flag_stride;    // flag slots per source rank (>= the batch)
+};
+int comm_p2p_ensure(rag_index* idx, uint32_t B, uint32_t k);            // collective when the mailboxes must grow
+bool comm_uses_p2p(const rag_index* idx);
+int comm_p2p_next(rag_index* idx, uint32_t B, uint32_t k, rag_p2p_view* v);  // view of the next exchange
 int comm_allgather_local(rag_index* idx, uint32_t B, uint32_t k);

@@ -9,18 +9,28 @@
 //   (16 KB) and its own HALF of the corpus tile (128 rows, 16 KB); UMMAs 256x256x16 issued by the
 //   leader read both CTAs' shared memory and write 128 lanes x 256 columns of fp32 into EACH
 //   CTA's TMEM. A 256-column accumulator is half of TMEM, so there are two: tile t+1 accumulates
-//   into one while the epilogue drains tile t from the other. The ring holds 6 stages of 32 KB
-//   (3 stages left the MMA waiting for TMA 13% of the time).
+//   into one while the epilogue drains tile t from the other. The ring holds 5 stages of 32 KB
+//   (4 for K' > 32); 5, 6 and 7 stages measure the same, 3 left the MMA waiting for TMA.
 //
-//   Epilogue = 4 warps, one LANE per query, 256 scores per tile each. The common case is branch-free:
-//   scale 32 scores by 1/||x||, take their maximum, one vote against the per-query threshold
-//   (~2 instructions per score). Survivors (rare once the threshold has risen) are appended to the
-//   query's 32-slot WINDOW in shared memory; a full window is bitonic-sorted by the warp and merged into
-//   the query's sorted K' best, which live directly in their output slot partial[q][pair][K'] (lane l
-//   owns rank l, so a lane only ever reads back what it wrote itself). The first tile of a CTA has no
-//   threshold yet: instead of appending all 256 scores, every lane first finds its exact K'-th largest
-//   score of the tile with a register sorting network (branch-free, all 32 queries at once) and starts
-//   from that threshold — the start-up transient used to stall the tensor pipe for ~10% of the kernel.
+//   Epilogue = 4 warps, one LANE per query, 256 scores per tile each (the score matrix is never written):
+//   * scan: scale 32 scores by 1/||x||, take their maximum, one vote against the per-query threshold
+//     (~2 instructions per score when nothing survives); otherwise 32 branch-free predicated appends
+//     to the query's 32-slot WINDOW in shared memory.
+//   * fold: a full window is merged into the query's sorted K' best (shared memory, XOR-swizzled by the
+//     lane like the window, so warp-cooperative and lane-local accesses are both conflict free).
+//     One query at a time by RANK COUNTING (k2p_fold_one: broadcast loads + a binary search by indexed
+//     shuffles — the warp is alone on its scheduler, so a dependent shuffle chain is pure latency),
+//     or, when several windows are full at once (the first tiles), LANE-LOCALLY (k2p_fold_local: 32
+//     register sorting networks side by side).
+//   * first tile: no threshold yet. Instead of appending all 256 scores every lane finds its exact K'-th
+//     largest score of the tile with a register sorting network and starts from that threshold
+//     (k2p_first_tile_threshold); the start-up transient used to stall the tensor pipe ~10% of the kernel.
+//   * cooperative threshold: the gridDim.x/2 pairs that share a query publish their ceil(K'/pairs)-th best
+//     score; at least K' rows score >= the minimum of the published values, so nothing below it can be a
+//     candidate anywhere. Cuts survivors and folds ~3x; the merged top-K' does not depend on timing.
+//   * lockstep of the query groups: the gridDim.y pairs with the same pair index read the same corpus
+//     tiles; a pair runs at most 2 tiles ahead of the slowest group, so the tile is still in L2 for the
+//     others (without it K2 is 19% slower at 50M rows: every group streams the corpus from HBM itself).
 //
 // Barriers: full[s] lives in the leader (it counts both CTAs' TMA bytes), empty[s] and
 // tmem_full[b] are signalled in both CTAs by multicast tcgen05.commit, tmem_empty[b] lives in the
@@ -68,6 +78,8 @@ struct kp_params {
   uint32_t Bpub, pub_rank, pub_every;
   uint32_t prefetch;   // k-slices of L2 prefetch ahead of the TMA loads
   uint32_t local_min;  // fold lane-locally (all 32 queries at once) when at least this many windows are full
+  uint32_t* prog;      // [groups][pairs] tiles started by each CTA pair (lockstep of the query groups)
+  uint32_t lockstep;   // a pair starts tile i only when every group's same-index pair has started tile i - lockstep (0 = off)
   float* dbg_scores;
   uint32_t mode;
   unsigned long long* cyc;  // diagnostics (RAGERA_K2_PROF): [ctas][8 warps][8] cycle counters
@@ -380,7 +392,25 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       };
       for (uint32_t i = 0; i < P.prefetch; i++) prefetch_next();
-      for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs) {
+      uint32_t it = 0;
+      for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
+        // Lockstep of the query groups: the gridDim.y pairs with this pair index read the SAME corpus tiles.
+        // Left alone they drift apart until L2 no longer holds a tile for the laggard and every group
+        // streams the corpus from HBM by itself (measured: DRAM traffic 1.85x algorithmic at 1M rows, K2
+        // 25% slower per flop at 25M rows). A pair may run at most P.lockstep tiles ahead of the slowest
+        // group; the wait is bounded, so it is a pacing hint and can never deadlock.
+        if (leader && P.lockstep && gridDim.y > 1) {
+          __stcg(P.prog + (size_t)blockIdx.y * P.pairs + pair, it + 1);
+          if (it >= P.lockstep) {
+            const uint32_t need = it + 1 - P.lockstep;
+            const long long t0 = clk();
+            for (;;) {
+              uint32_t slowest = 0xFFFFFFFFu;
+              for (uint32_t g = 0; g < gridDim.y; g++) slowest = min(slowest, __ldcg(P.prog + (size_t)g * P.pairs + pair));
+              if (slowest >= need || clk() - t0 > 200000) break;
+            }
+          }
+        }
         for (uint32_t kb = 0; kb < nkb; kb++) {
           prefetch_next();
           const long long t0 = cyc ? clk() : 0;
@@ -646,6 +676,7 @@ struct kp_state {
   uint32_t mode = 0;
   uint32_t prefetch = KP_PREFETCH;
   uint32_t local_min = 3;
+  uint32_t lockstep = 2;
   bool prof = false;
   unsigned long long* d_cyc = nullptr;
   uint32_t* d_pub = nullptr;  // cooperative-threshold board [pairs][Bpub]
@@ -679,6 +710,7 @@ int kp_init(rag_index* idx) {
   if (const char* m = getenv("RAGERA_K2_PROF")) st->prof = atoi(m) != 0;
   if (const char* m = getenv("RAGERA_K2_PREFETCH")) st->prefetch = (uint32_t)atoi(m);
   if (const char* m = getenv("RAGERA_K2_LOCAL_MIN")) st->local_min = (uint32_t)atoi(m);
+  if (const char* m = getenv("RAGERA_K2_LOCKSTEP")) st->lockstep = (uint32_t)atoi(m);
   cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, idx->device);
   idx->k2p_state = st;
   return RAG_OK;
@@ -761,7 +793,8 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     P.Bpub = groups_ * PAIR_M;
     P.pub_rank = (kp + P.pairs - 1) / P.pairs;  // pairs * pub_rank >= K'
     P.pub_every = P.pairs <= 24 ? 1 : 4;
-    const size_t need = (size_t)P.pairs * P.Bpub * sizeof(uint32_t);
+    const size_t pub_bytes = (size_t)P.pairs * P.Bpub * sizeof(uint32_t);
+    const size_t need = pub_bytes + (size_t)groups_ * P.pairs * sizeof(uint32_t);  // + the lockstep board
     if (need > st->c_pub) {
       if (st->d_pub) RAG_CUDA(cudaFree(st->d_pub));
       st->d_pub = nullptr;
@@ -771,6 +804,8 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     }
     RAG_CUDA(cudaMemsetAsync(st->d_pub, 0, need, idx->stream));
     P.pub = st->d_pub;
+    P.prog = st->d_pub + pub_bytes / sizeof(uint32_t);
+    P.lockstep = st->lockstep;
   }
   P.dbg_scores = st->dbg;
   P.mode = st->mode;

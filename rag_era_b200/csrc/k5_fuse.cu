@@ -85,8 +85,47 @@ __device__ __forceinline__ void emit_sorted(const fuse_smem& s, uint32_t n, uint
   }
 }
 
+// one record through L2 (ld.global.cg): mailbox records are written by PEER GPUs over NVLink, which this
+// SM's L1 knows nothing about
+__device__ __forceinline__ rag_rec rec_load(const rag_rec* r) {
+  union { rag_rec rec; uint4 q[3]; } u;
+  const uint4* p = reinterpret_cast<const uint4*>(r);
+  u.q[0] = __ldcg(p);
+  u.q[1] = __ldcg(p + 1);
+  u.q[2] = __ldcg(p + 2);
+  return u.rec;
+}
+
+// C1 fused into K5 (see comm.cu): store this rank's k records of query b into every rank's mailbox, raise the
+// flags, wait for every rank's flag. Returns the base of the gathered records [rank][B][k] (local mailbox).
+__device__ __forceinline__ const rag_rec* p2p_exchange(const rag_p2p_view& pv, const rag_rec* local, uint32_t B, uint32_t b,
+                                                       uint32_t k, int lane) {
+  const uint64_t half = (uint64_t)(pv.step & 1u) * pv.half_bytes;
+  const uint4* src = reinterpret_cast<const uint4*>(local + (size_t)b * k);
+  const uint32_t n16 = k * (uint32_t)(sizeof(rag_rec) / 16);
+  for (uint32_t g = 0; g < pv.nranks; g++) {
+    uint4* dst = reinterpret_cast<uint4*>(pv.base[g] + half) + ((size_t)pv.rank * B + b) * k * (sizeof(rag_rec) / 16);
+    for (uint32_t i = lane; i < n16; i += 32) dst[i] = src[i];
+  }
+  __threadfence_system();  // this lane's stores are visible system-wide before the flags go up
+  __syncwarp();
+  if ((uint32_t)lane < pv.nranks) {
+    uint32_t* f = reinterpret_cast<uint32_t*>(pv.base[lane] + half + pv.flags_off) + (size_t)pv.rank * pv.flag_stride + b;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(pv.step) : "memory");
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(pv.base[pv.rank] + half + pv.flags_off) + (size_t)lane * pv.flag_stride + b;
+    const long long t0 = clock64();
+    uint32_t seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
+      if (seen != pv.step && clock64() - t0 > 40000000000ll) __trap();  // ~20 s: a peer never arrived
+    } while (seen != pv.step);
+  }
+  __syncwarp();
+  return reinterpret_cast<const rag_rec*>(pv.base[pv.rank] + half);
+}
+
 __global__ void __launch_bounds__(32)
-k5_fuse_kernel(const rag_rec* __restrict__ recs, rag_fuse_args a, const uint64_t* __restrict__ kw,
+k5_fuse_kernel(const rag_rec* __restrict__ recs, rag_p2p_view pv, rag_fuse_args a, const uint64_t* __restrict__ kw,
                const uint32_t* __restrict__ kwc, uint64_t* __restrict__ o_key, double* __restrict__ o_score,
                uint8_t* __restrict__ o_src, uint8_t* __restrict__ o_ct, uint32_t* __restrict__ o_cnt,
                uint8_t* __restrict__ o_rrf, uint64_t* __restrict__ v_ids, double* __restrict__ v_scores,
@@ -97,14 +136,17 @@ k5_fuse_kernel(const rag_rec* __restrict__ recs, rag_fuse_args a, const uint64_t
   const uint32_t b = blockIdx.x;
   const uint32_t k = a.k;
 
+  // ---- 0. sharded: exchange the ranks' lists through the peer mailboxes -----------------
+  if (pv.nranks > 1) recs = p2p_exchange(pv, recs, a.B, b, k, lane);
+
   // ---- 1. gather the ranks' exact top-k lists and merge on (score desc, id asc) -------
   const uint32_t m = a.nranks * k;
   uint32_t uncert = 0;
   for (uint32_t i = lane; i < m; i += 32) {
     const uint32_t g = i / k, slot = i % k;
-    const rag_rec* r = recs + ((size_t)g * a.B + b) * k + slot;
-    s.m_score[i] = r->score; s.m_id[i] = r->id; s.m_src[i] = (uint16_t)i;
-    if (slot == 0) uncert |= r->flags & 1u;
+    const rag_rec r = rec_load(recs + ((size_t)g * a.B + b) * k + slot);
+    s.m_score[i] = r.score; s.m_id[i] = r.id; s.m_src[i] = (uint16_t)i;
+    if (slot == 0) uncert |= r.flags & 1u;
   }
   uncert = __any_sync(0xFFFFFFFFu, uncert != 0);
   __syncwarp();
@@ -120,9 +162,9 @@ k5_fuse_kernel(const rag_rec* __restrict__ recs, rag_fuse_args a, const uint64_t
     }
     if (rank < k) {
       const uint32_t g = i / k, slot = i % k;
-      const rag_rec* r = recs + ((size_t)g * a.B + b) * k + slot;
-      s.v_score[rank] = si; s.v_id[rank] = ii; s.v_key[rank] = r->key;
-      s.v_fresh[rank] = r->fresh; s.v_ct[rank] = (uint8_t)r->ctype;
+      const rag_rec r = rec_load(recs + ((size_t)g * a.B + b) * k + slot);
+      s.v_score[rank] = si; s.v_id[rank] = ii; s.v_key[rank] = r.key;
+      s.v_fresh[rank] = r.fresh; s.v_ct[rank] = (uint8_t)r.ctype;
       n_top++;
     }
   }
@@ -258,8 +300,11 @@ __global__ void k5_freshness_kernel(uint64_t n, const double* __restrict__ conf,
 
 int k5_launch(rag_index* idx, const rag_fuse_args* a) {
   rag_prof_scope ps(idx, RAG_PROF_FUSE);
-  const rag_rec* recs = a->nranks > 1 ? idx->cur->d_gather : idx->cur->d_local;
-  k5_fuse_kernel<<<a->B, 32, 0, idx->stream>>>(recs, *a, idx->cur->d_kw, idx->cur->d_kwc, idx->cur->d_out_keys,
+  rag_p2p_view pv;
+  RAG_CHECK(comm_p2p_next(idx, a->B, a->k, &pv));  // nranks 1 unless the peer-to-peer exchange is active
+  // peer-to-peer: K5 reads this rank's records and gathers them itself; NCCL fallback: already gathered
+  const rag_rec* recs = (a->nranks > 1 && pv.nranks <= 1) ? idx->cur->d_gather : idx->cur->d_local;
+  k5_fuse_kernel<<<a->B, 32, 0, idx->stream>>>(recs, pv, *a, idx->cur->d_kw, idx->cur->d_kwc, idx->cur->d_out_keys,
                                                 idx->cur->d_out_scores, idx->cur->d_out_src, idx->cur->d_out_ct, idx->cur->d_out_cnt,
                                                 idx->cur->d_out_rrf, idx->cur->d_vec_ids, idx->cur->d_vec_scores, idx->cur->d_vec_cnt,
                                                 idx->cur->d_cert, idx->cur->d_aux0, idx->cur->d_aux1);
