@@ -300,8 +300,12 @@ int rag_profile_read(rag_index* idx, float ms[RAG_PROF_CLASSES], uint32_t counts
 void* rag_host_alloc(uint64_t bytes);
 void rag_host_free(void* p);
 
-/* ---- row-sharded multi-GPU (one process per GPU; NCCL all-gather of each rank's
- *      local top-k, final merge on every rank — rank 0 is the consumer) ---------- */
+/* ---- row-sharded multi-GPU (one process per GPU of one node; every rank's exact local top-k is
+ *      exchanged and merged on every rank — rank 0 is the consumer). Default exchange: peer-to-peer
+ *      mailboxes over NVLink (CUDA IPC), written and awaited inside the final fusion kernel; NCCL carries
+ *      the mailbox handles at set-up and is the fallback exchange (environment RAGERA_COMM=nccl, or GPUs
+ *      without peer access). All ranks must issue the same sequence of search calls (same batch size and
+ *      k): the exchange, like a collective, pairs the i-th call of every rank. ---------------------- */
 #define RAG_COMM_ID_BYTES 128
 int rag_comm_unique_id(uint8_t id[RAG_COMM_ID_BYTES]);            /* rank 0 creates, host broadcasts */
 int rag_comm_init(rag_index* idx, int nranks, int rank, const uint8_t id[RAG_COMM_ID_BYTES]);
