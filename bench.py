@@ -297,6 +297,10 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     out = idx.alloc_fused(B, o)
     lat = []
     uncert = 0
+    e2e_prof = os.environ.get("RAGERA_BENCH_E2E_PROF") == "1"   # diagnosis only: per-kernel device time inside the e2e calls
+    if e2e_prof:
+        idx.profile_enable(True)
+        idx.profile_read()
     for i in range(total):
         lo = (i % n_pool) * B
         if world > 1:
@@ -308,6 +312,11 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
             lat.append(t1 - t0)
             uncert += int(B - r.certified.sum())
     e2e_s = float(np.sum(lat))
+    e2e_kernel_ms = None
+    if e2e_prof:
+        pr = idx.profile_read()
+        idx.profile_enable(False)
+        e2e_kernel_ms = {k: v[0] / total for k, v in pr.items() if v[1]}
     if world > 1:
         import torch
 
@@ -362,6 +371,7 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
                 "uncertified_after_escalation": uncert},
         "roofline": roof,
         "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items() if v[1]},
+        **({"e2e_kernel_ms_per_call": e2e_kernel_ms} if e2e_kernel_ms else {}),
         "certified": {"setup_queries": certified_setup, "of": n_pool * B, "last_step": int(last.certified.sum()), "last_step_of": B},
     }
     if world > 1:
@@ -430,7 +440,7 @@ def run_ours(args):
         if res["roofline"].get("bound") == "tensor":
             # the batched path selects on tcgen05 products of bf16 (or tf32) operands; ids and scores are still decided in fp64
             line["dtype"] = "tf32" if "operand" in res["roofline"] else "bf16"
-        for key in ("per_rank_kernel_ms", "exchange"):
+        for key in ("per_rank_kernel_ms", "exchange", "e2e_kernel_ms_per_call"):
             if key in res:
                 line[key] = res[key]
         if "cpu_baseline" in res:
