@@ -252,16 +252,21 @@ int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fr
   if (p.path == RAG_PATH_STREAM) RAG_CHECK(k1_launch(idx, B, p.kp, parts));
   else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_launch(idx, B, p.kp, parts));
   else RAG_CHECK(k1x_launch(idx, B, p.kp, parts));
+  fa.B = B;
+  fa.k = k;
+  fa.nranks = (uint32_t)idx->nranks;
+  // small batches on one GPU: the last CTA of each query in the K3+K4 kernel runs K5 in place
+  static const bool k5_in_place = !(getenv("RAGERA_FUSE_K5") && atoi(getenv("RAGERA_FUSE_K5")) == 0);
+  bool fused = false;
   if (k34_small_ok(idx, B, p.kp, parts)) {
-    RAG_CHECK(k34_small_launch(idx, B, p.kp, parts, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
+    fused = k5_in_place && idx->nranks == 1;
+    RAG_CHECK(k34_small_launch(idx, B, p.kp, parts, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus, fused ? &fa : nullptr));
   } else {
     RAG_CHECK(k3_launch(idx, B, p.kp, parts));
     RAG_CHECK(k4_launch(idx, B, p.kp, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
   }
+  if (fused) return RAG_OK;
   RAG_CHECK(comm_allgather_local(idx, B, k));
-  fa.B = B;
-  fa.k = k;
-  fa.nranks = (uint32_t)idx->nranks;
   RAG_CHECK(k5_launch(idx, &fa));
   return RAG_OK;
 }

@@ -230,7 +230,7 @@ int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, double eps, i
 // K3+K4 fused, latency variant for small batches (k4_rescore.cu)
 bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, double eps, int key_has_qnorm,
-                     int64_t now_ms, double decay, double bonus);
+                     int64_t now_ms, double decay, double bonus, const struct rag_fuse_args* fuse /* non-null: run K5 in place */);
 // K5 — cross-rank merge, min-cosine filter, RRF / freshness fusion, memory blend (k5_fuse.cu)
 struct rag_fuse_args {
   uint32_t B, k, nranks;

@@ -62,7 +62,7 @@ constexpr int B_BYTES = HALF_N * ROW_BYTES;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int KP_THREADS = 256;        // w0 TMA · w1 MMA · w2 TMEM alloc · w3 inv-norm loader · w4..7 epilogue
 constexpr int KP_WARPS = KP_THREADS / 32;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 5;         // 5, 6 and 7 measure the same; shared memory goes to the windows and best lists
 constexpr int TMEM_COLS = 512;
 constexpr int WIN = 32;                // append window per query (shared memory), entries
 constexpr int KP_PREFETCH = 8;         // k-slices of L2 prefetch ahead of the TMA loads
@@ -510,7 +510,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint32_t* my_pub = P.pub + (size_t)pair * P.Bpub + qg;
     const uint32_t* q_pub = P.pub + qg;
     uint32_t last_pub = 0;
-    long long c_wait = 0, c_first = 0, n_fold = 0, n_fold4 = 0, c_fold = 0, n_slow = 0, c_ld = 0;
+    long long c_wait = 0, c_first = 0, n_fold = 0, n_fold_local = 0, c_fold = 0, n_slow = 0, c_ld = 0;
     const long long t_begin = clk();
 
     // fold the windows of the lanes in `need` into their best lists and raise those lanes' thresholds
@@ -545,7 +545,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       } else {
         // several at once (the first tiles of a CTA): every lane folds its own window, side by side
-        n_fold4++;
+        n_fold_local++;
         const int c = (int)(off >> 3);
         if (__any_sync(0xFFFFFFFFu, c != 0)) {
           const uint64_t t = k2p_fold_local(mywin, warp_best + (size_t)lane * best_stride, c, nbest, kp, lane);
@@ -644,7 +644,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     if (cyc && lane == 0) {
       cyc[0] = (unsigned long long)(clk() - t_begin); cyc[1] = (unsigned long long)c_wait; cyc[2] = (unsigned long long)c_first;
-      cyc[3] = (unsigned long long)n_fold; cyc[4] = (unsigned long long)c_fold; cyc[5] = (unsigned long long)n_slow; cyc[6] = (unsigned long long)c_ld; cyc[7] = (unsigned long long)n_fold4;
+      cyc[3] = (unsigned long long)n_fold; cyc[4] = (unsigned long long)c_fold; cyc[5] = (unsigned long long)n_slow; cyc[6] = (unsigned long long)c_ld; cyc[7] = (unsigned long long)n_fold_local;
     }
     // fold what is left in the windows
     fold_lanes(__ballot_sync(0xFFFFFFFFu, live && off != 0));

@@ -21,6 +21,7 @@
 // local top-k equals an exact scan. Otherwise the query is flagged and the host
 // escalates it to a stronger path.
 #include "exact_chain.cuh"
+#include "k5_body.cuh"
 
 namespace {
 using namespace rag_exact;
@@ -220,7 +221,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
                  const uint64_t* __restrict__ partial, uint32_t parts, uint32_t kp, uint32_t k, double eps,
                  int key_has_qnorm, k4_meta M, double* __restrict__ scratch /*[B][2*128+2]*/,
                  unsigned int* __restrict__ ticket /*[B]*/, uint64_t* __restrict__ cand_out /*[B][128]*/,
-                 rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt) {
+                 rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt, int fuse_k5, rag_k5::k5_io io) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* stg = reinterpret_cast<uint64_t*>(smem);               // [parts][kp] staged lists
   uint64_t* wl = stg + (size_t)parts * kp;                         // [2][K4S_WARPS][kp] per-warp merged lists
@@ -313,6 +314,14 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
     k4_finalize(j, kp, k, valid, row, score, nq, s_cand[kp - 1], eps, key_has_qnorm, M, s_score, s_row, &s_kth,
                 local + (size_t)b * k, local_cnt + b);
   }
+  // ---- K5 in place (single GPU): filter + fusion of this query by warp 0 — one launch less on the
+  //      batch-1 latency path. The product scratch is free by now and hosts K5's working set.
+  if (fuse_k5) {
+    __threadfence();  // the records above are read back through L2
+    __syncthreads();
+    static_assert(sizeof(rag_k5::fuse_smem) <= sizeof(s_prod), "K5 working set must fit the product scratch");
+    if (warp == 0) rag_k5::k5_fuse_body(*reinterpret_cast<rag_k5::fuse_smem*>(&s_prod[0][0]), local, io, b, lane);
+  }
 }
 
 }  // namespace
@@ -341,7 +350,7 @@ bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts)
 }
 
 int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, double eps, int key_has_qnorm,
-                     int64_t now_ms, double decay, double bonus) {
+                     int64_t now_ms, double decay, double bonus, const rag_fuse_args* fuse) {
   rag_prof_scope ps(idx, RAG_PROF_RESCORE);
   rag_batch* bt = idx->cur;
   const bool bf16 = idx->desc.dtype == RAG_BF16;
@@ -352,7 +361,8 @@ int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, ui
   const uint32_t slices = (kp + K4S_CW - 1) / K4S_CW;
   kern<<<dim3(B, slices), K4S_THREADS, smem, idx->stream>>>(idx->corpus, idx->ld, bt->d_q, bt->d_partial, parts, kp, k, eps,
                                                              key_has_qnorm, M, bt->d_k4s, bt->d_ticket, bt->d_cand, bt->d_local,
-                                                             bt->d_local_cnt);
+                                                             bt->d_local_cnt, fuse ? 1 : 0,
+                                                             fuse ? k5_make_io(idx, fuse) : rag_k5::k5_io());
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   return RAG_OK;

@@ -1,0 +1,254 @@
+// k5_body.cuh — the per-query body of K5 (merge of the ranks' exact top-k lists, min-cosine filter,
+// Reciprocal Rank Fusion / MemoryStore blend / vector-only branch), shared by k5_fuse_kernel and by the
+// small-batch K3+K4 kernel, whose last CTA of a query runs it in place on a single GPU (one launch less on
+// the batch-1 latency path). One warp per query. Reference lines are cited in k5_fuse.cu.
+#pragma once
+#include "common.cuh"
+
+namespace rag_k5 {
+
+constexpr int MAXM = 8 * RAG_MAX_TOPK;                                   // merge inputs (8 ranks)
+constexpr int MAXE = RAG_MAX_TOPK + RAG_MAX_KEYWORDS + RAG_MAX_FRESH;    // fused entries
+
+struct fuse_smem {
+  double m_score[MAXM];
+  uint64_t m_id[MAXM];
+  uint16_t m_src[MAXM];   // rank*k + slot
+  // vector stage in rank order
+  double v_score[RAG_MAX_TOPK];
+  uint64_t v_id[RAG_MAX_TOPK];
+  uint64_t v_key[RAG_MAX_TOPK];
+  double v_fresh[RAG_MAX_TOPK];
+  uint8_t v_ct[RAG_MAX_TOPK];
+  // fusion map (insertion order)
+  uint64_t e_key[MAXE];
+  double e_score[MAXE];
+  uint8_t e_src[MAXE];
+  uint8_t e_ct[MAXE];
+  uint64_t f_key[RAG_MAX_FRESH];
+};
+
+// one sequential RRF pass over `n` keys; all lanes execute, lane 0 mutates the map.
+// first_pass: vector pass semantics (:147-166), else keyword pass semantics (:169-188).
+__device__ __forceinline__ void rrf_pass(fuse_smem& s, uint32_t& n_entries, const uint64_t* keys,
+                                         const uint8_t* cts, uint32_t n, double weight, double kconst,
+                                         double bonus, bool first_pass, uint8_t new_src, uint8_t new_ct,
+                                         int lane) {
+  for (uint32_t r = 0; r < n; r++) {
+    const uint64_t key = keys[r];
+    const double rrf = __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)r), 1.0));
+    int found = -1;
+    for (uint32_t base = 0; base < n_entries; base += 32) {
+      const uint32_t i = base + lane;
+      const unsigned hit = __ballot_sync(0xFFFFFFFFu, i < n_entries && s.e_key[i] == key);
+      if (hit) { found = (int)base + __ffs(hit) - 1; break; }
+    }
+    if (lane == 0) {
+      if (found >= 0) {
+        const double e = s.e_score[found];
+        s.e_score[found] = first_pass ? __dadd_rn(e, rrf)
+                                      : __dadd_rn(e, __dadd_rn(rrf, __dmul_rn(bonus, e)));
+        s.e_src[found] = RAG_SRC_BOTH;
+      } else {
+        s.e_key[n_entries] = key;
+        s.e_score[n_entries] = rrf;
+        s.e_src[n_entries] = new_src;
+        s.e_ct[n_entries] = cts ? cts[r] : new_ct;
+      }
+    }
+    if (found < 0) n_entries++;
+    __syncwarp();
+  }
+}
+
+// stable sort by score desc over the map (insertion index breaks ties) and emit
+__device__ __forceinline__ void emit_sorted(const fuse_smem& s, uint32_t n, uint64_t* o_key, double* o_score,
+                                            uint8_t* o_src, uint8_t* o_ct, int lane) {
+  for (uint32_t i = lane; i < n; i += 32) {
+    const double si = s.e_score[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; j++) {
+      const double sj = s.e_score[j];
+      rank += (sj > si || (sj == si && j < i)) ? 1u : 0u;
+    }
+    o_key[rank] = s.e_key[i]; o_score[rank] = si; o_src[rank] = s.e_src[i]; o_ct[rank] = s.e_ct[i];
+  }
+}
+
+// one record through L2 (ld.global.cg): mailbox records are written by PEER GPUs over NVLink, which this
+// SM's L1 knows nothing about
+__device__ __forceinline__ rag_rec rec_load(const rag_rec* r) {
+  union { rag_rec rec; uint4 q[3]; } u;
+  const uint4* p = reinterpret_cast<const uint4*>(r);
+  u.q[0] = __ldcg(p);
+  u.q[1] = __ldcg(p + 1);
+  u.q[2] = __ldcg(p + 2);
+  return u.rec;
+}
+
+// everything K5 reads and writes besides the records
+struct k5_io {
+  rag_fuse_args a;
+  const uint64_t* kw;
+  const uint32_t* kwc;
+  uint64_t* o_key;
+  double* o_score;
+  uint8_t* o_src;
+  uint8_t* o_ct;
+  uint32_t* o_cnt;
+  uint8_t* o_rrf;
+  uint64_t* v_ids;
+  double* v_scores;
+  uint32_t* v_cnt;
+  uint8_t* o_cert;
+  double* o_aux0;
+  double* o_aux1;
+};
+
+// recs: [nranks][B][k] records; executed by one full warp for query b
+__device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, const k5_io io, uint32_t b, int lane) {
+  const rag_fuse_args a = io.a;
+  const uint32_t k = a.k;
+  const uint64_t* kw = io.kw;
+  const uint32_t* kwc = io.kwc;
+  uint64_t* o_key = io.o_key;
+  double* o_score = io.o_score;
+  uint8_t* o_src = io.o_src;
+  uint8_t* o_ct = io.o_ct;
+  uint32_t* o_cnt = io.o_cnt;
+  uint8_t* o_rrf = io.o_rrf;
+  uint64_t* v_ids = io.v_ids;
+  double* v_scores = io.v_scores;
+  uint32_t* v_cnt = io.v_cnt;
+  uint8_t* o_cert = io.o_cert;
+  double* o_aux0 = io.o_aux0;
+  double* o_aux1 = io.o_aux1;
+
+  // ---- 1. gather the ranks' exact top-k lists and merge on (score desc, id asc) -------
+  const uint32_t m = a.nranks * k;
+  uint32_t uncert = 0;
+  for (uint32_t i = lane; i < m; i += 32) {
+    const uint32_t g = i / k, slot = i % k;
+    const rag_rec r = rec_load(recs + ((size_t)g * a.B + b) * k + slot);
+    s.m_score[i] = r.score; s.m_id[i] = r.id; s.m_src[i] = (uint16_t)i;
+    if (slot == 0) uncert |= r.flags & 1u;
+  }
+  uncert = __any_sync(0xFFFFFFFFu, uncert != 0);
+  __syncwarp();
+  uint32_t n_top = 0;
+  for (uint32_t i = lane; i < m; i += 32) {
+    const double si = s.m_score[i];
+    const uint64_t ii = s.m_id[i];
+    if (si == -INFINITY) continue;
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < m; j++) {
+      const double sj = s.m_score[j];
+      rank += (sj != -INFINITY && (sj > si || (sj == si && s.m_id[j] < ii))) ? 1u : 0u;
+    }
+    if (rank < k) {
+      const uint32_t g = i / k, slot = i % k;
+      const rag_rec r = rec_load(recs + ((size_t)g * a.B + b) * k + slot);
+      s.v_score[rank] = si; s.v_id[rank] = ii; s.v_key[rank] = r.key;
+      s.v_fresh[rank] = r.fresh; s.v_ct[rank] = (uint8_t)r.ctype;
+      n_top++;
+    }
+  }
+  n_top = __reduce_add_sync(0xFFFFFFFFu, n_top);
+  __syncwarp();
+
+  // ---- 2. min-cosine filter (hybrid-search.ts:308-314); list is sorted so survivors are a prefix
+  uint32_t nv = n_top;
+  if (a.mode == 0) {
+    uint32_t keep = 0;
+    for (uint32_t i = lane; i < n_top; i += 32) keep += (s.v_score[i] < a.min_score) ? 0u : 1u;
+    nv = __reduce_add_sync(0xFFFFFFFFu, keep);
+  }
+  if (v_ids) {
+    for (uint32_t i = lane; i < k; i += 32) {
+      v_ids[(size_t)b * k + i] = i < nv ? s.v_id[i] : ~0ull;
+      v_scores[(size_t)b * k + i] = i < nv ? s.v_score[i] : -INFINITY;
+    }
+    if (lane == 0) v_cnt[b] = nv;
+  }
+  if (lane == 0 && o_cert) o_cert[b] = uncert ? 0 : 1;
+
+  uint64_t* ok = o_key + (size_t)b * a.out_cap;
+  double* os = o_score + (size_t)b * a.out_cap;
+  uint8_t* osrc = o_src + (size_t)b * a.out_cap;
+  uint8_t* oct = o_ct + (size_t)b * a.out_cap;
+
+  // ---- 3a. MemoryStore.retrieve blend (store.ts:119-175) -----------------------------
+  if (a.mode == 1) {
+    uint32_t n = 0;  // map reused: e_key = id, e_score = blended; insertion order = retriever rank
+    for (uint32_t i = 0; i < nv; i++) {
+      const bool take = s.v_ct[i] == RAG_CT_MEMORY && !(s.v_score[i] < a.mem_min_relevance);
+      if (take) {
+        if (lane == 0) {
+          s.e_key[n] = s.v_id[i];
+          s.e_score[n] = __dadd_rn(__dmul_rn(s.v_score[i], 0.7), __dmul_rn(s.v_fresh[i], 0.3));
+          s.e_src[n] = (uint8_t)i; s.e_ct[n] = RAG_CT_MEMORY;
+        }
+        n++;
+      }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {
+      const double si = s.e_score[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < n; j++) {
+        const double sj = s.e_score[j];
+        rank += (sj > si || (sj == si && j < i)) ? 1u : 0u;
+      }
+      if (rank < a.mem_limit) {
+        const uint32_t src = s.e_src[i];
+        ok[rank] = s.e_key[i]; os[rank] = si; osrc[rank] = RAG_SRC_VECTOR; oct[rank] = RAG_CT_MEMORY;
+        o_aux0[(size_t)b * a.out_cap + rank] = s.v_score[src];
+        o_aux1[(size_t)b * a.out_cap + rank] = s.v_fresh[src];
+      }
+    }
+    if (lane == 0) { o_cnt[b] = n < a.mem_limit ? n : a.mem_limit; o_rrf[b] = 0; }
+    return;
+  }
+
+  const uint32_t nk = (a.mode == 0 && kwc) ? kwc[b] : 0u;
+  // ---- 3b. vector-only branch (hybrid-search.ts:346-354) -----------------------------
+  if (nk == 0) {
+    for (uint32_t i = lane; i < nv; i += 32) {
+      ok[i] = s.v_id[i]; os[i] = s.v_score[i]; osrc[i] = RAG_SRC_VECTOR; oct[i] = s.v_ct[i];
+    }
+    if (lane == 0) { o_cnt[b] = nv; o_rrf[b] = 0; }
+    return;
+  }
+
+  // ---- 3c. reciprocalRankFusion (hybrid-search.ts:129-208) ---------------------------
+  uint32_t n = 0;
+  rrf_pass(s, n, s.v_key, s.v_ct, nv, a.rrf.vector_weight, a.rrf.k, a.rrf.both_bonus, true,
+           RAG_SRC_VECTOR, RAG_CT_DOCUMENT, lane);
+  rrf_pass(s, n, kw + (size_t)b * a.kw_stride, nullptr, nk, a.rrf.keyword_weight, a.rrf.k, a.rrf.both_bonus,
+           false, RAG_SRC_KEYWORD, RAG_CT_DOCUMENT, lane);
+  if (a.fresh_limit > 0) {
+    // north-star extension (SURVEY N-c4 ii): memory hits of the vector stage ranked by
+    // freshness desc (ties → lower chunk id), fused like a keyword list
+    uint32_t nf = 0;
+    for (uint32_t i = lane; i < nv; i += 32) {
+      if (s.v_ct[i] != RAG_CT_MEMORY) continue;
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < nv; j++) {
+        if (s.v_ct[j] != RAG_CT_MEMORY) continue;
+        rank += (s.v_fresh[j] > s.v_fresh[i] || (s.v_fresh[j] == s.v_fresh[i] && s.v_id[j] < s.v_id[i])) ? 1u : 0u;
+      }
+      if (rank < a.fresh_limit) { s.f_key[rank] = s.v_key[i]; nf++; }
+    }
+    nf = __reduce_add_sync(0xFFFFFFFFu, nf);
+    __syncwarp();
+    rrf_pass(s, n, s.f_key, nullptr, nf, a.fresh_weight, a.rrf.k, a.rrf.both_bonus, false,
+             RAG_SRC_FRESHNESS, RAG_CT_MEMORY, lane);
+  }
+  emit_sorted(s, n, ok, os, osrc, oct, lane);
+  if (lane == 0) { o_cnt[b] = n; o_rrf[b] = 1; }
+}
+
+}  // namespace rag_k5
+
+// host: the k5_io of the current batch (k5_fuse.cu)
+rag_k5::k5_io k5_make_io(const rag_index* idx, const rag_fuse_args* a);
