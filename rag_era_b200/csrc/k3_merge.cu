@@ -99,15 +99,13 @@ int k3_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   rag_prof_scope ps(idx, RAG_PROF_MERGE);
   const size_t per_query = (size_t)parts * kp * 8;
   if (parts <= 32 * K3T_LISTS_PER_LANE && per_query <= K3T_SMEM_BUDGET) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      RAG_CUDA(cudaFuncSetAttribute(k3_tournament_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3T_SMEM_BUDGET));
-      attr_set = true;
-    }
     uint32_t warps = (uint32_t)(K3T_SMEM_BUDGET / per_query);
     if (warps > K3T_MAX_WARPS) warps = K3T_MAX_WARPS;
     // spread small batches over the SMs instead of packing 8 queries into few CTAs
     while (warps > 1 && (B + warps - 1) / warps < (uint32_t)idx->sm_count) warps >>= 1;
+    // the attribute is per device: set it whenever the launch needs more than the default 48 KB
+    if (warps * per_query > 48 * 1024)
+      RAG_CUDA(cudaFuncSetAttribute(k3_tournament_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3T_SMEM_BUDGET));
     k3_tournament_kernel<<<(B + warps - 1) / warps, warps * 32, warps * per_query, idx->stream>>>(idx->cur->d_partial, B, parts, kp,
                                                                                                  idx->cur->d_cand);
   } else {
