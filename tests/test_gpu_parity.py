@@ -547,6 +547,30 @@ def test_c4_memory_rag_three_lists_full_size(rb, native, oracle):
         assert n_fresh_both > 0                                                  # the freshness list was exercised
 
 
+def test_c5_shard_size_tensor_path_properties(rb, native, oracle):
+    """C5: one rank's shard of the 8-GPU configuration (50M/8 = 6.25M x 1536 bf16, batch 1024, tcgen05 path).
+    Size-independent properties: every query certified, the planted row wins, reported scores are the oracle's
+    bit for bit, the stream path (different kernel, fp32 selection) returns the same ids and scores, idempotent."""
+    n, d, B = 6_250_000, 1536, 1024
+    go, gn = gen(oracle, native, n)
+    with rb.VectorIndex(d, n, dtype=native.BF16) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, B)
+        r = idx.query(Q, 10, path=native.PATH_TENSOR)
+        assert r.certified.all() and (r.counts == 10).all()
+        assert (np.diff(r.scores, axis=1) <= 0).all()
+        for b in range(0, B, 64):
+            ids, sc = r.row(b)
+            assert int(ids[0]) == int(oracle_planted(go, b))
+            for i, s in zip(ids[:3], sc[:3]):
+                assert oracle.cosine(Q[b], oracle.gen_rows(go, int(i), 1, d, dtype=oracle.BF16)[0]) == s
+        sub = np.arange(0, B, 128)
+        rs = idx.query(Q[sub], 10, path=native.PATH_STREAM)
+        assert np.array_equal(rs.ids, r.ids[sub]) and np.array_equal(rs.scores, r.scores[sub])
+        r2 = idx.query(Q, 10, path=native.PATH_TENSOR)
+        assert np.array_equal(r.ids, r2.ids) and np.array_equal(r.scores, r2.scores)
+
+
 def test_wide_rows_and_long_lists_fall_back_gracefully(rb, native, oracle):
     """dim 4096 with K'=70: the 8-query kernel does not fit in shared memory; the library picks a smaller
     grouping instead of failing, and results stay exact."""
