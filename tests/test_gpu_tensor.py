@@ -99,6 +99,9 @@ def test_bf16_selection_error_is_within_the_stated_tolerance(rb, native, oracle)
 def test_tf32_path_on_fp32_index_without_shadow(rb, native, oracle):
     """An fp32 index without a bf16 shadow is scored by the same tcgen05 kernel in kind::tf32 (TMA rounds the
     fp32 rows and queries to tf32): stated tolerance 0.006/sqrt(ld), ids and scores still the oracle's."""
+    import os
+    if os.environ.get("RAGERA_K2_IMPL") == "1":
+        pytest.skip("the single-CTA predecessor kernel has no tf32 mode")
     n, d, B = 30000, 1536, 200
     go = oracle.make_gen(n, n_clusters=64, dup_period=23)
     gn = native.GenDesc.from_buffer_copy(bytes(go))
