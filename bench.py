@@ -212,7 +212,12 @@ def config_of(w, name, gpus):
             "min_vector_score": w["min_score"], "rrf": {"k": 60, "vector_weight": 1.0, "keyword_weight": 1.0, "both_bonus": 0.1},
             "display_top": w["show"], "sharding": f"rows/{gpus}" if gpus > 1 else "none",
             "cache": "corpus streamed per step is larger than L2 (126 MB); no flush needed" if w["rows"] * w["dim"] * 4 > 2.5e8
-            else "corpus is L2-resident (latency-bound case); reported as such"}
+            else "corpus is L2-resident (latency-bound case); reported as such",
+            "baseline_config": {"c1": "BASELINE.json configs[0]", "c2": "configs[1] (batch 1)", "c2b": "configs[1] (batch 1024)",
+                                "c3": "configs[2] — the north_star target (>= 80% of HBM roofline, batch-1 top-k over 10M x 1536 fp32 on one "
+                                      "B200) and the default line: its 10M rows still give every GPU real work when the same corpus is "
+                                      "sharded over 8; configs[1] is reported in the same line under extra.c2 / extra.c2b",
+                                "c4": "configs[3]", "c4f": "configs[3], fp32 operand", "c5": "configs[4]"}.get(name, name)}
 
 
 # --------------------------------------------------------------------------------------------
