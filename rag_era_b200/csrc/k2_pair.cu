@@ -29,8 +29,10 @@
 //     score; at least K' rows score >= the minimum of the published values, so nothing below it can be a
 //     candidate anywhere. Cuts survivors and folds ~3x; the merged top-K' does not depend on timing.
 //   * lockstep of the query groups: the gridDim.y pairs with the same pair index read the same corpus
-//     tiles; a pair runs at most 2 tiles ahead of the slowest group, so the tile is still in L2 for the
-//     others (without it K2 is 19% slower at 50M rows: every group streams the corpus from HBM itself).
+//     tiles; a pair runs at most 1 tile ahead of the slowest group, so the tile is still in L2 for the
+//     others (without it K2 is 18% slower at 50M rows: every group streams the corpus from HBM itself,
+//     and under the power cap the extra DRAM traffic also costs SM clock; leads of 0/1/2/4/8 tiles measure
+//     137.6/135.7/138.9/147.2/150.8 ms there).
 //
 // Barriers: full[s] lives in the leader (it counts both CTAs' TMA bytes), empty[s] and
 // tmem_full[b] are signalled in both CTAs by multicast tcgen05.commit, tmem_empty[b] lives in the
@@ -397,7 +399,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // Lockstep of the query groups: the gridDim.y pairs with this pair index read the SAME corpus tiles.
         // Left alone they drift apart until L2 no longer holds a tile for the laggard and every group
         // streams the corpus from HBM by itself (measured: DRAM traffic 1.85x algorithmic at 1M rows, K2
-        // 25% slower per flop at 25M rows). A pair may run at most P.lockstep tiles ahead of the slowest
+        // 25% slower per flop at 25M rows). A pair may run at most P.lockstep tiles (default 1) ahead of the slowest
         // group; the wait is bounded, so it is a pacing hint and can never deadlock.
         if (leader && P.lockstep && gridDim.y > 1) {
           __stcg(P.prog + (size_t)blockIdx.y * P.pairs + pair, it + 1);
@@ -676,7 +678,7 @@ struct kp_state {
   uint32_t mode = 0;
   uint32_t prefetch = KP_PREFETCH;
   uint32_t local_min = 3;
-  uint32_t lockstep = 2;
+  uint32_t lockstep = 1;
   bool prof = false;
   unsigned long long* d_cyc = nullptr;
   uint32_t* d_pub = nullptr;  // cooperative-threshold board [pairs][Bpub]
