@@ -10,6 +10,10 @@
 // cp.async in 512-byte column chunks (double buffered); 16-byte slot c of row j is stored
 // at slot (c ^ j) so the per-lane 128-bit reads (lane j reads row j) are bank-conflict
 // free. The sums are latency-bound dependent chains — 32 rows advance in lock step.
+// The query chunk is widened to binary64 ONCE per warp (each lane converts its share into a
+// shared buffer that all lanes then read by broadcast) instead of once per lane, and ||q||^2 —
+// the same chain for every row — is left to the caller (query_norm_sq, once per query):
+// ncu showed the fp32->fp64 conversions (XU pipe) and the fp64 pipe as the busiest units.
 #pragma once
 #include "common.cuh"
 
@@ -24,19 +28,33 @@ __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_g
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct chains {
-  double dot, nx, nq;
+  double dot, nx, nq;  // nq is filled in by the caller (query_norm_sq)
 };
-__device__ __forceinline__ void step(chains& c, float q, float x) {
-  const double qd = (double)q, xd = (double)x;
+__device__ __forceinline__ void step(chains& c, double qd, float x) {
+  const double xd = (double)x;
   c.dot = __dadd_rn(c.dot, __dmul_rn(qd, xd));
   c.nx = __dadd_rn(c.nx, __dmul_rn(xd, xd));
-  c.nq = __dadd_rn(c.nq, __dmul_rn(qd, qd));
+}
+
+// sum of q[i]*q[i], left to right (the reference's third chain; identical for every row). Whole warp: the
+// lanes form 32 exact products at a time, then every lane replays the adds in order, fetching product i
+// from lane i with a shuffle — only the dependent fp64 adds are on the critical path. ld % 32 == 0.
+__device__ __forceinline__ double query_norm_sq(const float* __restrict__ q, uint32_t ld, int lane) {
+  double nq = 0.0;
+  for (uint32_t c = 0; c < ld; c += 32) {
+    const double qd = (double)__ldg(q + c + lane);
+    const long long p = __double_as_longlong(__dmul_rn(qd, qd));
+#pragma unroll
+    for (int l = 0; l < 32; l++) nq = __dadd_rn(nq, __longlong_as_double(__shfl_sync(0xFFFFFFFFu, p, l)));
+  }
+  return nq;
 }
 
 constexpr int X_BYTES = 32 * 512;  // 32 rows x 512 B per stage
 constexpr int Q_BYTES = 1024;      // up to 256 fp32 query elements per stage
 constexpr int STAGE_BYTES = X_BYTES + Q_BYTES;
-constexpr int WARP_BYTES = 2 * STAGE_BYTES;
+constexpr int QD_BYTES = 256 * 8;  // the current query chunk as binary64
+constexpr int WARP_BYTES = 2 * STAGE_BYTES + QD_BYTES;
 
 // Exact sums for row `row` (one per lane; every lane must pass a readable row) against q[0..ld).
 // wsm: this warp's WARP_BYTES of shared memory. All 32 lanes must call.
@@ -71,25 +89,31 @@ __device__ __forceinline__ chains warp_exact_sums(const void* __restrict__ X, ui
     cp_async_wait1();
     __syncwarp();
     const unsigned char* xs = wsm + (ch & 1) * STAGE_BYTES;
-    const float4* qv = reinterpret_cast<const float4*>(xs + X_BYTES);
+    // widen this chunk of the query once per warp: lane l converts elements l, l+32, ...
+    const float* qf = reinterpret_cast<const float*>(xs + X_BYTES);
+    double* qd = reinterpret_cast<double*>(wsm + 2 * STAGE_BYTES);
+#pragma unroll
+    for (int i = 0; i < ELEMS / 32; i++) qd[lane + 32 * i] = (double)qf[lane + 32 * i];
+    __syncwarp();
+    const double2* qv = reinterpret_cast<const double2*>(qd);  // every lane reads the same address: broadcast
     if (!BF16) {
       const float4* xrow = reinterpret_cast<const float4*>(xs + lane * 512);
 #pragma unroll 4
       for (int s = 0; s < 32; s++) {
         const float4 x = xrow[s ^ lane];
-        const float4 qq = qv[s];
-        step(c, qq.x, x.x); step(c, qq.y, x.y); step(c, qq.z, x.z); step(c, qq.w, x.w);
+        const double2 qa = qv[2 * s], qb = qv[2 * s + 1];
+        step(c, qa.x, x.x); step(c, qa.y, x.y); step(c, qb.x, x.z); step(c, qb.y, x.w);
       }
     } else {
       const uint4* xrow = reinterpret_cast<const uint4*>(xs + lane * 512);
 #pragma unroll 2
       for (int s = 0; s < 32; s++) {
         const uint4 x = xrow[s ^ lane];
-        const float4 qa = qv[2 * s], qb = qv[2 * s + 1];
-        step(c, qa.x, __uint_as_float(x.x << 16)); step(c, qa.y, __uint_as_float(x.x & 0xFFFF0000u));
-        step(c, qa.z, __uint_as_float(x.y << 16)); step(c, qa.w, __uint_as_float(x.y & 0xFFFF0000u));
-        step(c, qb.x, __uint_as_float(x.z << 16)); step(c, qb.y, __uint_as_float(x.z & 0xFFFF0000u));
-        step(c, qb.z, __uint_as_float(x.w << 16)); step(c, qb.w, __uint_as_float(x.w & 0xFFFF0000u));
+        const double2 q0 = qv[4 * s], q1 = qv[4 * s + 1], q2 = qv[4 * s + 2], q3 = qv[4 * s + 3];
+        step(c, q0.x, __uint_as_float(x.x << 16)); step(c, q0.y, __uint_as_float(x.x & 0xFFFF0000u));
+        step(c, q1.x, __uint_as_float(x.y << 16)); step(c, q1.y, __uint_as_float(x.y & 0xFFFF0000u));
+        step(c, q2.x, __uint_as_float(x.z << 16)); step(c, q2.y, __uint_as_float(x.z & 0xFFFF0000u));
+        step(c, q3.x, __uint_as_float(x.w << 16)); step(c, q3.y, __uint_as_float(x.w & 0xFFFF0000u));
       }
     }
     __syncwarp();

@@ -6,7 +6,8 @@
 //
 // This is the escalation target for queries the stream / tensor paths cannot certify
 // (near-ties across the K' boundary), and RAG_PATH_EXACT for callers who want it.
-// Roofline: FP64 pipe — 3 dependent chains of D steps per row (6 fp64 ops per element).
+// Roofline: FP64 pipe — 2 dependent chains of D steps per row (4 fp64 ops + 1 conversion per element;
+// the ||q||^2 chain runs once per warp).
 // Each warp takes 32 consecutive rows at a time; rows past the end are clamped to the last
 // row and discarded.
 #include "exact_chain.cuh"
@@ -31,12 +32,16 @@ k1x_exact_kernel(const void* __restrict__ X, uint32_t n_rows, uint32_t ld, const
   for (uint32_t i = lane; i < kp; i += 32) mylist[i] = 0ull;
   __syncwarp();
 
+  // ||q||^2 is the same chain for every row: once per warp
+  const double nq = query_norm_sq(q, ld, lane);
+
   uint64_t thresh = 0ull;
   const uint32_t n_blocks = (n_rows + 31) / 32;
   for (uint32_t blk = blockIdx.x * K1X_WARPS + warp; blk < n_blocks; blk += gridDim.x * K1X_WARPS) {
     const uint32_t row = blk * 32 + lane;
     const bool in_range = row < n_rows;
-    const chains c = warp_exact_sums<BF16>(X, ld, q, in_range ? row : n_rows - 1, wsm, lane);
+    chains c = warp_exact_sums<BF16>(X, ld, q, in_range ? row : n_rows - 1, wsm, lane);
+    c.nq = nq;
     const double s = finish(c);
     // zero-norm rows: NaN in the reference; defined as never selected (SURVEY N-nan)
     const float sf = (in_range && s == s) ? __double2float_rn(s) : -INFINITY;

@@ -105,7 +105,7 @@ __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k,
 
 // ---- throughput variant (large batches): one CTA per query, one LANE per candidate ---------------
 template <bool BF16>
-__global__ void __launch_bounds__(RAG_MAX_CANDIDATES)
+__global__ void __launch_bounds__(RAG_MAX_CANDIDATES + 32)
 k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restrict__ Q,
                   const uint64_t* __restrict__ cand, uint32_t kp, uint32_t k, double eps,
                   int key_has_qnorm, k4_meta M, rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt) {
@@ -124,10 +124,17 @@ k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restri
   const uint64_t key0 = cand[(size_t)b * RAG_MAX_CANDIDATES];
   const uint32_t row = valid ? rag_key_row(key) : (key0 != 0ull ? rag_key_row(key0) : 0u);
 
-  unsigned char* wsm = smem + (size_t)warp * K4_WARP_BYTES;
-  const chains c = warp_exact_sums<BF16>(X, ld, Q + (size_t)b * ld, row, wsm, lane);
-  if (j == 0) s_nq = c.nq;
+  // the last warp of the CTA holds no candidates: it runs the ||q||^2 chain meanwhile
+  chains c = {0.0, 0.0, 0.0};
+  if ((uint32_t)warp * 32 < kp) {
+    unsigned char* wsm = smem + (size_t)warp * K4_WARP_BYTES;
+    c = warp_exact_sums<BF16>(X, ld, Q + (size_t)b * ld, row, wsm, lane);
+  } else {
+    const double nq = query_norm_sq(Q + (size_t)b * ld, ld, lane);
+    if (lane == 0) s_nq = nq;
+  }
   __syncthreads();
+  c.nq = s_nq;
   k4_finalize(j, kp, k, valid, row, finish(c), s_nq, cand[(size_t)b * RAG_MAX_CANDIDATES + kp - 1], eps, key_has_qnorm, M,
               s_score, s_row, &s_kth, local + (size_t)b * k, local_cnt + b);
 }
@@ -335,7 +342,7 @@ int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, double eps, i
   const k4_meta M = {idx->desc.id_base, idx->ctype, idx->conf, idx->access, idx->last_ms, idx->row_keys, now_ms, decay, bonus};
   auto kern = bf16 ? k4_rescore_kernel<true> : k4_rescore_kernel<false>;
   RAG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * K4_WARP_BYTES)));
-  kern<<<B, nw * 32, smem, idx->stream>>>(idx->corpus, idx->ld, idx->cur->d_q, idx->cur->d_cand, kp, k, eps, key_has_qnorm,
+  kern<<<B, (nw + 1) * 32, smem, idx->stream>>>(idx->corpus, idx->ld, idx->cur->d_q, idx->cur->d_cand, kp, k, eps, key_has_qnorm,
                                            M, idx->cur->d_local, idx->cur->d_local_cnt);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
