@@ -180,6 +180,10 @@ int rag_index_set_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, const 
  * default key = chunk id */
 int rag_index_set_row_keys(rag_index* idx, uint64_t row0, uint64_t nrows, const uint64_t* keys);
 int rag_index_read_rows(rag_index* idx, uint64_t row0, uint64_t nrows, void* host_rows);
+/* read back what rag_index_set_row_meta / rag_index_set_row_keys hold (any pointer may be NULL); rows whose metadata
+ * was never set read as documents with zeroed Memory columns, keys default to the chunk id */
+int rag_index_read_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, uint8_t* content_type, double* confidence,
+                            int32_t* access_count, int64_t* last_access_ms, uint64_t* keys);
 uint64_t rag_index_rows(const rag_index* idx);
 /* synthetic queries of ragera_gen.h, generated on the device, copied to host_out [B][dim] */
 int rag_generate_queries(rag_index* idx, const rag_gen_desc* gen, uint64_t b0, uint32_t B, float* host_out);
@@ -195,6 +199,46 @@ int rag_parse_vector_store_json(const char* path, uint32_t dim, uint64_t slab_ro
                                 int (*on_rows)(void* user, uint64_t first_row, uint64_t nrows, const float* rows),
                                 void* user, uint64_t* rows_out, char** ids, uint64_t* ids_bytes);
 void rag_free(void* p);
+/* second pass over the same file: "metadataDict" (node metadata next to the embeddings). content_type[row] follows
+ * vectorSearch's rule (src/lib/hybrid-search.ts:229-234, without the per-call isCodebase flag): metadata.type ===
+ * 'memory' → RAG_CT_MEMORY, else metadata.language !== undefined (key present) → RAG_CT_CODE, else RAG_CT_DOCUMENT. memory_ids (optional):
+ * metadata.memoryId per row (src/lib/memory/store.ts:58-61), '\0'-terminated, empty when absent, rag_free() it — the
+ * host joins it with the Prisma Memory rows for rag_index_set_row_meta. ids/ids_bytes: the blob of the first pass.
+ * *found = 0 when the file has no metadataDict. Host-only. rag_index_load_vector_store applies content_type itself. */
+int rag_parse_vector_store_metadata(const char* path, const char* ids, uint64_t ids_bytes, uint64_t rows,
+                                    uint8_t* content_type, char** memory_ids, uint64_t* memory_ids_bytes, int* found);
+
+/* ---- binary sidecar of a persisted index: the parsed rows in the index dtype + row metadata +
+ *      fusion keys + node ids, checksummed per 4096-row block, stamped with size/mtime of the JSON it was made from
+ *      (index.insert appends to the JSON — src/lib/memory/store.ts:67 — which makes the sidecar stale). Cold start
+ *      (loadIndex, src/lib/llm/index-manager.ts:246-275) then streams binary rows into HBM instead of parsing text. */
+#define RAG_CACHE_META 1u /* content_type / confidence / access_count / last_access_ms present */
+#define RAG_CACHE_KEYS 2u /* fusion keys present                                                */
+typedef struct rag_cache_info {
+  uint32_t version, dtype, dim, flags;
+  uint64_t rows, ids_bytes;
+  uint64_t source_size;     /* of the vector_store.json the sidecar was written from (0 = unknown) */
+  int64_t  source_mtime_ns;
+} rag_cache_info;
+/* host-only: header (validated), freshness against the JSON (1 fresh / 0 stale, missing or malformed), whole-file
+ * write and read with every checksum verified (any output pointer may be NULL; metadata arrays: all four or none) */
+int rag_cache_info_read(const char* cache_path, rag_cache_info* out);
+int rag_cache_is_fresh(const char* cache_path, const char* source_json);
+int rag_cache_write_host(const char* cache_path, uint32_t dtype, uint32_t dim, uint64_t rows, const void* host_rows,
+                         const uint8_t* content_type, const double* confidence, const int32_t* access_count,
+                         const int64_t* last_access_ms, const uint64_t* keys, const char* ids, uint64_t ids_bytes,
+                         const char* source_json /* may be NULL */);
+int rag_cache_read_host(const char* cache_path, uint64_t first_row, uint64_t nrows, void* host_rows, uint8_t* content_type,
+                        double* confidence, int32_t* access_count, int64_t* last_access_ms, uint64_t* keys, char** ids,
+                        uint64_t* ids_bytes);
+/* device side: save this handle's rows (+ metadata / keys if set) with the caller's node ids; append a row range of
+ * a sidecar to the handle (nrows = 0: to the end; a shard passes its own range); open a store through its sidecar
+ * when fresh, else parse the JSON and rewrite the sidecar (cache_path NULL → "<json>.ragera") */
+int rag_index_save_cache(rag_index* idx, const char* cache_path, const char* ids, uint64_t ids_bytes, const char* source_json);
+int rag_index_load_cache(rag_index* idx, const char* cache_path, uint64_t first_row, uint64_t nrows, uint64_t* rows_loaded,
+                         char** ids, uint64_t* ids_bytes);
+int rag_index_open_store(rag_index* idx, const char* vector_store_json, const char* cache_path, uint64_t* rows_loaded,
+                         char** ids, uint64_t* ids_bytes, int* from_cache);
 
 /* ---- search: replaces retriever.retrieve → SimpleVectorStore.query →
  *      getTopKEmbeddings (src/lib/hybrid-search.ts:223-224) ---------------------- */

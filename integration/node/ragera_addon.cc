@@ -10,7 +10,7 @@
 // JS surface (see native-retrieval.ts):
 //   createIndex({rows, dim, dtype:'f32'|'bf16', device, bf16Shadow}) -> handle (External)
 //   uploadRows(handle, Float32Array rows, nrows, row0 = append) -> first row
-//   loadVectorStore(handle, path) -> string[] node ids          (llamaindex vector_store.json)
+//   loadVectorStore(handle, path) -> string[] node ids          (llamaindex vector_store.json, via its binary sidecar)
 //   setRowMeta(handle, row0, Uint8Array contentType, Float64Array confidence, Int32Array accessCount, BigInt64Array lastAccessMs)
 //   setRowKeys(handle, row0, BigUint64Array keys)
 //   hybridSearch(handle, Float32Array queries, B, opts, BigUint64Array kwKeys, Uint32Array kwCounts) -> Promise<result>
@@ -224,7 +224,10 @@ napi_value LoadVectorStore(napi_env env, napi_callback_info info) {  // loadVect
   NAPI_OK(env, napi_get_value_string_utf8(env, argv[1], path, sizeof path, &len));
   uint64_t rows = 0, bytes = 0;
   char* ids = nullptr;
-  const int rc = rag_index_load_vector_store(idx, path, &rows, &ids, &bytes);
+  // through the binary sidecar (<path>.ragera) when it is fresh, else the JSON is parsed and the sidecar rewritten;
+  // contentType per row comes from the file's metadataDict either way
+  int from_cache = 0;
+  const int rc = rag_index_open_store(idx, path, nullptr, &rows, &ids, &bytes, &from_cache);
   if (rc != RAG_OK) return throw_rag(env, rc);
   napi_value arr;
   NAPI_OK(env, napi_create_array_with_length(env, (size_t)rows, &arr));

@@ -23,6 +23,7 @@ SRC_VECTOR, SRC_KEYWORD, SRC_BOTH, SRC_FRESHNESS = 0, 1, 2, 3
 CT_DOCUMENT, CT_MEMORY, CT_CODE = 0, 1, 2
 PATH_AUTO, PATH_STREAM, PATH_TENSOR, PATH_EXACT = 0, 1, 2, 3
 INDEX_BF16_SHADOW = 1
+CACHE_META, CACHE_KEYS = 1, 2
 SEARCH_NO_ESCALATE = 1
 PROF_CLASSES = 6
 PROF_NAMES = ("stream", "tensor", "merge", "rescore", "fuse", "comm")
@@ -105,6 +106,13 @@ class MemoryOut(C.Structure):
 
 # every symbol include/ragera.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
+class CacheInfo(C.Structure):
+    """rag_cache_info (include/ragera.h): header of a binary sidecar."""
+    _fields_ = [("version", C.c_uint32), ("dtype", C.c_uint32), ("dim", C.c_uint32), ("flags", C.c_uint32),
+                ("rows", C.c_uint64), ("ids_bytes", C.c_uint64), ("source_size", C.c_uint64),
+                ("source_mtime_ns", C.c_int64)]
+
+
 SYMBOLS = {
     "rag_version": (C.c_int, []),
     "rag_last_error": (C.c_char_p, []),
@@ -117,11 +125,25 @@ SYMBOLS = {
     "rag_index_set_row_keys": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "rag_index_read_rows": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "rag_index_rows": (C.c_uint64, [_vp]),
+    "rag_index_read_row_meta": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp]),
     "rag_generate_queries": (C.c_int, [_vp, C.POINTER(GenDesc), C.c_uint64, C.c_uint32, _vp]),
     "rag_index_load_vector_store": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "rag_parse_vector_store_json": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint64),
                                               C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "rag_free": (None, [_vp]),
+    "rag_parse_vector_store_metadata": (C.c_int, [C.c_char_p, _vp, C.c_uint64, C.c_uint64, _vp, C.POINTER(_vp),
+                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "rag_cache_info_read": (C.c_int, [C.c_char_p, C.POINTER(CacheInfo)]),
+    "rag_cache_is_fresh": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "rag_cache_write_host": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       C.c_uint64, C.c_char_p]),
+    "rag_cache_read_host": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp),
+                                      C.POINTER(C.c_uint64)]),
+    "rag_index_save_cache": (C.c_int, [_vp, C.c_char_p, _vp, C.c_uint64, C.c_char_p]),
+    "rag_index_load_cache": (C.c_int, [_vp, C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(_vp),
+                                       C.POINTER(C.c_uint64)]),
+    "rag_index_open_store": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(_vp),
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "rag_search": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(SearchOpts), C.POINTER(TopkOut)]),
     "rag_hybrid_search": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(HybridOpts), _vp, _vp, C.POINTER(FusedOut)]),
     "rag_rrf_fuse": (C.c_int, [_vp, C.c_uint32, C.POINTER(RRFConfigC), _vp, _vp, _vp, C.c_uint32, _vp, _vp,
@@ -211,6 +233,73 @@ def parse_vector_store_json(path: str, dim: int, slab_rows: int = 4096):
     lib.rag_free(blob)
     X = np.vstack(chunks) if chunks else np.zeros((0, dim), np.float32)
     return ids, X
+
+
+def _ids_blob(ids) -> bytes:
+    return b"".join(i.encode("utf-8") + b"\0" for i in ids)
+
+
+def _split_blob(blob, nbytes) -> list:
+    out = C.string_at(blob, nbytes).decode("utf-8").split("\0")[:-1] if nbytes else []
+    load().rag_free(blob)
+    return out
+
+
+def parse_vector_store_metadata(path: str, ids: list):
+    """Host-only second pass: ``metadataDict`` → (content_type uint8 [rows], memory ids [rows], found)."""
+    import numpy as np
+
+    blob = _ids_blob(ids)
+    ct = np.zeros(len(ids), np.uint8)
+    mem, nbytes, found = C.c_void_p(), C.c_uint64(0), C.c_int(0)
+    check(load().rag_parse_vector_store_metadata(path.encode(), blob, len(blob), len(ids), ct.ctypes.data_as(C.c_void_p),
+                                                 C.byref(mem), C.byref(nbytes), C.byref(found)))
+    return ct, _split_blob(mem, nbytes.value), bool(found.value)
+
+
+def cache_info(path: str) -> CacheInfo:
+    info = CacheInfo()
+    check(load().rag_cache_info_read(path.encode(), C.byref(info)))
+    return info
+
+
+def cache_is_fresh(cache_path: str, source_json: str) -> bool:
+    return bool(load().rag_cache_is_fresh(cache_path.encode(), source_json.encode()))
+
+
+def cache_write_host(path: str, rows, ids=None, meta=None, keys=None, source_json=None, dtype=F32):
+    """Host-only writer of the binary sidecar. rows: float32 [n, dim] (or uint16 bf16 bits with dtype=BF16);
+    meta: (content_type u8, confidence f64, access_count i32, last_access_ms i64) or None."""
+    import numpy as np
+
+    rows = np.ascontiguousarray(rows, dtype=np.uint16 if dtype == BF16 else np.float32)
+    n, dim = rows.shape
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    m = [None] * 4 if meta is None else [np.ascontiguousarray(a, dtype=t) for a, t in
+                                         zip(meta, (np.uint8, np.float64, np.int32, np.int64))]
+    k = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+    blob = _ids_blob(ids) if ids is not None else None
+    check(load().rag_cache_write_host(path.encode(), dtype, dim, n, ptr(rows), *[ptr(a) for a in m], ptr(k), blob,
+                                      len(blob) if blob else 0, source_json.encode() if source_json else None))
+
+
+def cache_read_host(path: str, first_row: int = 0, nrows: int | None = None) -> dict:
+    """Host-only reader (every checksum verified) → dict(rows, ids, content_type, confidence, access_count,
+    last_access_ms, keys); absent sections are None."""
+    import numpy as np
+
+    info = cache_info(path)
+    n = info.rows - first_row if nrows is None else nrows
+    rows = np.empty((n, info.dim), np.uint16 if info.dtype == BF16 else np.float32)
+    has_meta, has_keys = bool(info.flags & CACHE_META), bool(info.flags & CACHE_KEYS)
+    m = [np.empty(n, t) if has_meta else None for t in (np.uint8, np.float64, np.int32, np.int64)]
+    k = np.empty(n, np.uint64) if has_keys else None
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    blob, nbytes = C.c_void_p(), C.c_uint64(0)
+    check(load().rag_cache_read_host(path.encode(), first_row, n, ptr(rows), *[ptr(a) for a in m], ptr(k), C.byref(blob),
+                                     C.byref(nbytes)))
+    return dict(rows=rows, ids=_split_blob(blob, nbytes.value), content_type=m[0], confidence=m[1], access_count=m[2],
+                last_access_ms=m[3], keys=k, info=info)
 
 
 def check(rc: int) -> None:

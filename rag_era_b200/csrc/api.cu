@@ -546,6 +546,32 @@ int rag_index_set_row_keys(rag_index* idx, uint64_t row0, uint64_t nrows, const 
   return RAG_OK;
 }
 
+int rag_index_read_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, uint8_t* content_type, double* confidence,
+                            int32_t* access_count, int64_t* last_access_ms, uint64_t* keys) {
+  RAG_CHECK(check_handle(idx));
+  if (row0 + nrows > idx->rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_read_row_meta: range exceeds rows");
+  if (nrows == 0) return RAG_OK;
+  RAG_CUDA(cudaSetDevice(idx->device));
+  // metadata never set: every row is a document with zeroed Memory columns; keys default to the chunk id
+  if (!idx->ctype) {
+    if (content_type) memset(content_type, RAG_CT_DOCUMENT, nrows);
+    if (confidence) memset(confidence, 0, nrows * 8);
+    if (access_count) memset(access_count, 0, nrows * 4);
+    if (last_access_ms) memset(last_access_ms, 0, nrows * 8);
+  } else {
+    if (content_type) RAG_CUDA(cudaMemcpyAsync(content_type, idx->ctype + row0, nrows, cudaMemcpyDeviceToHost, idx->stream));
+    if (confidence) RAG_CUDA(cudaMemcpyAsync(confidence, idx->conf + row0, nrows * 8, cudaMemcpyDeviceToHost, idx->stream));
+    if (access_count) RAG_CUDA(cudaMemcpyAsync(access_count, idx->access + row0, nrows * 4, cudaMemcpyDeviceToHost, idx->stream));
+    if (last_access_ms) RAG_CUDA(cudaMemcpyAsync(last_access_ms, idx->last_ms + row0, nrows * 8, cudaMemcpyDeviceToHost, idx->stream));
+  }
+  if (keys) {
+    if (idx->row_keys) RAG_CUDA(cudaMemcpyAsync(keys, idx->row_keys + row0, nrows * 8, cudaMemcpyDeviceToHost, idx->stream));
+    else for (uint64_t r = 0; r < nrows; r++) keys[r] = idx->desc.id_base + row0 + r;
+  }
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  return RAG_OK;
+}
+
 int rag_index_read_rows(rag_index* idx, uint64_t row0, uint64_t nrows, void* host_rows) {
   RAG_CHECK(check_handle(idx));
   if (row0 + nrows > idx->rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_read_rows: range exceeds rows");

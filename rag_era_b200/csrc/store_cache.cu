@@ -1,0 +1,454 @@
+// store_cache.cu — §8f N1: binary sidecar of a persisted index.
+//
+// The reference reloads ./storage/kb_<id>/vector_store.json (decimal text, ~20 bytes per value) on every cold
+// start (src/lib/llm/index-manager.ts:246-275). Parsing that text is the slow part of bringing a shard up, so
+// the first load writes the parsed rows next to it in the index dtype, and later loads stream that file straight
+// into HBM. The sidecar is only a cache: it records size + mtime of the JSON it was made from and is ignored
+// when they no longer match (index.insert appends to the JSON — src/lib/memory/store.ts:67).
+//
+// File layout (little endian, every section 16-byte aligned):
+//   [0,128)   rag_cache_header (magic, shape, section sizes, source stamp, checksums; written LAST, so an
+//             interrupted writer leaves a file without a valid magic; the file is renamed into place when done)
+//   rows      rows x dim elements of the index dtype, row-major, unpadded
+//   blocks    one FNV-1a-64 per block of `block_rows` rows — a shard can load and verify only its own row range
+//   meta      (flag META) content_type u8[rows] · confidence f64[rows] · access_count i32[rows] · last_access_ms i64[rows]
+//   keys      (flag KEYS) fusion key u64[rows]
+//   ids       node ids, '\0'-separated, row order
+// tail_sum covers blocks..ids; head_sum covers the header itself.
+//
+// Everything except rag_index_save_cache / rag_index_load_cache is host-only and usable without a GPU.
+#include "common.cuh"
+
+#include <errno.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr char kMagic[8] = {'R', 'A', 'G', 'E', 'R', 'A', 'C', '1'};
+constexpr uint32_t kVersion = 1;
+constexpr uint32_t kBlockRows = 4096;
+constexpr uint64_t kFnvBasis = 0xcbf29ce484222325ull, kFnvPrime = 0x100000001b3ull;
+
+struct rag_cache_header {
+  char magic[8];
+  uint32_t version, dtype, dim, flags;
+  uint64_t rows, ids_bytes;
+  uint64_t source_size;
+  int64_t source_mtime_ns;
+  uint32_t block_rows, reserved0;
+  uint64_t tail_sum;
+  uint64_t reserved[6];
+  uint64_t head_sum;  // FNV-1a-64 of the 120 bytes before it
+};
+static_assert(sizeof(rag_cache_header) == 128, "cache header layout");
+
+// FNV-1a over 8-byte words (the tail, if any, byte by byte): one multiply per 8 bytes keeps up with the disk
+uint64_t fnv64(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (; n >= 8; n -= 8, p += 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    h = (h ^ w) * kFnvPrime;
+  }
+  for (; n; n--, p++) h = (h ^ *p) * kFnvPrime;
+  return h;
+}
+
+size_t pad16(size_t n) { return (n + 15) & ~(size_t)15; }
+size_t esize(uint32_t dtype) { return dtype == RAG_BF16 ? 2 : 4; }
+
+struct sections {
+  uint64_t rows_off, blocks_off, nblocks, ct_off, conf_off, acc_off, last_off, keys_off, ids_off, end;
+};
+sections layout(const rag_cache_header& h) {
+  sections s;
+  uint64_t o = sizeof(rag_cache_header);
+  auto take = [&](uint64_t bytes) { const uint64_t at = o; o += pad16(bytes); return at; };
+  s.rows_off = take(h.rows * h.dim * esize(h.dtype));
+  s.nblocks = (h.rows + h.block_rows - 1) / h.block_rows;
+  s.blocks_off = take(s.nblocks * 8);
+  s.ct_off = s.conf_off = s.acc_off = s.last_off = s.keys_off = 0;
+  if (h.flags & RAG_CACHE_META) {
+    s.ct_off = take(h.rows);
+    s.conf_off = take(h.rows * 8);
+    s.acc_off = take(h.rows * 4);
+    s.last_off = take(h.rows * 8);
+  }
+  if (h.flags & RAG_CACHE_KEYS) s.keys_off = take(h.rows * 8);
+  s.ids_off = take(h.ids_bytes);
+  s.end = o;
+  return s;
+}
+
+bool stat_source(const char* path, uint64_t* size, int64_t* mtime_ns) {
+  struct stat st;
+  if (!path || stat(path, &st) != 0) return false;
+  *size = (uint64_t)st.st_size;
+  *mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+  return true;
+}
+
+// ---- streaming writer: begin → append_rows* → finish ------------------------------------------------------------
+struct cache_writer {
+  FILE* f = nullptr;
+  std::string path, tmp;
+  rag_cache_header h;
+  uint64_t written = 0;        // rows so far
+  uint64_t in_block = 0, block_sum = kFnvBasis;
+  std::vector<uint64_t> blocks;
+
+  ~cache_writer() {
+    if (f) { fclose(f); remove(tmp.c_str()); }
+  }
+  int begin(const char* p, uint32_t dtype, uint32_t dim, uint64_t rows) {
+    path = p;
+    tmp = path + ".tmp";
+    f = fopen(tmp.c_str(), "wb");
+    if (!f) return rag_set_error(RAG_ERR_INVALID, "cannot create %s: %s", tmp.c_str(), strerror(errno));
+    memset(&h, 0, sizeof(h));
+    h.version = kVersion;
+    h.dtype = dtype;
+    h.dim = dim;
+    h.rows = rows;
+    h.block_rows = kBlockRows;
+    char zero[sizeof(rag_cache_header)] = {0};  // the real header goes in last
+    return put(zero, sizeof(zero));
+  }
+  int put(const void* p, size_t n) {
+    if (n && fwrite(p, 1, n, f) != n) return rag_set_error(RAG_ERR_INVALID, "write to %s failed: %s", tmp.c_str(), strerror(errno));
+    return RAG_OK;
+  }
+  int put_padded(const void* p, size_t n, uint64_t* sum) {
+    static const char zeros[16] = {0};
+    RAG_CHECK(put(p, n));
+    if (sum) *sum = fnv64(*sum, p, n);
+    return put(zeros, pad16(n) - n);
+  }
+  int append_rows(const void* rows, uint64_t n) {
+    if (written + n > h.rows) return rag_set_error(RAG_ERR_INVALID, "cache writer: more rows than announced");
+    const size_t rb = (size_t)h.dim * esize(h.dtype);
+    const char* p = (const char*)rows;
+    RAG_CHECK(put(p, (size_t)n * rb));
+    while (n) {
+      const uint64_t take = std::min<uint64_t>(n, h.block_rows - in_block);
+      block_sum = fnv64(block_sum, p, (size_t)take * rb);
+      p += (size_t)take * rb;
+      n -= take;
+      written += take;
+      if ((in_block += take) == h.block_rows) { blocks.push_back(block_sum); block_sum = kFnvBasis; in_block = 0; }
+    }
+    return RAG_OK;
+  }
+  int finish(const uint8_t* ct, const double* conf, const int32_t* acc, const int64_t* last, const uint64_t* keys,
+             const char* ids, uint64_t ids_bytes, const char* source_json) {
+    if (written != h.rows) return rag_set_error(RAG_ERR_INVALID, "cache writer: %llu of %llu rows written",
+                                                (unsigned long long)written, (unsigned long long)h.rows);
+    if (in_block) blocks.push_back(block_sum);
+    static const char zeros[16] = {0};
+    const size_t rows_bytes = (size_t)h.rows * h.dim * esize(h.dtype);
+    RAG_CHECK(put(zeros, pad16(rows_bytes) - rows_bytes));
+    const bool meta = ct && conf && acc && last;
+    h.flags = (meta ? RAG_CACHE_META : 0u) | (keys ? RAG_CACHE_KEYS : 0u);
+    h.ids_bytes = ids ? ids_bytes : 0;
+    uint64_t sum = kFnvBasis;
+    RAG_CHECK(put_padded(blocks.data(), blocks.size() * 8, &sum));
+    if (meta) {
+      RAG_CHECK(put_padded(ct, h.rows, &sum));
+      RAG_CHECK(put_padded(conf, h.rows * 8, &sum));
+      RAG_CHECK(put_padded(acc, h.rows * 4, &sum));
+      RAG_CHECK(put_padded(last, h.rows * 8, &sum));
+    }
+    if (keys) RAG_CHECK(put_padded(keys, h.rows * 8, &sum));
+    RAG_CHECK(put_padded(ids, h.ids_bytes, &sum));
+    h.tail_sum = sum;
+    if (source_json && !stat_source(source_json, &h.source_size, &h.source_mtime_ns))
+      return rag_set_error(RAG_ERR_INVALID, "cannot stat %s: %s", source_json, strerror(errno));
+    memcpy(h.magic, kMagic, 8);
+    h.head_sum = fnv64(kFnvBasis, &h, offsetof(rag_cache_header, head_sum));
+    if (fseek(f, 0, SEEK_SET) != 0) return rag_set_error(RAG_ERR_INVALID, "seek in %s failed", tmp.c_str());
+    RAG_CHECK(put(&h, sizeof(h)));
+    if (fflush(f) != 0 || fclose(f) != 0) { f = nullptr; remove(tmp.c_str()); return rag_set_error(RAG_ERR_INVALID, "closing %s failed: %s", tmp.c_str(), strerror(errno)); }
+    f = nullptr;
+    if (rename(tmp.c_str(), path.c_str()) != 0) {
+      remove(tmp.c_str());
+      return rag_set_error(RAG_ERR_INVALID, "rename %s -> %s failed: %s", tmp.c_str(), path.c_str(), strerror(errno));
+    }
+    return RAG_OK;
+  }
+};
+
+// ---- reader ------------------------------------------------------------------------------------------------------
+struct cache_reader {
+  FILE* f = nullptr;
+  std::string path;
+  rag_cache_header h;
+  sections s;
+  std::vector<uint64_t> blocks;
+  std::vector<char> tail;  // blocks..ids, verified against tail_sum
+
+  ~cache_reader() { if (f) fclose(f); }
+  int bad(const char* what) { return rag_set_error(RAG_ERR_INVALID, "%s: %s", path.c_str(), what); }
+  int read_at(uint64_t off, void* dst, size_t n) {
+    if (n == 0) return RAG_OK;
+    if (fseeko(f, (off_t)off, SEEK_SET) != 0 || fread(dst, 1, n, f) != n) return bad("short read (truncated cache)");
+    return RAG_OK;
+  }
+  int open(const char* p, bool want_tail) {
+    path = p ? p : "";
+    if (!p) return rag_set_error(RAG_ERR_INVALID, "null cache path");
+    f = fopen(p, "rb");
+    if (!f) return rag_set_error(RAG_ERR_INVALID, "cannot open %s: %s", p, strerror(errno));
+    if (fread(&h, 1, sizeof(h), f) != sizeof(h)) return bad("not a ragera cache (too short)");
+    if (memcmp(h.magic, kMagic, 8) != 0) return bad("not a ragera cache (bad magic)");
+    if (h.head_sum != fnv64(kFnvBasis, &h, offsetof(rag_cache_header, head_sum))) return bad("header checksum mismatch");
+    if (h.version != kVersion) return bad("unsupported cache version");
+    if ((h.dtype != RAG_F32 && h.dtype != RAG_BF16) || h.dim == 0 || h.dim > 8192 || h.block_rows == 0) return bad("bad header fields");
+    s = layout(h);
+    struct stat st;
+    if (fstat(fileno(f), &st) != 0 || (uint64_t)st.st_size != s.end) return bad("file size does not match the header (truncated cache)");
+    if (!want_tail) return RAG_OK;
+    tail.resize((size_t)(s.end - s.blocks_off));
+    RAG_CHECK(read_at(s.blocks_off, tail.data(), tail.size()));
+    // the checksum runs over the unpadded sections, in file order
+    uint64_t sum = kFnvBasis;
+    auto sec = [&](uint64_t off, uint64_t n) { sum = fnv64(sum, tail.data() + (off - s.blocks_off), (size_t)n); };
+    sec(s.blocks_off, s.nblocks * 8);
+    if (h.flags & RAG_CACHE_META) { sec(s.ct_off, h.rows); sec(s.conf_off, h.rows * 8); sec(s.acc_off, h.rows * 4); sec(s.last_off, h.rows * 8); }
+    if (h.flags & RAG_CACHE_KEYS) sec(s.keys_off, h.rows * 8);
+    sec(s.ids_off, h.ids_bytes);
+    if (sum != h.tail_sum) return bad("metadata checksum mismatch");
+    blocks.resize((size_t)s.nblocks);
+    memcpy(blocks.data(), tail.data(), blocks.size() * 8);
+    return RAG_OK;
+  }
+  const char* at(uint64_t off) const { return tail.data() + (off - s.blocks_off); }
+  // rows [first, first+n) through on_rows in slabs of whole blocks; every touched block is verified
+  template <typename F>
+  int rows(uint64_t first, uint64_t n, void* slab, uint64_t slab_rows, F&& on_rows) {
+    if (first + n > h.rows) return bad("row range exceeds the cache");
+    if (n == 0) return RAG_OK;
+    const size_t rb = (size_t)h.dim * esize(h.dtype);
+    const uint64_t b0 = first / h.block_rows, b1 = (first + n - 1) / h.block_rows;
+    const uint64_t per_slab = std::max<uint64_t>(1, slab_rows / h.block_rows);
+    for (uint64_t b = b0; b <= b1; b += per_slab) {
+      const uint64_t be = std::min(b1 + 1, b + per_slab);
+      const uint64_t r0 = b * h.block_rows, r1 = std::min<uint64_t>(h.rows, be * h.block_rows);
+      RAG_CHECK(read_at(s.rows_off + r0 * rb, slab, (size_t)(r1 - r0) * rb));
+      for (uint64_t k = b; k < be; k++) {
+        const uint64_t k0 = k * h.block_rows, k1 = std::min<uint64_t>(h.rows, k0 + h.block_rows);
+        if (fnv64(kFnvBasis, (const char*)slab + (size_t)(k0 - r0) * rb, (size_t)(k1 - k0) * rb) != blocks[(size_t)k])
+          return rag_set_error(RAG_ERR_INVALID, "%s: rows %llu..%llu are corrupt (block checksum mismatch)", path.c_str(),
+                               (unsigned long long)k0, (unsigned long long)k1);
+      }
+      const uint64_t u0 = std::max(first, r0), u1 = std::min(first + n, r1);
+      RAG_CHECK(on_rows(u0, u1 - u0, (const char*)slab + (size_t)(u0 - r0) * rb));
+    }
+    return RAG_OK;
+  }
+};
+
+int copy_ids(const cache_reader& r, char** ids, uint64_t* ids_bytes) {
+  if (!ids) return RAG_OK;
+  char* blob = (char*)malloc(r.h.ids_bytes ? (size_t)r.h.ids_bytes : 1);
+  if (!blob) return rag_set_error(RAG_ERR_NOMEM, "out of host memory");
+  memcpy(blob, r.at(r.s.ids_off), (size_t)r.h.ids_bytes);
+  *ids = blob;
+  if (ids_bytes) *ids_bytes = r.h.ids_bytes;
+  return RAG_OK;
+}
+
+void fill_info(const rag_cache_header& h, rag_cache_info* out) {
+  out->version = h.version;
+  out->dtype = h.dtype;
+  out->dim = h.dim;
+  out->flags = h.flags;
+  out->rows = h.rows;
+  out->ids_bytes = h.ids_bytes;
+  out->source_size = h.source_size;
+  out->source_mtime_ns = h.source_mtime_ns;
+}
+
+}  // namespace
+
+extern "C" {
+
+// header of a sidecar (validated: magic, header checksum, version, file size)
+int rag_cache_info_read(const char* cache_path, rag_cache_info* out) {
+  if (!out) return rag_set_error(RAG_ERR_INVALID, "rag_cache_info_read: null out");
+  cache_reader r;
+  RAG_CHECK(r.open(cache_path, false));
+  fill_info(r.h, out);
+  return RAG_OK;
+}
+
+// 1 = the sidecar exists, is well formed and was made from `source_json` as it is now (same size and mtime);
+// 0 = missing, unreadable or stale — re-parse the JSON. Never an error.
+int rag_cache_is_fresh(const char* cache_path, const char* source_json) {
+  cache_reader r;
+  uint64_t size = 0;
+  int64_t mtime = 0;
+  if (r.open(cache_path, false) != RAG_OK) return 0;
+  if (!stat_source(source_json, &size, &mtime)) return 0;
+  return (r.h.source_size == size && r.h.source_mtime_ns == mtime) ? 1 : 0;
+}
+
+// write a sidecar from host arrays (rows in `dtype`, [rows][dim]); meta needs all four arrays or none
+int rag_cache_write_host(const char* cache_path, uint32_t dtype, uint32_t dim, uint64_t rows, const void* host_rows,
+                         const uint8_t* content_type, const double* confidence, const int32_t* access_count,
+                         const int64_t* last_access_ms, const uint64_t* keys, const char* ids, uint64_t ids_bytes,
+                         const char* source_json) {
+  if (!cache_path || (dtype != RAG_F32 && dtype != RAG_BF16) || dim == 0 || dim > 8192 || (rows && !host_rows))
+    return rag_set_error(RAG_ERR_INVALID, "rag_cache_write_host: bad argument");
+  const int nmeta = (content_type != nullptr) + (confidence != nullptr) + (access_count != nullptr) + (last_access_ms != nullptr);
+  if (nmeta != 0 && nmeta != 4) return rag_set_error(RAG_ERR_INVALID, "rag_cache_write_host: give all four metadata arrays or none");
+  cache_writer w;
+  RAG_CHECK(w.begin(cache_path, dtype, dim, rows));
+  RAG_CHECK(w.append_rows(host_rows, rows));
+  return w.finish(content_type, confidence, access_count, last_access_ms, keys, ids, ids_bytes, source_json);
+}
+
+// read a sidecar into host arrays (any pointer may be NULL; sizes from rag_cache_info_read). Verifies every checksum.
+int rag_cache_read_host(const char* cache_path, uint64_t first_row, uint64_t nrows, void* host_rows, uint8_t* content_type,
+                        double* confidence, int32_t* access_count, int64_t* last_access_ms, uint64_t* keys, char** ids,
+                        uint64_t* ids_bytes) {
+  cache_reader r;
+  RAG_CHECK(r.open(cache_path, true));
+  if (first_row + nrows > r.h.rows) return r.bad("row range exceeds the cache");
+  const size_t rb = (size_t)r.h.dim * esize(r.h.dtype);
+  if (host_rows && nrows) {
+    const uint64_t slab_rows = std::min<uint64_t>((uint64_t)r.h.block_rows * 4, ((nrows + 2 * r.h.block_rows - 1) / r.h.block_rows) * r.h.block_rows);
+    std::unique_ptr<char[]> slab(new (std::nothrow) char[(size_t)slab_rows * rb]);  // uninitialised on purpose
+    if (!slab) return rag_set_error(RAG_ERR_NOMEM, "out of host memory");
+    RAG_CHECK(r.rows(first_row, nrows, slab.get(), slab_rows, [&](uint64_t r0, uint64_t n, const char* p) {
+      memcpy((char*)host_rows + (size_t)(r0 - first_row) * rb, p, (size_t)n * rb);
+      return (int)RAG_OK;
+    }));
+  }
+  if ((content_type || confidence || access_count || last_access_ms) && !(r.h.flags & RAG_CACHE_META))
+    return r.bad("the cache holds no row metadata");
+  if (keys && !(r.h.flags & RAG_CACHE_KEYS)) return r.bad("the cache holds no fusion keys");
+  if (content_type) memcpy(content_type, r.at(r.s.ct_off) + first_row, (size_t)nrows);
+  if (confidence) memcpy(confidence, r.at(r.s.conf_off) + first_row * 8, (size_t)nrows * 8);
+  if (access_count) memcpy(access_count, r.at(r.s.acc_off) + first_row * 4, (size_t)nrows * 4);
+  if (last_access_ms) memcpy(last_access_ms, r.at(r.s.last_off) + first_row * 8, (size_t)nrows * 8);
+  if (keys) memcpy(keys, r.at(r.s.keys_off) + first_row * 8, (size_t)nrows * 8);
+  return copy_ids(r, ids, ids_bytes);
+}
+
+// ---- device side -------------------------------------------------------------------------------------------------
+
+// write rows [0, rows) of this handle (its shard), their metadata / fusion keys if set, and the caller's node ids
+int rag_index_save_cache(rag_index* idx, const char* cache_path, const char* ids, uint64_t ids_bytes, const char* source_json) {
+  if (!idx || !cache_path) return rag_set_error(RAG_ERR_INVALID, "rag_index_save_cache: null argument");
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const uint64_t rows = idx->rows;
+  const size_t rb = (size_t)idx->dim * (idx->desc.dtype == RAG_BF16 ? 2 : 4);
+  cache_writer w;
+  RAG_CHECK(w.begin(cache_path, idx->desc.dtype, idx->dim, rows));
+  const uint64_t slab_rows = 4 * kBlockRows;
+  void* slab = nullptr;
+  RAG_CUDA(cudaHostAlloc(&slab, (size_t)slab_rows * rb, cudaHostAllocDefault));
+  int rc = RAG_OK;
+  for (uint64_t r = 0; r < rows && rc == RAG_OK; r += slab_rows) {
+    const uint64_t n = std::min(slab_rows, rows - r);
+    if ((rc = rag_index_read_rows(idx, r, n, slab)) == RAG_OK) rc = w.append_rows(slab, n);
+  }
+  cudaFreeHost(slab);
+  RAG_CHECK(rc);
+  std::vector<uint8_t> ct;
+  std::vector<double> conf;
+  std::vector<int32_t> acc;
+  std::vector<int64_t> last;
+  std::vector<uint64_t> keys;
+  if (idx->ctype && rows) {
+    ct.resize(rows); conf.resize(rows); acc.resize(rows); last.resize(rows);
+    RAG_CUDA(cudaMemcpyAsync(ct.data(), idx->ctype, rows, cudaMemcpyDeviceToHost, idx->stream));
+    RAG_CUDA(cudaMemcpyAsync(conf.data(), idx->conf, rows * 8, cudaMemcpyDeviceToHost, idx->stream));
+    RAG_CUDA(cudaMemcpyAsync(acc.data(), idx->access, rows * 4, cudaMemcpyDeviceToHost, idx->stream));
+    RAG_CUDA(cudaMemcpyAsync(last.data(), idx->last_ms, rows * 8, cudaMemcpyDeviceToHost, idx->stream));
+  }
+  if (idx->row_keys && rows) {
+    keys.resize(rows);
+    RAG_CUDA(cudaMemcpyAsync(keys.data(), idx->row_keys, rows * 8, cudaMemcpyDeviceToHost, idx->stream));
+  }
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  const bool meta = !ct.empty();
+  return w.finish(meta ? ct.data() : nullptr, meta ? conf.data() : nullptr, meta ? acc.data() : nullptr,
+                  meta ? last.data() : nullptr, keys.empty() ? nullptr : keys.data(), ids, ids_bytes, source_json);
+}
+
+// append rows [first_row, first_row + nrows) of the sidecar (nrows = 0: to its end) after the handle's rows, with
+// their metadata and keys. A shard passes its own range (rag_era_b200.sharded.shard_range); ids come back whole.
+int rag_index_load_cache(rag_index* idx, const char* cache_path, uint64_t first_row, uint64_t nrows, uint64_t* rows_loaded,
+                         char** ids, uint64_t* ids_bytes) {
+  if (!idx) return rag_set_error(RAG_ERR_INVALID, "null index handle");
+  cache_reader r;
+  RAG_CHECK(r.open(cache_path, true));
+  if (r.h.dtype != idx->desc.dtype || r.h.dim != idx->dim)
+    return rag_set_error(RAG_ERR_INVALID, "%s holds %s rows of dim %u; the index is %s, dim %u", cache_path,
+                         r.h.dtype == RAG_BF16 ? "bf16" : "f32", r.h.dim, idx->desc.dtype == RAG_BF16 ? "bf16" : "f32", idx->dim);
+  if (first_row > r.h.rows) return r.bad("first_row is past the end of the cache");
+  if (nrows == 0) nrows = r.h.rows - first_row;
+  if (first_row + nrows > r.h.rows) return r.bad("row range exceeds the cache");
+  const uint64_t row0 = idx->rows;
+  if (row0 + nrows > idx->desc.capacity_rows)
+    return rag_set_error(RAG_ERR_INVALID, "rag_index_load_cache: %llu rows exceed capacity %llu",
+                         (unsigned long long)(row0 + nrows), (unsigned long long)idx->desc.capacity_rows);
+  RAG_CUDA(cudaSetDevice(idx->device));
+  const size_t rb = (size_t)r.h.dim * esize(r.h.dtype);
+  const uint64_t slab_rows = 4 * kBlockRows;
+  void* slab = nullptr;
+  RAG_CUDA(cudaHostAlloc(&slab, (size_t)slab_rows * rb, cudaHostAllocDefault));
+  const int rc = r.rows(first_row, nrows, slab, slab_rows, [&](uint64_t r0, uint64_t n, const char* p) {
+    return rag_index_upload(idx, row0 + (r0 - first_row), n, p);  // synchronous: the slab is free again on return
+  });
+  cudaFreeHost(slab);
+  RAG_CHECK(rc);
+  if ((r.h.flags & RAG_CACHE_META) && nrows)
+    RAG_CHECK(rag_index_set_row_meta(idx, row0, nrows, (const uint8_t*)r.at(r.s.ct_off) + first_row,
+                                     (const double*)r.at(r.s.conf_off) + first_row, (const int32_t*)r.at(r.s.acc_off) + first_row,
+                                     (const int64_t*)r.at(r.s.last_off) + first_row));
+  if ((r.h.flags & RAG_CACHE_KEYS) && nrows)
+    RAG_CHECK(rag_index_set_row_keys(idx, row0, nrows, (const uint64_t*)r.at(r.s.keys_off) + first_row));
+  if (rows_loaded) *rows_loaded = nrows;
+  return copy_ids(r, ids, ids_bytes);
+}
+
+// loadIndex (src/lib/llm/index-manager.ts:246-275) for an EMPTY handle: stream the sidecar if it is fresh, else parse
+// the JSON and (re)write the sidecar. cache_path NULL → "<vector_store_json>.ragera". *from_cache reports which.
+// A failure to WRITE the sidecar (read-only storage) is not an error: the index is loaded either way.
+int rag_index_open_store(rag_index* idx, const char* vector_store_json, const char* cache_path, uint64_t* rows_loaded,
+                         char** ids, uint64_t* ids_bytes, int* from_cache) {
+  if (!idx || !vector_store_json) return rag_set_error(RAG_ERR_INVALID, "rag_index_open_store: null argument");
+  if (idx->rows != 0) return rag_set_error(RAG_ERR_STATE, "rag_index_open_store needs an empty index (rows=%llu)", (unsigned long long)idx->rows);
+  const std::string cp = cache_path ? std::string(cache_path) : std::string(vector_store_json) + ".ragera";
+  if (from_cache) *from_cache = 0;
+  if (rag_cache_is_fresh(cp.c_str(), vector_store_json)) {
+    rag_cache_info info;
+    if (rag_cache_info_read(cp.c_str(), &info) == RAG_OK && info.dtype == idx->desc.dtype && info.dim == idx->dim) {
+      const int rc = rag_index_load_cache(idx, cp.c_str(), 0, 0, rows_loaded, ids, ids_bytes);
+      if (rc == RAG_OK) { if (from_cache) *from_cache = 1; return RAG_OK; }
+      if (idx->rows != 0) return rc;  // corrupt half-way: the handle already holds rows, the caller must start over
+    }
+  }
+  char* blob = nullptr;
+  uint64_t nbytes = 0, n = 0;
+  RAG_CHECK(rag_index_load_vector_store(idx, vector_store_json, &n, &blob, &nbytes));
+  (void)rag_index_save_cache(idx, cp.c_str(), blob, nbytes, vector_store_json);  // best effort
+  if (rows_loaded) *rows_loaded = n;
+  if (ids) { *ids = blob; if (ids_bytes) *ids_bytes = nbytes; }
+  else free(blob);
+  return RAG_OK;
+}
+
+}  // extern "C"

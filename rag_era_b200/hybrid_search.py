@@ -135,10 +135,11 @@ class KnowledgeIndex:
 
 
 def classify_content_type(metadata: dict, is_codebase: bool) -> str:
-    """hybrid-search.ts:229-234."""
+    """hybrid-search.ts:229-234. ``metadata.language !== undefined``: a present key counts even when its value is
+    null or '' (JSON cannot hold undefined, so presence is the test)."""
     if (metadata or {}).get("type") == "memory":
         return "memory"
-    if is_codebase or (metadata or {}).get("language") is not None:
+    if is_codebase or "language" in (metadata or {}):
         return "code"
     return "document"
 

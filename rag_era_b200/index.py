@@ -148,6 +148,27 @@ class VectorIndex:
         self._lib.rag_free(blob)
         return ids
 
+    def save_cache(self, cache_path: str, ids=None, source_json: str | None = None):
+        """Write the binary sidecar of this handle's rows (+ row metadata / fusion keys if set)."""
+        blob = N._ids_blob(ids) if ids is not None else None
+        N.check(self._lib.rag_index_save_cache(self._h, cache_path.encode(), blob, len(blob) if blob else 0,
+                                               source_json.encode() if source_json else None))
+
+    def load_cache(self, cache_path: str, first_row: int = 0, nrows: int = 0) -> list:
+        """Append rows [first_row, first_row+nrows) of a sidecar (nrows=0: to its end); returns ALL node ids of the file."""
+        rows, blob, nbytes = C.c_uint64(0), C.c_void_p(), C.c_uint64(0)
+        N.check(self._lib.rag_index_load_cache(self._h, cache_path.encode(), first_row, nrows, C.byref(rows), C.byref(blob),
+                                               C.byref(nbytes)))
+        return N._split_blob(blob, nbytes.value)
+
+    def open_store(self, vector_store_json: str, cache_path: str | None = None):
+        """loadIndex (index-manager.ts:246-275) for an empty handle: the sidecar when it is fresh, else the JSON
+        (and the sidecar is rewritten). Returns (node ids, from_cache)."""
+        rows, blob, nbytes, hit = C.c_uint64(0), C.c_void_p(), C.c_uint64(0), C.c_int(0)
+        N.check(self._lib.rag_index_open_store(self._h, vector_store_json.encode(), cache_path.encode() if cache_path else None,
+                                               C.byref(rows), C.byref(blob), C.byref(nbytes), C.byref(hit)))
+        return N._split_blob(blob, nbytes.value), bool(hit.value)
+
     def generate(self, gen: N.GenDesc, nrows: int):
         N.check(self._lib.rag_index_generate(self._h, C.byref(gen), nrows))
 
@@ -162,6 +183,14 @@ class VectorIndex:
     def set_row_keys(self, row0: int, keys):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         N.check(self._lib.rag_index_set_row_keys(self._h, row0, len(keys), _ptr(keys)))
+
+    def read_row_meta(self, row0: int, nrows: int) -> dict:
+        """content_type / confidence / access_count / last_access_ms / keys of rows [row0, row0+nrows)."""
+        out = dict(content_type=np.empty(nrows, np.uint8), confidence=np.empty(nrows, np.float64),
+                   access_count=np.empty(nrows, np.int32), last_access_ms=np.empty(nrows, np.int64),
+                   keys=np.empty(nrows, np.uint64))
+        N.check(self._lib.rag_index_read_row_meta(self._h, row0, nrows, *[_ptr(a) for a in out.values()]))
+        return out
 
     def read_rows(self, row0: int, nrows: int) -> np.ndarray:
         out = np.empty((nrows, self.dim), dtype=self._np_dtype())

@@ -37,6 +37,9 @@ def test_content_type_rule():
     assert hs.classify_content_type({"language": "ts"}, False) == "code"
     assert hs.classify_content_type({}, True) == "code"
     assert hs.classify_content_type({}, False) == "document"
+    # `metadata.language !== undefined` (hybrid-search.ts:230): null and '' are not undefined
+    assert hs.classify_content_type({"language": None}, False) == "code"
+    assert hs.classify_content_type({"language": ""}, False) == "code"
 
 
 def test_format_and_stats():

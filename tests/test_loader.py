@@ -76,3 +76,176 @@ def test_load_vector_store_into_index(native, oracle, tmp_path):
     with rb.VectorIndex(dim, n, dtype=native.BF16) as idx:     # a bf16 index narrows with RNE
         idx.load_vector_store(p)
         assert np.array_equal(idx.read_rows(0, n), oracle.f32_to_bf16(X))
+
+
+# ---- metadataDict (contentType rule of hybrid-search.ts:229-234) and the binary sidecar ---------------------------
+def write_store_with_metadata(path, ids, X, shuffle_meta=False):
+    """metadataDict as SimpleVectorStore.add writes it: flat node metadata per id, after embeddingDict."""
+    meta = {}
+    for k, i in enumerate(ids):
+        m = {"_node_type": "TextNode", "document_id": "doc-" + i, "nested": {"type": "memory", "x": [1, "]}"]}}
+        if k % 5 == 0:
+            m.update(type="memory", memoryId=f"mem-{k}", memoryType="preference")
+        elif k % 5 == 1:
+            m["language"] = "typescript"
+        elif k % 5 == 2:
+            m["language"] = ""            # `!== undefined` → still code
+        elif k % 5 == 3:
+            m.update(type="note", memoryId=7)
+        meta[i] = m
+    if shuffle_meta:
+        order = list(meta)
+        np.random.default_rng(0).shuffle(order)
+        meta = {i: meta[i] for i in order}
+        del meta[ids[4]]                   # a node without an entry is a document
+    with open(path, "w") as f:
+        json.dump({"embeddingDict": {i: [float(v) for v in row] for i, row in zip(ids, X)}, "textIdToRefDocId": {},
+                   "metadataDict": meta}, f)
+
+
+def expected_ctype(native, n):
+    ct = np.full(n, native.CT_DOCUMENT, np.uint8)
+    ct[0::5] = native.CT_MEMORY
+    ct[1::5] = native.CT_CODE
+    ct[2::5] = native.CT_CODE
+    return ct
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_parse_vector_store_metadata(native, tmp_path, shuffle):
+    rng = np.random.default_rng(3)
+    n, dim = 103, 8
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = [f"node-{k:03d}" for k in range(n)]
+    p = str(tmp_path / "vector_store.json")
+    write_store_with_metadata(p, ids, X, shuffle_meta=shuffle)
+    ct, mem, found = native.parse_vector_store_metadata(p, ids)
+    assert found
+    assert np.array_equal(ct, expected_ctype(native, n))
+    assert mem == [f"mem-{k}" if k % 5 == 0 else "" for k in range(n)]
+    # a store without metadataDict: every row a document
+    with open(p, "w") as f:
+        json.dump({"embeddingDict": {i: [0.0] * dim for i in ids}}, f)
+    ct, mem, found = native.parse_vector_store_metadata(p, ids)
+    assert not found and not ct.any() and mem == [""] * n
+
+
+def make_cache_inputs(n, dim, seed=5):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = [f"id-{k}-{'x' * (k % 7)}" for k in range(n)]
+    meta = (rng.integers(0, 3, n).astype(np.uint8), rng.random(n), rng.integers(0, 50, n).astype(np.int32),
+            rng.integers(1_700_000_000_000, 1_800_000_000_000, n).astype(np.int64))
+    keys = rng.integers(0, 2**63, n).astype(np.uint64)
+    return X, ids, meta, keys
+
+
+@pytest.mark.parametrize("n,dim", [(0, 16), (1, 3), (4096, 16), (4097, 24), (10000, 100)])
+def test_cache_round_trip_on_the_host(native, tmp_path, n, dim):
+    X, ids, meta, keys = make_cache_inputs(n, dim)
+    p = str(tmp_path / "kb.ragera")
+    native.cache_write_host(p, X, ids=ids, meta=meta, keys=keys)
+    info = native.cache_info(p)
+    assert (info.rows, info.dim, info.dtype, info.flags) == (n, dim, native.F32, native.CACHE_META | native.CACHE_KEYS)
+    assert not os.path.exists(p + ".tmp")
+    got = native.cache_read_host(p)
+    assert np.array_equal(got["rows"], X) and got["ids"] == ids and np.array_equal(got["keys"], keys)
+    for a, b in zip((got["content_type"], got["confidence"], got["access_count"], got["last_access_ms"]), meta):
+        assert np.array_equal(a, b)
+    if n > 4096:                                              # a shard's row range crosses a checksum block
+        part = native.cache_read_host(p, first_row=4000, nrows=n - 4000 - 1)
+        assert np.array_equal(part["rows"], X[4000:n - 1]) and np.array_equal(part["keys"], keys[4000:n - 1])
+        assert part["ids"] == ids                             # ids come back whole
+    # rows only (no metadata, keys, ids), bf16 bits
+    bits = (X.view(np.uint32) >> 16).astype(np.uint16)
+    native.cache_write_host(p, bits, dtype=native.BF16)
+    got = native.cache_read_host(p)
+    assert got["info"].dtype == native.BF16 and got["info"].flags == 0 and got["ids"] == []
+    assert np.array_equal(got["rows"], bits) and got["content_type"] is None and got["keys"] is None
+
+
+def test_cache_detects_corruption_and_staleness(native, tmp_path):
+    n, dim = 9000, 32
+    X, ids, meta, keys = make_cache_inputs(n, dim, seed=6)
+    src = str(tmp_path / "vector_store.json")
+    open(src, "w").write("{}")
+    p = str(tmp_path / "kb.ragera")
+    native.cache_write_host(p, X, ids=ids, meta=meta, keys=keys, source_json=src)
+    assert native.cache_is_fresh(p, src)
+    good = open(p, "rb").read()
+
+    def corrupt(offset, what):
+        b = bytearray(good)
+        b[offset] ^= 0x40
+        open(p, "wb").write(bytes(b))
+        with pytest.raises(native.RagError) as e:
+            native.cache_read_host(p)
+        assert what in str(e.value), str(e.value)
+
+    corrupt(3, "bad magic")
+    corrupt(40, "header checksum")
+    corrupt(128 + 5000 * dim * 4 + 7, "rows 4096..8192 are corrupt")       # one flipped bit in row 5000
+    corrupt(len(good) - 20, "metadata checksum")
+    open(p, "wb").write(good[:-16])
+    with pytest.raises(native.RagError) as e:
+        native.cache_info(p)
+    assert "truncated" in str(e.value)
+    assert not native.cache_is_fresh(p, src)                                # malformed → not fresh, never an error
+    # a row range that avoids the corrupt block still loads (per-block checksums)
+    b = bytearray(good)
+    b[128 + 5000 * dim * 4 + 7] ^= 0x40
+    open(p, "wb").write(bytes(b))
+    part = native.cache_read_host(p, first_row=8192, nrows=n - 8192)
+    assert np.array_equal(part["rows"], X[8192:])
+    # staleness: the JSON grew (index.insert) or was rewritten
+    open(p, "wb").write(good)
+    assert native.cache_is_fresh(p, src)
+    open(src, "a").write(" ")
+    assert not native.cache_is_fresh(p, src)
+    assert not native.cache_is_fresh(str(tmp_path / "missing.ragera"), src)
+    with pytest.raises(native.RagError):
+        native.cache_write_host(str(tmp_path / "no_such_dir" / "x.ragera"), X)
+
+
+@pytest.mark.gpu
+def test_open_store_through_the_sidecar(native, oracle, tmp_path):
+    import rag_era_b200 as rb
+
+    rng = np.random.default_rng(7)
+    n, dim = 5000, 128
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = [f"node-{k:04d}" for k in range(n)]
+    src = str(tmp_path / "vector_store.json")
+    write_store_with_metadata(src, ids, X)
+    q = (X[321] + 0.1 * rng.standard_normal(dim)).astype(np.float32)
+    ei, es = oracle.topk(X, q, 8)
+    with rb.VectorIndex(dim, n) as idx:                                    # cold: parses the JSON, writes the sidecar
+        got, hit = idx.open_store(src)
+        assert got == ids and not hit and idx.rows == n
+        assert np.array_equal(idx.read_row_meta(0, n)["content_type"], expected_ctype(native, n))
+        keys = np.arange(n, dtype=np.uint64)[::-1].copy()
+        idx.set_row_keys(0, keys)
+        idx.set_row_meta(0, expected_ctype(native, n), rng.random(n), np.arange(n, dtype=np.int32), np.full(n, 1_700_000_000_000, np.int64))
+        want_meta = idx.read_row_meta(0, n)
+        idx.save_cache(src + ".ragera", ids=ids, source_json=src)           # now with Memory columns and fusion keys
+    assert native.cache_is_fresh(src + ".ragera", src)
+    with rb.VectorIndex(dim, n) as idx:                                    # warm: binary rows straight to HBM
+        got, hit = idx.open_store(src)
+        assert got == ids and hit and idx.rows == n
+        assert np.array_equal(idx.read_rows(0, n), X)
+        for k, v in idx.read_row_meta(0, n).items():
+            assert np.array_equal(v, want_meta[k]), k
+        gi, gs = idx.query(q, 8).row(0)
+        assert np.array_equal(gi, ei) and np.array_equal(gs, es)
+    with rb.VectorIndex(dim, 3000, id_base=1000) as idx:                   # a shard loads only its own row range
+        idx.load_cache(src + ".ragera", first_row=1000, nrows=3000)
+        assert idx.rows == 3000 and np.array_equal(idx.read_rows(0, 3000), X[1000:4000])
+        assert np.array_equal(idx.read_row_meta(0, 3000)["keys"], want_meta["keys"][1000:4000])
+    with rb.VectorIndex(dim, n, dtype=native.BF16) as idx:                 # dtype mismatch: the sidecar is ignored
+        got, hit = idx.open_store(src, cache_path=src + ".ragera")
+        assert not hit and np.array_equal(idx.read_rows(0, n), oracle.f32_to_bf16(X))
+    open(src, "a").write("\n")                                             # the JSON changed: stale sidecar
+    with rb.VectorIndex(dim, n) as idx:
+        got, hit = idx.open_store(src)
+        assert got == ids and not hit
+    assert native.cache_is_fresh(src + ".ragera", src)                     # ... and it was rewritten
