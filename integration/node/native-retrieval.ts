@@ -89,6 +89,9 @@ export async function hybridSearchNative(index: NativeKnowledgeIndex, knowledgeB
   const useKeyword = options.useKeyword ?? true;
   const minVectorScore = options.minVectorScore ?? presetConfig.minVectorScore;
   const rrf: RRFConfig = { ...presetConfig.rrf, ...options.rrfConfig };          // :292-295
+  // :296 — per-call flag: every non-memory VECTOR hit of a codebase search is 'code' (:229-234)
+  const isCodebase = (options.preset || 'document') === 'code' || knowledgeBaseId.startsWith('codebase_');
+  const ctypeOf = (c: number) => (isCodebase && CTYPE[c] === 'document' ? 'code' : CTYPE[c]);
 
   const [q, hits] = await Promise.all([
     index.embedQuery(query),                                                      // network, as today
@@ -113,13 +116,13 @@ export async function hybridSearchNative(index: NativeKnowledgeIndex, knowledgeB
     if (!r.usedRrf[0]) {                                                          // vector-only branch :346-354
       const n = index.nodes[Number(r.keys[i])];
       out.push({ id: n.id, documentName: docName(n.metadata), content: n.text, score: r.scores[i], source: 'vector',
-                 contentType: CTYPE[r.contentType[i]], metadata: n.metadata });
+                 contentType: ctypeOf(r.contentType[i]), metadata: n.metadata });
       continue;
     }
     const e = first.get(r.keys[i])!;
     if (e.n) {
       out.push({ id: index.keyString(r.keys[i]), documentName: docName(e.n.metadata), content: e.n.text, score: r.scores[i],
-                 source: SOURCE[r.source[i]], contentType: CTYPE[r.contentType[i]], metadata: e.n.metadata });
+                 source: SOURCE[r.source[i]], contentType: ctypeOf(r.contentType[i]), metadata: e.n.metadata });
     } else {
       out.push({ id: index.keyString(r.keys[i]), documentId: e.h!.documentId, documentName: e.h!.documentName, content: e.h!.content,
                  score: r.scores[i], source: SOURCE[r.source[i]], contentType: 'document' });

@@ -13,11 +13,13 @@ from .hybrid_search import (PRESET_CONFIGS, HybridSearchResult, KeywordHit, Know
                             get_preset_config, get_source_stats, hybrid_search, reciprocal_rank_fusion)
 from .memory import Memory, MemoryStore, ScoredMemory, batch_calculate_freshness, calculate_freshness_score
 from .sharded import create_sharded_index, shard_range
-from .context import FusedResult, process_results
+from .context import (FusedResult, RetrievalDecision, SearchResult, ToolContext, calculate_retrieval_count, deep_search,
+                      get_unified_results, process_results, search_knowledge)
 
 __all__ = [
     "RagError", "Batcher", "VectorIndex", "RRFConfig", "TopK", "Fused", "hybrid_opts", "PRESET_CONFIGS", "HybridSearchResult",
     "KeywordHit", "KnowledgeIndex", "Node", "format_search_results", "get_preset_config", "get_source_stats",
     "hybrid_search", "reciprocal_rank_fusion", "Memory", "MemoryStore", "ScoredMemory", "batch_calculate_freshness",
-    "calculate_freshness_score", "create_sharded_index", "shard_range", "FusedResult", "process_results",
+    "calculate_freshness_score", "create_sharded_index", "shard_range", "FusedResult", "process_results", "RetrievalDecision",
+    "SearchResult", "ToolContext", "calculate_retrieval_count", "deep_search", "get_unified_results", "search_knowledge",
 ]

@@ -192,6 +192,10 @@ def hybrid_search(index: KnowledgeIndex, knowledge_base_id: str, query, options:
     options = options or {}
     preset = options.get("preset") or "document"
     pc = PRESET_CONFIGS[preset]
+    # :296 — a per-call flag: every non-memory VECTOR hit of a codebase search is 'code' (:229-234); rows inserted with
+    # is_codebase or carrying metadata.language already read as code from the device
+    is_codebase = preset == "code" or knowledge_base_id.startswith("codebase_")
+    ctype_of = lambda ct: "code" if is_codebase and CONTENT_TYPE[int(ct)] == "document" else CONTENT_TYPE[int(ct)]
     opt = lambda name: options[name] if options.get(name) is not None else pc[name]
     vector_top_k, keyword_limit, min_vector_score = opt("vectorTopK"), opt("keywordLimit"), opt("minVectorScore")
     use_keyword = options["useKeyword"] if options.get("useKeyword") is not None else True
@@ -220,7 +224,7 @@ def hybrid_search(index: KnowledgeIndex, knowledge_base_id: str, query, options:
             md = node.metadata or {}
             out.append(HybridSearchResult(id=node.id_, documentName=_document_name(md, CONTENT_TYPE[int(ct)] == "memory"),
                                           content=node.text or "", score=score, source="vector",
-                                          contentType=CONTENT_TYPE[int(ct)], metadata=md))
+                                          contentType=ctype_of(ct), metadata=md))
         return out
 
     first: dict[int, tuple[str, Any]] = {}
@@ -236,7 +240,7 @@ def hybrid_search(index: KnowledgeIndex, knowledge_base_id: str, query, options:
             out.append(HybridSearchResult(id=index.keys.string(int(key)),
                                           documentName=_document_name(md, CONTENT_TYPE[int(ct)] == "memory"),
                                           content=r.text or "", score=float(score), source=SOURCE[int(src)],
-                                          contentType=CONTENT_TYPE[int(ct)], metadata=md))
+                                          contentType=ctype_of(ct), metadata=md))
         else:
             out.append(HybridSearchResult(id=index.keys.string(int(key)), documentName=r.documentName, content=r.content,
                                           score=float(score), source=SOURCE[int(src)], contentType="document",

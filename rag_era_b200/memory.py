@@ -29,6 +29,7 @@ class Memory:
     confidence: float
     accessCount: int
     lastAccessedAt: int  # epoch milliseconds (Date.getTime())
+    type: str = "context"  # MemoryType (types.ts:10-17); carried, never read by the hot path
 
 
 @dataclass

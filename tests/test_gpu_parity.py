@@ -375,9 +375,99 @@ def test_hybrid_search_host_mirror(rb, native, oracle):
         m.up = True
         res3 = hs.hybrid_search(index, "kb1", "alpha", dict(vectorTopK=5, keywordLimit=0, minVectorScore=0.0), keyword_service=m)
         assert [r.id for r in res3] == [r.id for r in res2]
+        # preset 'code' (hybrid-search.ts:98-104,296): RRF {40, 1, 1.3, 0.15}, vectorTopK 6, keywordLimit 5, min 0.25 — and
+        # every non-memory VECTOR hit reads as 'code'; keyword-only hits stay 'document' (:178-187), memories stay memories
+        res4 = hs.hybrid_search(index, "kb1", "alpha", dict(preset="code", minVectorScore=0.0), keyword_service=m)
+        ei6, _ = oracle.topk(E, vocab["alpha"], 6)
+        keys4 = hs.KeyInterner()
+        vk4 = [keys4.key(nodes[int(i)].text) for i in ei6]
+        kk4 = [keys4.key(t) for t in (nodes[10].text, "**alpha** raw text", nodes[11].text)]
+        ek4, esc4, esrc4, _ = oracle.rrf(vk4, kk4, oracle.RRFConfig(40.0, 1.0, 1.3, 0.15))
+        assert [r.id for r in res4] == [keys4.string(int(k)) for k in ek4] and [r.score for r in res4] == list(esc4)
+        vec_texts = {nodes[int(i)].text for i in ei6}
+        for r in res4:
+            want = "memory" if r.content == nodes[10].text else "code" if r.content in vec_texts else "document"
+            assert r.contentType == want, (r.content[:30], r.contentType, want)
+        res5 = hs.hybrid_search(index, "codebase_7", "alpha", dict(vectorTopK=5, minVectorScore=0.0), keyword_service=m)
+        assert [r.score for r in res5] == [r.score for r in res] and {r.contentType for r in res5} == {"memory", "code", "document"}
         # reciprocal_rank_fusion drop-in on result objects
         fused = hs.reciprocal_rank_fusion(res2, m.search("kb1", "alpha", 3), store=index.store)
         assert [r.score for r in fused] == [r.score for r in res]
+    finally:
+        index.close()
+
+
+def test_context_engine_and_search_tools_mirror(rb, native, oracle):
+    """The callers named by north_star — getUnifiedResults (engine.ts:225-299), search_knowledge / deep_search
+    (search-tools.ts:12-95) — against the oracle's top-k + RRF on the same inputs."""
+    hs = importlib.import_module("rag_era_b200.hybrid_search")
+    rng = np.random.default_rng(41)
+    d, n = 96, 600
+    centre = rng.standard_normal(d).astype(np.float32)
+    E = (centre + 0.9 * rng.standard_normal((n, d))).astype(np.float32)          # cosines to the query ~0.7: clear the 0.4 filter
+    nodes = [hs.Node(f"node-{i}", f"retrieval augmented generation chunk {i}: " + " ".join(f"w{(i * 7 + j) % 97}" for j in range(12)),
+                     dict(documentName=f"doc{i % 9}.md")) for i in range(n)]
+    for i in range(0, n, 6):
+        nodes[i].metadata = dict(type="memory", memoryId=f"mem-{i}", memoryType="preference")
+    index = hs.KnowledgeIndex(d, n, embed_model=lambda s: centre)
+    try:
+        index.insert_nodes(nodes, E)
+        vi29, _ = oracle.topk(E, centre, 29)
+
+        class Meili:
+            def is_available(self):
+                return True
+
+            def search(self, kb, query, limit):
+                hits = [hs.KeywordHit(f"h{j}", f"D{j}", f"doc{j}.md", nodes[int(vi29[2 * j + 1])].text) for j in range(4)]
+                hits.insert(2, hs.KeywordHit("hx", "DX", "other.md", "retrieval generation keyword-only hit with enough text"))
+                return hits[:limit]
+
+        def expect(top_k, kw_limit, min_score):
+            vi, vs = oracle.topk(E, centre, top_k)
+            keep = [(int(i), s) for i, s in zip(vi, vs) if s >= min_score]
+            keys = hs.KeyInterner()
+            vk = [keys.key(nodes[i].text) for i, _ in keep]
+            hits = Meili().search("kb", "q", kw_limit)
+            ek, esc, esrc, _ = oracle.rrf(vk, [keys.key(h.content) for h in hits])
+            return keys, keep, hits, [int(k) for k in ek], list(esc), [int(s) for s in esrc]
+
+        # --- ContextEngine.getUnifiedResults: default decision → hybridSearch(vectorTopK 18, keywordLimit 6, min 0.4)
+        got = rb.get_unified_results(index, "kb1", "retrieval generation", keyword_service=Meili(), now_ms=123)
+        keys, keep, hits, ek, esc, esrc = expect(18, 6, 0.4)
+        by_key = {}
+        for i, _ in keep:
+            by_key.setdefault(keys.key(nodes[i].text), nodes[i])
+        e_mem = [(k, s) for k, s in zip(ek, esc) if k in by_key and (by_key[k].metadata or {}).get("type") == "memory"]
+        e_doc = [(k, s, src) for k, s, src in zip(ek, esc, esrc) if not (k in by_key and (by_key[k].metadata or {}).get("type") == "memory")]
+        assert len(e_mem) >= 1 and len(e_doc) >= 5
+        assert [(m.id, m.score) for m in got["memories"]] == [(by_key[k].metadata["memoryId"], s) for k, s in e_mem][:10]
+        assert all(m.relevanceScore == m.score and m.freshnessScore == 0.5 and m.confidence == 0.8 and m.type == "preference"
+                   for m in got["memories"])
+        assert [(r.id, r.score) for r in got["raw_documents"]] == [(keys.string(k), s) for k, s, _ in e_doc]
+        assert [r.source for r in got["raw_documents"]] == [{0: "vector", 1: "keyword", 2: "hybrid"}[s] for _, _, s in e_doc]
+        assert got["documents"] == rb.process_results(got["raw_documents"], "retrieval generation") and len(got["documents"]) <= 10
+        # a semantic high-priority decision asks for k = 19 + 10 = 29 and no keyword list → vector-only branch, raw cosines
+        sem = rb.get_unified_results(index, "kb1", "retrieval generation", rb.RetrievalDecision(queryType="semantic", priority="high"),
+                                     keyword_service=Meili())
+        vi, vs = oracle.topk(E, centre, 29)
+        e = [(int(i), s) for i, s in zip(vi, vs) if s >= 0.4]
+        assert [r.score for r in sem["raw_documents"]] == [s for i, s in e if i % 6 != 0]
+        assert [m.score for m in sem["memories"]] == [s for i, s in e if i % 6 == 0][:10]
+
+        # --- the agent's tools: top-5 → show 3, top-10 → show 8 (preset minVectorScore 0.3)
+        for tool, name, top_k, show in ((rb.search_knowledge, "search_knowledge", 5, 3), (rb.deep_search, "deep_search", 10, 8)):
+            ctx = rb.ToolContext(index, "kb1", keyword_service=Meili())
+            text = tool(ctx, "retrieval generation")
+            keys, keep, hits, ek, esc, esrc = expect(top_k, top_k, 0.3)
+            assert [r.id for r in ctx.searchResults] == [keys.string(k) for k in ek]
+            assert [r.score for r in ctx.searchResults] == esc
+            assert text == hs.format_search_results(ctx.searchResults, show)
+            assert text.count("[来源") == min(show, len(ek)) and ctx.toolCalls[0]["tool"] == name
+            assert ctx.toolCalls[0]["output"] == hs.js_substring(text, 0, 200)
+            first = len(ctx.searchResults)
+            tool(ctx, "retrieval generation")                                    # results are saved once (:33-35)
+            assert len(ctx.searchResults) == first and len(ctx.toolCalls) == 2
     finally:
         index.close()
 

@@ -67,3 +67,20 @@ def test_shard_ranges_partition_rows():
 def test_merge_reference_order_ties_by_id():
     ids, sc = merge_reference_order([[5, 9], [2, 7]], [[0.9, 0.5], [0.9, 0.5]], 3)
     assert ids.tolist() == [2, 5, 7] and sc.tolist() == [0.9, 0.9, 0.5]
+
+
+def test_calculate_retrieval_count_matches_reference_table():
+    """retrieval-decision.ts:144-195 — and the engine's k = vectorTopK + 10 stays within RAG_MAX_TOPK (12..29)."""
+    import rag_era_b200 as rb
+    from rag_era_b200 import _native as N
+
+    D = rb.RetrievalDecision
+    assert rb.calculate_retrieval_count(D()) == dict(vectorTopK=8, keywordLimit=6, graphLimit=0)          # floor(13*1.0)=13 → ceil(7.8), ceil(5.2)
+    assert rb.calculate_retrieval_count(D(priority="high")) == dict(vectorTopK=12, keywordLimit=8, graphLimit=0)   # 19 → ceil(11.4), ceil(7.6)
+    assert rb.calculate_retrieval_count(D(priority="low")) == dict(vectorTopK=6, keywordLimit=4, graphLimit=0)     # floor(9.1)=9 → ceil(5.4), ceil(3.6)
+    assert rb.calculate_retrieval_count(D(queryType="semantic", priority="high")) == dict(vectorTopK=19, keywordLimit=0, graphLimit=0)
+    assert rb.calculate_retrieval_count(D(queryType="keyword")) == dict(vectorTopK=2, keywordLimit=13, graphLimit=0)
+    assert rb.calculate_retrieval_count(D(queryType="graph", priority="low")) == dict(vectorTopK=3, keywordLimit=0, graphLimit=9)
+    ks = {rb.calculate_retrieval_count(D(queryType=t, priority=p))["vectorTopK"] + 10
+          for t in ("semantic", "keyword", "graph", "hybrid") for p in ("high", "medium", "low")}
+    assert min(ks) == 12 and max(ks) == 29 and max(ks) <= N.MAX_TOPK
