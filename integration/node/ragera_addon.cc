@@ -14,7 +14,7 @@
 //   setRowMeta(handle, row0, Uint8Array contentType, Float64Array confidence, Int32Array accessCount, BigInt64Array lastAccessMs)
 //   setRowKeys(handle, row0, BigUint64Array keys)
 //   hybridSearch(handle, Float32Array queries, B, opts, BigUint64Array kwKeys, Uint32Array kwCounts) -> Promise<result>
-//   createBatcher(handle, opts, maxBatch, maxWaitUs) -> batcher; submit(batcher, Float32Array q, BigUint64Array kwKeys) -> Promise<result>
+//   createBatcher(handle, opts, maxBatch, maxWaitUs) -> batcher; submit(batcher, opts, Float32Array q, BigUint64Array kwKeys) -> Promise<result>
 //   destroy(handle) / destroyBatcher(batcher)
 #include <node_api.h>
 
@@ -279,13 +279,18 @@ napi_value HybridSearch(napi_env env, napi_callback_info info) {
   size_t argc = 6;
   napi_value argv[6];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  auto* w = new SearchWork();
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&w->idx));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
   const float* q = nullptr;
   size_t nq = 0;
-  if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { delete w; napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
-  NAPI_OK(env, napi_get_value_uint32(env, argv[2], &w->B));
+  if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
+  uint32_t B = 0;
+  NAPI_OK(env, napi_get_value_uint32(env, argv[2], &B));
+  auto* w = new SearchWork();  // owned by the async work from here on (search_complete deletes it)
+  w->idx = idx;
+  w->B = B;
   read_opts(env, argv[3], &w->opts);
+  if ((size_t)B * w->opts.vector_top_k == 0 || nq % B != 0) { delete w; napi_throw_type_error(env, nullptr, "queries must hold B rows of dim values, B and vectorTopK >= 1"); return nullptr; }
   w->q.assign(q, q + nq);  // copied: the JS buffer may be reused before the worker runs
   const uint64_t* kk = nullptr; const uint32_t* kc = nullptr;
   size_t nk = 0, nc = 0;
@@ -320,12 +325,14 @@ napi_value Submit(napi_env env, napi_callback_info info) {  // submit(batcher, o
   size_t argc = 4;
   napi_value argv[4];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  auto* w = new SearchWork();
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&w->batcher));
-  read_opts(env, argv[1], &w->opts);  // must equal the batcher's options (sizes the result arrays)
+  rag_batcher* batcher = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&batcher));
   const float* q = nullptr;
   size_t nq = 0;
-  if (!typed(env, argv[2], napi_float32_array, &q, &nq)) { delete w; napi_throw_type_error(env, nullptr, "query must be a Float32Array"); return nullptr; }
+  if (!typed(env, argv[2], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "query must be a Float32Array"); return nullptr; }
+  auto* w = new SearchWork();
+  w->batcher = batcher;
+  read_opts(env, argv[1], &w->opts);  // must equal the batcher's options (sizes the result arrays)
   w->q.assign(q, q + nq);
   const uint64_t* kk = nullptr;
   size_t nk = 0;

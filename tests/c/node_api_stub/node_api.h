@@ -1,0 +1,124 @@
+/*
+ * node_api.h — TEST STUB. Node.js is not available in the build container, so the N-API addon
+ * (integration/node/ragera_addon.cc) cannot be built against the real header there. This file declares the
+ * subset of Node-API (v8) the addon uses, with the signatures of the public, ABI-stable Node-API documentation,
+ * so that `g++ -fsyntax-only` type-checks the addon (tests/test_abi.py::test_napi_addon_type_checks).
+ * It is NOT shipped and never linked: a real build uses the header that comes with Node.
+ */
+#ifndef TEST_NODE_API_STUB_H_
+#define TEST_NODE_API_STUB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAPI_AUTO_LENGTH SIZE_MAX
+
+typedef struct napi_env__* napi_env;
+typedef struct napi_value__* napi_value;
+typedef struct napi_callback_info__* napi_callback_info;
+typedef struct napi_deferred__* napi_deferred;
+typedef struct napi_async_work__* napi_async_work;
+
+typedef enum {
+  napi_ok,
+  napi_invalid_arg,
+  napi_object_expected,
+  napi_string_expected,
+  napi_name_expected,
+  napi_function_expected,
+  napi_number_expected,
+  napi_boolean_expected,
+  napi_array_expected,
+  napi_generic_failure,
+  napi_pending_exception,
+  napi_cancelled
+} napi_status;
+
+typedef enum {
+  napi_default = 0,
+  napi_writable = 1 << 0,
+  napi_enumerable = 1 << 1,
+  napi_configurable = 1 << 2,
+  napi_static = 1 << 10
+} napi_property_attributes;
+
+typedef enum {
+  napi_int8_array,
+  napi_uint8_array,
+  napi_uint8_clamped_array,
+  napi_int16_array,
+  napi_uint16_array,
+  napi_int32_array,
+  napi_uint32_array,
+  napi_float32_array,
+  napi_float64_array,
+  napi_bigint64_array,
+  napi_biguint64_array
+} napi_typedarray_type;
+
+typedef napi_value (*napi_callback)(napi_env env, napi_callback_info info);
+typedef void (*napi_finalize)(napi_env env, void* finalize_data, void* finalize_hint);
+typedef void (*napi_async_execute_callback)(napi_env env, void* data);
+typedef void (*napi_async_complete_callback)(napi_env env, napi_status status, void* data);
+
+typedef struct {
+  const char* utf8name;
+  napi_value name;
+  napi_callback method;
+  napi_callback getter;
+  napi_callback setter;
+  napi_value value;
+  napi_property_attributes attributes;
+  void* data;
+} napi_property_descriptor;
+
+napi_status napi_get_cb_info(napi_env env, napi_callback_info cbinfo, size_t* argc, napi_value* argv, napi_value* this_arg, void** data);
+napi_status napi_throw_error(napi_env env, const char* code, const char* msg);
+napi_status napi_throw_type_error(napi_env env, const char* code, const char* msg);
+napi_status napi_create_error(napi_env env, napi_value code, napi_value msg, napi_value* result);
+napi_status napi_create_object(napi_env env, napi_value* result);
+napi_status napi_create_array_with_length(napi_env env, size_t length, napi_value* result);
+napi_status napi_create_double(napi_env env, double value, napi_value* result);
+napi_status napi_create_uint32(napi_env env, uint32_t value, napi_value* result);
+napi_status napi_create_string_utf8(napi_env env, const char* str, size_t length, napi_value* result);
+napi_status napi_create_external(napi_env env, void* data, napi_finalize finalize_cb, void* finalize_hint, napi_value* result);
+napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void** data, napi_value* result);
+napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset, napi_value* result);
+napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type, size_t* length, void** data, napi_value* arraybuffer, size_t* byte_offset);
+napi_status napi_get_value_double(napi_env env, napi_value value, double* result);
+napi_status napi_get_value_uint32(napi_env env, napi_value value, uint32_t* result);
+napi_status napi_get_value_external(napi_env env, napi_value value, void** result);
+napi_status napi_get_value_string_utf8(napi_env env, napi_value value, char* buf, size_t bufsize, size_t* result);
+napi_status napi_set_element(napi_env env, napi_value object, uint32_t index, napi_value value);
+napi_status napi_set_named_property(napi_env env, napi_value object, const char* utf8name, napi_value value);
+napi_status napi_get_named_property(napi_env env, napi_value object, const char* utf8name, napi_value* result);
+napi_status napi_has_named_property(napi_env env, napi_value object, const char* utf8name, bool* result);
+napi_status napi_define_properties(napi_env env, napi_value object, size_t property_count, const napi_property_descriptor* properties);
+napi_status napi_create_promise(napi_env env, napi_deferred* deferred, napi_value* promise);
+napi_status napi_resolve_deferred(napi_env env, napi_deferred deferred, napi_value resolution);
+napi_status napi_reject_deferred(napi_env env, napi_deferred deferred, napi_value rejection);
+napi_status napi_create_async_work(napi_env env, napi_value async_resource, napi_value async_resource_name, napi_async_execute_callback execute, napi_async_complete_callback complete, void* data, napi_async_work* result);
+napi_status napi_queue_async_work(napi_env env, napi_async_work work);
+napi_status napi_delete_async_work(napi_env env, napi_async_work work);
+
+typedef napi_value (*napi_addon_register_func)(napi_env env, napi_value exports);
+
+#ifdef __cplusplus
+}
+#endif
+
+/* as in the real header: the initializer is declared with C linkage, then defined by the addon */
+#ifdef __cplusplus
+#define NAPI_STUB_EXTERN_C extern "C"
+#else
+#define NAPI_STUB_EXTERN_C
+#endif
+#define NAPI_MODULE_INIT()                                                               \
+  NAPI_STUB_EXTERN_C napi_value napi_register_module_v1(napi_env env, napi_value exports); \
+  napi_value napi_register_module_v1(napi_env env, napi_value exports)
+
+#endif

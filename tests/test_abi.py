@@ -117,3 +117,17 @@ def test_product_never_touches_the_oracle():
                 assert "oracle.h" not in text and "oracle/" not in text, f
     deps = subprocess.run(["ldd", os.path.join(pkg, "libragera.so")], capture_output=True, text=True).stdout
     assert "oracle" not in deps
+
+
+def test_napi_addon_type_checks():
+    """§8f N2: Node is absent here, so the addon cannot be built — but it must at least be valid C++ against the
+    Node-API signatures it uses and against include/ragera.h (a stub header with the documented declarations)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror",
+                        "-I" + os.path.join(ROOT, "tests", "c", "node_api_stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "node", "ragera_addon.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
