@@ -61,8 +61,35 @@ bool parse_string(reader& r, std::string* out) {
     if (c == '\\') {
       c = r.get();
       if (c == EOF) return false;
-      if (c == 'u') {  // keep \uXXXX escapes verbatim: node ids are UUIDs, this is only for robustness
-        if (out) out->append("\\u");
+      if (c == 'u') {  // \uXXXX → UTF-8; a surrogate pair becomes one code point, a lone surrogate U+FFFD
+        auto hex4 = [&](uint32_t* v) {
+          *v = 0;
+          for (int i = 0; i < 4; i++) {
+            const int h = r.get();
+            const int d = (h >= '0' && h <= '9') ? h - '0' : (h >= 'a' && h <= 'f') ? h - 'a' + 10 : (h >= 'A' && h <= 'F') ? h - 'A' + 10 : -1;
+            if (d < 0) return false;
+            *v = *v * 16 + (uint32_t)d;
+          }
+          return true;
+        };
+        uint32_t cp;
+        if (!hex4(&cp)) return false;
+        if (cp >= 0xD800 && cp <= 0xDBFF) {
+          uint32_t lo = 0;
+          if (r.peek() == '\\') {
+            r.get();
+            if (r.get() != 'u' || !hex4(&lo)) return false;
+            if (lo >= 0xDC00 && lo <= 0xDFFF) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+            else { if (out) out->append("\xEF\xBF\xBD"); cp = lo; if (cp >= 0xD800 && cp <= 0xDFFF) cp = 0xFFFD; }
+          } else cp = 0xFFFD;
+        } else if (cp >= 0xDC00 && cp <= 0xDFFF) cp = 0xFFFD;
+        if (cp == 0) cp = 0xFFFD;  // ids travel as '\0'-separated blobs
+        if (out) {
+          if (cp < 0x80) out->push_back((char)cp);
+          else if (cp < 0x800) { out->push_back((char)(0xC0 | (cp >> 6))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+          else if (cp < 0x10000) { out->push_back((char)(0xE0 | (cp >> 12))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+          else { out->push_back((char)(0xF0 | (cp >> 18))); out->push_back((char)(0x80 | ((cp >> 12) & 0x3F))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+        }
         continue;
       }
       const char* map = "\"\"\\\\//b\bf\fn\nr\rt\t";

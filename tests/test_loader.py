@@ -249,3 +249,49 @@ def test_open_store_through_the_sidecar(native, oracle, tmp_path):
         got, hit = idx.open_store(src)
         assert got == ids and not hit
     assert native.cache_is_fresh(src + ".ragera", src)                     # ... and it was rewritten
+
+
+# ---- the parser against Python's json on arbitrary stores (hypothesis) -------------------------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+_id = st.text(st.characters(blacklist_categories=("Cs",), blacklist_characters="\0"), min_size=1, max_size=12)
+_scalar = st.one_of(st.none(), st.booleans(), st.integers(-10**6, 10**6), st.floats(allow_nan=False, allow_infinity=False, width=32),
+                    st.text(st.characters(blacklist_categories=("Cs",)), max_size=8))
+_json = st.recursive(_scalar, lambda c: st.one_of(st.lists(c, max_size=3), st.dictionaries(st.text(max_size=5), c, max_size=3)), max_leaves=6)
+
+
+@st.composite
+def _stores(draw):
+    ids = draw(st.lists(_id, min_size=0, max_size=6, unique=True))
+    dim = draw(st.integers(1, 5))
+    rows = [[draw(st.floats(allow_nan=False, allow_infinity=False, width=32)) for _ in range(dim)] for _ in ids]
+    meta = {}
+    for i in draw(st.lists(st.sampled_from(ids), unique=True, max_size=len(ids))) if ids else []:
+        m = draw(st.dictionaries(st.sampled_from(["type", "language", "memoryId", "documentName", "x"]), _json, max_size=4))
+        meta[i] = m
+    extra = draw(st.dictionaries(st.sampled_from(["textIdToRefDocId", "a", "zz"]), _json, max_size=2))
+    order = draw(st.permutations(["embeddingDict", "metadataDict"] + sorted(extra)))
+    doc = {}
+    for k in order:
+        doc[k] = {"embeddingDict": dict(zip(ids, rows)), "metadataDict": meta}.get(k, extra.get(k))
+    return ids, dim, rows, meta, doc, draw(st.booleans()), draw(st.sampled_from([None, 1, 2]))
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(_stores())
+def test_parser_agrees_with_python_json_on_arbitrary_stores(native, tmp_path, store):
+    ids, dim, rows, meta, doc, ascii_only, indent = store
+    p = str(tmp_path / "fuzz.json")
+    with open(p, "w", encoding="utf-8") as f:
+        json.dump(doc, f, ensure_ascii=ascii_only, indent=indent)      # \\uXXXX escapes (incl. surrogate pairs) or raw UTF-8
+    got_ids, X = native.parse_vector_store_json(p, dim, slab_rows=2)
+    assert got_ids == ids
+    assert np.array_equal(X.view(np.uint32), np.array(rows, np.float32).reshape(len(ids), dim).view(np.uint32))
+    ct, mem, found = native.parse_vector_store_metadata(p, ids)
+    assert found
+    for r, i in enumerate(ids):
+        m = meta.get(i, {})
+        want = native.CT_MEMORY if m.get("type") == "memory" else native.CT_CODE if "language" in m else native.CT_DOCUMENT
+        assert ct[r] == want, (i, m)
+        want_mem = m.get("memoryId") if isinstance(m.get("memoryId"), str) else ""
+        assert mem[r] == want_mem.replace("\0", "�"), (i, m)
