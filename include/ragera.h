@@ -146,6 +146,10 @@ typedef struct rag_memory_opts {
   int64_t  now_ms;
   double   time_decay_factor; /* 0 → 0.05                                           */
   double   frequency_bonus;   /* 0 → 0.1                                            */
+  uint32_t similarity_top_k;  /* retriever similarityTopK; 0 → limit * 2 (store.ts:112). A host that must drop
+                                 memories whose DB record is gone (`if (dbMemory)`, store.ts:153) asks for
+                                 limit = similarity_top_k = 2L, filters, and keeps the first L        */
+  uint32_t reserved;
 } rag_memory_opts;
 
 typedef struct rag_memory_out {

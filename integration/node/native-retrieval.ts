@@ -130,3 +130,64 @@ export async function hybridSearchNative(index: NativeKnowledgeIndex, knowledgeB
   }
   return out;
 }
+
+/**
+ * The llamaindex seam (SURVEY §8b): a vector store whose `query` runs on the GPU. Handed to
+ * `storageContextFromDefaults({ persistDir, vectorStore })` in index-manager.ts:218-220,264-270, EVERY caller of
+ * `index.asRetriever({similarityTopK}).retrieve(q)` — hybridSearch's vectorSearch (hybrid-search.ts:223-224),
+ * MemoryStore.retrieve (memory/store.ts:111-116), summarize_topic (llm/tools/summarize-tool.ts:46-47), the query
+ * engine (llm/agent.ts:143-163) — scans on the device with no edit at the call site. Shapes follow
+ * `BaseVectorStore` of llamaindex@0.12.1: query({queryEmbedding, similarityTopK}) → {ids, similarities}.
+ */
+export class NativeVectorStore {
+  storesText = false;
+  constructor(private readonly index: NativeKnowledgeIndex) {}
+  client(): unknown { return this.index.handle; }
+
+  /** SimpleVectorStore.add: rows are appended in order (index.insert — memory/store.ts:67). */
+  async add(nodes: Array<{ id_: string; getEmbedding(): number[]; getContent?(mode?: unknown): string; metadata?: Record<string, any> }>): Promise<string[]> {
+    if (nodes.length === 0) return [];
+    const dim = this.index.dim;
+    const rows = new Float32Array(nodes.length * dim);
+    nodes.forEach((n, i) => rows.set(n.getEmbedding(), i * dim));
+    const row0: number = native.uploadRows(this.index.handle, rows, nodes.length);
+    const ctype = new Uint8Array(nodes.length);
+    const keys = new BigUint64Array(nodes.length);
+    nodes.forEach((n, i) => {
+      const metadata = n.metadata ?? {};
+      const text = n.getContent ? n.getContent() : '';
+      this.index.nodes.push({ id: n.id_, text, metadata });
+      ctype[i] = metadata.type === 'memory' ? 1 : metadata.language !== undefined ? 2 : 0;
+      keys[i] = this.index.keyOf(text);
+    });
+    native.setRowMeta(this.index.handle, row0, ctype);
+    native.setRowKeys(this.index.handle, row0, keys);
+    return nodes.map(n => n.id_);
+  }
+
+  /** getTopKEmbeddings: score all rows, stable sort, first k — ties to the earlier row. Exact fp64 cosines. */
+  async query(q: { queryEmbedding?: number[]; similarityTopK: number }): Promise<{ ids: string[]; similarities: number[] }> {
+    if (!q.queryEmbedding) throw new Error('NativeVectorStore.query needs queryEmbedding');
+    const r = await native.search(this.index.handle, Float32Array.from(q.queryEmbedding), 1, q.similarityTopK);
+    const n: number = r.counts[0];
+    const ids: string[] = [];
+    const similarities: number[] = [];
+    for (let i = 0; i < n; i++) { ids.push(this.index.nodes[Number(r.ids[i])].id); similarities.push(r.scores[i]); }
+    return { ids, similarities };
+  }
+
+  /**
+   * MemoryStore.retrieve's device half (memory/store.ts:119-175): memory rows of the top-2·limit, cos ≥ minRelevance,
+   * 0.7·cos + 0.3·freshness, stable sort. Needs the Memory columns on the device (setRowMeta after prisma writes).
+   * All 2·limit blended candidates come back so the caller can drop rows whose DB record is gone before slicing (:153,:175).
+   */
+  async memoryCandidates(queryEmbedding: Float32Array, limit: number, minRelevance: number, nowMs: number):
+      Promise<Array<{ node: NodeRow; score: number; relevanceScore: number; freshnessScore: number }>> {
+    const r = await native.memoryRetrieve(this.index.handle, queryEmbedding, 1,
+      { limit: 2 * limit, similarityTopK: 2 * limit, minRelevance, nowMs });
+    const out = [];
+    for (let i = 0; i < r.counts[0]; i++)
+      out.push({ node: this.index.nodes[Number(r.ids[i])], score: r.scores[i], relevanceScore: r.relevance[i], freshnessScore: r.freshness[i] });
+    return out;
+  }
+}

@@ -14,6 +14,8 @@
 //   setRowMeta(handle, row0, Uint8Array contentType, Float64Array confidence, Int32Array accessCount, BigInt64Array lastAccessMs)
 //   setRowKeys(handle, row0, BigUint64Array keys)
 //   hybridSearch(handle, Float32Array queries, B, opts, BigUint64Array kwKeys, Uint32Array kwCounts) -> Promise<result>
+//   search(handle, Float32Array queries, B, k) -> Promise<{ids, scores, counts, certified}>      (retriever.retrieve / VectorStore.query)
+//   memoryRetrieve(handle, Float32Array queries, B, {limit, minRelevance, nowMs, similarityTopK}) -> Promise<{ids, scores, relevance, freshness, counts}>
 //   createBatcher(handle, opts, maxBatch, maxWaitUs) -> batcher; submit(batcher, opts, Float32Array q, BigUint64Array kwKeys) -> Promise<result>
 //   destroy(handle) / destroyBatcher(batcher)
 #include <node_api.h>
@@ -169,6 +171,75 @@ napi_value queue_search(napi_env env, SearchWork* w) {
   return promise;
 }
 
+// ---- retriever.retrieve (SimpleVectorStore.query) and MemoryStore.retrieve as async work -----------------------------
+struct TopkWork {
+  napi_async_work work = nullptr;
+  napi_deferred deferred = nullptr;
+  rag_index* idx = nullptr;
+  std::vector<float> q;
+  uint32_t B = 1;
+  bool memory = false;
+  rag_search_opts sopts;
+  rag_memory_opts mopts;
+  std::vector<uint64_t> ids;
+  std::vector<double> scores, relevance, freshness;
+  std::vector<uint32_t> counts;
+  std::vector<uint8_t> certified;
+  int rc = RAG_OK;
+  std::string err;
+};
+
+void topk_execute(napi_env, void* data) {
+  auto* w = static_cast<TopkWork*>(data);
+  const uint32_t width = w->memory ? w->mopts.limit : w->sopts.k;
+  w->ids.resize((size_t)w->B * width); w->scores.resize((size_t)w->B * width); w->counts.resize(w->B);
+  if (w->memory) {
+    w->relevance.resize((size_t)w->B * width); w->freshness.resize((size_t)w->B * width);
+    rag_memory_out out = {w->ids.data(), w->scores.data(), w->relevance.data(), w->freshness.data(), w->counts.data()};
+    w->rc = rag_memory_retrieve(w->idx, w->q.data(), w->B, &w->mopts, &out);
+  } else {
+    w->certified.resize(w->B);
+    rag_topk_out out = {w->ids.data(), w->scores.data(), w->counts.data(), w->certified.data()};
+    w->rc = rag_search(w->idx, w->q.data(), w->B, &w->sopts, &out);
+  }
+  if (w->rc != RAG_OK) w->err = rag_last_error();
+}
+
+void topk_complete(napi_env env, napi_status, void* data) {
+  auto* w = static_cast<TopkWork*>(data);
+  if (w->rc != RAG_OK) {
+    napi_value msg, e;
+    std::string m = "libragera error " + std::to_string(w->rc) + ": " + w->err;
+    napi_create_string_utf8(env, m.c_str(), NAPI_AUTO_LENGTH, &msg);
+    napi_create_error(env, nullptr, msg, &e);
+    napi_reject_deferred(env, w->deferred, e);
+  } else {
+    napi_value r;
+    napi_create_object(env, &r);
+    napi_set_named_property(env, r, "ids", make_typed(env, napi_biguint64_array, w->ids));        // [B][k] chunk ids, rank order
+    napi_set_named_property(env, r, "scores", make_typed(env, napi_float64_array, w->scores));    // similarities (or the 0.7/0.3 blend)
+    napi_set_named_property(env, r, "counts", make_typed(env, napi_uint32_array, w->counts));
+    if (w->memory) {
+      napi_set_named_property(env, r, "relevance", make_typed(env, napi_float64_array, w->relevance));
+      napi_set_named_property(env, r, "freshness", make_typed(env, napi_float64_array, w->freshness));
+    } else {
+      napi_set_named_property(env, r, "certified", make_typed(env, napi_uint8_array, w->certified));
+    }
+    napi_resolve_deferred(env, w->deferred, r);
+  }
+  napi_delete_async_work(env, w->work);
+  delete w;
+}
+
+napi_value queue_topk(napi_env env, TopkWork* w) {
+  napi_value promise, name;
+  NAPI_OK(env, napi_create_promise(env, &w->deferred, &promise));
+  NAPI_OK(env, napi_create_string_utf8(env, "ragera.search", NAPI_AUTO_LENGTH, &name));
+  NAPI_OK(env, napi_create_async_work(env, nullptr, name, topk_execute, topk_complete, w, &w->work));
+  NAPI_OK(env, napi_queue_async_work(env, w->work));
+  return promise;
+}
+
 // ---- exported functions ------------------------------------------------------------------------------
 napi_value CreateIndex(napi_env env, napi_callback_info info) {
   size_t argc = 1;
@@ -301,6 +372,63 @@ napi_value HybridSearch(napi_env env, napi_callback_info info) {
   return queue_search(env, w);
 }
 
+// search(handle, Float32Array queries, B, k) -> Promise<{ids, scores, counts, certified}> — what a llamaindex
+// BaseVectorStore.query({queryEmbedding, similarityTopK}) → {ids, similarities} binds (src/lib/hybrid-search.ts:223-224)
+napi_value Search(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value argv[4];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  const float* q = nullptr;
+  size_t nq = 0;
+  if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
+  uint32_t B = 0, k = 0;
+  NAPI_OK(env, napi_get_value_uint32(env, argv[2], &B));
+  NAPI_OK(env, napi_get_value_uint32(env, argv[3], &k));
+  if (B == 0 || k == 0 || nq % B != 0) { napi_throw_type_error(env, nullptr, "queries must hold B rows of dim values, B and k >= 1"); return nullptr; }
+  auto* w = new TopkWork();
+  w->idx = idx;
+  w->B = B;
+  w->q.assign(q, q + nq);
+  memset(&w->sopts, 0, sizeof w->sopts);
+  w->sopts.k = k;
+  return queue_topk(env, w);
+}
+
+// memoryRetrieve(handle, Float32Array queries, B, {limit, minRelevance, nowMs, similarityTopK}) ->
+//   Promise<{ids, scores, relevance, freshness, counts}> — MemoryStore.retrieve's filter/blend/sort (src/lib/memory/store.ts:119-175)
+napi_value MemoryRetrieve(napi_env env, napi_callback_info info) {
+  size_t argc = 4;
+  napi_value argv[4];
+  NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  rag_index* idx = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  const float* q = nullptr;
+  size_t nq = 0;
+  if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
+  uint32_t B = 0;
+  NAPI_OK(env, napi_get_value_uint32(env, argv[2], &B));
+  rag_memory_opts mo;
+  memset(&mo, 0, sizeof mo);
+  mo.limit = 10;            // store.ts:104
+  mo.min_relevance = 0.5;   // store.ts:105
+  double now_ms = 0.0;
+  get_u32(env, argv[3], "limit", &mo.limit);
+  get_f64(env, argv[3], "minRelevance", &mo.min_relevance);
+  get_f64(env, argv[3], "nowMs", &now_ms);
+  get_u32(env, argv[3], "similarityTopK", &mo.similarity_top_k);
+  mo.now_ms = (int64_t)now_ms;
+  if (B == 0 || mo.limit == 0 || nq % B != 0) { napi_throw_type_error(env, nullptr, "queries must hold B rows of dim values, B and limit >= 1"); return nullptr; }
+  auto* w = new TopkWork();
+  w->idx = idx;
+  w->B = B;
+  w->memory = true;
+  w->mopts = mo;
+  w->q.assign(q, q + nq);
+  return queue_topk(env, w);
+}
+
 napi_value CreateBatcher(napi_env env, napi_callback_info info) {  // createBatcher(handle, opts, maxBatch, maxWaitUs)
   size_t argc = 4;
   napi_value argv[4];
@@ -373,6 +501,8 @@ NAPI_MODULE_INIT() {
       {"setRowMeta", nullptr, SetRowMeta, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"setRowKeys", nullptr, SetRowKeys, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"hybridSearch", nullptr, HybridSearch, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"search", nullptr, Search, nullptr, nullptr, nullptr, napi_default, nullptr},
+      {"memoryRetrieve", nullptr, MemoryRetrieve, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"createBatcher", nullptr, CreateBatcher, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"submit", nullptr, Submit, nullptr, nullptr, nullptr, napi_default, nullptr},
       {"destroy", nullptr, Destroy, nullptr, nullptr, nullptr, napi_default, nullptr},

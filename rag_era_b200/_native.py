@@ -96,7 +96,8 @@ class BatcherDesc(C.Structure):
 
 class MemoryOpts(C.Structure):
     _fields_ = [("limit", C.c_uint32), ("path", C.c_uint32), ("min_relevance", C.c_double), ("now_ms", C.c_int64),
-                ("time_decay_factor", C.c_double), ("frequency_bonus", C.c_double)]
+                ("time_decay_factor", C.c_double), ("frequency_bonus", C.c_double), ("similarity_top_k", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class MemoryOut(C.Structure):

@@ -896,10 +896,12 @@ int rag_memory_retrieve(rag_index* idx, const float* queries, uint32_t B, const 
   RAG_CHECK(check_handle(idx));
   if (!queries || !o || !out || !out->ids || !out->scores || !out->counts || B == 0)
     return rag_set_error(RAG_ERR_INVALID, "rag_memory_retrieve: null argument or empty batch");
-  if (o->limit == 0 || o->limit * 2 > RAG_MAX_TOPK) return rag_set_error(RAG_ERR_INVALID, "limit must be in 1..%d", RAG_MAX_TOPK / 2);
+  // similarityTopK: limit * 2 — src/lib/memory/store.ts:112 (or the caller's own value)
+  const uint32_t k = o->similarity_top_k ? o->similarity_top_k : o->limit * 2;
+  if (o->limit == 0 || o->limit > RAG_MAX_TOPK || k > RAG_MAX_TOPK)
+    return rag_set_error(RAG_ERR_INVALID, "limit must be in 1..%d (similarityTopK = %u must not exceed %d)", RAG_MAX_TOPK / 2, k, RAG_MAX_TOPK);
   if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
   RAG_CUDA(cudaSetDevice(idx->device));
-  const uint32_t k = o->limit * 2;  // similarityTopK: limit * 2 — src/lib/memory/store.ts:112
   const uint32_t out_cap = o->limit;
   plan p;
   RAG_CHECK(make_plan(idx, B, k, o->path, 0, 0.0, &p));

@@ -290,14 +290,15 @@ class VectorIndex:
         return out
 
     def memory_retrieve(self, queries, limit: int, min_relevance: float = 0.5, now_ms: int = 0,
-                        path: int = N.PATH_AUTO, time_decay_factor: float = 0.0, frequency_bonus: float = 0.0):
-        """MemoryStore.retrieve post-processing on the device (memory/store.ts:102-180)."""
+                        path: int = N.PATH_AUTO, time_decay_factor: float = 0.0, frequency_bonus: float = 0.0,
+                        similarity_top_k: int = 0):
+        """MemoryStore.retrieve post-processing on the device (memory/store.ts:102-180); similarity_top_k=0 → 2*limit."""
         q = self._queries(queries)
         B = q.shape[0]
         ids = np.empty((B, limit), np.uint64)
         sc, rel, fr = (np.empty((B, limit), np.float64) for _ in range(3))
         cnt = np.empty(B, np.uint32)
-        o = N.MemoryOpts(limit, path, min_relevance, now_ms, time_decay_factor, frequency_bonus)
+        o = N.MemoryOpts(limit, path, min_relevance, now_ms, time_decay_factor, frequency_bonus, similarity_top_k, 0)
         c = N.MemoryOut(_ptr(ids), _ptr(sc), _ptr(rel), _ptr(fr), _ptr(cnt))
         N.check(self._lib.rag_memory_retrieve(self._h, _ptr(q), B, C.byref(o), C.byref(c)))
         return dict(ids=ids, scores=sc, relevance=rel, freshness=fr, counts=cnt)

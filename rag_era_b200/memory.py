@@ -76,10 +76,15 @@ class MemoryStore:
         self._row_memory[row0] = memory.id
 
     def retrieve(self, query, limit: int = 10, min_relevance: float = 0.5, now_ms: int = 0) -> list[ScoredMemory]:
-        """retrieve — store.ts:102-180. Errors degrade to [] exactly like the reference's catch (:176-179)."""
+        """retrieve — store.ts:102-180. Errors degrade to [] exactly like the reference's catch (:176-179).
+
+        The device does top-2·limit → memory rows → cos ≥ minRelevance → 0.7·cos + 0.3·fresh → stable sort. Rows whose DB
+        record is gone (``delete`` leaves the vector node behind, :240-251) or belongs to another knowledge base are
+        dropped HERE, after the sort and before the slice — the same set and order as ``if (dbMemory)`` (:153) followed
+        by ``sort`` and ``slice(0, limit)`` — so the device is asked for all 2·limit blended candidates."""
         try:
             q = self.index.embed(query)
-            r = self.index.store.memory_retrieve(q, limit, min_relevance, now_ms)
+            r = self.index.store.memory_retrieve(q, 2 * limit, min_relevance, now_ms, similarity_top_k=2 * limit)
             n = int(r["counts"][0])
             out = []
             for i in range(n):
@@ -90,9 +95,42 @@ class MemoryStore:
                 out.append(ScoredMemory(**vars(mem), score=float(r["scores"][0, i]),
                                         relevanceScore=float(r["relevance"][0, i]),
                                         freshnessScore=float(r["freshness"][0, i])))
-            return out
+            return out[:limit]
         except N.RagError:
             return []
+
+    def _push_meta(self, memory_id: str) -> None:
+        m = self._db[memory_id]
+        for row, mid in self._row_memory.items():
+            if mid == memory_id:
+                self.index.store.set_row_meta(row, content_type=[N.CT_MEMORY], confidence=[m.confidence],
+                                              access_count=[m.accessCount], last_access_ms=[m.lastAccessedAt])
+
+    def touch(self, memory_id: str, now_ms: int) -> None:
+        """touch — store.ts:207-215: accessCount += 1, lastAccessedAt = now; the device copy of the row follows, so the
+        next retrieve computes freshness from the new values."""
+        m = self._db[memory_id]
+        m.accessCount += 1
+        m.lastAccessedAt = now_ms
+        self._push_meta(memory_id)
+
+    def touch_many(self, memory_ids: Sequence[str], now_ms: int) -> None:
+        """touchMany — store.ts:220-235."""
+        for mid in memory_ids:
+            self.touch(mid, now_ms)
+
+    def delete(self, memory_id: str) -> None:
+        """delete — store.ts:240-251: only the DB record goes; the vector node stays in the index (it keeps showing up
+        in hybridSearch as a memory hit, exactly as in the reference) and ``retrieve`` filters it out."""
+        del self._db[memory_id]
+
+    def get_all(self) -> list[Memory]:
+        """getAll — store.ts:254-260."""
+        return [m for m in self._db.values() if m.knowledgeBaseId == self.knowledge_base_id]
+
+    def count(self) -> int:
+        """count — store.ts:265-269."""
+        return len(self.get_all())
 
     def has_similar(self, content_embedding, threshold: float = 0.9, now_ms: int = 0) -> bool:
         """hasSimilar — store.ts:274-285: retrieve(content, 1) and compare relevance."""

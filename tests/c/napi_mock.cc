@@ -4,7 +4,7 @@
 // plain C++ objects — numbers, strings, objects, arrays, externals, ArrayBuffers, typed arrays, promises, async work
 // (execute on a worker thread, complete on the "main" thread, like libuv's pool) — and a driver that plays the calls
 // native-retrieval.ts makes: createIndex → uploadRows → setRowMeta → setRowKeys → hybridSearch (Promise) → createBatcher /
-// submit → a rejected Promise → destroy. Results are printed as JSON; tests/test_gpu_napi.py compares them with the oracle.
+// submit → search / memoryRetrieve → a rejected Promise → destroy. Results are printed as JSON; tests/test_gpu_napi.py compares them with the oracle.
 //
 // usage: napi_mock <input.bin>   (layout written by the test: see read_input)
 #include <node_api.h>
@@ -236,6 +236,10 @@ struct input {
   std::vector<uint8_t> ctype;
   std::vector<uint64_t> row_keys, kw_keys;
   std::vector<uint32_t> kw_counts;
+  std::vector<double> conf;
+  std::vector<int32_t> acc;
+  std::vector<int64_t> last;
+  int64_t now_ms;
 };
 template <typename T>
 static void read_vec(FILE* f, std::vector<T>& v, size_t n) {
@@ -243,7 +247,7 @@ static void read_vec(FILE* f, std::vector<T>& v, size_t n) {
   if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short input\n"); exit(2); }
 }
 // u32 n, dim, B, k, kw_limit, pad; f64 min_score; f32 rows[n][dim]; f32 queries[B][dim]; u8 ctype[n]; u64 row_keys[n];
-// u64 kw_keys[B][kw_limit]; u32 kw_counts[B]
+// u64 kw_keys[B][kw_limit]; u32 kw_counts[B]; f64 confidence[n]; i32 access_count[n]; i64 last_access_ms[n]; i64 now_ms
 static input read_input(const char* path) {
   FILE* f = fopen(path, "rb");
   if (!f) { perror(path); exit(2); }
@@ -257,6 +261,10 @@ static input read_input(const char* path) {
   read_vec(f, in.row_keys, in.n);
   read_vec(f, in.kw_keys, (size_t)in.B * in.kw_limit);
   read_vec(f, in.kw_counts, in.B);
+  read_vec(f, in.conf, in.n);
+  read_vec(f, in.acc, in.n);
+  read_vec(f, in.last, in.n);
+  if (fread(&in.now_ms, 8, 1, f) != 1) { fprintf(stderr, "short input\n"); exit(2); }
   fclose(f);
   return in;
 }
@@ -274,11 +282,8 @@ int main(int argc, char** argv) {
   if (env->pending) { fprintf(stderr, "createIndex threw: %s\n", env->exception.c_str()); return 3; }
   napi_value r0 = call(env, exports, "uploadRows", {h, typed_array(env, napi_float32_array, in.rows.data(), in.rows.size()), num(env, in.n)});
   if (env->pending || r0->num != 0) { fprintf(stderr, "uploadRows threw: %s\n", env->exception.c_str()); return 3; }
-  std::vector<double> conf(in.n, 0.0);
-  std::vector<int32_t> acc(in.n, 0);
-  std::vector<int64_t> last(in.n, 0);
-  call(env, exports, "setRowMeta", {h, num(env, 0), typed_array(env, napi_uint8_array, in.ctype.data(), in.n), typed_array(env, napi_float64_array, conf.data(), in.n),
-                                    typed_array(env, napi_int32_array, acc.data(), in.n), typed_array(env, napi_bigint64_array, last.data(), in.n)});
+  call(env, exports, "setRowMeta", {h, num(env, 0), typed_array(env, napi_uint8_array, in.ctype.data(), in.n), typed_array(env, napi_float64_array, in.conf.data(), in.n),
+                                    typed_array(env, napi_int32_array, in.acc.data(), in.n), typed_array(env, napi_bigint64_array, in.last.data(), in.n)});
   if (env->pending) { fprintf(stderr, "setRowMeta threw: %s\n", env->exception.c_str()); return 3; }
   call(env, exports, "setRowKeys", {h, num(env, 0), typed_array(env, napi_biguint64_array, in.row_keys.data(), in.n)});
   if (env->pending) { fprintf(stderr, "setRowKeys threw: %s\n", env->exception.c_str()); return 3; }
@@ -312,6 +317,16 @@ int main(int argc, char** argv) {
                                                     typed_array(env, napi_biguint64_array, in.kw_keys.data() + (size_t)b * in.kw_limit, in.kw_counts[b])}));
   run_event_loop(env);
   call(env, exports, "destroyBatcher", {bt});
+  // the retriever seam (NativeVectorStore.query) and MemoryStore.retrieve's device half, one Promise per query
+  std::vector<napi_value> topk, mem;
+  for (uint32_t b = 0; b < in.B; b++) {
+    napi_value qv = typed_array(env, napi_float32_array, in.queries.data() + (size_t)b * in.dim, in.dim);
+    topk.push_back(call(env, exports, "search", {h, qv, num(env, 1), num(env, in.k)}));
+    run_event_loop(env);
+    mem.push_back(call(env, exports, "memoryRetrieve", {h, qv, num(env, 1), object(env, {{"limit", num(env, in.k)}, {"similarityTopK", num(env, in.k)},
+                                                                                        {"minRelevance", num(env, in.min_score)}, {"nowMs", num(env, (double)in.now_ms)}})}));
+    run_event_loop(env);
+  }
   // a failing call rejects the Promise with rag_last_error() (k beyond RAG_MAX_TOPK); a bad argument throws synchronously
   napi_value bad = call(env, exports, "hybridSearch", {h, typed_array(env, napi_float32_array, in.queries.data(), in.dim), num(env, 1), opts(1000),
                                                        typed_array(env, napi_biguint64_array, in.kw_keys.data(), 0), typed_array(env, napi_uint32_array, in.kw_counts.data(), 0)});
@@ -341,6 +356,28 @@ int main(int argc, char** argv) {
     for (uint32_t i = 0; i < counts[b]; i++) printf("%s%llu", i ? ", " : "", (unsigned long long)keys[(size_t)b * cap + i]);
     printf("], \"scores\": [");
     for (uint32_t i = 0; i < counts[b]; i++) printf("%s%.17g", i ? ", " : "", scores[(size_t)b * cap + i]);
+    printf("]}%s\n", b + 1 == in.B ? "" : ",");
+  }
+  printf("], \"search\": [\n");
+  for (uint32_t b = 0; b < in.B; b++) {
+    if (!topk[b] || topk[b]->state != 1 || !mem[b] || mem[b]->state != 1) { fprintf(stderr, "search/memoryRetrieve promise %u not fulfilled\n", b); return 4; }
+    napi_value t = topk[b]->settled, m = mem[b]->settled;
+    const uint32_t tc = view<uint32_t>(t, "counts", &n)[0], mc = view<uint32_t>(m, "counts", &n)[0];
+    const uint64_t* ti = view<uint64_t>(t, "ids", &n); const double* ts = view<double>(t, "scores", &n);
+    const uint64_t* mi = view<uint64_t>(m, "ids", &n); const double* ms = view<double>(m, "scores", &n);
+    const double* mr = view<double>(m, "relevance", &n); const double* mf = view<double>(m, "freshness", &n);
+    printf("{\"ids\": [");
+    for (uint32_t i = 0; i < tc; i++) printf("%s%llu", i ? ", " : "", (unsigned long long)ti[i]);
+    printf("], \"scores\": [");
+    for (uint32_t i = 0; i < tc; i++) printf("%s%.17g", i ? ", " : "", ts[i]);
+    printf("], \"certified\": %u, \"mem_ids\": [", view<uint8_t>(t, "certified", &n)[0]);
+    for (uint32_t i = 0; i < mc; i++) printf("%s%llu", i ? ", " : "", (unsigned long long)mi[i]);
+    printf("], \"mem_scores\": [");
+    for (uint32_t i = 0; i < mc; i++) printf("%s%.17g", i ? ", " : "", ms[i]);
+    printf("], \"mem_relevance\": [");
+    for (uint32_t i = 0; i < mc; i++) printf("%s%.17g", i ? ", " : "", mr[i]);
+    printf("], \"mem_freshness\": [");
+    for (uint32_t i = 0; i < mc; i++) printf("%s%.17g", i ? ", " : "", mf[i]);
     printf("]}%s\n", b + 1 == in.B ? "" : ",");
   }
   std::string rej = bad && bad->kind == napi_value__::Promise && bad->state == 2 && bad->settled ? bad->settled->str : "";

@@ -27,11 +27,17 @@ def build_host(tmp_path) -> str:
     return exe
 
 
-def write_input(path, X, Q, k, kw_limit, min_score, ctype, row_keys, kw_keys, kw_counts):
+def write_input(path, X, Q, k, kw_limit, min_score, ctype, row_keys, kw_keys, kw_counts, conf=None, acc=None, last=None, now_ms=0):
+    n = X.shape[0]
+    conf = np.zeros(n) if conf is None else conf
+    acc = np.zeros(n) if acc is None else acc
+    last = np.zeros(n) if last is None else last
     with open(path, "wb") as f:
-        f.write(struct.pack("<6Id", X.shape[0], X.shape[1], Q.shape[0], k, kw_limit, 0, min_score))
-        for a, t in ((X, np.float32), (Q, np.float32), (ctype, np.uint8), (row_keys, np.uint64), (kw_keys, np.uint64), (kw_counts, np.uint32)):
+        f.write(struct.pack("<6Id", n, X.shape[1], Q.shape[0], k, kw_limit, 0, min_score))
+        for a, t in ((X, np.float32), (Q, np.float32), (ctype, np.uint8), (row_keys, np.uint64), (kw_keys, np.uint64), (kw_counts, np.uint32),
+                     (conf, np.float64), (acc, np.int32), (last, np.int64)):
             f.write(np.ascontiguousarray(a, dtype=t).tobytes())
+        f.write(struct.pack("<q", now_ms))
 
 
 def test_addon_links_and_refuses_without_a_device(native, tmp_path):
@@ -63,12 +69,15 @@ def test_addon_results_equal_the_oracle(native, oracle, tmp_path):
         vi, _ = oracle.topk(X, Q[b], k)
         picks = [row_keys[int(vi[0])], 999_999 + b, row_keys[int(vi[min(3, len(vi) - 1)])], 5, row_keys[int(vi[-1])]]
         kw_keys[b, :kw_counts[b]] = picks[:kw_counts[b]]
+    now = 1_760_000_000_000
+    conf, acc = 0.5 + 0.5 * rng.random(n), rng.integers(0, 40, n).astype(np.int32)
+    last = now - rng.integers(0, 72 * 3_600_000, n)
     inp = str(tmp_path / "in.bin")
-    write_input(inp, X, Q, k, kw_limit, min_score, ctype, row_keys, kw_keys, kw_counts)
+    write_input(inp, X, Q, k, kw_limit, min_score, ctype, row_keys, kw_keys, kw_counts, conf, acc, last, now)
     r = subprocess.run([exe, inp], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     out = json.loads(r.stdout)
-    assert len(out["single"]) == B and len(out["batched"]) == B and len(out["one_call"]) == B
+    assert len(out["single"]) == B and len(out["batched"]) == B and len(out["one_call"]) == B and len(out["search"]) == B
     for b in range(B):
         e = oracle.hybrid_search(X, Q[b], k, min_score, kw_keys[b, :kw_counts[b]], row_keys=row_keys, row_ctype=ctype)
         g = out["single"][b]
@@ -80,5 +89,13 @@ def test_addon_results_equal_the_oracle(native, oracle, tmp_path):
         # the micro-batcher (concurrent submits from worker threads) and the one-call batch give the same answers
         assert out["batched"][b] == g
         assert out["one_call"][b]["keys"] == g["keys"] and out["one_call"][b]["scores"] == g["scores"]
+        # the retriever seam (NativeVectorStore.query) and MemoryStore.retrieve's device half (similarityTopK = limit = k)
+        t = out["search"][b]
+        vi, vs = oracle.topk(X, Q[b], k)
+        assert t["ids"] == [int(i) for i in vi] and t["scores"] == [float(x) for x in vs] and t["certified"] == 1
+        vj = vi.astype(np.int64)
+        oi, osc, ofr = oracle.memory_rank(vs, ctype[vj], conf[vj], acc[vj], last[vj], now, k, min_score)
+        assert t["mem_ids"] == [int(vi[i]) for i in oi] and t["mem_relevance"] == [float(vs[i]) for i in oi]
+        assert np.allclose(t["mem_scores"], osc, rtol=0, atol=1e-15) and np.allclose(t["mem_freshness"], ofr, rtol=0, atol=1e-15)
     assert "libragera error" in out["rejected"] and "64" in out["rejected"]        # k beyond RAG_MAX_TOPK rejects the Promise
     assert "Float32Array" in out["thrown"]                                         # a bad argument throws synchronously

@@ -498,6 +498,26 @@ def test_memory_store_mirror(rb, native, oracle):
         assert np.allclose([g.score for g in got], osc, rtol=0, atol=1e-15)
         assert [g.relevanceScore for g in got] == [vs[i] for i in oi]
         assert ms.has_similar(embs[0], 0.9, now) == (oracle.cosine(embs[0], embs[0]) >= 0.9)
+        # touch (store.ts:207-215): accessCount + 1, lastAccessedAt = now — the device copy follows, freshness changes
+        later = now + 3_600_000
+        ms.touch_many([mems[2].id, mems[4].id], later)
+        assert (mems[2].accessCount, mems[2].lastAccessedAt) == (3, later)
+        acc2 = [mems[int(i) - 50].accessCount if i >= 50 else 0 for i in vi]
+        la2 = [mems[int(i) - 50].lastAccessedAt if i >= 50 else 0 for i in vi]
+        oi2, osc2, ofr2 = oracle.memory_rank(vs, ism, conf, acc2, la2, later, 3, 0.5)
+        got2 = ms.retrieve(q, 3, 0.5, now_ms=later)
+        assert [g.id for g in got2] == [mems[int(vi[i]) - 50].id for i in oi2]
+        assert np.allclose([g.score for g in got2], osc2, rtol=0, atol=1e-15) and np.allclose([g.freshnessScore for g in got2], ofr2, rtol=0, atol=1e-15)
+        # delete (store.ts:240-251) removes only the DB record: the vector node stays, retrieve skips it (`if (dbMemory)`, :153)
+        # BEFORE the slice, so the next-best memory moves up instead of leaving a hole
+        gone = got2[0].id
+        ms.delete(gone)
+        oi6, _, _ = oracle.memory_rank(vs, ism, conf, acc2, la2, later, 6, 0.5)
+        want = [mems[int(vi[i]) - 50].id for i in oi6 if mems[int(vi[i]) - 50].id != gone][:3]
+        got3 = ms.retrieve(q, 3, 0.5, now_ms=later)
+        assert [g.id for g in got3] == want and len(want) == 3 and ms.count() == 5
+        hs_res = hs.hybrid_search(index, "kb1", q, dict(vectorTopK=6, minVectorScore=0.0))
+        assert any(r.contentType == "memory" and r.id == f"memory_{gone}" for r in hs_res)      # still a memory hit of hybridSearch
     finally:
         index.close()
 
