@@ -46,6 +46,18 @@ def create_sharded_index(dist, total_rows: int, dim: int, dtype: int, device: in
     return idx
 
 
+def open_sharded_cache(dist, cache_path: str, device: int, bf16_shadow: bool = False):
+    """Bring a row-sharded index up from ONE binary sidecar (store_cache.cu): every rank reads the header, creates its
+    shard and streams only its own row range (verified block by block) into HBM. Returns (index, all node ids)."""
+    from . import _native as N
+
+    info = N.cache_info(cache_path)
+    idx = create_sharded_index(dist, info.rows, info.dim, info.dtype, device, bf16_shadow=bf16_shadow)
+    base, n = shard_range(info.rows, dist.get_world_size(), dist.get_rank())
+    ids = idx.load_cache(cache_path, first_row=base, nrows=n) if n else []
+    return idx, ids
+
+
 def merge_reference_order(ids_per_shard, scores_per_shard, k: int):
     """The order every rank's K5 merge implements, stated on host arrays for tests of the
     exchange protocol: (score desc, chunk id asc), first k. Not used by the product path."""

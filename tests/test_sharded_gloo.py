@@ -40,10 +40,18 @@ def _worker(rank: int, world: int, port: int, ret):
         all_sc = [torch.empty_like(sc_t) for _ in range(world)]
         dist.all_gather(all_ids, ids_t)
         dist.all_gather(all_sc, sc_t)
+        # one binary sidecar, every rank reads (and verifies) only its own row range — what open_sharded_cache streams to HBM
+        from rag_era_b200 import _native as N
+        cache = os.path.join(os.environ["RAGERA_TEST_TMP"], "kb.ragera")
+        if rank == 0:
+            N.cache_write_host(cache, oracle.gen_rows(g, 0, total, d, threads=1), ids=[f"n{i}" for i in range(total)])
+        dist.barrier()
+        part = N.cache_read_host(cache, first_row=base, nrows=n)
+        shard_ok = np.array_equal(part["rows"], X) and part["info"].rows == total and len(part["ids"]) == total
         # the unique-id broadcast used for the NCCL communicator (id generation stubbed: no GPU here)
         VectorIndex.comm_unique_id = staticmethod(lambda: bytes(range(128)))
         uid = broadcast_unique_id(dist, rank)
-        ok = uid == bytes(range(128))
+        ok = uid == bytes(range(128)) and shard_ok
         if rank == 0:
             Xall = oracle.gen_rows(g, 0, total, d, threads=1)
             for b in range(4):
@@ -60,6 +68,10 @@ def _worker(rank: int, world: int, port: int, ret):
 def test_two_rank_shard_exchange_merge(world):
     import torch.multiprocessing as mp
 
+    import tempfile
+
+    tmp = tempfile.mkdtemp(prefix="ragera_gloo_")
+    os.environ["RAGERA_TEST_TMP"] = tmp          # inherited by the spawned ranks
     ctx = mp.get_context("spawn")
     mgr = ctx.Manager()
     ret = mgr.dict()
@@ -70,4 +82,7 @@ def test_two_rank_shard_exchange_merge(world):
     for p in procs:
         p.join(180)
         assert p.exitcode == 0
+    import shutil
+
+    shutil.rmtree(tmp, ignore_errors=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
