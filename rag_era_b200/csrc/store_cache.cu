@@ -10,7 +10,7 @@
 //   [0,128)   rag_cache_header (magic, shape, section sizes, source stamp, checksums; written LAST, so an
 //             interrupted writer leaves a file without a valid magic; the file is renamed into place when done)
 //   rows      rows x dim elements of the index dtype, row-major, unpadded
-//   blocks    one FNV-1a-64 per block of `block_rows` rows — a shard can load and verify only its own row range
+//   blocks    one 64-bit FNV-style checksum per block of `block_rows` rows — a shard can load and verify only its own row range
 //   meta      (flag META) content_type u8[rows] · confidence f64[rows] · access_count i32[rows] · last_access_ms i64[rows]
 //   keys      (flag KEYS) fusion key u64[rows]
 //   ids       node ids, '\0'-separated, row order
@@ -52,9 +52,25 @@ struct rag_cache_header {
 };
 static_assert(sizeof(rag_cache_header) == 128, "cache header layout");
 
-// FNV-1a over 8-byte words (the tail, if any, byte by byte): one multiply per 8 bytes keeps up with the disk
+// FNV-1a-style checksum over 8-byte words in four interleaved lanes (word i goes to lane i % 4; the lanes are folded
+// into the running value at the end of every call, the tail byte by byte): four independent multiply chains keep up
+// with the page cache, one chain does not. Call boundaries are part of the definition — writer and reader both feed
+// whole sections / whole row blocks.
 uint64_t fnv64(uint64_t h, const void* data, size_t n) {
   const unsigned char* p = (const unsigned char*)data;
+  uint64_t l0 = h, l1 = h ^ 0x9e3779b97f4a7c15ull, l2 = h ^ 0xc2b2ae3d27d4eb4full, l3 = h ^ 0x165667b19e3779f9ull;
+  for (; n >= 32; n -= 32, p += 32) {
+    uint64_t w[4];
+    memcpy(w, p, 32);
+    l0 = (l0 ^ w[0]) * kFnvPrime;
+    l1 = (l1 ^ w[1]) * kFnvPrime;
+    l2 = (l2 ^ w[2]) * kFnvPrime;
+    l3 = (l3 ^ w[3]) * kFnvPrime;
+  }
+  h = l0;
+  h = (h ^ l1) * kFnvPrime;
+  h = (h ^ l2) * kFnvPrime;
+  h = (h ^ l3) * kFnvPrime;
   for (; n >= 8; n -= 8, p += 8) {
     uint64_t w;
     memcpy(&w, p, 8);
@@ -104,7 +120,8 @@ struct cache_writer {
   std::string path, tmp;
   rag_cache_header h;
   uint64_t written = 0;        // rows so far
-  uint64_t in_block = 0, block_sum = kFnvBasis;
+  uint64_t in_block = 0;
+  std::vector<char> pending;   // rows of the block being filled
   std::vector<uint64_t> blocks;
 
   ~cache_writer() {
@@ -139,13 +156,21 @@ struct cache_writer {
     const size_t rb = (size_t)h.dim * esize(h.dtype);
     const char* p = (const char*)rows;
     RAG_CHECK(put(p, (size_t)n * rb));
-    while (n) {
+    while (n) {  // a block is always hashed in ONE call (the reader does the same): partial blocks wait in `pending`
       const uint64_t take = std::min<uint64_t>(n, h.block_rows - in_block);
-      block_sum = fnv64(block_sum, p, (size_t)take * rb);
+      if (in_block == 0 && take == h.block_rows) {
+        blocks.push_back(fnv64(kFnvBasis, p, (size_t)take * rb));
+      } else {
+        pending.insert(pending.end(), p, p + (size_t)take * rb);
+        if ((in_block += take) == h.block_rows) {
+          blocks.push_back(fnv64(kFnvBasis, pending.data(), pending.size()));
+          pending.clear();
+          in_block = 0;
+        }
+      }
       p += (size_t)take * rb;
       n -= take;
       written += take;
-      if ((in_block += take) == h.block_rows) { blocks.push_back(block_sum); block_sum = kFnvBasis; in_block = 0; }
     }
     return RAG_OK;
   }
@@ -153,7 +178,7 @@ struct cache_writer {
              const char* ids, uint64_t ids_bytes, const char* source_json) {
     if (written != h.rows) return rag_set_error(RAG_ERR_INVALID, "cache writer: %llu of %llu rows written",
                                                 (unsigned long long)written, (unsigned long long)h.rows);
-    if (in_block) blocks.push_back(block_sum);
+    if (in_block) blocks.push_back(fnv64(kFnvBasis, pending.data(), pending.size()));
     static const char zeros[16] = {0};
     const size_t rows_bytes = (size_t)h.rows * h.dim * esize(h.dtype);
     RAG_CHECK(put(zeros, pad16(rows_bytes) - rows_bytes));
