@@ -33,6 +33,7 @@ struct rag_batcher_req {
   int rc = RAG_OK;
   bool done = false;
   std::string err;
+  std::chrono::steady_clock::time_point t_enq;
 };
 
 struct rag_batcher {
@@ -100,8 +101,9 @@ void worker_main(rag_batcher* b) {
       std::unique_lock<std::mutex> lk(b->mu);
       b->cv_work.wait(lk, [&] { return b->stop || !b->queue.empty(); });
       if (b->stop && b->queue.empty()) return;
-      // the first request opens a collection window; leave early once the batch is full
-      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(b->desc.max_wait_us);
+      // the OLDEST waiting request opens the collection window (requests that queued up behind a running batch have
+      // already waited: they go out at once); leave early once the batch is full
+      const auto deadline = b->queue.front()->t_enq + std::chrono::microseconds(b->desc.max_wait_us);
       b->cv_work.wait_until(lk, deadline, [&] { return b->stop || b->queue.size() >= b->desc.max_batch; });
       batch.clear();
       while (!b->queue.empty() && batch.size() < b->desc.max_batch) {
@@ -168,6 +170,7 @@ int rag_batcher_submit(rag_batcher* b, const float* query, const uint64_t* kw_ke
   {
     std::unique_lock<std::mutex> lk(b->mu);
     if (b->stop) return rag_set_error(RAG_ERR_STATE, "rag_batcher_submit: batcher is shutting down");
+    r.t_enq = std::chrono::steady_clock::now();
     b->queue.push_back(&r);
     b->cv_work.notify_one();
     b->cv_done.wait(lk, [&] { return r.done; });
