@@ -64,6 +64,31 @@ def main():
                     ok = False
                     print(f"MISMATCH (escalation) rows={total} query={b}", flush=True)
         idx.close()
+    # one binary sidecar, every rank streams only its own row range into HBM (open_sharded_cache)
+    import tempfile
+    from rag_era_b200.sharded import open_sharded_cache
+
+    total, d = 30_011, 128
+    go = oracle.make_gen(total, n_clusters=16)
+    path = os.path.join(tempfile.gettempdir(), "ragera_sharded_check.ragera")
+    Xc = oracle.gen_rows(go, 0, total, d)
+    if rank == 0:
+        N.cache_write_host(path, Xc, ids=[f"n{i}" for i in range(total)])
+    dist.barrier()
+    idx, ids = open_sharded_cache(dist, path, local, bf16_shadow=True)
+    Qc = oracle.gen_queries(go, 0, 12, d)
+    for pth in (N.PATH_STREAM, N.PATH_TENSOR):
+        top = idx.query(Qc, 10, path=pth)
+        if rank == 0:
+            for b in range(12):
+                ei, es = oracle.topk(Xc, Qc[b], 10)
+                if not (np.array_equal(top.row(b)[0], ei) and np.array_equal(top.row(b)[1], es) and len(ids) == total):
+                    ok = False
+                    print(f"MISMATCH (sidecar shards) path={pth} query={b}", flush=True)
+    idx.close()
+    dist.barrier()
+    if rank == 0:
+        os.remove(path)
     t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
