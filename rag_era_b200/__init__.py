@@ -11,7 +11,8 @@ from ._native import RagError
 from .index import Batcher, VectorIndex, RRFConfig, TopK, Fused, hybrid_opts
 from .hybrid_search import (PRESET_CONFIGS, HybridSearchResult, KeywordHit, KnowledgeIndex, Node, format_search_results,
                             get_preset_config, get_source_stats, hybrid_search, reciprocal_rank_fusion)
-from .memory import Memory, MemoryStore, ScoredMemory, batch_calculate_freshness, calculate_freshness_score
+from .memory import (Memory, MemoryStore, ScoredMemory, batch_calculate_freshness, calculate_freshness_score,
+                     sort_by_freshness)
 from .sharded import create_sharded_index, open_sharded_cache, shard_range
 from .context import (FusedResult, RetrievalDecision, SearchResult, ToolContext, calculate_retrieval_count, deep_search,
                       get_unified_results, process_results, search_knowledge)
@@ -20,6 +21,6 @@ __all__ = [
     "RagError", "Batcher", "VectorIndex", "RRFConfig", "TopK", "Fused", "hybrid_opts", "PRESET_CONFIGS", "HybridSearchResult",
     "KeywordHit", "KnowledgeIndex", "Node", "format_search_results", "get_preset_config", "get_source_stats",
     "hybrid_search", "reciprocal_rank_fusion", "Memory", "MemoryStore", "ScoredMemory", "batch_calculate_freshness",
-    "calculate_freshness_score", "create_sharded_index", "open_sharded_cache", "shard_range", "FusedResult", "process_results", "RetrievalDecision",
+    "calculate_freshness_score", "sort_by_freshness", "create_sharded_index", "open_sharded_cache", "shard_range", "FusedResult", "process_results", "RetrievalDecision",
     "SearchResult", "ToolContext", "calculate_retrieval_count", "deep_search", "get_unified_results", "search_knowledge",
 ]

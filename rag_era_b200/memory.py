@@ -56,6 +56,12 @@ def batch_calculate_freshness(memories: Sequence[Memory], now_ms: int, *, store)
     return [dict(memory=m, freshnessScore=float(s)) for m, s in zip(memories, sc)]
 
 
+def sort_by_freshness(memories: Sequence[Memory], now_ms: int, *, store) -> list:
+    """sortByFreshness — freshness.ts:74-83: freshness from the device, V8's stable sort (ties keep their order)."""
+    scored = batch_calculate_freshness(memories, now_ms, store=store)
+    return [s["memory"] for s in sorted(scored, key=lambda s: -s["freshnessScore"])]
+
+
 class MemoryStore:
     """MemoryStore of src/lib/memory/store.ts bound to one knowledge base's unified index."""
 

@@ -498,6 +498,12 @@ def test_memory_store_mirror(rb, native, oracle):
         assert np.allclose([g.score for g in got], osc, rtol=0, atol=1e-15)
         assert [g.relevanceScore for g in got] == [vs[i] for i in oi]
         assert ms.has_similar(embs[0], 0.9, now) == (oracle.cosine(embs[0], embs[0]) >= 0.9)
+        # sortByFreshness (freshness.ts:74-83): device freshness, stable order for ties (two identical memories keep their order)
+        twins = mems + [rb.Memory("twin", "kb1", "same as m1", mems[1].confidence, mems[1].accessCount, mems[1].lastAccessedAt)]
+        of = [oracle.freshness(m.confidence, m.accessCount, m.lastAccessedAt, now) for m in twins]
+        want_order = [twins[i].id for i in sorted(range(len(twins)), key=lambda i: -of[i])]
+        assert [m.id for m in rb.sort_by_freshness(twins, now, store=index.store)] == want_order
+        assert want_order.index("m1") < want_order.index("twin")
         # touch (store.ts:207-215): accessCount + 1, lastAccessedAt = now — the device copy follows, freshness changes
         later = now + 3_600_000
         ms.touch_many([mems[2].id, mems[4].id], later)
