@@ -389,7 +389,8 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     if do_cpu and rank == 0:
         # reference-faithful: ONE thread (the reference is single-threaded JS), full stable sort
         sample_rows = min(rows, 1_000_000)
-        n_q = 2 if sample_rows >= 500_000 else 20
+        # about 10-15 s of single-thread CPU work: 4 queries x 1M rows (2.7 s each), or 200 queries of a 10k-row corpus
+        n_q = 4 if sample_rows >= 500_000 else (40 if sample_rows >= 100_000 else 200)
         qps, per_query, sample = cpu_reference_leg(w, n_q, 0, 1, sample_rows)   # queries/s (batching does not help a scalar loop)
         res["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                "ms_per_query": per_query * 1e3}
