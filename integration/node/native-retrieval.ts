@@ -55,7 +55,10 @@ export class NativeKnowledgeIndex {
     const ctype = new Uint8Array(ids.length);
     const keys = new BigUint64Array(ids.length);
     ids.forEach((id, r) => {
-      const d = docs[id]?.__data__ ?? {};
+      // SimpleDocumentStore persists each node as {__data__, __type__}; __data__ is the node's JSON — a string in
+      // current llamaindex (serializer.toPersistence = JSON.stringify), a plain object in older stores: accept both
+      const raw = docs[id]?.__data__;
+      const d = typeof raw === 'string' ? JSON.parse(raw) : raw ?? {};
       const metadata = d.metadata ?? {};
       const text: string = d.text ?? '';
       idx.nodes.push({ id, text, metadata });
