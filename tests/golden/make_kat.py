@@ -16,6 +16,8 @@ Reference lines followed:
   min-cosine filter      src/lib/hybrid-search.ts:308-314
   calculateFreshness     src/lib/memory/freshness.ts:37-56
   MemoryStore blend      src/lib/memory/store.ts:148-175
+  similarity / getTopKEmbeddings   llamaindex@0.12.1 / @llamaindex/core@0.6.22 (un-vendored; published algorithm,
+                         "upstream-recalled"), call site src/lib/hybrid-search.ts:223-224
 
 Run:  python tests/golden/make_kat.py   (rewrites tests/golden/kat_rrf.json)
 """
@@ -84,6 +86,54 @@ def pack(name, cfg, vec, kw):
                              score=r["score"], hex=float(r["score"]).hex()) for r in res])
 
 
+def similarity_cosine(e1, e2):
+    """llamaindex `similarity(e1, e2, SimilarityType.DEFAULT)` (embeddings utils of @llamaindex/core@0.6.22, upstream-
+    recalled): dot product and both norms as three sequential left-to-right loops over JS numbers, no epsilon."""
+    def norm(x):
+        result = 0.0
+        for v in x:
+            result += v * v
+        return math.sqrt(result)
+    result = 0.0
+    for a, b in zip(e1, e2):
+        result += a * b
+    return result / (norm(e1) * norm(e2))
+
+
+def get_top_k_embeddings(query, embeddings, k):
+    """llamaindex `getTopKEmbeddings` as reached from SimpleVectorStore.query (no cutoff): score ALL rows in insertion
+    order, `sort((a, b) => b.similarity - a.similarity)` (stable in V8), first k."""
+    sims = [dict(similarity=similarity_cosine(query, e), id=i) for i, e in enumerate(embeddings)]
+    sims.sort(key=lambda s: -s["similarity"])
+    return [s["id"] for s in sims[:k]], [s["similarity"] for s in sims[:k]]
+
+
+def f32(x):
+    """The stored values are fp32-precision numbers (what an embeddings API returns, and what the index dtype holds)."""
+    import struct
+    return struct.unpack("<f", struct.pack("<f", x))[0]
+
+
+def cosine_topk_cases():
+    rng = random.Random(7_2026)
+    cases = []
+    for name, n, d, k, twist in [("tiny", 5, 4, 3, None), ("ties-identical-rows", 12, 8, 6, "dup"), ("k-exceeds-n", 4, 16, 10, None),
+                                 ("scaled-rows", 10, 8, 10, "scale"), ("negative-and-orthogonal", 9, 6, 9, "signs"),
+                                 ("d-not-multiple-of-4", 20, 13, 8, None), ("wide", 40, 96, 10, "dup"), ("search_knowledge-k5", 60, 32, 5, None)]:
+        X = [[f32(rng.gauss(0.0, 1.0)) for _ in range(d)] for _ in range(n)]
+        q = [f32(X[n // 2][j] + 0.3 * rng.gauss(0.0, 1.0)) for j in range(d)]
+        if twist == "dup":                      # exact ties: the earlier row must come first
+            X[n - 1] = list(X[1]); X[n // 3] = list(X[1])
+        if twist == "scale":                    # power-of-two scaling leaves the cosine bit-identical (ties again)
+            X[7] = [f32(4.0 * v) for v in X[2]]; X[5] = [f32(0.5 * v) for v in X[2]]
+        if twist == "signs":
+            X[0] = [f32(-v) for v in q]; X[1] = [0.0] * (d - 1) + [1.0]; X[2] = list(q)
+        ids, sims = get_top_k_embeddings(q, X, k)
+        cases.append(dict(name=name, dim=d, k=k, rows=[[float(v).hex() for v in r] for r in X], query=[float(v).hex() for v in q],
+                          ids=ids, similarities=[float(s).hex() for s in sims]))
+    return cases
+
+
 def main():
     D = "document"
     cases = [
@@ -120,7 +170,8 @@ def main():
     filt = dict(scores=[0.9, 0.31, 0.30, 0.2999], min=0.3, kept=filter_min([0.9, 0.31, 0.30, 0.2999], 0.3))
 
     out = dict(note="derived by tests/golden/make_kat.py from the cited reference lines; PARITY UNPINNED "
-                    "(the reference ships no golden vectors)", rrf=cases, freshness=fresh, blend=blends, filter=filt)
+                    "(the reference ships no golden vectors)", rrf=cases, freshness=fresh, blend=blends, filter=filt,
+               cosine_topk=cosine_topk_cases())
     with open(os.path.join(HERE, "kat_rrf.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(f"wrote {len(cases)} rrf cases")

@@ -169,6 +169,23 @@ def test_api_errors(rb, native):
 # ------------------------------------------------------------------------------------------
 # RRF / filter / hybrid
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["stream", "exact", "tensor"])
+def test_topk_kernels_on_golden_vectors(rb, native, golden, path):
+    """K1 / K1x / K2 (+K3, K4) against the golden cosine/top-k cases of tests/golden/make_kat.py: ids in the reference's
+    order (exact ties to the earlier row) and every similarity bit for bit."""
+    p = {"stream": native.PATH_STREAM, "exact": native.PATH_EXACT, "tensor": native.PATH_TENSOR}[path]
+    for c in golden["cosine_topk"]:
+        X = np.array([[float.fromhex(v) for v in r] for r in c["rows"]], dtype=np.float32)
+        q = np.array([float.fromhex(v) for v in c["query"]], dtype=np.float32)
+        with rb.VectorIndex(c["dim"], len(X), bf16_shadow=(path == "tensor")) as idx:
+            idx.upload(X)
+            r = idx.query(q, c["k"], path=p)
+            ids, sc = r.row(0)
+            assert [int(i) for i in ids] == c["ids"], (path, c["name"])
+            assert [float(s).hex() for s in sc] == c["similarities"], (path, c["name"])
+            assert r.certified[0], (path, c["name"])
+
+
 def test_rrf_kernel_on_golden_vectors(rb, native, golden):
     SRC = {0: "vector", 1: "keyword", 2: "both"}
     with rb.VectorIndex(64, 4) as idx:

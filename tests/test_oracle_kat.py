@@ -124,6 +124,22 @@ def test_cosine_topk_semantics(oracle):
     assert s1 == dot / (math.sqrt(nq) * math.sqrt(nx))
 
 
+def test_cosine_topk_golden_bit_exact(oracle, golden):
+    """The C oracle against the independent Python transliteration of llamaindex's similarity / getTopKEmbeddings
+    (tests/golden/make_kat.py): ids, order under exact ties, and every similarity bit for bit."""
+    assert len(golden["cosine_topk"]) >= 8
+    for c in golden["cosine_topk"]:
+        X = np.array([[float.fromhex(v) for v in r] for r in c["rows"]], dtype=np.float64)
+        q = np.array([float.fromhex(v) for v in c["query"]], dtype=np.float64)
+        assert np.array_equal(X, X.astype(np.float32)) and np.array_equal(q, q.astype(np.float32))   # fp32-representable
+        for faithful in (False, True):
+            ids, sc = oracle.topk(X.astype(np.float32), q.astype(np.float32), c["k"], faithful_sort=faithful)
+            assert [int(i) for i in ids] == c["ids"], c["name"]
+            assert [float(s).hex() for s in sc] == c["similarities"], c["name"]
+        for i, h in zip(c["ids"], c["similarities"]):
+            assert float(oracle.cosine(q.astype(np.float32), X[i].astype(np.float32))).hex() == h
+
+
 def test_threads_do_not_change_bits(oracle):
     rng = np.random.default_rng(11)
     X = rng.standard_normal((3000, 64)).astype(np.float32)
