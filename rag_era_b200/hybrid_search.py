@@ -126,12 +126,38 @@ class KnowledgeIndex:
         self.nodes.extend(nodes)
         return row0
 
+    def as_retriever(self, similarity_top_k: int = 2, path: int = N.PATH_AUTO) -> "Retriever":
+        """index.asRetriever({ similarityTopK }) — llamaindex's default similarityTopK is 2."""
+        return Retriever(self, similarity_top_k, path)
+
     def embed(self, query) -> np.ndarray:
         if isinstance(query, str):
             if self.embed_model is None:
                 raise ValueError("a string query needs an embed_model")
             query = self.embed_model(query)
         return np.ascontiguousarray(query, dtype=np.float32)
+
+
+@dataclass
+class NodeWithScore:
+    """What ``retriever.retrieve`` returns per hit (llamaindex NodeWithScore): the node and its cosine."""
+    node: Node
+    score: float
+
+
+class Retriever:
+    """``index.asRetriever({ similarityTopK })`` (hybrid-search.ts:223, memory/store.ts:111-113, summarize-tool.ts:46):
+    ``retrieve(query)`` embeds the query and returns the top-k nodes in rank order with exact fp64 cosines —
+    SimpleVectorStore.query → getTopKEmbeddings, run by ``rag_search`` on the device."""
+
+    def __init__(self, index: "KnowledgeIndex", similarity_top_k: int = 2, path: int = N.PATH_AUTO):
+        self.index, self.similarity_top_k, self.path = index, similarity_top_k, path
+
+    def retrieve(self, query) -> list[NodeWithScore]:
+        q = self.index.embed(query)
+        ids, scores = self.index.store.query(q, self.similarity_top_k, path=self.path).row(0)
+        base = self.index.store.id_base
+        return [NodeWithScore(self.index.nodes[int(i) - base], float(s)) for i, s in zip(ids, scores)]
 
 
 def classify_content_type(metadata: dict, is_codebase: bool) -> str:

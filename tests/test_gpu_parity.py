@@ -383,6 +383,10 @@ def test_hybrid_search_host_mirror(rb, native, oracle):
         assert res[0].documentName == "用户记忆" and res[0].documentId is None
         kw_only = [r for r in res if r.source == "keyword"]
         assert any(r.documentId == "D9" and r.contentType == "document" for r in kw_only)
+        # index.asRetriever({similarityTopK}).retrieve(query) — the seam every caller goes through (:223-224)
+        hits = index.as_retriever(similarity_top_k=5).retrieve("alpha")
+        assert [h.node.id_ for h in hits] == [f"node-{int(i)}" for i in ei] and [h.score for h in hits] == list(es)
+        assert len(index.as_retriever().retrieve("alpha")) == 2                  # llamaindex default similarityTopK
         # Meilisearch down → vector-only branch: raw cosines, node ids
         m.up = False
         res2 = hs.hybrid_search(index, "kb1", "alpha", dict(vectorTopK=5, minVectorScore=0.0), keyword_service=m)
