@@ -34,7 +34,7 @@ const PRESETS: Record<SearchPreset, { rrf: RRFConfig; vectorTopK: number; keywor
   code: { rrf: { k: 40, vectorWeight: 1.0, keywordWeight: 1.3, bothBonus: 0.15 }, vectorTopK: 6, keywordLimit: 5, minVectorScore: 0.25 },
 };
 
-interface NodeRow { id: string; text: string; metadata: Record<string, any> }
+export interface NodeRow { id: string; text: string; metadata: Record<string, any> }
 
 export class NativeKnowledgeIndex {
   /** row r of the device matrix ↔ nodes[r] (insertion order of embeddingDict). */
