@@ -117,6 +117,13 @@ def test_product_never_touches_the_oracle():
                 assert "oracle.h" not in text and "oracle/" not in text, f
     deps = subprocess.run(["ldd", os.path.join(pkg, "libragera.so")], capture_output=True, text=True).stdout
     assert "oracle" not in deps
+    # ... and outside tests/ only bench.py (cpu_baseline / --impl reference legs) and __graft_entry__.py (smoke) import it
+    for sub in ("tools", "integration", "include"):
+        for base, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cc", ".ts", ".h", ".sh")):
+                    text = open(os.path.join(base, f), errors="replace").read()
+                    assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, os.path.join(sub, f)
 
 
 def test_napi_addon_type_checks():

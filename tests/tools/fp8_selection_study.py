@@ -5,14 +5,14 @@ the batched tensor path (K4 would still rescore exactly)? Measures, on the synth
   (2) the gap between the k-th and the K'-th exact cosine per query,
 and from both the fraction of queries the certification rule (exact k-th > approx K'-th + eps) would pass.
 
-    python tools/fp8_selection_study.py [rows] [queries]
+    python tests/tools/fp8_selection_study.py [rows] [queries]
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402  (a study script, not product code)
 

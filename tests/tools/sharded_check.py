@@ -5,14 +5,14 @@ ids, scores, fused order and source flags bit for bit — on the stream, tensor 
 including exact ties that straddle the shard boundary and queries that must escalate.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/sharded_check.py
+        --master-port 29511 tests/tools/sharded_check.py
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

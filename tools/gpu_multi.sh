@@ -10,7 +10,7 @@ try:
 except Exception as e: print("parse failed", sys.argv[1], e)
 PY
 }
-timeout 600 $TR tools/sharded_check.py > $OUT/sharded_check_n$N.log 2>&1; echo "sharded check exit $?"; grep -E "parity|MISMATCH" $OUT/sharded_check_n$N.log | head
+timeout 600 $TR tests/tools/sharded_check.py > $OUT/sharded_check_n$N.log 2>&1; echo "sharded check exit $?"; grep -E "parity|MISMATCH" $OUT/sharded_check_n$N.log | head
 timeout 600 $TR bench.py --gpus $N > $OUT/bench_c3_n$N.json 2> $OUT/bench_c3_n$N.err; echo "bench c3 n=$N exit $?"; show $OUT/bench_c3_n$N.json; grep -v "OMP_NUM\|\*\*\*" $OUT/bench_c3_n$N.err | tail -3
 timeout 600 $TR bench.py --gpus $N --workload c5 --steps 30 --warmup 4 > $OUT/bench_c5_n$N.json 2> $OUT/bench_c5_n$N.err; echo "bench c5 n=$N exit $?"; show $OUT/bench_c5_n$N.json; grep -v "OMP_NUM\|\*\*\*" $OUT/bench_c5_n$N.err | tail -3
 timeout 600 $TR bench.py --gpus $N --workload c2b --steps 50 --warmup 5 > $OUT/bench_c2b_n$N.json 2> $OUT/bench_c2b_n$N.err; echo "bench c2b n=$N exit $?"; show $OUT/bench_c2b_n$N.json

@@ -10,7 +10,7 @@ try:
 except Exception as e: print("parse failed", sys.argv[1], e)
 PY
 }
-timeout 300 $TR tools/sharded_check.py > $OUT/sharded_check_p2p_n$N.log 2>&1; echo "sharded check exit $?"; grep -E "parity|MISMATCH" $OUT/sharded_check_p2p_n$N.log | head -3
+timeout 300 $TR tests/tools/sharded_check.py > $OUT/sharded_check_p2p_n$N.log 2>&1; echo "sharded check exit $?"; grep -E "parity|MISMATCH" $OUT/sharded_check_p2p_n$N.log | head -3
 timeout 400 $TR bench.py --gpus $N --no-extra > $OUT/bench_c3_p2p_n$N.json 2> $OUT/bench_c3_p2p_n$N.err; echo "bench c3 p2p n=$N exit $?"; show $OUT/bench_c3_p2p_n$N.json
 RAGERA_COMM=nccl timeout 400 $TR bench.py --gpus $N --no-extra > $OUT/bench_c3_nccl_n$N.json 2> $OUT/bench_c3_nccl_n$N.err; echo "bench c3 nccl n=$N exit $?"; show $OUT/bench_c3_nccl_n$N.json
 timeout 500 $TR bench.py --gpus $N --workload c5 --no-extra --steps 30 --warmup 4 > $OUT/bench_c5_p2p_n$N.json 2> $OUT/bench_c5_p2p_n$N.err; echo "bench c5 n=$N exit $?"; show $OUT/bench_c5_p2p_n$N.json

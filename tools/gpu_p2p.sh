@@ -10,7 +10,7 @@ try:
 except Exception as e: print("parse failed", sys.argv[1], e)
 PY
 }
-timeout 300 $TR tools/sharded_check.py > $OUT/sharded_check_p2p_n$N.log 2>&1; echo "sharded check (p2p) exit $?"; grep -E "parity|MISMATCH|rror" $OUT/sharded_check_p2p_n$N.log | head
+timeout 300 $TR tests/tools/sharded_check.py > $OUT/sharded_check_p2p_n$N.log 2>&1; echo "sharded check (p2p) exit $?"; grep -E "parity|MISMATCH|rror" $OUT/sharded_check_p2p_n$N.log | head
 for MODE in p2p nccl; do
   RAGERA_COMM=$MODE timeout 400 $TR bench.py --gpus $N --workload c2 --no-extra --steps 300 --warmup 20 > $OUT/bench_c2_${MODE}_n$N.json 2> $OUT/bench_c2_${MODE}_n$N.err; echo "bench c2 $MODE n=$N exit $?"; show $OUT/bench_c2_${MODE}_n$N.json; grep -i "error\|trap\|fail" $OUT/bench_c2_${MODE}_n$N.err | head -3
 done
