@@ -52,6 +52,8 @@ int main(void) {
   printf("rag_text %zu\n", sizeof(rag_text));
   printf("rag_process_opts %zu\n", sizeof(rag_process_opts));
   printf("rag_processed_out %zu\n", sizeof(rag_processed_out));
+  printf("rag_cache_info %zu\n", sizeof(rag_cache_info));
+  printf("off_memory_topk %zu\n", offsetof(rag_memory_opts, similarity_top_k));
   printf("off_hybrid_now_ms %zu\n", offsetof(rag_hybrid_opts, now_ms));
   printf("off_hybrid_epsilon %zu\n", offsetof(rag_hybrid_opts, epsilon));
   printf("off_fused_certified %zu\n", offsetof(rag_fused_out, certified));
@@ -79,6 +81,8 @@ int main(void) {
     assert int(got["rag_text"]) == C.sizeof(N.Text)
     assert int(got["rag_process_opts"]) == C.sizeof(N.ProcessOpts)
     assert int(got["rag_processed_out"]) == C.sizeof(N.ProcessedOut)
+    assert int(got["rag_cache_info"]) == C.sizeof(N.CacheInfo)
+    assert int(got["off_memory_topk"]) == N.MemoryOpts.similarity_top_k.offset
     assert int(got["off_hybrid_now_ms"]) == N.HybridOpts.now_ms.offset
     assert int(got["off_hybrid_epsilon"]) == N.HybridOpts.epsilon.offset
     assert int(got["off_fused_certified"]) == N.FusedOut.certified.offset
