@@ -253,7 +253,7 @@ struct cache_reader {
     sec(s.ids_off, h.ids_bytes);
     if (sum != h.tail_sum) return bad("metadata checksum mismatch");
     blocks.resize((size_t)s.nblocks);
-    memcpy(blocks.data(), tail.data(), blocks.size() * 8);
+    if (!blocks.empty()) memcpy(blocks.data(), tail.data(), blocks.size() * 8);
     return RAG_OK;
   }
   const char* at(uint64_t off) const { return tail.data() + (off - s.blocks_off); }
@@ -286,7 +286,7 @@ int copy_ids(const cache_reader& r, char** ids, uint64_t* ids_bytes) {
   if (!ids) return RAG_OK;
   char* blob = (char*)malloc(r.h.ids_bytes ? (size_t)r.h.ids_bytes : 1);
   if (!blob) return rag_set_error(RAG_ERR_NOMEM, "out of host memory");
-  memcpy(blob, r.at(r.s.ids_off), (size_t)r.h.ids_bytes);
+  if (r.h.ids_bytes) memcpy(blob, r.at(r.s.ids_off), (size_t)r.h.ids_bytes);
   *ids = blob;
   if (ids_bytes) *ids_bytes = r.h.ids_bytes;
   return RAG_OK;

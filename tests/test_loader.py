@@ -295,3 +295,50 @@ def test_parser_agrees_with_python_json_on_arbitrary_stores(native, tmp_path, st
         assert ct[r] == want, (i, m)
         want_mem = m.get("memoryId") if isinstance(m.get("memoryId"), str) else ""
         assert mem[r] == want_mem.replace("\0", "�"), (i, m)
+
+
+def test_loader_and_sidecar_under_sanitizers(tmp_path):
+    """loader.cu + store_cache.cu are host-only: built as plain C++ with ASAN + UBSAN (tests/c/host_asan.cc) and driven over good,
+    truncated, malformed, unicode and deeply nested stores, then over truncated / bit-flipped sidecars. No sanitizer report, every
+    malformed input rejected with a message, no corrupted sidecar ever returns wrong data."""
+    import shutil
+    import subprocess
+
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "rag_era_b200", "csrc")
+    exe = str(tmp_path / "host_asan")
+    r = subprocess.run(["g++", "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-x", "c++",
+                        "-I" + cuda_inc, "-I" + os.path.join(root, "include"), "-I" + csrc, os.path.join(root, "tests", "c", "host_asan.cc"),
+                        os.path.join(csrc, "loader.cu"), os.path.join(csrc, "store_cache.cu"), "-o", exe, "-L" + cuda_lib, "-lcudart",
+                        "-Wl,-rpath," + cuda_lib], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr and "cannot find" in r.stderr:
+        pytest.skip("libasan / libubsan are not installed")
+    assert r.returncode == 0, r.stderr[-2000:]
+    rng = np.random.default_rng(9)
+    dim = 6
+    ids = [f"id{i}" for i in range(9000)]
+    good = json.dumps({"embeddingDict": {i: [float(v) for v in rng.random(dim)] for i in ids},
+                       "metadataDict": {i: {"type": "memory", "memoryId": "m" + i, "language": None} for i in ids[::3]}})
+    cases = {
+        "good": (good, True), "truncated": (good[:len(good) // 2], False), "badnum": (good.replace("0.", "x.", 1), False),
+        "badtype": ('{"embeddingDict": {"a": [1,2,3,4,5,6], "b": "oops"}}', False), "empty": ('{"embeddingDict": {}}', True),
+        "emptyfile": ("", False),
+        "unicode": ('{"embeddingDict": {"\\ud83d\\ude00\\u0000": [1e999,-1e-999,0,1,2,3]}, "metadataDict": {"\\ud83d\\ude00\\u0000": '
+                    '{"type": "memory", "memoryId": "\\ud800"}}}', True),
+        "dupkeys": ('{"embeddingDict": {"a": [1,1,1,1,1,1]}, "metadataDict": {"zzz": {"type":"memory"}, "a": 5, "a": {"language": {"x": [1,2,{"y":"}"}]}}}}', True),
+        "deepnest": ('{"x": ' + "[" * 5000 + "]" * 5000 + ', "embeddingDict": {"a": [1,2,3,4,5,6]}}', True),
+    }
+    for name, (text, ok) in cases.items():
+        p = str(tmp_path / (name + ".json"))
+        open(p, "w").write(text)
+        r = subprocess.run([exe, p, str(dim), str(tmp_path / (name + ".ragera"))], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
+        assert r.returncode == 0, (name, r.stderr[-1500:])
+        assert "AddressSanitizer" not in r.stderr and "LeakSanitizer" not in r.stderr and "runtime error" not in r.stderr, (name, r.stderr[-1500:])
+        assert ("parse rc=0" in r.stdout) == ok, (name, r.stdout)
+        assert "ACCEPTED CORRUPT DATA" not in r.stdout, (name, r.stdout)
+        if ok:
+            assert "read rc=0 same=1" in r.stdout and "write rc=0 fresh=1" in r.stdout, (name, r.stdout)
