@@ -149,3 +149,30 @@ texts = st.text(alphabet=alphabet, min_size=0, max_size=80)
 def test_process_results_property(native, contents, scores, query, noise, rerank):
     rs = [R(c, s, ["vector", "keyword", "hybrid"][i % 3]) for i, (c, s) in enumerate(zip(contents, scores))]
     check(rs, query, enable_noise_filter=noise, enable_rerank=rerank)
+
+
+def test_process_results_under_sanitizers(tmp_path):
+    """postfilter.cu is host-only: built as plain C++ with ASAN + UBSAN (tests/c/postfilter_asan.cc) and driven with random UTF-16
+    inputs (empty strings, lone surrogates, CJK punctuation, multi-KB runs, exact duplicates) and random options."""
+    import os
+    import shutil
+    import subprocess
+
+    import pytest
+
+    cuda_inc, cuda_lib = "/usr/local/cuda/include", "/usr/local/cuda/lib64"
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "rag_era_b200", "csrc")
+    exe = str(tmp_path / "postfilter_asan")
+    r = subprocess.run(["g++", "-std=c++17", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-x", "c++",
+                        "-I" + cuda_inc, "-I" + os.path.join(root, "include"), "-I" + csrc, os.path.join(root, "tests", "c", "postfilter_asan.cc"),
+                        os.path.join(csrc, "postfilter.cu"), "-o", exe, "-L" + cuda_lib, "-lcudart", "-Wl,-rpath," + cuda_lib],
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr and "cannot find" in r.stderr:
+        pytest.skip("libasan / libubsan are not installed")
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe, "400"], capture_output=True, text=True, timeout=300, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
+    assert r.returncode == 0 and "0 failures" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+    assert "AddressSanitizer" not in r.stderr and "LeakSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-1500:]
