@@ -1,0 +1,99 @@
+// batcher_tsan.cc — TEST HARNESS: the micro-batcher (batcher.cu, host-only) compiled as plain C++ with -fsanitize=thread and
+// driven by many concurrent submitters against a STUB rag_hybrid_search that derives every output from the query it was
+// given. Checks: every submitter gets exactly its own result back (no cross-talk between slots of a batch), errors of a
+// batch reach every waiter, batches really form (largest batch > 1), shutdown with submitters still arriving is clean, and
+// ThreadSanitizer reports no race. Run by tests/test_gpu_batcher.py::test_batcher_threads_under_tsan (CPU).
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <vector>
+static thread_local char g_err[1024];
+int rag_set_error(int code, const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); return code; }
+static std::atomic<int> g_calls{0}, g_fail_every{0};
+extern "C" {
+const char* rag_last_error(void) { return g_err; }
+void* rag_host_alloc(uint64_t bytes) { return malloc(bytes); }
+void rag_host_free(void* p) { free(p); }
+// the stub: result of query b = f(query[b][0], its keyword keys); sleeps like a corpus pass so that requests pile up
+int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const rag_hybrid_opts* o, const uint64_t* kw_keys,
+                      const uint32_t* kw_counts, rag_fused_out* out) {
+  std::this_thread::sleep_for(std::chrono::microseconds(300));
+  const int call = ++g_calls;
+  if (g_fail_every && call % g_fail_every == 0) return rag_set_error(RAG_ERR_CUDA, "injected failure of batch %d", call);
+  const uint32_t k = o->vector_top_k, cap = out->capacity;
+  for (uint32_t b = 0; b < B; b++) {
+    const uint64_t tag = (uint64_t)queries[(size_t)b * idx->dim];
+    const uint32_t n = 1 + (uint32_t)(tag % k);
+    for (uint32_t i = 0; i < n; i++) { out->keys[(size_t)b * cap + i] = tag * 1000 + i; out->scores[(size_t)b * cap + i] = (double)tag + 0.001 * i; }
+    uint64_t kwsum = 0;
+    for (uint32_t i = 0; i < kw_counts[b]; i++) kwsum += kw_keys[(size_t)b * o->keyword_limit + i];
+    out->keys[(size_t)b * cap + n] = kwsum;  // one extra slot carries the keyword list's checksum
+    out->counts[b] = n + 1;
+    if (out->used_rrf) out->used_rrf[b] = kw_counts[b] ? 1 : 0;
+    if (out->certified) out->certified[b] = 1;
+    if (out->vec_ids && out->vec_counts) { out->vec_counts[b] = 1; out->vec_ids[(size_t)b * k] = tag; out->vec_scores[(size_t)b * k] = (double)tag; }
+  }
+  return RAG_OK;
+}
+}
+int main() {
+  rag_index idx;  // never touched by the batcher except for dim and as an opaque handle for the stub
+  idx.dim = 16;
+  rag_batcher_desc d;
+  memset(&d, 0, sizeof d);
+  d.max_batch = 8;
+  d.max_wait_us = 200;
+  d.opts.vector_top_k = 5;
+  d.opts.keyword_limit = 4;
+  rag_batcher* bt = nullptr;
+  if (rag_batcher_create(&idx, &d, &bt) != RAG_OK) { printf("create failed: %s\n", g_err); return 1; }
+  std::atomic<int> wrong{0}, failed{0}, done{0};
+  auto submitter = [&](int tid, int n) {
+    for (int r = 0; r < n; r++) {
+      const uint64_t tag = (uint64_t)tid * 100000 + r + 1;
+      float q[16] = {(float)tag};
+      uint64_t kw[4] = {tag, tag + 1, 7, 9};
+      const uint32_t kwc = (uint32_t)(tag % 5);  // 0..4
+      uint64_t keys[9]; double scores[9]; uint8_t src[9], ct[9], rrf, cert; uint32_t cnt, vcnt; uint64_t vid[5]; double vs[5];
+      rag_fused_out out = {9, keys, scores, src, ct, &cnt, &rrf, vid, vs, &vcnt, &cert};
+      const int rc = rag_batcher_submit(bt, q, kw, kwc, &out);
+      if (rc != RAG_OK) { failed++; continue; }
+      const uint32_t n_exp = 1 + (uint32_t)(tag % 5);
+      uint64_t kwsum = 0;
+      for (uint32_t i = 0; i < kwc; i++) kwsum += kw[i];
+      bool ok = cnt == n_exp + 1 && keys[n_exp] == kwsum && vid[0] == tag && rrf == (kwc ? 1 : 0);
+      for (uint32_t i = 0; ok && i < n_exp; i++) ok = keys[i] == tag * 1000 + i && scores[i] == (double)tag + 0.001 * i;
+      if (!ok) wrong++;
+      done++;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < 24; t++) th.emplace_back(submitter, t, 40);
+  for (auto& t : th) t.join();
+  uint64_t batches = 0, queries = 0, largest = 0;
+  rag_batcher_stats(bt, &batches, &queries, &largest);
+  printf("phase 1: done=%d wrong=%d failed=%d batches=%llu queries=%llu largest=%llu\n", done.load(), wrong.load(), failed.load(),
+         (unsigned long long)batches, (unsigned long long)queries, (unsigned long long)largest);
+  const bool p1 = done == 24 * 40 && wrong == 0 && failed == 0 && queries == 24 * 40 && largest > 1 && largest <= 8;
+  // phase 2: every 3rd batch fails: all its waiters must see the error, the others their own results
+  g_fail_every = 3;
+  done = 0; wrong = 0; failed = 0;
+  th.clear();
+  for (int t = 0; t < 12; t++) th.emplace_back(submitter, 100 + t, 20);
+  for (auto& t : th) t.join();
+  printf("phase 2: done=%d wrong=%d failed=%d\n", done.load(), wrong.load(), failed.load());
+  const bool p2 = done + failed == 12 * 20 && wrong == 0 && failed > 0 && done > 0;
+  // phase 3: bad arguments are refused without touching the queue
+  float q[16] = {1.f};
+  uint64_t keys[2]; double scores[2]; uint32_t cnt;
+  rag_fused_out small = {2, keys, scores, nullptr, nullptr, &cnt, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const bool p3 = rag_batcher_submit(bt, q, nullptr, 0, &small) == RAG_ERR_INVALID && rag_batcher_submit(bt, nullptr, nullptr, 0, &small) == RAG_ERR_INVALID;
+  rag_batcher_destroy(bt);
+  printf("result: %s\n", (p1 && p2 && p3) ? "OK" : "FAILED");
+  return (p1 && p2 && p3) ? 0 : 1;
+}
