@@ -93,6 +93,14 @@ typedef struct rag_search_opts {
 } rag_search_opts;
 
 #define RAG_SEARCH_NO_ESCALATE 1u /* do not re-run uncertified queries on a stronger path */
+/* Certification bound of the tensor path (K2). Default: RIGOROUS — a deterministic bound on
+ * |selected score - exact cosine| from the measured rounding residuals of the operands
+ * (||q - round(q)|| / ||q|| per query, max over rows of ||x - round(x)|| / ||x||, Cauchy-Schwarz), plus the
+ * fp32 accumulation and normalisation terms: certified = 1 is then a proof that the ids equal an exact scan.
+ * RAG_SEARCH_STAT_EPS selects the round-1 statistical bound instead (0.024/sqrt(ld) for bf16 operands,
+ * 0.006/sqrt(ld) for tf32: ~11 sigma on near-Gaussian rows — tighter, certifies more queries in the first
+ * pass, but NOT a proof: rows whose rounding errors align can exceed it). */
+#define RAG_SEARCH_STAT_EPS 2u
 
 /* result of SimpleVectorStore.query → {ids, similarities} (llamaindex, via
  * src/lib/hybrid-search.ts:223-224); rank-ordered, scores are exact fp64 cosines */
@@ -149,7 +157,7 @@ typedef struct rag_memory_opts {
   uint32_t similarity_top_k;  /* retriever similarityTopK; 0 → limit * 2 (store.ts:112). A host that must drop
                                  memories whose DB record is gone (`if (dbMemory)`, store.ts:153) asks for
                                  limit = similarity_top_k = 2L, filters, and keeps the first L        */
-  uint32_t reserved;
+  uint32_t flags;             /* RAG_SEARCH_* (escalation is always on here)                       */
 } rag_memory_opts;
 
 typedef struct rag_memory_out {
@@ -331,6 +339,11 @@ int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, fl
  *      so the fused tcgen05 selection can be checked exactly (ties included) on small inputs */
 int rag_debug_tensor_candidates(rag_index* idx, const float* queries, uint32_t B, uint32_t kp, float* out_scores,
                                 uint64_t* out_keys);
+
+/*      rho_x of the rigorous certification bound: max over the loaded rows of ||x - operand(x)|| / ||x||, where
+ *      operand(x) is what the tensor path multiplies (the bf16 shadow row, or the row read as tf32; 0 for a bf16
+ *      corpus, whose rows are the operand). Returns a negative rag_status on error. */
+double rag_index_row_residual(rag_index* idx);
 
 /* ---- measurement helpers (CUDA events on the library's own stream) ------------ */
 int rag_timer_start(rag_index* idx);

@@ -25,6 +25,7 @@ PATH_AUTO, PATH_STREAM, PATH_TENSOR, PATH_EXACT = 0, 1, 2, 3
 INDEX_BF16_SHADOW = 1
 CACHE_META, CACHE_KEYS = 1, 2
 SEARCH_NO_ESCALATE = 1
+SEARCH_STAT_EPS = 2
 PROF_CLASSES = 6
 PROF_NAMES = ("stream", "tensor", "merge", "rescore", "fuse", "comm")
 COMM_ID_BYTES = 128
@@ -97,7 +98,7 @@ class BatcherDesc(C.Structure):
 class MemoryOpts(C.Structure):
     _fields_ = [("limit", C.c_uint32), ("path", C.c_uint32), ("min_relevance", C.c_double), ("now_ms", C.c_int64),
                 ("time_decay_factor", C.c_double), ("frequency_bonus", C.c_double), ("similarity_top_k", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32)]
 
 
 class MemoryOut(C.Structure):
@@ -165,6 +166,7 @@ SYMBOLS = {
     "rag_debug_tensor_candidates": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "rag_timer_start": (C.c_int, [_vp]),
     "rag_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "rag_index_row_residual": (C.c_double, [_vp]),
     "rag_launch_count": (C.c_uint64, [_vp]),
     "rag_profile_enable": (C.c_int, [_vp, C.c_int]),
     "rag_profile_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),

@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libragera.so (include/ragera.h): handle lifetime, staging, the
 // kernel pipeline  score+select (K1 | K2 | K1x) → merge (K3) → exact rescore (K4) →
-// [NCCL all-gather] → merge/filter/fuse (K5), certification-driven escalation, and the
+// [exchange of the ranks' local top-k: inside K5 over peer mailboxes, or ncclAllGather] →
+// merge/filter/fuse (K5), certification-driven escalation, and the
 // measurement helpers. Host code only; every kernel lives in its own .cu.
 //
 // There is no CPU implementation of any step in this library: without an sm_100 device
@@ -69,7 +70,7 @@ int grow_pinned(uint8_t** p, size_t* cap, size_t need) {
 }
 
 void free_batch(rag_batch* b) {
-  cudaFree(b->d_q); cudaFree(b->d_qb); cudaFree(b->d_in); cudaFree(b->d_sel); cudaFree(b->d_partial);
+  cudaFree(b->d_q); cudaFree(b->d_qb); cudaFree(b->d_rho_q); cudaFree(b->d_in); cudaFree(b->d_sel); cudaFree(b->d_partial);
   cudaFree(b->d_cand); cudaFree(b->d_local); cudaFree(b->d_gather); cudaFree(b->d_local_cnt); cudaFree(b->d_out);
   cudaFree(b->d_k4s); cudaFree(b->d_ticket);
   if (b->h_in) cudaFreeHost(b->h_in);
@@ -120,11 +121,24 @@ void bind_out(rag_batch* b, const out_layout& L) {
 struct plan {
   int path;          // rag_path (never AUTO)
   uint32_t kp;       // K'
-  double eps;        // selection-error bound used by K4's certification
+  double eps;        // selection-error bound used by K4's certification (the per-batch part)
+  bool eps_per_query;  // tensor path, rigorous bound: eps[b] = eps + rho_q[b] * eps_q_mul
+  double eps_q_mul;
   int key_has_qnorm; // K1x keys hold the cosine, K1/K2 keys hold dot/||x||
 };
 
-int make_plan(const rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_t slack, double eps,
+// host mirror of the rows' rounding residual (aux_build raises it on the device)
+int refresh_rho_x(rag_index* idx) {
+  if (!idx->rho_x_stale || !idx->d_rho_x) return RAG_OK;
+  uint32_t bits = 0;
+  RAG_CUDA(cudaMemcpyAsync(&bits, idx->d_rho_x, 4, cudaMemcpyDeviceToHost, idx->stream));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  memcpy(&idx->rho_x, &bits, 4);
+  idx->rho_x_stale = false;
+  return RAG_OK;
+}
+
+int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_t slack, double eps, uint32_t flags,
               plan* p) {
   int path = (int)req_path;
   if (path == RAG_PATH_AUTO)
@@ -134,40 +148,60 @@ int make_plan(const rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, u
     return rag_set_error(RAG_ERR_INVALID, "unknown rag_path %d", path);
   if (path == RAG_PATH_TENSOR && !k2_available(idx))
     return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path (K2) is not available for this index");
+  const bool stat_eps = (flags & RAG_SEARCH_STAT_EPS) != 0;
   uint32_t s = slack;
-  // the tensor path selects on bf16 scores: a wider window keeps (nearly) every query certifiable in one
-  // pass — an uncertified query costs a whole extra corpus pass on the stream path
-  if (s == 0) s = path == RAG_PATH_TENSOR ? std::max(22u, k) : 6u;
+  // the tensor path selects on bf16 / tf32 scores: a wider window keeps (nearly) every query certifiable in one
+  // pass — an uncertified query costs a whole extra corpus pass on the stream path. The rigorous bound of an
+  // fp32 index with a bf16 shadow carries the rounding of BOTH operands (~3.5e-3 at D=1536): widest window.
+  const bool both_rounded = idx->shadow && (const void*)idx->shadow != idx->corpus;
+  if (s == 0) s = path == RAG_PATH_TENSOR ? ((!stat_eps && eps <= 0.0 && both_rounded) ? 48u : std::max(22u, k)) : 6u;
   uint32_t kp = std::min<uint32_t>(path == RAG_PATH_TENSOR ? 48u : (uint32_t)RAG_MAX_CANDIDATES, k + s);
   if (kp < k) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path supports k <= 48 (k=%u)", k);
   p->path = path;
   p->kp = kp;
   p->key_has_qnorm = path == RAG_PATH_EXACT;
+  p->eps_per_query = false;
+  p->eps_q_mul = 0.0;
+  const double u24 = 5.9604644775390625e-08;  // 2^-24
   if (eps > 0.0) p->eps = eps;
   else if (path == RAG_PATH_STREAM)
     // fp32: <= ld/64 + 8 roundings per sum (2 accumulators per lane, 5 shuffle levels), twice
     // (dot and norm), with a safety factor — 4.8e-6 at D = 1536
-    p->eps = 2.5 * ((double)idx->ld / 64.0 + 8.0) * 5.9604644775390625e-08;
-  else if (path == RAG_PATH_TENSOR)
-    // bf16 rounding of both operands: measured per-score error sigma ~ 0.0022/sqrt(D) (5.6e-5 at
-    // D=1536, max 2.8e-4 over 5e5 pairs — tests/test_gpu_tensor.py). The bound is ~11 sigma:
-    // statistical, not a proof; callers can pass their own epsilon
-    // An fp32 index without a shadow is scored as tf32 (TMA rounds both operands to 10 mantissa bits):
-    // 4x finer than bf16, bound 0.006/sqrt(ld).
+    p->eps = 2.5 * ((double)idx->ld / 64.0 + 8.0) * u24;
+  else if (path == RAG_PATH_TENSOR && stat_eps)
+    // STATISTICAL (round 1): measured per-score error sigma ~ 0.0022/sqrt(D) for bf16 operands (5.6e-5 at
+    // D=1536, max 2.8e-4 over 5e5 pairs — tests/test_gpu_tensor.py); ~11 sigma, NOT a proof. tf32 is 4x finer.
     p->eps = (idx->shadow ? 0.024 : 0.006) / sqrt((double)idx->ld);
-  else
+  else if (path == RAG_PATH_TENSOR) {
+    // RIGOROUS (default). K2's key is fl32(acc * inv) with acc ~ q~.x~ (tensor core, fp32 accumulate),
+    // inv ~ 1/||x||; K4 divides by the exact ||q||. With e_q = q~ - q, e_x = x~ - x:
+    //   q~.x~ - q.x = e_q.x~ + q.e_x  =>  |.| <= ||e_q|| ||x~|| + ||q|| ||e_x||      (Cauchy-Schwarz)
+    //   in cosine units: rho_q (1 + rho_x) + rho_x, rho_q = ||e_q||/||q|| measured per query (q_operand_launch),
+    //   rho_x = max over rows of ||e_x||/||x|| measured when the rows were loaded (aux_build; 0 for a bf16 corpus).
+    // + accumulation: every one of the ld products enters an fp32 sum once, each add rounds (or truncates) at most
+    //   2^-23 relative to a partial sum that is <= sum|q~_i x~_i| <= ||q~|| ||x~||           => ld * 2^-23
+    // + inv: fp32 sum of ld squares (ld/32 sequential fmas per lane + 5 shuffle adds) and rsqrtf (2 ulp), halved
+    //   by the square root; + the fp32 rounding of the key itself. The residuals are computed in fp32 and inflated.
+    RAG_CHECK(refresh_rho_x(idx));
+    const double rx = (double)idx->rho_x * 1.001;
+    const double acc = (double)idx->ld * 2.0 * u24 * 1.02;
+    const double nrm = 0.5 * ((double)idx->ld / 32.0 + 8.0) * u24 + 4.0 * u24 + 1.0e-6;
+    p->eps = rx + acc + nrm;
+    p->eps_per_query = true;
+    p->eps_q_mul = (1.0 + rx) * 1.001;
+  } else
     p->eps = 2.0e-7;  // one fp32 rounding of the exact cosine
   return RAG_OK;
 }
 
-bool next_plan(const rag_index* idx, uint32_t k, const plan& cur, plan* nxt) {
+bool next_plan(rag_index* idx, uint32_t k, const plan& cur, plan* nxt) {
   *nxt = cur;
   if (cur.path == RAG_PATH_TENSOR) {
-    make_plan(idx, 1, k, RAG_PATH_STREAM, 0, 0.0, nxt);
+    make_plan(idx, 1, k, RAG_PATH_STREAM, 0, 0.0, 0, nxt);
     return true;
   }
   if (cur.path == RAG_PATH_STREAM) {
-    make_plan(idx, 1, k, RAG_PATH_EXACT, 0, 0.0, nxt);
+    make_plan(idx, 1, k, RAG_PATH_EXACT, 0, 0.0, 0, nxt);
     return true;
   }
   if (cur.kp < RAG_MAX_CANDIDATES) {  // exact path, wider candidate window (long runs of exact ties)
@@ -258,12 +292,13 @@ int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fr
   // small batches on one GPU: the last CTA of each query in the K3+K4 kernel runs K5 in place
   static const bool k5_in_place = !(getenv("RAGERA_FUSE_K5") && atoi(getenv("RAGERA_FUSE_K5")) == 0);
   bool fused = false;
+  const rag_eps eps = {p.eps, p.eps_per_query ? idx->cur->d_rho_q : nullptr, p.eps_q_mul};
   if (k34_small_ok(idx, B, p.kp, parts)) {
     fused = k5_in_place && idx->nranks == 1;
-    RAG_CHECK(k34_small_launch(idx, B, p.kp, parts, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus, fused ? &fa : nullptr));
+    RAG_CHECK(k34_small_launch(idx, B, p.kp, parts, k, eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus, fused ? &fa : nullptr));
   } else {
     RAG_CHECK(k3_launch(idx, B, p.kp, parts));
-    RAG_CHECK(k4_launch(idx, B, p.kp, k, p.eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
+    RAG_CHECK(k4_launch(idx, B, p.kp, k, eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus));
   }
   if (fused) return RAG_OK;
   RAG_CHECK(comm_allgather_local(idx, B, k));
@@ -435,6 +470,8 @@ int rag_index_create(const rag_index_desc* d, rag_index** out) {
     // 1/||x|| per row of the tensor-path operand (the bf16 rows, or the fp32 rows read as tf32)
     cap = 0;
     if ((rc = grow_dev(&idx->inv_norm, &cap, (size_t)d->capacity_rows * 4, true)) != RAG_OK) break;
+    cap = 0;
+    if ((rc = grow_dev(&idx->d_rho_x, &cap, 16, true)) != RAG_OK) break;
     if ((e = cudaStreamSynchronize(idx->stream)) != cudaSuccess) {
       rc = rag_set_error(RAG_ERR_CUDA, "rag_index_create: %s", cudaGetErrorString(e));
       break;
@@ -457,7 +494,7 @@ void rag_index_destroy(rag_index* idx) {
   free_batch(&idx->main);
   free_batch(&idx->esc);
   if (idx->shadow && (void*)idx->shadow != idx->corpus) cudaFree(idx->shadow);
-  cudaFree(idx->corpus); cudaFree(idx->inv_norm); cudaFree(idx->ctype); cudaFree(idx->conf);
+  cudaFree(idx->corpus); cudaFree(idx->inv_norm); cudaFree(idx->d_rho_x); cudaFree(idx->ctype); cudaFree(idx->conf);
   cudaFree(idx->access); cudaFree(idx->last_ms); cudaFree(idx->row_keys);
   if (idx->prof_spans) {
     for (uint32_t i = 0; i < idx->prof_cap; i++) { cudaEventDestroy(idx->prof_spans[i].a); cudaEventDestroy(idx->prof_spans[i].b); }
@@ -618,7 +655,7 @@ int rag_search(rag_index* idx, const float* queries, uint32_t B, const rag_searc
   RAG_CUDA(cudaSetDevice(idx->device));
   const uint32_t k = o->k;
   plan p;
-  RAG_CHECK(make_plan(idx, B, k, o->path, o->slack, o->epsilon, &p));
+  RAG_CHECK(make_plan(idx, B, k, o->path, o->slack, o->epsilon, o->flags, &p));
   rag_batch* bt = &idx->main;
   idx->cur = bt;
   out_layout L;
@@ -728,7 +765,7 @@ int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const ra
   RAG_CUDA(cudaSetDevice(idx->device));
   const uint32_t k = o->vector_top_k;
   plan p;
-  RAG_CHECK(make_plan(idx, B, k, o->path, o->slack, o->epsilon, &p));
+  RAG_CHECK(make_plan(idx, B, k, o->path, o->slack, o->epsilon, o->flags, &p));
   rag_batch* bt = &idx->main;
   idx->cur = bt;
   out_layout L;
@@ -795,7 +832,7 @@ int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* 
   RAG_CHECK(hybrid_args(idx, o, &fa, &fc, &out_cap));
   RAG_CUDA(cudaSetDevice(idx->device));
   plan p;
-  RAG_CHECK(make_plan(idx, B, o->vector_top_k, o->path, o->slack, o->epsilon, &p));
+  RAG_CHECK(make_plan(idx, B, o->vector_top_k, o->path, o->slack, o->epsilon, o->flags, &p));
   idx->cur = bt;
   out_layout L;
   RAG_CHECK(ensure_work(idx, bt, B, o->vector_top_k, out_cap, &L));
@@ -810,6 +847,8 @@ int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* 
   bt->c_partial = view.c_partial;
   bt->d_qb = view.d_qb;
   bt->c_qb = view.c_qb;
+  bt->d_rho_q = view.d_rho_q;
+  bt->c_rho_q = view.c_rho_q;
   idx->cur = bt;
   return rc;
 }
@@ -904,7 +943,7 @@ int rag_memory_retrieve(rag_index* idx, const float* queries, uint32_t B, const 
   RAG_CUDA(cudaSetDevice(idx->device));
   const uint32_t out_cap = o->limit;
   plan p;
-  RAG_CHECK(make_plan(idx, B, k, o->path, 0, 0.0, &p));
+  RAG_CHECK(make_plan(idx, B, k, o->path, 0, 0.0, o->flags, &p));
   rag_batch* bt = &idx->main;
   idx->cur = bt;
   bt->staged_B = bt->win_count = 0;
@@ -980,7 +1019,7 @@ int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, fl
   if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
   RAG_CUDA(cudaSetDevice(idx->device));
   plan p;
-  RAG_CHECK(make_plan(idx, B, 8, RAG_PATH_TENSOR, 0, 0.0, &p));
+  RAG_CHECK(make_plan(idx, B, 8, RAG_PATH_TENSOR, 0, 0.0, 0, &p));
   rag_batch* bt = &idx->main;
   idx->cur = bt;
   bt->staged_B = bt->win_count = 0;
@@ -1043,6 +1082,13 @@ int rag_debug_tensor_candidates(rag_index* idx, const float* queries, uint32_t B
   }
   cudaFree(d);
   return rc;
+}
+
+double rag_index_row_residual(rag_index* idx) {
+  if (!idx) return (double)rag_set_error(RAG_ERR_INVALID, "null index handle");
+  if (cudaSetDevice(idx->device) != cudaSuccess) return (double)rag_set_error(RAG_ERR_CUDA, "cudaSetDevice failed");
+  const int rc = refresh_rho_x(idx);
+  return rc != RAG_OK ? (double)rc : (double)idx->rho_x;
 }
 
 // ---- measurement ---------------------------------------------------------------------------------

@@ -114,6 +114,7 @@ struct rag_comm;
 struct rag_batch {
   float* d_q = nullptr;             size_t c_q = 0;        // [B][ld] fp32, zero padded
   __nv_bfloat16* d_qb = nullptr;    size_t c_qb = 0;       // [Bpad][ld] bf16 (tensor path operand)
+  float* d_rho_q = nullptr;         size_t c_rho_q = 0;    // [B] ||q - operand(q)|| / ||q|| (rigorous certification)
   uint8_t* d_in = nullptr;          size_t c_in = 0;       // small per-batch inputs, carved per call:
   uint8_t* h_in = nullptr;          size_t c_hin = 0;      //   pinned mirror of d_in
   uint64_t* d_kw = nullptr;                                //   [B][kw_stride] keyword keys (in d_in)
@@ -158,6 +159,11 @@ struct rag_index {
   int64_t* last_ms = nullptr;
   uint64_t* row_keys = nullptr;
   uint64_t aux_rows = 0;            // shadow / inv_norm are valid for rows [0, aux_rows)
+  // rigorous certification of the tensor path: max over rows of ||x - operand(x)|| / ||x|| (float bits on the
+  // device, raised by aux_build with atomicMax; 0 for a bf16 corpus) and its host mirror
+  uint32_t* d_rho_x = nullptr;
+  float rho_x = 0.f;
+  bool rho_x_stale = false;
 
   rag_batch main, esc;
   rag_batch* cur = nullptr;         // the batch the launchers operate on
@@ -173,8 +179,7 @@ struct rag_index {
   float prof_ms[RAG_PROF_CLASSES] = {0};
   uint32_t prof_cnt[RAG_PROF_CLASSES] = {0};
 
-  // tensor path (K2) state: single-CTA kernel / CTA-pair kernel
-  void* k2_state = nullptr;
+  // tensor path (K2) state of the CTA-pair kernel
   void* k2p_state = nullptr;
 };
 
@@ -211,25 +216,23 @@ int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // K1x — exact path: fp64 reference-order scan of every row (k1x_exact.cu)
 int k1x_plan(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
 int k1x_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
-// K2 — tensor path: tcgen05 bf16 GEMM + fused top-K' epilogue (k2_tensor.cu)
+// K2 — tensor path: tcgen05 GEMM on CTA pairs (cta_group::2) + fused top-K' epilogue (k2_pair.cu).
+// Operand: the bf16 corpus / bf16 shadow, or the fp32 rows read as tf32 when an fp32 index has no shadow.
 int k2_available(const rag_index* idx);
 int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
 int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 void k2_destroy(rag_index* idx);
-void k2_set_debug(rag_index* idx, float* d_scores);
-// K2 on CTA pairs (k2_pair.cu, cta_group::2) — what k2_* dispatch to by default
-int k2p_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
-int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
-void k2p_set_debug(rag_index* idx, float* d_scores);
-void k2p_destroy(rag_index* idx);  // diagnostics: dump the scaled score matrix of the next launch
+void k2_set_debug(rag_index* idx, float* d_scores);  // diagnostics: dump the scaled score matrix of the next launch
 // K3 — merge partial lists → K' candidates per query (k3_merge.cu)
 int k3_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // K4 — exact fp64 rescoring in reference order + local top-k + certification (k4_rescore.cu)
-int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, double eps, int key_has_qnorm,
+// eps_q (may be null): per-query addend to the selection-error bound, eps[b] = eps + eps_q[b] * eps_q_mul
+struct rag_eps { double eps; const float* eps_q; double eps_q_mul; };
+int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, rag_eps eps, int key_has_qnorm,
               int64_t now_ms, double decay, double bonus);
 // K3+K4 fused, latency variant for small batches (k4_rescore.cu)
 bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
-int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, double eps, int key_has_qnorm,
+int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, rag_eps eps, int key_has_qnorm,
                      int64_t now_ms, double decay, double bonus, const struct rag_fuse_args* fuse /* non-null: run K5 in place */);
 // K5 — cross-rank merge, min-cosine filter, RRF / freshness fusion, memory blend (k5_fuse.cu)
 struct rag_fuse_args {
@@ -254,7 +257,7 @@ int gen_corpus_launch(rag_index* idx, const rag_gen_desc* g, uint64_t nrows);
 int gen_queries_launch(rag_index* idx, const rag_gen_desc* g, uint64_t b0, uint32_t B, float* d_out);
 int gen_meta_launch(rag_index* idx, const rag_gen_desc* g, uint64_t nrows);
 int aux_build_launch(rag_index* idx, uint64_t row0, uint64_t nrows);  // shadow + inv_norm
-int q_to_bf16_launch(rag_index* idx, uint32_t B, uint32_t Bpad);
+int q_operand_launch(rag_index* idx, uint32_t B, uint32_t Bpad, bool tf32);  // bf16 cast (or none: tf32) + rho_q
 int gather_batch_launch(rag_index* idx, const rag_batch* src, rag_batch* dst, uint32_t n, uint32_t kw_stride);
 int iota_u64_launch(rag_index* idx, uint64_t* d, uint64_t n, uint64_t base);
 // comm (comm.cu): exchange of the ranks' local top-k records.

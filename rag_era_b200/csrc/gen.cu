@@ -67,16 +67,40 @@ __global__ void gen_meta_kernel(uint64_t nrows, uint64_t id_base, rag_gen_desc g
   last_ms[i] = rg_meta_last_access_ms(&g, r);
 }
 
-// one warp per row: bf16 shadow (fp32 corpus only) and 1/||x|| of the tensor-path operand
+// Rounding residual of one fp32 value against the operand the tensor path actually multiplies, squared.
+//   bf16 shadow: (v - bf16_rne(v))^2, exact in fp32 (the difference of two floats this close is representable).
+//   tf32 (fp32 rows read by TMA as TFLOAT32): the hardware keeps 10 mantissa bits, by truncation or by rounding
+//   — either way the operand is one of the two tf32 neighbours of v, so the bound is the distance to the
+//   FARTHER neighbour (0 when v is itself a tf32 value).
+__device__ __forceinline__ float resid2_bf16(float v, uint16_t b) {
+  const float e = __fsub_rn(v, rg_bf16_to_f32(b));
+  return e * e;
+}
+__device__ __forceinline__ float resid2_tf32(float v) {
+  const uint32_t u = __float_as_uint(v);
+  const uint32_t low = u & 0x1FFFu;
+  if (low == 0u) return 0.f;
+  const float lo = __uint_as_float(u & ~0x1FFFu);          // truncation towards zero
+  const float hi = __uint_as_float((u & ~0x1FFFu) + 0x2000u);  // next tf32 value away from zero
+  const float e = fmaxf(fabsf(__fsub_rn(v, lo)), fabsf(__fsub_rn(hi, v)));
+  return e * e;
+}
+
+// one warp per row: bf16 shadow (fp32 corpus only), 1/||x|| of the row itself (NOT of its rounded copy: the
+// selected score then differs from the exact cosine only by the operand rounding, which rho bounds), and
+// rho_x = max over rows of ||x - operand(x)|| / ||x|| (atomicMax on the float's bits; 0 for a bf16 corpus,
+// whose rows are the operand)
 template <bool SRC_BF16>
 __global__ void aux_build_kernel(const void* __restrict__ X, __nv_bfloat16* __restrict__ shadow,
-                                 float* __restrict__ inv_norm, uint64_t row0, uint64_t nrows, uint32_t ld) {
+                                 float* __restrict__ inv_norm, uint32_t* __restrict__ rho_bits, uint64_t row0,
+                                 uint64_t nrows, uint32_t ld) {
   const int lane = threadIdx.x & 31;
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  float rho_max = 0.f;
   for (uint64_t r = w; r < nrows; r += nw) {
     const uint64_t row = row0 + r;
-    float ss = 0.f;
+    float ss = 0.f, ee = 0.f;
     if (SRC_BF16) {
       const uint4* p = reinterpret_cast<const uint4*>((const uint16_t*)X + row * ld);
       for (uint32_t i = lane; i < ld / 8; i += 32) {
@@ -93,31 +117,73 @@ __global__ void aux_build_kernel(const void* __restrict__ X, __nv_bfloat16* __re
       uint2* sp = shadow ? reinterpret_cast<uint2*>(shadow + row * ld) : nullptr;
       for (uint32_t i = lane; i < ld / 4; i += 32) {
         const float4 v = p[i];
-        const uint16_t b0 = rg_f32_to_bf16(v.x), b1 = rg_f32_to_bf16(v.y), b2 = rg_f32_to_bf16(v.z),
-                       b3 = rg_f32_to_bf16(v.w);
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
         if (sp) {
+          const uint16_t b0 = rg_f32_to_bf16(v.x), b1 = rg_f32_to_bf16(v.y), b2 = rg_f32_to_bf16(v.z),
+                         b3 = rg_f32_to_bf16(v.w);
           sp[i] = make_uint2((uint32_t)b0 | ((uint32_t)b1 << 16), (uint32_t)b2 | ((uint32_t)b3 << 16));
-          const float a = rg_bf16_to_f32(b0), b = rg_bf16_to_f32(b1), c = rg_bf16_to_f32(b2), d = rg_bf16_to_f32(b3);
-          ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(c, c, ss); ss = fmaf(d, d, ss);
+          ee += resid2_bf16(v.x, b0) + resid2_bf16(v.y, b1) + resid2_bf16(v.z, b2) + resid2_bf16(v.w, b3);
         } else {
-          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+          ee += resid2_tf32(v.x) + resid2_tf32(v.y) + resid2_tf32(v.z) + resid2_tf32(v.w);
         }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
-    if (lane == 0) inv_norm[row] = ss > 0.f ? rsqrtf(ss) : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+      ee += __shfl_xor_sync(0xFFFFFFFFu, ee, o);
+    }
+    if (lane == 0) {
+      inv_norm[row] = ss > 0.f ? rsqrtf(ss) : 0.f;
+      if (!SRC_BF16 && ss > 0.f) rho_max = fmaxf(rho_max, sqrtf(ee / ss));
+    }
+  }
+  if (!SRC_BF16 && lane == 0 && rho_max > 0.f) atomicMax(rho_bits, __float_as_uint(rho_max));
+}
+
+// one warp per query: the bf16 operand of the tensor path (rows >= B are zero padding) and the query's
+// rounding residual rho_q[b] = ||q - bf16(q)|| / ||q|| for the rigorous certification bound
+__global__ void q_to_bf16_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ qb, float* __restrict__ rho_q,
+                                 uint32_t B, uint32_t Bpad, uint32_t ld) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t b = w; b < Bpad; b += nw) {
+    float ss = 0.f, ee = 0.f;
+    const float4* src = reinterpret_cast<const float4*>(q + (size_t)b * ld);
+    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(qb) + (size_t)b * ld);
+    for (uint32_t i = lane; i < ld / 4; i += 32) {
+      const float4 v = b < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint16_t b0 = rg_f32_to_bf16(v.x), b1 = rg_f32_to_bf16(v.y), b2 = rg_f32_to_bf16(v.z), b3 = rg_f32_to_bf16(v.w);
+      dst[i] = make_uint2((uint32_t)b0 | ((uint32_t)b1 << 16), (uint32_t)b2 | ((uint32_t)b3 << 16));
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      ee += resid2_bf16(v.x, b0) + resid2_bf16(v.y, b1) + resid2_bf16(v.z, b2) + resid2_bf16(v.w, b3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+      ee += __shfl_xor_sync(0xFFFFFFFFu, ee, o);
+    }
+    if (lane == 0 && b < B) rho_q[b] = ss > 0.f ? sqrtf(ee / ss) : 0.f;
   }
 }
 
-__global__ void q_to_bf16_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ qb, uint32_t B,
-                                 uint32_t Bpad, uint32_t ld) {
-  const uint64_t total = (uint64_t)Bpad * ld;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t b = t / ld;
-    const float v = b < B ? q[t] : 0.f;
-    reinterpret_cast<uint16_t*>(qb)[t] = rg_f32_to_bf16(v);
+// the same residual for queries the tensor path reads as tf32 (no cast: TMA converts the fp32 queries)
+__global__ void q_rho_tf32_kernel(const float* __restrict__ q, float* __restrict__ rho_q, uint32_t B, uint32_t ld) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t b = w; b < B; b += nw) {
+    float ss = 0.f, ee = 0.f;
+    for (uint32_t i = lane; i < ld; i += 32) {
+      const float v = q[(size_t)b * ld + i];
+      ss = fmaf(v, v, ss);
+      ee += resid2_tf32(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+      ee += __shfl_xor_sync(0xFFFFFFFFu, ee, o);
+    }
+    if (lane == 0) rho_q[b] = ss > 0.f ? sqrtf(ee / ss) : 0.f;
   }
 }
 
@@ -186,17 +252,30 @@ int aux_build_launch(rag_index* idx, uint64_t row0, uint64_t nrows) {
   if (nrows == 0 || !idx->inv_norm) return RAG_OK;
   const uint32_t grid = grid_for(nrows * 32, 256, idx->sm_count);
   if (idx->desc.dtype == RAG_BF16)
-    aux_build_kernel<true><<<grid, 256, 0, idx->stream>>>(idx->corpus, nullptr, idx->inv_norm, row0, nrows, idx->ld);
+    aux_build_kernel<true><<<grid, 256, 0, idx->stream>>>(idx->corpus, nullptr, idx->inv_norm, idx->d_rho_x, row0, nrows, idx->ld);
   else
-    aux_build_kernel<false><<<grid, 256, 0, idx->stream>>>(idx->corpus, idx->shadow, idx->inv_norm, row0, nrows, idx->ld);
+    aux_build_kernel<false><<<grid, 256, 0, idx->stream>>>(idx->corpus, idx->shadow, idx->inv_norm, idx->d_rho_x, row0, nrows, idx->ld);
   RAG_CUDA(cudaGetLastError());
+  idx->rho_x_stale = true;
   idx->launches++;
   return RAG_OK;
 }
 
-int q_to_bf16_launch(rag_index* idx, uint32_t B, uint32_t Bpad) {
-  const uint32_t grid = grid_for((uint64_t)Bpad * idx->ld, 256, idx->sm_count);
-  q_to_bf16_kernel<<<grid, 256, 0, idx->stream>>>(idx->cur->d_q, idx->cur->d_qb, B, Bpad, idx->ld);
+// the queries' tensor-path operand (bf16 cast, or nothing for tf32) and their rounding residuals rho_q
+int q_operand_launch(rag_index* idx, uint32_t B, uint32_t Bpad, bool tf32) {
+  rag_batch* bt = idx->cur;
+  if ((size_t)B * 4 > bt->c_rho_q || !bt->d_rho_q) {
+    if (bt->d_rho_q) RAG_CUDA(cudaFree(bt->d_rho_q));
+    bt->d_rho_q = nullptr;
+    bt->c_rho_q = 0;
+    const size_t need = (size_t)(B < 1024 ? 1024 : B) * 4;
+    RAG_CUDA(cudaMalloc((void**)&bt->d_rho_q, need));
+    bt->c_rho_q = need;
+  }
+  const uint32_t rows = tf32 ? B : Bpad;
+  const uint32_t grid = grid_for((uint64_t)rows * 32, 256, idx->sm_count);
+  if (tf32) q_rho_tf32_kernel<<<grid, 256, 0, idx->stream>>>(bt->d_q, bt->d_rho_q, B, idx->ld);
+  else q_to_bf16_kernel<<<grid, 256, 0, idx->stream>>>(bt->d_q, bt->d_qb, bt->d_rho_q, B, Bpad, idx->ld);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   return RAG_OK;

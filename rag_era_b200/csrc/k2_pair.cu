@@ -1,8 +1,7 @@
 // k2_pair.cu — K2 on CTA pairs: tcgen05.mma.cta_group::2 (UMMA M=256 across two SMs).
 //
-// Same job as k2_tensor.cu (batched cosine scoring + fused top-K' selection; the reference loop
-// it replaces is getTopKEmbeddings behind src/lib/hybrid-search.ts:223-224), re-tiled so that the
-// epilogue runs UNDER the next tile's MMAs:
+// Batched cosine scoring + fused top-K' selection (the reference loop it replaces is getTopKEmbeddings
+// behind src/lib/hybrid-search.ts:223-224), tiled so that the epilogue runs UNDER the next tile's MMAs:
 //
 //   cluster = 2 CTAs (one TPC). The pair owns 256 queries (128 TMEM lanes in each CTA) and walks
 //   corpus tiles of 256 rows. Per 64-element k-slice each CTA TMA-loads only its own 128 queries
@@ -733,7 +732,13 @@ int kp_make_map(kp_state* st, CUtensorMap* m, const void* base, uint64_t rows, u
 
 }  // namespace
 
-int k2p_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
+// bf16 operand (bf16 corpus / bf16 shadow), or the fp32 corpus read as tf32
+int k2_available(const rag_index* idx) {
+  if (!idx->inv_norm) return 0;
+  return idx->shadow != nullptr || idx->desc.dtype == RAG_F32;
+}
+
+int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   RAG_CHECK(kp_init(idx));
   kp_state* st = (kp_state*)idx->k2p_state;
   if (kp > KP_MAX_KP) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path keeps at most %d candidates per query (K'=%u)", KP_MAX_KP, kp);
@@ -750,7 +755,7 @@ int k2p_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   return RAG_OK;
 }
 
-int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
+int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
   if (idx->rows >= 0xFFFFFF00ull) return rag_set_error(RAG_ERR_UNSUPPORTED, "more than 2^32-257 rows per shard");
   RAG_CHECK(kp_init(idx));
@@ -769,11 +774,12 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
       RAG_CUDA(cudaMalloc((void**)&bt->d_qb, need));
       bt->c_qb = need;
     }
-    RAG_CHECK(q_to_bf16_launch(idx, B, Bpad));
+    RAG_CHECK(q_operand_launch(idx, B, Bpad, false));
     RAG_CHECK(kp_make_map(st, &map_q, bt->d_qb, Bpad, idx->ld, CTA_M, false));
     RAG_CHECK(kp_make_map(st, &map_x, idx->shadow, idx->rows, idx->ld, HALF_N, false));
   } else {
     // the fp32 queries as staged ([B][ld], zero padded columns); rows past B read as zeros (TMA OOB fill)
+    RAG_CHECK(q_operand_launch(idx, B, B, true));
     RAG_CHECK(kp_make_map(st, &map_q, bt->d_q, B, idx->ld, CTA_M, true));
     RAG_CHECK(kp_make_map(st, &map_x, idx->corpus, idx->rows, idx->ld, HALF_N, true));
   }
@@ -854,11 +860,11 @@ int k2p_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   return RAG_OK;
 }
 
-void k2p_set_debug(rag_index* idx, float* d_scores) {
+void k2_set_debug(rag_index* idx, float* d_scores) {
   if (kp_init(idx) == RAG_OK) ((kp_state*)idx->k2p_state)->dbg = d_scores;
 }
 
-void k2p_destroy(rag_index* idx) {
+void k2_destroy(rag_index* idx) {
   if (idx->k2p_state && ((kp_state*)idx->k2p_state)->d_cyc) cudaFree(((kp_state*)idx->k2p_state)->d_cyc);
   if (idx->k2p_state && ((kp_state*)idx->k2p_state)->d_pub) cudaFree(((kp_state*)idx->k2p_state)->d_pub);
   delete (kp_state*)idx->k2p_state;

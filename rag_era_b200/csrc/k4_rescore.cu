@@ -107,7 +107,7 @@ __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k,
 template <bool BF16>
 __global__ void __launch_bounds__(RAG_MAX_CANDIDATES + 32)
 k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restrict__ Q,
-                  const uint64_t* __restrict__ cand, uint32_t kp, uint32_t k, double eps,
+                  const uint64_t* __restrict__ cand, uint32_t kp, uint32_t k, rag_eps E,
                   int key_has_qnorm, k4_meta M, rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double s_score[RAG_MAX_CANDIDATES];
@@ -135,6 +135,7 @@ k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restri
   }
   __syncthreads();
   c.nq = s_nq;
+  const double eps = E.eps_q ? E.eps + (double)E.eps_q[b] * E.eps_q_mul : E.eps;
   k4_finalize(j, kp, k, valid, row, finish(c), s_nq, cand[(size_t)b * RAG_MAX_CANDIDATES + kp - 1], eps, key_has_qnorm, M,
               s_score, s_row, &s_kth, local + (size_t)b * k, local_cnt + b);
 }
@@ -225,7 +226,7 @@ __device__ __forceinline__ void warp_chain(const void* __restrict__ X, uint32_t 
 template <bool BF16>
 __global__ void __launch_bounds__(K4S_THREADS)
 k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restrict__ Q,
-                 const uint64_t* __restrict__ partial, uint32_t parts, uint32_t kp, uint32_t k, double eps,
+                 const uint64_t* __restrict__ partial, uint32_t parts, uint32_t kp, uint32_t k, rag_eps E,
                  int key_has_qnorm, k4_meta M, double* __restrict__ scratch /*[B][2*128+2]*/,
                  unsigned int* __restrict__ ticket /*[B]*/, uint64_t* __restrict__ cand_out /*[B][128]*/,
                  rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt, int fuse_k5, rag_k5::k5_io io) {
@@ -312,6 +313,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   __threadfence();
   const volatile double* vs = my_scratch;
   const double nq = vs[2 * RAG_MAX_CANDIDATES];
+  const double eps = E.eps_q ? E.eps + (double)E.eps_q[b] * E.eps_q_mul : E.eps;
   for (uint32_t j0 = 0; j0 < kp || j0 == 0; j0 += K4S_THREADS) {  // kp <= 128 <= K4S_THREADS: one pass
     const uint32_t j = j0 + threadIdx.x;
     const uint64_t key = j < kp ? s_cand[j] : 0ull;
@@ -333,7 +335,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
 
 }  // namespace
 
-int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, double eps, int key_has_qnorm,
+int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, rag_eps eps, int key_has_qnorm,
               int64_t now_ms, double decay, double bonus) {
   rag_prof_scope ps(idx, RAG_PROF_RESCORE);
   const uint32_t nw = (kp + 31) / 32;
@@ -356,7 +358,7 @@ bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts)
   return B <= 32 && (size_t)parts * kp * 8 <= K4S_MAX_STAGE && kp <= RAG_MAX_CANDIDATES;
 }
 
-int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, double eps, int key_has_qnorm,
+int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, rag_eps eps, int key_has_qnorm,
                      int64_t now_ms, double decay, double bonus, const rag_fuse_args* fuse) {
   rag_prof_scope ps(idx, RAG_PROF_RESCORE);
   rag_batch* bt = idx->cur;

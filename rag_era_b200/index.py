@@ -332,6 +332,13 @@ class VectorIndex:
         N.check(self._lib.rag_fetch_fused(self._h, B, C.byref(opts), C.byref(out._c)))
         return out
 
+    def row_residual(self) -> float:
+        """rho_x of the rigorous certification bound (max ||x - operand(x)|| / ||x|| over the loaded rows)."""
+        v = float(self._lib.rag_index_row_residual(self._h))
+        if v < 0:
+            N.check(int(v))
+        return v
+
     def debug_tensor_scores(self, queries) -> np.ndarray:
         q = self._queries(queries)
         out = np.empty((q.shape[0], self.rows), dtype=np.float32)

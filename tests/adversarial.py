@@ -1,0 +1,54 @@
+"""Adversarial corpus for the tensor path's certification (test infrastructure).
+
+Real embedding models have a few outlier dimensions that carry most of a vector's energy. When the values in
+those dimensions sit just below a bf16 rounding midpoint, the rounding errors of all of them have the same sign
+and the bf16 dot product is off by ~2^-8 RELATIVE — an order of magnitude more than the ~11 sigma statistical
+bound of round 1 (0.024/sqrt(ld)), which assumed independent errors.
+
+The construction (fp32 index + bf16 shadow, so both operands are rounded):
+  q      outlier dims = +-8*(1+0.98/256) (bf16 rounds them DOWN to +-8), the rest small bf16-exact values
+  star   row `star` = q itself: exact cosine 1.0, the true top-1; its bf16 score is (1-delta)^2 ~ 0.9924
+  decoys ~80 bf16-exact rows q~ + p_j with exact cosines 0.9975..0.9987: their bf16 scores lose only ONE factor
+         (1-delta) ~ 0.994, so all of them outrank `star` on the tensor path and push it out of the K'=48 candidates
+With the statistical bound the query certifies although `star` is missing from the answer; the rigorous bound
+(measured residuals rho_q, rho_x) refuses, the query escalates to the fp32 stream path and the answer is exact.
+"""
+import numpy as np
+
+import oracle
+
+
+def bf16_round(a):
+    return oracle.bf16_to_f32(oracle.f32_to_bf16(a))
+
+
+def build(n=6000, d=1536, n_out=16, n_decoy=80, seed=7):
+    rng = np.random.default_rng(seed)
+    q = bf16_round((0.01 * rng.standard_normal(d)).astype(np.float32))
+    sign = rng.choice([-1.0, 1.0], n_out).astype(np.float32)
+    q[:n_out] = sign * np.float32(8.0 * (1 + 0.98 / 256))
+    qt = bf16_round(q)
+    assert np.all(np.abs(qt[:n_out]) == 8.0)
+    X = (0.3 * rng.standard_normal((n, d))).astype(np.float32)
+    star = n - 5
+    X[star] = q
+    nq = np.linalg.norm(q.astype(np.float64))
+    rows = rng.choice(np.arange(10, n - 10), n_decoy, replace=False)
+    rows = rows[rows != star]
+    for j, r in enumerate(rows):
+        target = 0.9975 + 0.0012 * j / len(rows)          # exact cosine of this decoy
+        p = rng.standard_normal(d).astype(np.float32)
+        p[:n_out] = 0
+        p *= np.float32(nq * np.sqrt(2 * (1 - target)) / np.linalg.norm(p))
+        X[r] = bf16_round(qt + p)
+    return X, q, star, rows
+
+
+def emulate(X, q):
+    """(exact cosines, the tensor path's scores in cosine units, rho_q, rho_x) in fp64 emulation."""
+    Xd, qd = X.astype(np.float64), q.astype(np.float64)
+    nx, nq = np.linalg.norm(Xd, axis=1), np.linalg.norm(qd)
+    exact = (Xd @ qd) / nx / nq
+    Xt, qt = bf16_round(X).astype(np.float64), bf16_round(q).astype(np.float64)
+    approx = (Xt @ qt) / nx / nq
+    return exact, approx, np.linalg.norm(qt - qd) / nq, (np.linalg.norm(Xt - Xd, axis=1) / nx).max()

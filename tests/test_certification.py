@@ -1,0 +1,121 @@
+"""Certification of the tensor path: `certified = 1` must be a PROOF that the ids equal an exact scan.
+
+CPU part: the adversarial construction of tests/adversarial.py defeats the round-1 statistical bound and is
+covered by the rigorous one (fp64 emulation of the bf16 operands). GPU part: the library itself on that corpus.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import adversarial  # noqa: E402
+
+
+def tf32_residual(a):
+    """Per element: distance from an fp32 value to the FARTHER of its two tf32 neighbours (0 if it is one) — what
+    gen.cu's resid2_tf32 uses, valid whether the hardware truncates or rounds to 10 mantissa bits."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    lo = (u & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+    hi = ((u & np.uint32(0xFFFFE000)) + np.uint32(0x2000)).view(np.float32).astype(np.float64)
+    ad = a.astype(np.float64)
+    return np.where((u & np.uint32(0x1FFF)) == 0, 0.0, np.maximum(np.abs(ad - lo), np.abs(hi - ad)))
+
+
+def _rig_eps(rho_q, rho_x, ld):
+    return rho_q * (1 + rho_x) + rho_x + ld * 2.0 ** -23
+
+
+def test_adversarial_rows_defeat_the_statistical_bound_but_not_the_rigorous_one():
+    X, q, star, _ = adversarial.build()
+    exact, approx, rho_q, rho_x = adversarial.emulate(X, q)
+    n, k, kp, ld = len(X), 10, 48, 1536
+    true_top = np.lexsort((np.arange(n), -exact))[:k]
+    cand = np.lexsort((np.arange(n), -approx))[:kp]
+    assert true_top[0] == star and star not in cand                  # the best row is not even a candidate
+    t, kth = approx[cand[-1]], np.sort(exact[cand])[::-1][k - 1]
+    assert kth > t + 0.024 / np.sqrt(ld)                             # ... and the statistical bound certifies anyway
+    eps = _rig_eps(rho_q, rho_x, ld)
+    assert np.abs(exact - approx).max() <= eps                       # the rigorous bound holds on every row
+    assert not kth > t + eps                                         # so it refuses to certify
+    assert np.abs(exact - approx).max() > 10 * 0.024 / np.sqrt(ld)   # errors align: 12x the "11 sigma" figure
+
+
+def test_rigorous_bound_holds_on_random_and_scaled_rows():
+    """|approx - exact| <= rho_q (1 + rho_x) + rho_x on data of very different shapes (Cauchy-Schwarz)."""
+    rng = np.random.default_rng(3)
+    for d, scale in [(64, 1.0), (1536, 1e-3), (256, 3e4)]:
+        X = (scale * rng.standard_normal((500, d)) * rng.uniform(0.1, 10, (500, 1))).astype(np.float32)
+        X[:50, :4] *= 100                                            # outlier dimensions
+        for _ in range(20):
+            q = (X[rng.integers(0, 500)] + 0.5 * scale * rng.standard_normal(d)).astype(np.float32)
+            exact, approx, rho_q, rho_x = adversarial.emulate(X, q)
+            assert np.abs(exact - approx).max() <= rho_q * (1 + rho_x) + rho_x + 1e-12
+
+
+@pytest.mark.gpu
+def test_gpu_adversarial_corpus_rigorous_default_is_exact_and_statistical_is_not(native, oracle):
+    import rag_era_b200 as rb
+
+    X, q, star, _ = adversarial.build()
+    n, d = X.shape
+    rng = np.random.default_rng(11)
+    # a batch so that the tensor path is the natural choice: the adversarial query + ordinary ones
+    Q = np.stack([q] + [(X[i] + 0.2 * rng.standard_normal(d)).astype(np.float32) for i in rng.integers(0, 2000, 15)])
+    with rb.VectorIndex(d, n, bf16_shadow=True) as idx:
+        idx.upload(X)
+        assert 3.5e-3 < idx.row_residual() < 4.0e-3                  # rho_x: the star row rounds by ~2^-8 relative
+        ei, es = oracle.topk(X, q, 10)
+        assert int(ei[0]) == star
+        # default (rigorous): first pass does not certify the adversarial query, escalation makes it exact
+        raw = idx.query(Q, 10, path=native.PATH_TENSOR, flags=native.SEARCH_NO_ESCALATE)
+        assert raw.certified[0] == 0 and star not in raw.row(0)[0]
+        r = idx.query(Q, 10, path=native.PATH_TENSOR)
+        assert r.certified.all()
+        for b in range(len(Q)):
+            bi, bs = oracle.topk(X, Q[b], 10)
+            assert np.array_equal(r.row(b)[0], bi) and np.array_equal(r.row(b)[1], bs), b
+        # the round-1 statistical bound certifies the WRONG answer for the adversarial query
+        stat = idx.query(Q, 10, path=native.PATH_TENSOR, flags=native.SEARCH_NO_ESCALATE | native.SEARCH_STAT_EPS)
+        assert stat.certified[0] == 1 and star not in stat.row(0)[0]
+        # the measured tensor-path scores stay inside the rigorous bound on every row
+        S = idx.debug_tensor_scores(Q[:1]).astype(np.float64)[0] / np.linalg.norm(q.astype(np.float64))
+        exact, _, rho_q, rho_x = adversarial.emulate(X, q)
+        assert np.abs(S - exact).max() <= _rig_eps(rho_q, rho_x, 1536) + 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["bf16", "f32+shadow", "tf32"])
+def test_gpu_selected_scores_stay_within_the_rigorous_bound(native, oracle, kind):
+    """Outlier-dimension rows, three operand kinds: max |K2 score / ||q|| - exact cosine| <= the bound K4 uses."""
+    import rag_era_b200 as rb
+
+    rng = np.random.default_rng(5)
+    n, d, B = 3000, 1536, 64
+    X = (rng.standard_normal((n, d)) * rng.uniform(0.2, 5, (n, 1))).astype(np.float32)
+    X[:, :8] *= rng.choice([1.0, 40.0], (n, 1))                      # half the rows have outlier dimensions
+    Q = (X[rng.integers(0, n, B)] + 0.4 * rng.standard_normal((B, d))).astype(np.float32)
+    bf = kind == "bf16"
+    Xs = oracle.f32_to_bf16(X) if bf else X
+    with rb.VectorIndex(d, n, dtype=native.BF16 if bf else native.F32, bf16_shadow=(kind == "f32+shadow")) as idx:
+        idx.upload(Xs)
+        S = idx.debug_tensor_scores(Q).astype(np.float64)
+        rho_x = idx.row_residual()
+        r = idx.query(Q, 10, path=native.PATH_TENSOR)
+    Xd = (oracle.bf16_to_f32(Xs) if bf else X).astype(np.float64)
+    Qd = Q.astype(np.float64)
+    nq = np.linalg.norm(Qd, axis=1)
+    exact = (Qd @ Xd.T) / nq[:, None] / np.linalg.norm(Xd, axis=1)[None, :]
+    err = np.abs(S / nq[:, None] - exact).max(axis=1)
+    if kind == "tf32":
+        rho_q = np.linalg.norm(tf32_residual(Q), axis=1) / nq         # distance to the farther tf32 neighbour
+        assert 0 < rho_x <= 2.0 ** -10
+    else:
+        rho_q = np.linalg.norm(adversarial.bf16_round(Q).astype(np.float64) - Qd, axis=1) / nq
+        assert (rho_x == 0) if bf else (1e-3 < rho_x < 2.0 ** -8)
+    assert (err <= rho_q * (1 + rho_x) + rho_x + d * 2.0 ** -23 + 1e-5).all(), float(err.max())
+    assert r.certified.all()
+    for b in range(0, B, 7):
+        bi, bs = oracle.topk(Xs, Q[b], 10)
+        assert np.array_equal(r.row(b)[0], bi) and np.array_equal(r.row(b)[1], bs)

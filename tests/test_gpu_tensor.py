@@ -46,15 +46,22 @@ def test_tensor_topk_matches_oracle(rb, native, oracle, dtype_name, B, k):
         idx.generate(gn, n)
         Q = idx.generate_queries(gn, 0, B)
         r = idx.query(Q, k, path=native.PATH_TENSOR)
-        raw = idx.query(Q, k, path=native.PATH_TENSOR, flags=native.SEARCH_NO_ESCALATE)
+        raw = idx.query(Q, k, path=native.PATH_TENSOR, flags=native.SEARCH_NO_ESCALATE | native.SEARCH_STAT_EPS)
+        rig = idx.query(Q, k, path=native.PATH_TENSOR, flags=native.SEARCH_NO_ESCALATE)
         for b in range(0, B, max(1, B // 40)):
             ei, es = oracle.topk(X, Q[b], k)
             gi, gs = r.row(b)
             assert np.array_equal(gi, ei), (b, gi, ei)
             assert np.array_equal(gs, es)
         assert r.certified.all()
-        # the tensor path alone certifies nearly everything on this data; the rest was escalated
+        # under the statistical bound the tensor path alone certifies nearly everything on this data; the rigorous
+        # bound is wider (measured rounding residuals, no independence assumption; it compensates with a wider
+        # candidate window when both operands are rounded); whatever the first pass could not certify was escalated above
         assert raw.certified.mean() > 0.8
+        certified = np.flatnonzero(rig.certified)
+        for b in certified[:: max(1, len(certified) // 25)]:      # certified without escalation == exact
+            ei, es = oracle.topk(X, Q[b], k)
+            assert np.array_equal(rig.row(b)[0], ei) and np.array_equal(rig.row(b)[1], es)
 
 
 def test_tensor_hybrid_batch(rb, native, oracle):
@@ -78,8 +85,9 @@ def test_tensor_hybrid_batch(rb, native, oracle):
 
 
 def test_bf16_selection_error_is_within_the_stated_tolerance(rb, native, oracle):
-    """The stated bf16 tolerance: |cos_bf16 - cos_f64| has sigma ~ 0.0022/sqrt(D); the
-    certification bound is 0.024/sqrt(ld) (~11 sigma). Measure it on 0.5M (query,row) pairs."""
+    """The stated bf16 tolerance: |cos_bf16 - cos_f64| has sigma ~ 0.0022/sqrt(D) on near-Gaussian
+    rows; the STATISTICAL certification bound (RAG_SEARCH_STAT_EPS) is 0.024/sqrt(ld) (~11 sigma). Measure it on
+    0.5M (query,row) pairs. (The default bound is the rigorous one: tests/test_certification.py.)"""
     n, d, B = 2000, 1536, 256
     go = oracle.make_gen(n, n_clusters=16)
     gn = native.GenDesc.from_buffer_copy(bytes(go))
@@ -99,9 +107,6 @@ def test_bf16_selection_error_is_within_the_stated_tolerance(rb, native, oracle)
 def test_tf32_path_on_fp32_index_without_shadow(rb, native, oracle):
     """An fp32 index without a bf16 shadow is scored by the same tcgen05 kernel in kind::tf32 (TMA rounds the
     fp32 rows and queries to tf32): stated tolerance 0.006/sqrt(ld), ids and scores still the oracle's."""
-    import os
-    if os.environ.get("RAGERA_K2_IMPL") == "1":
-        pytest.skip("the single-CTA predecessor kernel has no tf32 mode")
     n, d, B = 30000, 1536, 200
     go = oracle.make_gen(n, n_clusters=64, dup_period=23)
     gn = native.GenDesc.from_buffer_copy(bytes(go))
