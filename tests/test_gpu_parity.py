@@ -603,6 +603,34 @@ def oracle_planted(g, b):
     return mix(g.query_seed ^ 0x9A17 ^ mix(b)) % g.total_rows
 
 
+def exhaustive_topk(oracle, idx, go, Q, k, slab=400_000):
+    """The oracle's getTopKEmbeddings over EVERY row the index holds, for each query of Q: the rows are read back
+    from the device slab by slab (so the oracle scores exactly the bytes the kernels scored; a few rows of every
+    slab are also checked against the host generator), scored with the reference's fp64 left-to-right chain on all
+    host threads, and the per-slab top-k lists are merged on (score desc, chunk id asc)."""
+    n, d = idx.rows, idx.dim
+    odt = oracle.F32 if idx._np_dtype() == np.float32 else oracle.BF16
+    ids = [[] for _ in range(len(Q))]
+    scs = [[] for _ in range(len(Q))]
+    rng = np.random.default_rng(n)
+    for lo in range(0, n, slab):
+        m = min(slab, n - lo)
+        X = idx.read_rows(lo, m)
+        for r in rng.integers(0, m, 3):
+            assert np.array_equal(X[r], oracle.gen_rows(go, idx.id_base + lo + int(r), 1, d, dtype=odt)[0])
+        for b in range(len(Q)):
+            i, s = oracle.topk(X, Q[b], k, id_base=idx.id_base + lo)
+            ids[b].append(i)
+            scs[b].append(s)
+        del X
+    out = []
+    for b in range(len(Q)):
+        i, s = np.concatenate(ids[b]), np.concatenate(scs[b])
+        order = np.lexsort((i, -s))[:k]
+        out.append((i[order], s[order]))
+    return out
+
+
 @pytest.mark.parametrize("B", [2, 4, 5, 8, 9, 17])
 @pytest.mark.parametrize("d", [1536, 100])
 def test_multi_query_stream_kernel(rb, native, oracle, B, d):
@@ -623,7 +651,8 @@ def test_multi_query_stream_kernel(rb, native, oracle, B, d):
 
 
 def test_c3_full_size_properties(rb, native, oracle):
-    """C3: 10M x 1536 fp32 (61 GB), batch 1 — size-independent properties of the north-star target config."""
+    """C3: 10M x 1536 fp32 (61 GB), batch 1 — the north-star target config: size-independent properties and an
+    exhaustive oracle scan of the whole corpus for every query."""
     n, d, B = 10_000_000, 1536, 4
     go, gn = gen(oracle, native, n)
     with rb.VectorIndex(d, n) as idx:
@@ -638,14 +667,10 @@ def test_c3_full_size_properties(rb, native, oracle):
             assert np.array_equal(rb4.row(b)[0], ids) and np.array_equal(rb4.row(b)[1], sc)
             for i, s in zip(ids, sc):                       # reported scores are the oracle's, bit for bit
                 assert oracle.cosine(Q[b], oracle.gen_rows(go, int(i), 1, d)[0]) == s
-            # exhaustive oracle scan of the 2 x 50k-row windows around the best and worst hit: nothing there beats the k-th
-            for centre in (int(ids[0]), int(ids[-1])):
-                lo = max(0, min(n - 50_000, centre - 25_000))
-                wi, ws = oracle.topk_generated(go, oracle.F32, lo, 50_000, d, Q[b], 10)
-                inside = [(int(i), float(s)) for i, s in zip(ids, sc) if lo <= int(i) < lo + 50_000]
-                assert [int(x) for x in wi[:len(inside)]] == [i for i, _ in inside]
-                if len(wi) > len(inside):
-                    assert ws[len(inside)] <= sc[-1]
+        # ONE exhaustive oracle scan of all 10M rows for every query: ids and scores bit-equal
+        for b, (ei, es) in enumerate(exhaustive_topk(oracle, idx, go, Q, 10)):
+            assert np.array_equal(r[b].row(0)[0], ei), (b, r[b].row(0)[0], ei)
+            assert np.array_equal(r[b].row(0)[1].view(np.uint64), es.view(np.uint64)), b
         # deep_search shape on top: RRF of the exact vector stage with a keyword list
         kw = [int(x) for x in r[0].row(0)[0][:3]] + [123, 9_999_999, 5_000_000, 77, 4_242_424, 31337, 2]
         f = idx.hybrid(Q[0:1], rb.hybrid_opts(10, 10, 0.3, path=native.PATH_STREAM), [kw]).row(0)
@@ -664,13 +689,22 @@ def test_c4_memory_rag_three_lists_full_size(rb, native, oracle):
         Q = idx.generate_queries(gn, 0, B)
         top = idx.query(Q, 10)                                                   # AUTO → tensor path
         assert top.certified.all()
+        # exhaustive oracle scan of all 7M rows for a sample of the batch: the tensor path's ids and scores are
+        # the oracle's, bit for bit (first pass certified by the rigorous bound, or escalated)
+        sub = np.arange(0, B, 32)
+        for b, (ei, es) in zip(sub, exhaustive_topk(oracle, idx, go, Q[sub], 10)):
+            assert np.array_equal(top.row(b)[0], ei), (b, top.row(b)[0], ei)
+            assert np.array_equal(top.row(b)[1].view(np.uint64), es.view(np.uint64)), b
+        first = idx.query(Q, 10, flags=native.SEARCH_NO_ESCALATE)
+        print(f"C4 first-pass certification (rigorous bound): {int(first.certified.sum())}/{B}")
         kw = [[int(x) for x in top.ids[b, :3]] + [(b * 7919 + j * 104729) % n for j in range(7)] for b in range(B)]
         two = idx.hybrid(Q, rb.hybrid_opts(10, 10, 0.3), kw)
         three = idx.hybrid(Q, rb.hybrid_opts(10, 10, 0.3, fresh_limit=10, fresh_weight=1.0, now_ms=now), kw)
         n_fresh_both = 0
         for b in range(0, B, 8):
             g2, g3 = two.row(b), three.row(b)
-            assert np.array_equal(g2["vec_ids"], top.row(b)[0][:len(g2["vec_ids"])])
+            fi, _ = oracle.filter_min_score(*top.row(b), 0.3)                    # top.row(b) == the oracle's (above)
+            assert np.array_equal(g2["vec_ids"], fi) and np.array_equal(g3["vec_ids"], fi)
             ek, es, esrc, _ = oracle.rrf(g2["vec_ids"], kw[b])                    # reference-faithful two-list fusion
             assert np.array_equal(g2["keys"], ek) and np.array_equal(g2["scores"], es) and np.array_equal(g2["source"], esrc)
             vi = [int(i) for i in g3["vec_ids"]]
@@ -686,8 +720,9 @@ def test_c4_memory_rag_three_lists_full_size(rb, native, oracle):
 
 def test_c5_shard_size_tensor_path_properties(rb, native, oracle):
     """C5: one rank's shard of the 8-GPU configuration (50M/8 = 6.25M x 1536 bf16, batch 1024, tcgen05 path).
-    Size-independent properties: every query certified, the planted row wins, reported scores are the oracle's
-    bit for bit, the stream path (different kernel, fp32 selection) returns the same ids and scores, idempotent."""
+    Every query certified, the planted row wins, reported scores are the oracle's bit for bit, the stream path
+    (different kernel, fp32 selection) returns the same ids and scores, idempotent — and an exhaustive oracle scan
+    of the whole shard for a sample of the batch."""
     n, d, B = 6_250_000, 1536, 1024
     go, gn = gen(oracle, native, n)
     with rb.VectorIndex(d, n, dtype=native.BF16) as idx:
@@ -704,6 +739,12 @@ def test_c5_shard_size_tensor_path_properties(rb, native, oracle):
         sub = np.arange(0, B, 128)
         rs = idx.query(Q[sub], 10, path=native.PATH_STREAM)
         assert np.array_equal(rs.ids, r.ids[sub]) and np.array_equal(rs.scores, r.scores[sub])
+        # exhaustive oracle scan of all 6.25M bf16 rows for those queries: ids and scores bit-equal
+        for b, (ei, es) in zip(sub, exhaustive_topk(oracle, idx, go, Q[sub], 10)):
+            assert np.array_equal(r.row(b)[0], ei), (b, r.row(b)[0], ei)
+            assert np.array_equal(r.row(b)[1].view(np.uint64), es.view(np.uint64)), b
+        first = idx.query(Q, 10, path=native.PATH_TENSOR, flags=native.SEARCH_NO_ESCALATE)
+        print(f"C5 shard first-pass certification (rigorous bound): {int(first.certified.sum())}/{B}")
         r2 = idx.query(Q, 10, path=native.PATH_TENSOR)
         assert np.array_equal(r.ids, r2.ids) and np.array_equal(r.scores, r2.scores)
 
