@@ -47,7 +47,8 @@ typedef enum rag_status {
   RAG_ERR_STATE = -4,       /* call order (e.g. search before any rows exist)     */
   RAG_ERR_UNSUPPORTED = -5, /* e.g. tensor path requested without a bf16 shadow   */
   RAG_ERR_NCCL = -6,
-  RAG_ERR_NO_DEVICE = -7    /* no sm_100 GPU: there is deliberately no fallback   */
+  RAG_ERR_NO_DEVICE = -7,   /* no sm_100 GPU: there is deliberately no fallback   */
+  RAG_ERR_TIMEOUT = -8      /* sharded search: a peer rank never arrived at the exchange */
 } rag_status;
 
 typedef enum rag_dtype { RAG_F32 = 0, RAG_BF16 = 1 } rag_dtype;
@@ -361,13 +362,39 @@ int rag_profile_read(rag_index* idx, float ms[RAG_PROF_CLASSES], uint32_t counts
 void* rag_host_alloc(uint64_t bytes);
 void rag_host_free(void* p);
 
-/* ---- row-sharded multi-GPU (one process per GPU of one node; every rank's exact local top-k is
- *      exchanged and merged on every rank — rank 0 is the consumer). Default exchange: peer-to-peer
- *      mailboxes over NVLink (CUDA IPC), written and awaited inside the final fusion kernel; NCCL carries
- *      the mailbox handles at set-up and is the fallback exchange (environment RAGERA_COMM=nccl, or GPUs
- *      without peer access). All ranks must issue the same sequence of search calls (same batch size and
- *      k): the exchange, like a collective, pairs the i-th call of every rank. ---------------------- */
+/* ---- row-sharded multi-GPU (one process per GPU of one node — or several processes on one GPU; every rank's
+ *      exact local top-k is exchanged and merged on every rank, rank 0 is the consumer).
+ *
+ *      Default exchange: peer-to-peer MAILBOXES (device memory shared through CUDA IPC, over NVLink between GPUs),
+ *      written and awaited inside the final fusion kernel — no collective call on the hot path. The bootstrap is
+ *      HOST-DRIVEN and needs no NCCL: every rank exports a 64-byte handle of its own mailbox, the host exchanges
+ *      the handles by whatever channel it has (torch.distributed, a pipe, Node's cluster messaging), every rank
+ *      imports all of them:
+ *          rag_comm_p2p_export(idx, nranks, rank, max_batch, max_k, mine);
+ *          ... host: all-gather of the RAG_COMM_HANDLE_BYTES-byte handles ...
+ *          rag_comm_p2p_import(idx, all_handles);
+ *      A search whose batch or k exceeds (max_batch, max_k) fails with RAG_ERR_STATE: export again, larger.
+ *      rag_comm_p2p_import returns RAG_ERR_UNSUPPORTED when a peer's memory cannot be mapped (no P2P access):
+ *      the host then falls back to the NCCL path below on ALL ranks.
+ *
+ *      NCCL path: rag_comm_unique_id / rag_comm_init — one ncclAllGather of the [B][k] records before the fusion
+ *      kernel (libnccl is dlopen'ed; environment RAGERA_COMM=nccl selects this exchange, otherwise rag_comm_init
+ *      bootstraps the same mailboxes by carrying the handles over NCCL).
+ *
+ *      All ranks must issue the same sequence of search calls (same batch size and k): the exchange, like a
+ *      collective, pairs the i-th call of every rank. A rank that waits longer than RAGERA_P2P_TIMEOUT_MS
+ *      (default 20000) for a peer gives up: the call returns RAG_ERR_TIMEOUT (no device trap, the context stays
+ *      usable), the communicator is marked broken and every later sharded call fails with RAG_ERR_STATE until the
+ *      ranks bootstrap again. ---------------------------------------------------------------------------- */
 #define RAG_COMM_ID_BYTES 128
+#define RAG_COMM_HANDLE_BYTES 64
+int rag_comm_p2p_export(rag_index* idx, int nranks, int rank, uint32_t max_batch, uint32_t max_k,
+                        uint8_t handle[RAG_COMM_HANDLE_BYTES]);
+int rag_comm_p2p_import(rag_index* idx, const uint8_t* handles /* [nranks][RAG_COMM_HANDLE_BYTES], by rank */);
+/* Teardown in two phases (freeing a mailbox a peer still maps is undefined in CUDA): every rank calls
+ * rag_comm_detach (closes its mappings of the peers' mailboxes), the host runs a barrier, then rag_comm_destroy /
+ * rag_index_destroy / a new rag_comm_p2p_export may free. */
+int rag_comm_detach(rag_index* idx);
 int rag_comm_unique_id(uint8_t id[RAG_COMM_ID_BYTES]);            /* rank 0 creates, host broadcasts */
 int rag_comm_init(rag_index* idx, int nranks, int rank, const uint8_t id[RAG_COMM_ID_BYTES]);
 int rag_comm_destroy(rag_index* idx);

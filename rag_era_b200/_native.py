@@ -18,6 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 RAGERA_VERSION = 0x00010000
 MAX_TOPK, MAX_CANDIDATES, MAX_KEYWORDS, MAX_FRESH = 64, 128, 64, 64
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6, -7
+ERR_TIMEOUT = -8
 F32, BF16 = 0, 1
 SRC_VECTOR, SRC_KEYWORD, SRC_BOTH, SRC_FRESHNESS = 0, 1, 2, 3
 CT_DOCUMENT, CT_MEMORY, CT_CODE = 0, 1, 2
@@ -29,6 +30,7 @@ SEARCH_STAT_EPS = 2
 PROF_CLASSES = 6
 PROF_NAMES = ("stream", "tensor", "merge", "rescore", "fuse", "comm")
 COMM_ID_BYTES = 128
+COMM_HANDLE_BYTES = 64
 
 class RagError(RuntimeError):
     def __init__(self, code: int, msg: str):
@@ -172,6 +174,9 @@ SYMBOLS = {
     "rag_profile_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "rag_host_alloc": (_vp, [C.c_uint64]),
     "rag_host_free": (None, [_vp]),
+    "rag_comm_p2p_export": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _vp]),
+    "rag_comm_p2p_import": (C.c_int, [_vp, _vp]),
+    "rag_comm_detach": (C.c_int, [_vp]),
     "rag_comm_unique_id": (C.c_int, [_vp]),
     "rag_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "rag_comm_destroy": (C.c_int, [_vp]),

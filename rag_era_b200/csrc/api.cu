@@ -294,7 +294,8 @@ int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fr
   bool fused = false;
   const rag_eps eps = {p.eps, p.eps_per_query ? idx->cur->d_rho_q : nullptr, p.eps_q_mul};
   if (k34_small_ok(idx, B, p.kp, parts)) {
-    fused = k5_in_place && idx->nranks == 1;
+    // one GPU, or sharded with the peer-to-peer exchange (which then runs inside the same kernel)
+    fused = k5_in_place && (idx->nranks == 1 || k34_small_fuses_exchange(idx));
     RAG_CHECK(k34_small_launch(idx, B, p.kp, parts, k, eps, p.key_has_qnorm, fc.now_ms, fc.decay, fc.bonus, fused ? &fa : nullptr));
   } else {
     RAG_CHECK(k3_launch(idx, B, p.kp, parts));
@@ -310,6 +311,7 @@ int fetch_out(rag_index* idx, rag_batch* bt, const out_layout& L, bool with_aux)
   RAG_CUDA(cudaMemcpyAsync(bt->h_out, bt->d_out, with_aux ? L.total : L.total_no_aux, cudaMemcpyDeviceToHost,
                            idx->stream));
   RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  RAG_CHECK(comm_check_status(idx));  // sharded: a peer that never arrived at the exchange
   return RAG_OK;
 }
 

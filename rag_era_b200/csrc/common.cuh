@@ -234,6 +234,7 @@ int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, rag_eps eps, 
 bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, uint32_t k, rag_eps eps, int key_has_qnorm,
                      int64_t now_ms, double decay, double bonus, const struct rag_fuse_args* fuse /* non-null: run K5 in place */);
+bool k34_small_fuses_exchange(const rag_index* idx);  // sharded: the in-place K5 also runs the peer-to-peer exchange
 // K5 — cross-rank merge, min-cosine filter, RRF / freshness fusion, memory blend (k5_fuse.cu)
 struct rag_fuse_args {
   uint32_t B, k, nranks;
@@ -268,12 +269,17 @@ int iota_u64_launch(rag_index* idx, uint64_t* d, uint64_t n, uint64_t base);
 struct rag_p2p_view {
   unsigned char* base[8];  // rank g's mailbox as mapped into this process (base[rank] is the local allocation)
   uint32_t nranks, rank;   // nranks <= 1: no exchange (single GPU, or the NCCL fallback already gathered)
-  uint32_t step;           // exchange number (parity selects the mailbox half, the value is the flag)
+  uint32_t step;           // exchange number: its parity selects the mailbox half
+  uint32_t flag;           // the value raised in / awaited from the flag words: step << 12 | hash(B, k) — ranks
+                           // that disagree on the call sequence or its shape time out instead of merging garbage
   uint64_t half_bytes;     // bytes of one parity half: [records | flags]
   uint64_t flags_off;      // offset of the flag words inside a half: [src rank][flag_stride] u32
   uint32_t flag_stride;    // flag slots per source rank (>= the batch)
+  long long timeout_cycles;  // a peer that has not arrived by then: give up (status word, no trap)
+  uint32_t* status;        // host-mapped word: set to 1 by a query whose exchange timed out
 };
-int comm_p2p_ensure(rag_index* idx, uint32_t B, uint32_t k);            // collective when the mailboxes must grow
+int comm_p2p_ensure(rag_index* idx, uint32_t B, uint32_t k);            // sizes / checks the mailboxes for this shape
 bool comm_uses_p2p(const rag_index* idx);
 int comm_p2p_next(rag_index* idx, uint32_t B, uint32_t k, rag_p2p_view* v);  // view of the next exchange
+int comm_check_status(rag_index* idx);  // after a stream sync: RAG_ERR_TIMEOUT if an exchange gave up
 int comm_allgather_local(rag_index* idx, uint32_t B, uint32_t k);

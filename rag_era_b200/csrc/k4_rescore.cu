@@ -229,7 +229,8 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
                  const uint64_t* __restrict__ partial, uint32_t parts, uint32_t kp, uint32_t k, rag_eps E,
                  int key_has_qnorm, k4_meta M, double* __restrict__ scratch /*[B][2*128+2]*/,
                  unsigned int* __restrict__ ticket /*[B]*/, uint64_t* __restrict__ cand_out /*[B][128]*/,
-                 rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt, int fuse_k5, rag_k5::k5_io io) {
+                 rag_rec* __restrict__ local, uint32_t* __restrict__ local_cnt, int fuse_k5, rag_k5::k5_io io,
+                 rag_p2p_view pv) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* stg = reinterpret_cast<uint64_t*>(smem);               // [parts][kp] staged lists
   uint64_t* wl = stg + (size_t)parts * kp;                         // [2][K4S_WARPS][kp] per-warp merged lists
@@ -323,13 +324,18 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
     k4_finalize(j, kp, k, valid, row, score, nq, s_cand[kp - 1], eps, key_has_qnorm, M, s_score, s_row, &s_kth,
                 local + (size_t)b * k, local_cnt + b);
   }
-  // ---- K5 in place (single GPU): filter + fusion of this query by warp 0 — one launch less on the
-  //      batch-1 latency path. The product scratch is free by now and hosts K5's working set.
+  // ---- K5 in place: filter + fusion of this query by warp 0 — one launch less on the batch-1 latency path.
+  //      Sharded (pv.nranks > 1): the same warp first exchanges this query's records with the peer ranks through
+  //      the mailboxes; every query's last CTA is resident (the grid is B x K'/4 <= 32 x 32 CTAs), so a rank's
+  //      wait for its peers cannot starve them. The product scratch is free by now and hosts K5's working set.
   if (fuse_k5) {
     __threadfence();  // the records above are read back through L2
     __syncthreads();
     static_assert(sizeof(rag_k5::fuse_smem) <= sizeof(s_prod), "K5 working set must fit the product scratch");
-    if (warp == 0) rag_k5::k5_fuse_body(*reinterpret_cast<rag_k5::fuse_smem*>(&s_prod[0][0]), local, io, b, lane);
+    if (warp == 0) {
+      const rag_rec* recs = pv.nranks > 1 ? rag_k5::p2p_exchange(pv, local, io.a.B, b, io.a.k, lane) : local;
+      rag_k5::k5_fuse_body(*reinterpret_cast<rag_k5::fuse_smem*>(&s_prod[0][0]), recs, io, b, lane);
+    }
   }
 }
 
@@ -353,6 +359,8 @@ int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, rag_eps eps, 
 
 // K3 + K4 in one launch for small batches (see k34_small_kernel). Returns RAG_ERR_UNSUPPORTED-free:
 // the caller asks k34_small_ok() first.
+bool k34_small_fuses_exchange(const rag_index* idx) { return comm_uses_p2p(idx); }
+
 bool k34_small_ok(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   (void)idx;
   return B <= 32 && (size_t)parts * kp * 8 <= K4S_MAX_STAGE && kp <= RAG_MAX_CANDIDATES;
@@ -368,10 +376,13 @@ int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, ui
   auto kern = bf16 ? k34_small_kernel<true> : k34_small_kernel<false>;
   RAG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K4S_MAX_STAGE + 2 * K4S_WARPS * RAG_MAX_CANDIDATES * 8)));
   const uint32_t slices = (kp + K4S_CW - 1) / K4S_CW;
+  rag_p2p_view pv = rag_p2p_view();
+  pv.nranks = 1;
+  if (fuse && idx->nranks > 1) RAG_CHECK(comm_p2p_next(idx, B, k, &pv));  // the in-place K5 runs the exchange as well
   kern<<<dim3(B, slices), K4S_THREADS, smem, idx->stream>>>(idx->corpus, idx->ld, bt->d_q, bt->d_partial, parts, kp, k, eps,
                                                              key_has_qnorm, M, bt->d_k4s, bt->d_ticket, bt->d_cand, bt->d_local,
                                                              bt->d_local_cnt, fuse ? 1 : 0,
-                                                             fuse ? k5_make_io(idx, fuse) : rag_k5::k5_io());
+                                                             fuse ? k5_make_io(idx, fuse) : rag_k5::k5_io(), pv);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   return RAG_OK;

@@ -86,6 +86,43 @@ __device__ __forceinline__ rag_rec rec_load(const rag_rec* r) {
   return u.rec;
 }
 
+// C1 fused into K5 (see comm.cu): store this rank's k records of query b into every rank's mailbox, raise the
+// flags, wait for every rank's flag. Returns the base of the gathered records [rank][B][k] (local mailbox).
+// One full warp. Lane g raises the flag in rank g's mailbox and waits for rank g's flag in its own. A peer that
+// does not arrive within pv.timeout_cycles is given up on: the host-mapped status word is raised (the call then
+// fails with RAG_ERR_TIMEOUT) and the merge runs on whatever the mailbox holds — no trap, no hang.
+__device__ __forceinline__ const rag_rec* p2p_exchange(const rag_p2p_view& pv, const rag_rec* local, uint32_t B, uint32_t b,
+                                                       uint32_t k, int lane) {
+  const uint64_t half = (uint64_t)(pv.step & 1u) * pv.half_bytes;
+  const uint4* src = reinterpret_cast<const uint4*>(local + (size_t)b * k);
+  const uint32_t n16 = k * (uint32_t)(sizeof(rag_rec) / 16);
+  // the records were written by other warps / CTAs of this kernel (or an earlier one): read them through L2
+  for (uint32_t i = lane; i < n16; i += 32) {
+    const uint4 v = __ldcg(src + i);
+    for (uint32_t g = 0; g < pv.nranks; g++)
+      (reinterpret_cast<uint4*>(pv.base[g] + half) + ((size_t)pv.rank * B + b) * n16)[i] = v;
+  }
+  __threadfence_system();  // this lane's stores are visible system-wide before the flags go up
+  __syncwarp();
+  if ((uint32_t)lane < pv.nranks) {
+    uint32_t* f = reinterpret_cast<uint32_t*>(pv.base[lane] + half + pv.flags_off) + (size_t)pv.rank * pv.flag_stride + b;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(pv.flag) : "memory");
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(pv.base[pv.rank] + half + pv.flags_off) + (size_t)lane * pv.flag_stride + b;
+    const long long t0 = clock64();
+    uint32_t seen;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
+      if (seen == pv.flag) break;
+      if (clock64() - t0 > pv.timeout_cycles) {
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(pv.status), "r"(1u) : "memory");
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  return reinterpret_cast<const rag_rec*>(pv.base[pv.rank] + half);
+}
+
 // everything K5 reads and writes besides the records
 struct k5_io {
   rag_fuse_args a;

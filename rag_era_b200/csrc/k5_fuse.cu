@@ -15,45 +15,24 @@
 //            cos*0.7 + fresh*0.3, stable sort desc, slice(limit)
 #include "k5_body.cuh"
 
+#include <algorithm>
+
 namespace {
 using namespace rag_k5;
 
-// C1 fused into K5 (see comm.cu): store this rank's k records of query b into every rank's mailbox, raise the
-// flags, wait for every rank's flag. Returns the base of the gathered records [rank][B][k] (local mailbox).
-__device__ __forceinline__ const rag_rec* p2p_exchange(const rag_p2p_view& pv, const rag_rec* local, uint32_t B, uint32_t b,
-                                                       uint32_t k, int lane) {
-  const uint64_t half = (uint64_t)(pv.step & 1u) * pv.half_bytes;
-  const uint4* src = reinterpret_cast<const uint4*>(local + (size_t)b * k);
-  const uint32_t n16 = k * (uint32_t)(sizeof(rag_rec) / 16);
-  for (uint32_t g = 0; g < pv.nranks; g++) {
-    uint4* dst = reinterpret_cast<uint4*>(pv.base[g] + half) + ((size_t)pv.rank * B + b) * k * (sizeof(rag_rec) / 16);
-    for (uint32_t i = lane; i < n16; i += 32) dst[i] = src[i];
-  }
-  __threadfence_system();  // this lane's stores are visible system-wide before the flags go up
-  __syncwarp();
-  if ((uint32_t)lane < pv.nranks) {
-    uint32_t* f = reinterpret_cast<uint32_t*>(pv.base[lane] + half + pv.flags_off) + (size_t)pv.rank * pv.flag_stride + b;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(pv.step) : "memory");
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(pv.base[pv.rank] + half + pv.flags_off) + (size_t)lane * pv.flag_stride + b;
-    const long long t0 = clock64();
-    uint32_t seen;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
-      if (seen != pv.step && clock64() - t0 > 40000000000ll) __trap();  // ~20 s: a peer never arrived
-    } while (seen != pv.step);
-  }
-  __syncwarp();
-  return reinterpret_cast<const rag_rec*>(pv.base[pv.rank] + half);
-}
-
+// One warp per query; the grid is capped (a CTA walks queries b, b + gridDim.x, ...) so that every CTA is resident:
+// with the exchange inside, CTA b of one rank waits for CTA b of its peers, and both ranks walk the queries in the
+// same order, so the lowest unfinished query of every rank is always being served.
 __global__ void __launch_bounds__(32)
 k5_fuse_kernel(const rag_rec* __restrict__ recs, rag_p2p_view pv, k5_io io) {
   __shared__ fuse_smem s;
   const int lane = threadIdx.x;
-  const uint32_t b = blockIdx.x;
-  // sharded: exchange the ranks' lists through the peer mailboxes
-  if (pv.nranks > 1) recs = p2p_exchange(pv, recs, io.a.B, b, io.a.k, lane);
-  k5_fuse_body(s, recs, io, b, lane);
+  for (uint32_t b = blockIdx.x; b < io.a.B; b += gridDim.x) {
+    // sharded: exchange the ranks' lists through the peer mailboxes
+    const rag_rec* r = pv.nranks > 1 ? p2p_exchange(pv, recs, io.a.B, b, io.a.k, lane) : recs;
+    k5_fuse_body(s, r, io, b, lane);
+    __syncwarp();
+  }
 }
 
 // fusion only (rag_rrf_fuse): lists given as keys
@@ -103,7 +82,8 @@ int k5_launch(rag_index* idx, const rag_fuse_args* a) {
   RAG_CHECK(comm_p2p_next(idx, a->B, a->k, &pv));  // nranks 1 unless the peer-to-peer exchange is active
   // peer-to-peer: K5 reads this rank's records and gathers them itself; NCCL fallback: already gathered
   const rag_rec* recs = (a->nranks > 1 && pv.nranks <= 1) ? idx->cur->d_gather : idx->cur->d_local;
-  k5_fuse_kernel<<<a->B, 32, 0, idx->stream>>>(recs, pv, k5_make_io(idx, a));
+  const uint32_t grid = std::min<uint32_t>(a->B, (uint32_t)idx->sm_count * 16u);
+  k5_fuse_kernel<<<grid, 32, 0, idx->stream>>>(recs, pv, k5_make_io(idx, a));
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   return RAG_OK;

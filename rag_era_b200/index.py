@@ -391,6 +391,22 @@ class VectorIndex:
         buf = (C.c_uint8 * N.COMM_ID_BYTES).from_buffer_copy(uid)
         N.check(self._lib.rag_comm_init(self._h, nranks, rank, buf))
 
+    def comm_p2p_export(self, nranks: int, rank: int, max_batch: int = 1024, max_k: int = N.MAX_TOPK) -> bytes:
+        """This rank's mailbox handle (64 bytes) for the host-driven bootstrap of the peer-to-peer exchange."""
+        buf = (C.c_uint8 * N.COMM_HANDLE_BYTES)()
+        N.check(self._lib.rag_comm_p2p_export(self._h, nranks, rank, max_batch, max_k, buf))
+        return bytes(buf)
+
+    def comm_p2p_import(self, handles: list[bytes]):
+        """All ranks' handles, ordered by rank (what the host all-gathered)."""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        N.check(self._lib.rag_comm_p2p_import(self._h, buf))
+
+    def comm_detach(self):
+        """Phase 1 of the teardown: close this rank's mappings of the peers' mailboxes (then barrier, then free)."""
+        N.check(self._lib.rag_comm_detach(self._h))
+
     def comm_destroy(self):
         N.check(self._lib.rag_comm_destroy(self._h))
 

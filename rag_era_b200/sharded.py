@@ -1,7 +1,11 @@
 """Row-sharded multi-GPU plumbing: one process per GPU, ``torch.distributed``
-for rendezvous only. The data path is libragera's own: each rank scores its shard, rescoring
-its survivors exactly, one ``ncclAllGather`` of the [B][k] exact records on the library
-stream, then every rank runs the same K5 merge (rank 0 is the consumer).
+for rendezvous only. The data path is libragera's own: each rank scores its shard and rescoring
+its survivors exactly; the ranks' [B][k] exact records are exchanged INSIDE the final fusion kernel
+through peer-to-peer mailboxes (CUDA IPC over NVLink), then every rank runs the same merge (rank 0
+is the consumer). Bootstrap is host-driven: each rank exports a 64-byte mailbox handle, the handles
+are all-gathered here, each rank imports them — no NCCL in the library. ``RAGERA_COMM=nccl`` (or
+GPUs without peer access) selects the fallback: one ``ncclAllGather`` of the records before the
+fusion kernel, on the library's own communicator.
 
 The reference has no counterpart (single Node process); this is the build's addition.
 """
@@ -33,16 +37,58 @@ def broadcast_unique_id(dist, rank: int, device=None) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def create_sharded_index(dist, total_rows: int, dim: int, dtype: int, device: int, bf16_shadow: bool = False) -> VectorIndex:
-    """Create this rank's shard and join the library communicator."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    base, n = shard_range(total_rows, world, rank)
-    idx = VectorIndex(dim, max(n, 1), dtype=dtype, device=device, bf16_shadow=bf16_shadow, id_base=base)
-    if world > 1:
-        import torch
+def allgather_bytes(dist, payload: bytes, device=None) -> list[bytes]:
+    """Every rank's ``payload`` (equal lengths), ordered by rank — the host channel of the mailbox bootstrap."""
+    import torch
 
-        uid = broadcast_unique_id(dist, rank, torch.device("cuda", device) if dist.get_backend() == "nccl" else None)
-        idx.comm_init(world, rank, uid)
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).clone()
+    if device is not None:
+        mine = mine.to(device)
+    parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    return [bytes(p.cpu().numpy().tobytes()) for p in parts]
+
+
+def join_exchange(dist, idx: VectorIndex, device: int, max_batch: int = 1024, max_k: int = 64) -> str:
+    """Bootstrap the exchange of this rank's index with its peers. Returns "p2p" or "nccl"."""
+    import os
+
+    import torch
+    from . import _native as N
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else None
+    if os.environ.get("RAGERA_COMM", "p2p") != "nccl":
+        handles = allgather_bytes(dist, idx.comm_p2p_export(world, rank, max_batch, max_k), dev)
+        try:
+            idx.comm_p2p_import(handles)
+            ok = 1
+        except N.RagError as e:
+            if e.code != N.ERR_UNSUPPORTED:
+                raise
+            ok = 0
+        if all(b[0] for b in allgather_bytes(dist, bytes([ok]), dev)):      # every rank mapped every peer
+            return "p2p"
+        idx.comm_destroy()
+    idx.comm_init(world, rank, broadcast_unique_id(dist, rank, dev))
+    return "nccl"
+
+
+def leave_exchange(dist, idx: VectorIndex):
+    """Two-phase teardown: every rank unmaps its peers' mailboxes, barrier, then the mailboxes may be freed
+    (freeing exported memory a peer still maps is undefined in CUDA)."""
+    idx.comm_detach()
+    dist.barrier()
+    idx.comm_destroy()
+
+
+def create_sharded_index(dist, total_rows: int, dim: int, dtype: int, device: int, bf16_shadow: bool = False,
+                         rows: tuple[int, int] | None = None, max_batch: int = 1024, max_k: int = 64) -> VectorIndex:
+    """Create this rank's shard ([base, base+n) = ``rows`` or the even split) and join the exchange."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    base, n = rows if rows is not None else shard_range(total_rows, world, rank)
+    idx = VectorIndex(dim, max(n, 1), dtype=dtype, device=device, bf16_shadow=bf16_shadow, id_base=base)
+    idx.exchange = join_exchange(dist, idx, device, max_batch, max_k) if world > 1 else "none"
     return idx
 
 

@@ -18,7 +18,7 @@ def _worker(rank: int, world: int, port: int, ret):
     import torch.distributed as dist
 
     import oracle
-    from rag_era_b200.sharded import broadcast_unique_id, merge_reference_order, shard_range
+    from rag_era_b200.sharded import allgather_bytes, broadcast_unique_id, merge_reference_order, shard_range
     from rag_era_b200.index import VectorIndex
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -52,6 +52,9 @@ def _worker(rank: int, world: int, port: int, ret):
         VectorIndex.comm_unique_id = staticmethod(lambda: bytes(range(128)))
         uid = broadcast_unique_id(dist, rank)
         ok = uid == bytes(range(128)) and shard_ok
+        # the host channel of the mailbox bootstrap: every rank's 64-byte handle, ordered by rank
+        hs = allgather_bytes(dist, bytes([rank]) * 64)
+        ok = ok and hs == [bytes([r]) * 64 for r in range(world)]
         if rank == 0:
             Xall = oracle.gen_rows(g, 0, total, d, threads=1)
             for b in range(4):

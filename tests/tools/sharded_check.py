@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Multi-GPU parity check (run under torchrun, one rank per GPU):
-row-sharded hybrid search over NCCL must equal the CPU oracle over the WHOLE corpus —
+row-sharded hybrid search (peer-to-peer mailbox exchange, or RAGERA_COMM=nccl) must equal the CPU oracle over the WHOLE corpus —
 ids, scores, fused order and source flags bit for bit — on the stream, tensor and exact paths,
 including exact ties that straddle the shard boundary and queries that must escalate.
 
@@ -23,7 +23,7 @@ def main():
     import oracle
     import rag_era_b200 as rb
     from rag_era_b200 import _native as N
-    from rag_era_b200.sharded import create_sharded_index, shard_range
+    from rag_era_b200.sharded import create_sharded_index, leave_exchange, shard_range
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -63,6 +63,7 @@ def main():
                 if not (np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es) and r.certified[b]):
                     ok = False
                     print(f"MISMATCH (escalation) rows={total} query={b}", flush=True)
+        leave_exchange(dist, idx)
         idx.close()
     # one binary sidecar, every rank streams only its own row range into HBM (open_sharded_cache)
     import tempfile
@@ -85,6 +86,7 @@ def main():
                 if not (np.array_equal(top.row(b)[0], ei) and np.array_equal(top.row(b)[1], es) and len(ids) == total):
                     ok = False
                     print(f"MISMATCH (sidecar shards) path={pth} query={b}", flush=True)
+    leave_exchange(dist, idx)
     idx.close()
     dist.barrier()
     if rank == 0:
