@@ -350,6 +350,9 @@ double rag_index_row_residual(rag_index* idx);
 int rag_timer_start(rag_index* idx);
 int rag_timer_stop(rag_index* idx, float* elapsed_ms);           /* synchronises */
 uint64_t rag_launch_count(const rag_index* idx);                 /* kernels launched so far */
+/* queries finished by the fusion kernel since the last call, and how many of them the scoring pass certified
+ * (counted on the device: covers the asynchronous *_staged runs, which fetch nothing) */
+int rag_certified_totals(rag_index* idx, uint64_t* certified, uint64_t* queries);
 /* per-kernel device time: when enabled, every pipeline kernel launch is bracketed by a
  * pair of events on the library stream; rag_profile_read synchronises and returns the
  * summed milliseconds and launch counts per kernel class since the last read. */

@@ -170,6 +170,7 @@ SYMBOLS = {
     "rag_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rag_index_row_residual": (C.c_double, [_vp]),
     "rag_launch_count": (C.c_uint64, [_vp]),
+    "rag_certified_totals": (C.c_int, [_vp, _vp, _vp]),
     "rag_profile_enable": (C.c_int, [_vp, C.c_int]),
     "rag_profile_read": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "rag_host_alloc": (_vp, [C.c_uint64]),

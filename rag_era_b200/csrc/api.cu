@@ -474,6 +474,8 @@ int rag_index_create(const rag_index_desc* d, rag_index** out) {
     if ((rc = grow_dev(&idx->inv_norm, &cap, (size_t)d->capacity_rows * 4, true)) != RAG_OK) break;
     cap = 0;
     if ((rc = grow_dev(&idx->d_rho_x, &cap, 16, true)) != RAG_OK) break;
+    cap = 0;
+    if ((rc = grow_dev(&idx->d_counters, &cap, 16, true)) != RAG_OK) break;
     if ((e = cudaStreamSynchronize(idx->stream)) != cudaSuccess) {
       rc = rag_set_error(RAG_ERR_CUDA, "rag_index_create: %s", cudaGetErrorString(e));
       break;
@@ -496,7 +498,7 @@ void rag_index_destroy(rag_index* idx) {
   free_batch(&idx->main);
   free_batch(&idx->esc);
   if (idx->shadow && (void*)idx->shadow != idx->corpus) cudaFree(idx->shadow);
-  cudaFree(idx->corpus); cudaFree(idx->inv_norm); cudaFree(idx->d_rho_x); cudaFree(idx->ctype); cudaFree(idx->conf);
+  cudaFree(idx->corpus); cudaFree(idx->inv_norm); cudaFree(idx->d_rho_x); cudaFree(idx->d_counters); cudaFree(idx->ctype); cudaFree(idx->conf);
   cudaFree(idx->access); cudaFree(idx->last_ms); cudaFree(idx->row_keys);
   if (idx->prof_spans) {
     for (uint32_t i = 0; i < idx->prof_cap; i++) { cudaEventDestroy(idx->prof_spans[i].a); cudaEventDestroy(idx->prof_spans[i].b); }
@@ -1113,6 +1115,20 @@ int rag_timer_stop(rag_index* idx, float* elapsed_ms) {
 }
 
 uint64_t rag_launch_count(const rag_index* idx) { return idx ? idx->launches : 0; }
+
+// device-side totals of the fusion kernel since the last call: how many queries it finished and how many of them
+// were certified by the scoring pass that produced them (escalated re-runs count as their own queries)
+int rag_certified_totals(rag_index* idx, uint64_t* certified, uint64_t* queries) {
+  RAG_CHECK(check_handle(idx));
+  RAG_CUDA(cudaSetDevice(idx->device));
+  unsigned long long h[2] = {0, 0};
+  RAG_CUDA(cudaMemcpyAsync(h, idx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, idx->stream));
+  RAG_CUDA(cudaMemsetAsync(idx->d_counters, 0, sizeof(h), idx->stream));
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  if (certified) *certified = h[0];
+  if (queries) *queries = h[1];
+  return RAG_OK;
+}
 
 int rag_profile_enable(rag_index* idx, int on) {
   RAG_CHECK(check_handle(idx));

@@ -169,6 +169,7 @@ struct rag_index {
   rag_batch* cur = nullptr;         // the batch the launchers operate on
 
   uint64_t launches = 0;
+  unsigned long long* d_counters = nullptr;  // [2] certified / total queries that went through K5 (rag_certified_totals)
   rag_comm* comm = nullptr;
   int nranks = 1, rank = 0;
 

@@ -140,6 +140,7 @@ struct k5_io {
   uint8_t* o_cert;
   double* o_aux0;
   double* o_aux1;
+  unsigned long long* counters;  // [2] device-side totals since the last rag_certified_totals: certified, queries
 };
 
 // recs: [nranks][B][k] records; executed by one full warp for query b
@@ -208,6 +209,10 @@ __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, 
     if (lane == 0) v_cnt[b] = nv;
   }
   if (lane == 0 && o_cert) o_cert[b] = uncert ? 0 : 1;
+  if (lane == 0 && io.counters) {
+    atomicAdd(io.counters + 1, 1ull);
+    if (!uncert) atomicAdd(io.counters, 1ull);
+  }
 
   uint64_t* ok = o_key + (size_t)b * a.out_cap;
   double* os = o_score + (size_t)b * a.out_cap;

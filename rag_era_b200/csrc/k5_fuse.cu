@@ -73,7 +73,8 @@ __global__ void k5_freshness_kernel(uint64_t n, const double* __restrict__ conf,
 rag_k5::k5_io k5_make_io(const rag_index* idx, const rag_fuse_args* a) {
   const rag_batch* bt = idx->cur;
   return rag_k5::k5_io{*a, bt->d_kw, bt->d_kwc, bt->d_out_keys, bt->d_out_scores, bt->d_out_src, bt->d_out_ct, bt->d_out_cnt,
-                       bt->d_out_rrf, bt->d_vec_ids, bt->d_vec_scores, bt->d_vec_cnt, bt->d_cert, bt->d_aux0, bt->d_aux1};
+                       bt->d_out_rrf, bt->d_vec_ids, bt->d_vec_scores, bt->d_vec_cnt, bt->d_cert, bt->d_aux0, bt->d_aux1,
+                       idx->d_counters};
 }
 
 int k5_launch(rag_index* idx, const rag_fuse_args* a) {

@@ -332,6 +332,12 @@ class VectorIndex:
         N.check(self._lib.rag_fetch_fused(self._h, B, C.byref(opts), C.byref(out._c)))
         return out
 
+    def certified_totals(self) -> tuple[int, int]:
+        """(certified, queries) finished by the fusion kernel since the last call (device-side counters)."""
+        c, q = C.c_uint64(0), C.c_uint64(0)
+        N.check(self._lib.rag_certified_totals(self._h, C.byref(c), C.byref(q)))
+        return int(c.value), int(q.value)
+
     def row_residual(self) -> float:
         """rho_x of the rigorous certification bound (max ||x - operand(x)|| / ||x|| over the loaded rows)."""
         v = float(self._lib.rag_index_row_residual(self._h))

@@ -24,7 +24,10 @@ def check_reference_line(stdout, n_gpus):
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "rows" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "rows" in cb["sample"]   # variant A: one thread
+    ex = d["extrapolated"]
+    assert ex["threads"] == 1 and ex["sample_rows"] <= ex["rows"] and ex["scale_scoring"] >= 1 and ex["scale_sort_nlogn"] >= ex["scale_scoring"]
+    assert d["all_threads_courtesy"]["cores"] >= 1 and d["all_threads_courtesy"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     return d
 
