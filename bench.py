@@ -52,14 +52,17 @@ WORKLOADS = {
     "c3h": dict(rows=10_000_000, dim=1536, dtype="bf16", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                 desc="C3 with a bf16 corpus: 10M x 1536 bf16, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1 (stream path)"),
     "c2b": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
-                path="tensor", shadow=True,
-                desc="C2 deep_search batched: 1M x 1536 fp32 (+bf16 shadow), vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 path"),
+                path="tensor", shadow="f16",
+                desc="C2 deep_search batched: 1M x 1536 fp32 (+fp16 shadow of the normalised rows), vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 kind::f16 path"),
+    "c2bb": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+                 path="tensor", shadow="bf16",
+                 desc="C2 batched with a BF16 shadow: 1M x 1536 fp32 (+bf16 shadow), batch 1024, tcgen05 path (wider candidate window: bf16's rounding bound)"),
     "c4f": dict(rows=7_000_000, dim=1536, dtype="f32", batch=256, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
-                path="tensor", shadow=False, memory_rows=2_000_000, fresh_limit=10,
+                path="tensor", shadow=None, memory_rows=2_000_000, fresh_limit=10,
                 desc="C4 memory+RAG unified, fp32 operand: 2M memory + 5M doc rows x 1536 fp32 scored as tf32 (no shadow), vector+keyword+freshness lists fused by RRF, batch 256, tcgen05 kind::tf32"),
     "c4": dict(rows=7_000_000, dim=1536, dtype="f32", batch=256, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
-               path="tensor", shadow=True, memory_rows=2_000_000, fresh_limit=10,
-               desc="C4 memory+RAG unified: 2M memory + 5M doc rows x 1536 fp32 (+bf16 shadow), vector+keyword+freshness lists fused by RRF, batch 256, tcgen05 path"),
+               path="tensor", shadow="f16", memory_rows=2_000_000, fresh_limit=10,
+               desc="C4 memory+RAG unified: 2M memory + 5M doc rows x 1536 fp32 (+fp16 shadow of the normalised rows), vector+keyword+freshness lists fused by RRF, batch 256, tcgen05 kind::f16 path"),
     "c5": dict(rows=50_000_000, dim=1536, dtype="bf16", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                path="tensor",
                desc="C5: 50M x 1536 bf16 row-sharded, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 path, "
@@ -264,12 +267,12 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
                     w.get("memory_rows", 0), now_ms)
     tensor = w.get("path") == "tensor"
     path = N.PATH_TENSOR if tensor else N.PATH_STREAM
-    shadow = bool(w.get("shadow")) and dt == N.F32
+    shadow = w.get("shadow") if dt == N.F32 else None
     if world > 1:
-        idx = create_sharded_index(dist, rows, d, dt, device, bf16_shadow=shadow, max_batch=max(B, 32), max_k=w["vector_top_k"])
+        idx = create_sharded_index(dist, rows, d, dt, device, shadow=shadow, max_batch=max(B, 32), max_k=w["vector_top_k"])
         base, n_local = shard_range(rows, world, rank)
     else:
-        idx = rb.VectorIndex(d, rows, dtype=dt, device=device, bf16_shadow=shadow)
+        idx = rb.VectorIndex(d, rows, dtype=dt, device=device, shadow=shadow)
         base, n_local = 0, rows
     idx.generate(gen, n_local)
     total = steps + warmup
@@ -378,11 +381,12 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         k_ms, k_n = prof["tensor"]
         flops = 2.0 * n_local * idx_ld(d) * B                                 # dot products only
         ach = flops / (k_ms / max(k_n, 1) * 1e-3) / 1e12 if k_n else None
-        op_bytes = 2 if (dt == N.BF16 or shadow) else 4                       # bf16 operand, or fp32 rows read as tf32
+        op_bytes = 2 if (dt == N.BF16 or shadow) else 4                       # 16-bit operand, or fp32 rows read as tf32
         roof = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": (ach / tf_sus) if ach else None,
                 "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": (ach / tf_burst) if ach else None,
-                "kernel": "k2_pair (tcgen05 cta_group::2 bf16 GEMM + fused top-K' epilogue)", "algorithmic_flops_per_launch": flops,
+                "kernel": "k2_pair (tcgen05 cta_group::2 kind::f16 GEMM, fp16 queries x " + ("bf16 corpus rows" if dt == N.BF16 else
+                          f"{shadow} shadow rows" if shadow else "tf32") + " + fused top-K' epilogue)", "algorithmic_flops_per_launch": flops,
                 "algorithmic_bytes_per_launch": int(n_local * idx_ld(d) * op_bytes), "avg_launch_ms": k_ms / max(k_n, 1),
                 "launches_timed": int(k_n)}
         if op_bytes == 4:
@@ -505,8 +509,9 @@ def run_ours(args):
                 "kernel_ms_per_step": res["kernel_ms_per_step"], "certified": res["certified"],
                 "arithmetic": "fp32 scoring selects K' candidates; fp64 reference-order rescoring decides ids/scores/ties"}
         if res["roofline"].get("bound") == "tensor":
-            # the batched path selects on tcgen05 products of bf16 (or tf32) operands; ids and scores are still decided in fp64
-            line["dtype"] = "tf32" if "operand" in res["roofline"] else "bf16"
+            # the batched path selects on tcgen05 products of 16-bit (fp16 queries x fp16/bf16 rows) or tf32 operands;
+            # ids and scores are still decided in fp64
+            line["dtype"] = "tf32" if "operand" in res["roofline"] else ("f16xbf16" if w["dtype"] == "bf16" or w.get("shadow") == "bf16" else "f16")
         for key in ("per_rank_kernel_ms", "exchange", "e2e_kernel_ms_per_call", "first_pass_certification", "shard_rows"):
             if key in res:
                 line[key] = res[key]

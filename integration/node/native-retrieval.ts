@@ -47,7 +47,7 @@ export class NativeKnowledgeIndex {
   /** Load ./storage/kb_<id>/ as written by storageContextFromDefaults (index-manager.ts:218-220,264-270). */
   static fromPersistDir(dir: string, dim: number, capacityRows: number, embed: (q: string) => Promise<Float32Array>,
                         isCodebase = false): NativeKnowledgeIndex {
-    const handle = native.createIndex({ rows: capacityRows, dim, device: 0, bf16Shadow: 1 });
+    const handle = native.createIndex({ rows: capacityRows, dim, device: 0, f16Shadow: 1 });
     const idx = new NativeKnowledgeIndex(handle, dim, embed);
     const ids: string[] = native.loadVectorStore(handle, path.join(dir, 'vector_store.json'));
     const docstore = JSON.parse(fs.readFileSync(path.join(dir, 'doc_store.json'), 'utf8'));

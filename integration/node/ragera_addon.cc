@@ -8,7 +8,7 @@
 // because JS callers await each call (or go through the batcher, which has its own worker thread).
 //
 // JS surface (see native-retrieval.ts):
-//   createIndex({rows, dim, dtype:'f32'|'bf16', device, bf16Shadow}) -> handle (External)
+//   createIndex({rows, dim, dtype:'f32'|'bf16', device, f16Shadow | bf16Shadow}) -> handle (External)
 //   uploadRows(handle, Float32Array rows, nrows, row0 = append) -> first row
 //   loadVectorStore(handle, path) -> string[] node ids          (llamaindex vector_store.json, via its binary sidecar)
 //   setRowMeta(handle, row0, Uint8Array contentType, Float64Array confidence, Int32Array accessCount, BigInt64Array lastAccessMs)
@@ -247,15 +247,16 @@ napi_value CreateIndex(napi_env env, napi_callback_info info) {
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
   rag_index_desc d;
   memset(&d, 0, sizeof d);
-  uint32_t rows = 0, dev = 0, shadow = 0;
+  uint32_t rows = 0, dev = 0, shadow = 0, shadow16 = 0;
   get_u32(env, argv[0], "rows", &rows);
   get_u32(env, argv[0], "dim", &d.dim);
   get_u32(env, argv[0], "device", &dev);
   get_u32(env, argv[0], "bf16Shadow", &shadow);
+  get_u32(env, argv[0], "f16Shadow", &shadow16);
   d.capacity_rows = rows;
   d.device = (int32_t)dev;
   d.dtype = RAG_F32;
-  d.flags = shadow ? RAG_INDEX_BF16_SHADOW : 0;
+  d.flags = shadow16 ? RAG_INDEX_F16_SHADOW : (shadow ? RAG_INDEX_BF16_SHADOW : 0);
   rag_index* idx = nullptr;
   const int rc = rag_index_create(&d, &idx);
   if (rc != RAG_OK) return throw_rag(env, rc);

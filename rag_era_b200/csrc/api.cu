@@ -150,16 +150,17 @@ int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_
     return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path (K2) is not available for this index");
   const bool stat_eps = (flags & RAG_SEARCH_STAT_EPS) != 0;
   uint32_t s = slack;
-  // the tensor path selects on bf16 / tf32 scores: a wider window keeps (nearly) every query certifiable in one
+  // the tensor path selects on 16-bit / tf32 scores: a wider window keeps (nearly) every query certifiable in one
   // pass — an uncertified query costs a whole extra corpus pass on the stream path. The rigorous bound of an
-  // fp32 index with a bf16 shadow carries the rounding of BOTH operands (~3.5e-3 at D=1536): widest window.
-  const bool both_rounded = idx->shadow && (const void*)idx->shadow != idx->corpus;
-  if (s == 0) s = path == RAG_PATH_TENSOR ? ((!stat_eps && eps <= 0.0 && both_rounded) ? 48u : std::max(22u, k)) : 6u;
+  // fp32 index with a BF16 shadow carries bf16's 8-bit rounding of every row (~2e-3 at D=1536): widest window.
+  const bool bf16_shadow = idx->shadow && (const void*)idx->shadow != idx->corpus && !idx->shadow_f16;
+  if (s == 0) s = path == RAG_PATH_TENSOR ? ((!stat_eps && eps <= 0.0 && bf16_shadow) ? 48u : std::max(22u, k)) : 6u;
   uint32_t kp = std::min<uint32_t>(path == RAG_PATH_TENSOR ? 48u : (uint32_t)RAG_MAX_CANDIDATES, k + s);
   if (kp < k) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path supports k <= 48 (k=%u)", k);
   p->path = path;
   p->kp = kp;
-  p->key_has_qnorm = path == RAG_PATH_EXACT;
+  // K1x keys hold the cosine; so do K2's on the 16-bit path (its query operand is q/||q||); K1 and K2-tf32 keys hold dot/||x||
+  p->key_has_qnorm = path == RAG_PATH_EXACT || (path == RAG_PATH_TENSOR && idx->shadow != nullptr);
   p->eps_per_query = false;
   p->eps_q_mul = 0.0;
   const double u24 = 5.9604644775390625e-08;  // 2^-24
@@ -173,19 +174,20 @@ int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_
     // D=1536, max 2.8e-4 over 5e5 pairs — tests/test_gpu_tensor.py); ~11 sigma, NOT a proof. tf32 is 4x finer.
     p->eps = (idx->shadow ? 0.024 : 0.006) / sqrt((double)idx->ld);
   else if (path == RAG_PATH_TENSOR) {
-    // RIGOROUS (default). K2's key is fl32(acc * inv) with acc ~ q~.x~ (tensor core, fp32 accumulate),
-    // inv ~ 1/||x||; K4 divides by the exact ||q||. With e_q = q~ - q, e_x = x~ - x:
-    //   q~.x~ - q.x = e_q.x~ + q.e_x  =>  |.| <= ||e_q|| ||x~|| + ||q|| ||e_x||      (Cauchy-Schwarz)
-    //   in cosine units: rho_q (1 + rho_x) + rho_x, rho_q = ||e_q||/||q|| measured per query (q_operand_launch),
-    //   rho_x = max over rows of ||e_x||/||x|| measured when the rows were loaded (aux_build; 0 for a bf16 corpus).
+    // RIGOROUS (default). In cosine units K2's key is acc (* inv_x) with acc ~ q~.x~ (tensor core, fp32 accumulate)
+    // over the operands q~, x~ of gen.cu's table. With u_q = q/||q||, u_x = x/||x||, e_q = q~ - u_q, e_x = x~ - u_x:
+    //   q~.x~ - u_q.u_x = e_q.x~ + u_q.e_x  =>  |.| <= ||e_q|| ||x~|| + ||e_x||  <=  rho_q (1 + rho_x) + rho_x   (Cauchy-Schwarz)
+    //   rho_q = ||e_q|| measured per query (q_operand_launch), rho_x = max over rows of ||e_x|| measured when the rows
+    //   were loaded (aux_build; 0 for a bf16 corpus, whose rows are the operand).
     // + accumulation: every one of the ld products enters an fp32 sum once, each add rounds (or truncates) at most
     //   2^-23 relative to a partial sum that is <= sum|q~_i x~_i| <= ||q~|| ||x~||           => ld * 2^-23
-    // + inv: fp32 sum of ld squares (ld/32 sequential fmas per lane + 5 shuffle adds) and rsqrtf (2 ulp), halved
-    //   by the square root; + the fp32 rounding of the key itself. The residuals are computed in fp32 and inflated.
+    // + the two normalisations: fp32 sum of ld squares (ld/32 sequential fmas per lane + 5 shuffle adds) and rsqrtf
+    //   (2 ulp), halved by the square root, once for the query and once for the row; + the fp32 roundings of the
+    //   scaled element / of the key itself. The residuals are computed in fp32 and inflated.
     RAG_CHECK(refresh_rho_x(idx));
     const double rx = (double)idx->rho_x * 1.001;
     const double acc = (double)idx->ld * 2.0 * u24 * 1.02;
-    const double nrm = 0.5 * ((double)idx->ld / 32.0 + 8.0) * u24 + 4.0 * u24 + 1.0e-6;
+    const double nrm = 2.0 * (0.5 * ((double)idx->ld / 32.0 + 8.0) * u24 + 4.0 * u24) + 1.0e-6;
     p->eps = rx + acc + nrm;
     p->eps_per_query = true;
     p->eps_q_mul = (1.0 + rx) * 1.001;
@@ -465,7 +467,8 @@ int rag_index_create(const rag_index_desc* d, rag_index** out) {
     }
     if (d->dtype == RAG_BF16) {
       idx->shadow = (__nv_bfloat16*)idx->corpus;
-    } else if (d->flags & RAG_INDEX_BF16_SHADOW) {
+    } else if (d->flags & (RAG_INDEX_BF16_SHADOW | RAG_INDEX_F16_SHADOW)) {
+      idx->shadow_f16 = (d->flags & RAG_INDEX_F16_SHADOW) != 0;
       cap = 0;
       if ((rc = grow_dev(&idx->shadow, &cap, (size_t)d->capacity_rows * idx->ld * 2, false)) != RAG_OK) break;
     }

@@ -3,7 +3,8 @@
 // Data layout in HBM:
 //   corpus    [capacity][ld]   fp32 or bf16, row-major, ld = dim rounded up to 256 elements,
 //                              padding columns are zero (they add 0 to dot and norm)
-//   shadow    [capacity][ld]   bf16 copy of an fp32 corpus (tensor path operand B)
+//   shadow    [capacity][ld]   16-bit copy of an fp32 corpus (tensor path operand B): fp16 of the NORMALISED row
+//                              (RAG_INDEX_F16_SHADOW) or bf16 of the row as it is (RAG_INDEX_BF16_SHADOW)
 //   inv_norm  [capacity]       fp32 1/||x|| of the operand the tensor path reads
 //   row meta  ctype u8, confidence f64, access i32, last_ms i64, key u64 (optional)
 //
@@ -113,7 +114,7 @@ struct rag_comm;
 // batch) and `esc` (the compacted sub-batch of queries escalated to a stronger path).
 struct rag_batch {
   float* d_q = nullptr;             size_t c_q = 0;        // [B][ld] fp32, zero padded
-  __nv_bfloat16* d_qb = nullptr;    size_t c_qb = 0;       // [Bpad][ld] bf16 (tensor path operand)
+  __nv_bfloat16* d_qb = nullptr;    size_t c_qb = 0;       // [Bpad][ld] 16-bit tensor path operand: fp16( q / ||q|| )
   float* d_rho_q = nullptr;         size_t c_rho_q = 0;    // [B] ||q - operand(q)|| / ||q|| (rigorous certification)
   uint8_t* d_in = nullptr;          size_t c_in = 0;       // small per-batch inputs, carved per call:
   uint8_t* h_in = nullptr;          size_t c_hin = 0;      //   pinned mirror of d_in
@@ -151,7 +152,8 @@ struct rag_index {
   uint64_t rows = 0;
   uint32_t dim = 0, ld = 0;
   void* corpus = nullptr;
-  __nv_bfloat16* shadow = nullptr;  // == corpus for a bf16 index
+  __nv_bfloat16* shadow = nullptr;  // 16-bit tensor-path operand: == corpus for a bf16 index, else the bf16 or fp16 copy
+  bool shadow_f16 = false;          // the shadow holds fp16( x / ||x|| ) (RAG_INDEX_F16_SHADOW), not bf16( x )
   float* inv_norm = nullptr;
   uint8_t* ctype = nullptr;
   double* conf = nullptr;
@@ -259,6 +261,7 @@ int gen_corpus_launch(rag_index* idx, const rag_gen_desc* g, uint64_t nrows);
 int gen_queries_launch(rag_index* idx, const rag_gen_desc* g, uint64_t b0, uint32_t B, float* d_out);
 int gen_meta_launch(rag_index* idx, const rag_gen_desc* g, uint64_t nrows);
 int aux_build_launch(rag_index* idx, uint64_t row0, uint64_t nrows);  // shadow + inv_norm
+bool rag_q16_is_bf16();  // diagnostic switch RAGERA_K2_QFMT=bf16
 int q_operand_launch(rag_index* idx, uint32_t B, uint32_t Bpad, bool tf32);  // bf16 cast (or none: tf32) + rho_q
 int gather_batch_launch(rag_index* idx, const rag_batch* src, rag_batch* dst, uint32_t n, uint32_t kw_stride);
 int iota_u64_launch(rag_index* idx, uint64_t* d, uint64_t n, uint64_t base);

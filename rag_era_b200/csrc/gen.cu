@@ -3,6 +3,9 @@
 // shadow + inverse-norm builder for the tensor path, and the query fp32→bf16 cast.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 namespace {
 
 // one thread produces 8 consecutive columns of one row (two float4 / one uint4 store)
@@ -67,31 +70,46 @@ __global__ void gen_meta_kernel(uint64_t nrows, uint64_t id_base, rag_gen_desc g
   last_ms[i] = rg_meta_last_access_ms(&g, r);
 }
 
-// Rounding residual of one fp32 value against the operand the tensor path actually multiplies, squared.
-//   bf16 shadow: (v - bf16_rne(v))^2, exact in fp32 (the difference of two floats this close is representable).
-//   tf32 (fp32 rows read by TMA as TFLOAT32): the hardware keeps 10 mantissa bits, by truncation or by rounding
-//   — either way the operand is one of the two tf32 neighbours of v, so the bound is the distance to the
-//   FARTHER neighbour (0 when v is itself a tf32 value).
-__device__ __forceinline__ float resid2_bf16(float v, uint16_t b) {
-  const float e = __fsub_rn(v, rg_bf16_to_f32(b));
-  return e * e;
-}
+// ---- tensor-path operands and their rounding residuals (the rigorous certification bound, api.cu::make_plan) ------
+// What K2 multiplies:            queries                       rows
+//   fp32 index + fp16 shadow     fp16( q / ||q|| )             fp16( x / ||x|| )      (pre-normalised: no scaling in the epilogue)
+//   fp32 index + bf16 shadow     fp16( q / ||q|| )             bf16( x ),   scaled by 1/||x|| in the epilogue
+//   bf16 index                   fp16( q / ||q|| )             x itself,    scaled by 1/||x||
+//   fp32 index, no shadow        q (tf32, converted by TMA)    x (tf32),    scaled by 1/||x||
+// fp16 keeps 11 significant bits against bf16's 8, at the same tensor-core rate (kind::f16 takes the operand types
+// independently); the normalisation puts every element in [-1, 1], far from fp16's range limits. The residuals
+//   rho_q[b] = || operand(q) - q/||q|| ||           rho_x = max over rows || operand(x) - x || / ||x||
+// are MEASURED here (fp32 arithmetic, differences of nearby floats are exact), so outliers, subnormals or a value
+// that sits on a rounding midpoint are accounted for as they are — there is no statistical assumption.
+__device__ __forceinline__ float sq(float e) { return e * e; }
+__device__ __forceinline__ float resid2_bf16(float v, uint16_t b) { return sq(__fsub_rn(v, rg_bf16_to_f32(b))); }
+__device__ __forceinline__ float resid2_f16(float v, __half h) { return sq(__fsub_rn(v, __half2float(h))); }
+// tf32 (fp32 rows read by TMA as TFLOAT32): the hardware keeps 10 mantissa bits, by truncation or by rounding —
+// either way the operand is one of the two tf32 neighbours of v, so the bound is the distance to the FARTHER
+// neighbour (0 when v is itself a tf32 value).
 __device__ __forceinline__ float resid2_tf32(float v) {
   const uint32_t u = __float_as_uint(v);
-  const uint32_t low = u & 0x1FFFu;
-  if (low == 0u) return 0.f;
-  const float lo = __uint_as_float(u & ~0x1FFFu);          // truncation towards zero
+  if ((u & 0x1FFFu) == 0u) return 0.f;
+  const float lo = __uint_as_float(u & ~0x1FFFu);              // truncation towards zero
   const float hi = __uint_as_float((u & ~0x1FFFu) + 0x2000u);  // next tf32 value away from zero
-  const float e = fmaxf(fabsf(__fsub_rn(v, lo)), fabsf(__fsub_rn(hi, v)));
-  return e * e;
+  return sq(fmaxf(fabsf(__fsub_rn(v, lo)), fabsf(__fsub_rn(hi, v))));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b, float& ee) {
+  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+  ee += resid2_f16(a, ha) + resid2_f16(b, hb);
+  return (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+}
+__device__ __forceinline__ uint32_t pack_b2(float a, float b, float& ee) {
+  const uint16_t ba = rg_f32_to_bf16(a), bb = rg_f32_to_bf16(b);
+  ee += resid2_bf16(a, ba) + resid2_bf16(b, bb);
+  return (uint32_t)ba | ((uint32_t)bb << 16);
 }
 
-// one warp per row: bf16 shadow (fp32 corpus only), 1/||x|| of the row itself (NOT of its rounded copy: the
-// selected score then differs from the exact cosine only by the operand rounding, which rho bounds), and
-// rho_x = max over rows of ||x - operand(x)|| / ||x|| (atomicMax on the float's bits; 0 for a bf16 corpus,
-// whose rows are the operand)
-template <bool SRC_BF16>
-__global__ void aux_build_kernel(const void* __restrict__ X, __nv_bfloat16* __restrict__ shadow,
+// one warp per row. SHADOW: 0 = none (bf16 corpus: rho 0; fp32 corpus: the tf32 residual), 1 = bf16 copy,
+// 2 = fp16 copy of the NORMALISED row (a zero row becomes NaNs: it can never be selected).
+// inv_norm = 1/||x|| of the row itself (not of its rounded copy).
+template <bool SRC_BF16, int SHADOW>
+__global__ void aux_build_kernel(const void* __restrict__ X, uint16_t* __restrict__ shadow,
                                  float* __restrict__ inv_norm, uint32_t* __restrict__ rho_bits, uint64_t row0,
                                  uint64_t nrows, uint32_t ld) {
   const int lane = threadIdx.x & 31;
@@ -114,60 +132,74 @@ __global__ void aux_build_kernel(const void* __restrict__ X, __nv_bfloat16* __re
       }
     } else {
       const float4* p = reinterpret_cast<const float4*>((const float*)X + row * ld);
-      uint2* sp = shadow ? reinterpret_cast<uint2*>(shadow + row * ld) : nullptr;
+      uint2* sp = reinterpret_cast<uint2*>(shadow + row * ld);
       for (uint32_t i = lane; i < ld / 4; i += 32) {
         const float4 v = p[i];
         ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-        if (sp) {
+        if (SHADOW == 1) {
           const uint16_t b0 = rg_f32_to_bf16(v.x), b1 = rg_f32_to_bf16(v.y), b2 = rg_f32_to_bf16(v.z),
                          b3 = rg_f32_to_bf16(v.w);
           sp[i] = make_uint2((uint32_t)b0 | ((uint32_t)b1 << 16), (uint32_t)b2 | ((uint32_t)b3 << 16));
           ee += resid2_bf16(v.x, b0) + resid2_bf16(v.y, b1) + resid2_bf16(v.z, b2) + resid2_bf16(v.w, b3);
-        } else {
+        } else if (SHADOW == 0) {
           ee += resid2_tf32(v.x) + resid2_tf32(v.y) + resid2_tf32(v.z) + resid2_tf32(v.w);
         }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
-      ee += __shfl_xor_sync(0xFFFFFFFFu, ee, o);
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
+    if (!SRC_BF16 && SHADOW == 2) {
+      // second walk over the row (L1/L2 hits): the fp16 copy of x * (1/||x||) and its residual, already relative
+      const float4* p = reinterpret_cast<const float4*>((const float*)X + row * ld);
+      uint2* sp = reinterpret_cast<uint2*>(shadow + row * ld);
+      for (uint32_t i = lane; i < ld / 4; i += 32) {
+        const float4 v = p[i];
+        if (inv > 0.f) sp[i] = make_uint2(pack_h2(v.x * inv, v.y * inv, ee), pack_h2(v.z * inv, v.w * inv, ee));
+        else sp[i] = make_uint2(0x7E007E00u, 0x7E007E00u);
+      }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ee += __shfl_xor_sync(0xFFFFFFFFu, ee, o);
     if (lane == 0) {
-      inv_norm[row] = ss > 0.f ? rsqrtf(ss) : 0.f;
-      if (!SRC_BF16 && ss > 0.f) rho_max = fmaxf(rho_max, sqrtf(ee / ss));
+      inv_norm[row] = inv;
+      if (!SRC_BF16 && ss > 0.f) rho_max = fmaxf(rho_max, SHADOW == 2 ? sqrtf(ee) : sqrtf(ee / ss));
     }
   }
   if (!SRC_BF16 && lane == 0 && rho_max > 0.f) atomicMax(rho_bits, __float_as_uint(rho_max));
 }
 
-// one warp per query: the bf16 operand of the tensor path (rows >= B are zero padding) and the query's
-// rounding residual rho_q[b] = ||q - bf16(q)|| / ||q|| for the rigorous certification bound
-__global__ void q_to_bf16_kernel(const float* __restrict__ q, __nv_bfloat16* __restrict__ qb, float* __restrict__ rho_q,
-                                 uint32_t B, uint32_t Bpad, uint32_t ld) {
+// one warp per query: the fp16 operand q / ||q|| of the 16-bit tensor path (rows >= B are zero padding) and the
+// query's residual rho_q[b] = || fp16(q/||q||) - q/||q|| ||. QBF16: bf16 instead (diagnostic, RAGERA_K2_QFMT=bf16).
+template <bool QBF16>
+__global__ void q_to_f16_kernel(const float* __restrict__ q, uint16_t* __restrict__ qh, float* __restrict__ rho_q,
+                                uint32_t B, uint32_t Bpad, uint32_t ld) {
   const int lane = threadIdx.x & 31;
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t b = w; b < Bpad; b += nw) {
-    float ss = 0.f, ee = 0.f;
     const float4* src = reinterpret_cast<const float4*>(q + (size_t)b * ld);
-    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(qb) + (size_t)b * ld);
+    uint2* dst = reinterpret_cast<uint2*>(qh + (size_t)b * ld);
+    float ss = 0.f, ee = 0.f;
+    if (b < B)
+      for (uint32_t i = lane; i < ld / 4; i += 32) {
+        const float4 v = src[i];
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    const float inv = ss > 0.f ? rsqrtf(ss) : 0.f;
     for (uint32_t i = lane; i < ld / 4; i += 32) {
       const float4 v = b < B ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const uint16_t b0 = rg_f32_to_bf16(v.x), b1 = rg_f32_to_bf16(v.y), b2 = rg_f32_to_bf16(v.z), b3 = rg_f32_to_bf16(v.w);
-      dst[i] = make_uint2((uint32_t)b0 | ((uint32_t)b1 << 16), (uint32_t)b2 | ((uint32_t)b3 << 16));
-      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-      ee += resid2_bf16(v.x, b0) + resid2_bf16(v.y, b1) + resid2_bf16(v.z, b2) + resid2_bf16(v.w, b3);
+      dst[i] = QBF16 ? make_uint2(pack_b2(v.x * inv, v.y * inv, ee), pack_b2(v.z * inv, v.w * inv, ee))
+                     : make_uint2(pack_h2(v.x * inv, v.y * inv, ee), pack_h2(v.z * inv, v.w * inv, ee));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
-      ee += __shfl_xor_sync(0xFFFFFFFFu, ee, o);
-    }
-    if (lane == 0 && b < B) rho_q[b] = ss > 0.f ? sqrtf(ee / ss) : 0.f;
+    for (int o = 16; o > 0; o >>= 1) ee += __shfl_xor_sync(0xFFFFFFFFu, ee, o);
+    if (lane == 0 && b < B) rho_q[b] = sqrtf(ee);
   }
 }
 
-// the same residual for queries the tensor path reads as tf32 (no cast: TMA converts the fp32 queries)
+// the residual of queries the tensor path reads as tf32 (no cast: TMA converts the fp32 queries)
 __global__ void q_rho_tf32_kernel(const float* __restrict__ q, float* __restrict__ rho_q, uint32_t B, uint32_t ld) {
   const int lane = threadIdx.x & 31;
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -208,6 +240,15 @@ __global__ void iota_u64_kernel(uint64_t* d, uint64_t n, uint64_t base) {
   if (i < n) d[i] = base + i;
 }
 
+}  // namespace
+
+// diagnostic: RAGERA_K2_QFMT=bf16 casts the (normalised) queries to bf16 instead of fp16
+bool rag_q16_is_bf16() {
+  static const int v = [] { const char* e = getenv("RAGERA_K2_QFMT"); return (e && e[0] == 'b') ? 1 : 0; }();
+  return v != 0;
+}
+
+namespace {
 uint32_t grid_for(uint64_t work, uint32_t threads, int sm_count) {
   uint64_t blocks = (work + threads - 1) / threads;
   uint64_t cap = (uint64_t)sm_count * 32;
@@ -251,17 +292,20 @@ int gen_meta_launch(rag_index* idx, const rag_gen_desc* g, uint64_t nrows) {
 int aux_build_launch(rag_index* idx, uint64_t row0, uint64_t nrows) {
   if (nrows == 0 || !idx->inv_norm) return RAG_OK;
   const uint32_t grid = grid_for(nrows * 32, 256, idx->sm_count);
-  if (idx->desc.dtype == RAG_BF16)
-    aux_build_kernel<true><<<grid, 256, 0, idx->stream>>>(idx->corpus, nullptr, idx->inv_norm, idx->d_rho_x, row0, nrows, idx->ld);
-  else
-    aux_build_kernel<false><<<grid, 256, 0, idx->stream>>>(idx->corpus, idx->shadow, idx->inv_norm, idx->d_rho_x, row0, nrows, idx->ld);
+  uint16_t* sh = reinterpret_cast<uint16_t*>(idx->shadow);
+#define AUX_GO(SRC, MODE) aux_build_kernel<SRC, MODE><<<grid, 256, 0, idx->stream>>>(idx->corpus, sh, idx->inv_norm, idx->d_rho_x, row0, nrows, idx->ld)
+  if (idx->desc.dtype == RAG_BF16) AUX_GO(true, 0);
+  else if (!idx->shadow) AUX_GO(false, 0);
+  else if (idx->shadow_f16) AUX_GO(false, 2);
+  else AUX_GO(false, 1);
+#undef AUX_GO
   RAG_CUDA(cudaGetLastError());
   idx->rho_x_stale = true;
   idx->launches++;
   return RAG_OK;
 }
 
-// the queries' tensor-path operand (bf16 cast, or nothing for tf32) and their rounding residuals rho_q
+// the queries' tensor-path operand (normalised fp16, or nothing for tf32) and their rounding residuals rho_q
 int q_operand_launch(rag_index* idx, uint32_t B, uint32_t Bpad, bool tf32) {
   rag_batch* bt = idx->cur;
   if ((size_t)B * 4 > bt->c_rho_q || !bt->d_rho_q) {
@@ -275,7 +319,8 @@ int q_operand_launch(rag_index* idx, uint32_t B, uint32_t Bpad, bool tf32) {
   const uint32_t rows = tf32 ? B : Bpad;
   const uint32_t grid = grid_for((uint64_t)rows * 32, 256, idx->sm_count);
   if (tf32) q_rho_tf32_kernel<<<grid, 256, 0, idx->stream>>>(bt->d_q, bt->d_rho_q, B, idx->ld);
-  else q_to_bf16_kernel<<<grid, 256, 0, idx->stream>>>(bt->d_q, bt->d_qb, bt->d_rho_q, B, Bpad, idx->ld);
+  else if (rag_q16_is_bf16()) q_to_f16_kernel<true><<<grid, 256, 0, idx->stream>>>(bt->d_q, reinterpret_cast<uint16_t*>(bt->d_qb), bt->d_rho_q, B, Bpad, idx->ld);
+  else q_to_f16_kernel<false><<<grid, 256, 0, idx->stream>>>(bt->d_q, reinterpret_cast<uint16_t*>(bt->d_qb), bt->d_rho_q, B, Bpad, idx->ld);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   return RAG_OK;

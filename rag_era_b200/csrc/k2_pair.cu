@@ -68,11 +68,11 @@ constexpr int TMEM_COLS = 512;
 constexpr int WIN = 32;                // append window per query (shared memory), entries
 constexpr int KP_PREFETCH = 8;         // k-slices of L2 prefetch ahead of the TMA loads
 constexpr int KP_MAX_KP = 64;          // two ranks per lane
-constexpr uint32_t kIdescBf16 = idesc_bf16(PAIR_M, TILE_N);
 constexpr uint32_t kIdescTf32 = idesc_tf32(PAIR_M, TILE_N);
 
 struct kp_params {
   uint32_t n_rows, ld, B, kp, parts, stages, n_tiles, pairs;
+  uint32_t idesc;      // kind::f16 instruction descriptor: A = fp16 queries, B = fp16 shadow or bf16 rows
   const float* inv_norm;
   uint64_t* partial;
   uint32_t* pub;       // [pairs][Bpub] ordered score of each (pair, query)'s pub_rank-th best so far (0 = none yet)
@@ -264,23 +264,32 @@ __device__ __forceinline__ void reg_merge32_desc(float (&v)[32]) {  // bitonic -
 }
 // 32 accumulator columns of this lane's query, scaled by 1/||x||; rows that must never be selected
 // (inverse norm = NaN) read as -inf
+template <bool SCALED>
 __device__ __forceinline__ void load32_scaled(uint32_t taddr, const float* inv, float (&s)[32]) {
   uint32_t va[16], vb[16];
   tmem_ld16(taddr, va);
   tmem_ld16(taddr + 16, vb);
   tmem_ld_wait();
+  if constexpr (!SCALED) {  // pre-normalised rows: the accumulator is the score
 #pragma unroll
-  for (int i = 0; i < 16; i += 4) {
-    const float4 wa = *reinterpret_cast<const float4*>(inv + i);
-    const float4 wb = *reinterpret_cast<const float4*>(inv + 16 + i);
-    s[i] = __uint_as_float(va[i]) * wa.x;
-    s[i + 1] = __uint_as_float(va[i + 1]) * wa.y;
-    s[i + 2] = __uint_as_float(va[i + 2]) * wa.z;
-    s[i + 3] = __uint_as_float(va[i + 3]) * wa.w;
-    s[16 + i] = __uint_as_float(vb[i]) * wb.x;
-    s[16 + i + 1] = __uint_as_float(vb[i + 1]) * wb.y;
-    s[16 + i + 2] = __uint_as_float(vb[i + 2]) * wb.z;
-    s[16 + i + 3] = __uint_as_float(vb[i + 3]) * wb.w;
+    for (int i = 0; i < 16; i++) {
+      s[i] = __uint_as_float(va[i]);
+      s[16 + i] = __uint_as_float(vb[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 wa = *reinterpret_cast<const float4*>(inv + i);
+      const float4 wb = *reinterpret_cast<const float4*>(inv + 16 + i);
+      s[i] = __uint_as_float(va[i]) * wa.x;
+      s[i + 1] = __uint_as_float(va[i + 1]) * wa.y;
+      s[i + 2] = __uint_as_float(va[i + 2]) * wa.z;
+      s[i + 3] = __uint_as_float(va[i + 3]) * wa.w;
+      s[16 + i] = __uint_as_float(vb[i]) * wb.x;
+      s[16 + i + 1] = __uint_as_float(vb[i + 1]) * wb.y;
+      s[16 + i + 2] = __uint_as_float(vb[i + 2]) * wb.z;
+      s[16 + i + 3] = __uint_as_float(vb[i + 3]) * wb.w;
+    }
   }
 }
 // First tile of a CTA: a score T such that at least K' of this lane's 256 scores are >= T, found without
@@ -288,6 +297,7 @@ __device__ __forceinline__ void load32_scaled(uint32_t taddr, const float* inv, 
 // each new group of 32 scores is sorted by a network and merged (half-cleaner + bitonic merge).
 // 32 < K' <= 64: the same over the 128 minima of adjacent score pairs — the ceil(K'/2)-th largest minimum
 // has that many PAIRS, so at least K' scores, at or above it. Branch-free: ~5k instructions per warp, once.
+template <bool SCALED>
 __device__ __noinline__ float k2p_first_tile_threshold(uint32_t taddr, const float* inv, int kp) {
   float R[32];
 #pragma unroll
@@ -297,15 +307,15 @@ __device__ __noinline__ float k2p_first_tile_threshold(uint32_t taddr, const flo
   for (uint32_t c0 = 0; c0 < TILE_N; c0 += by_pairs ? 64u : 32u) {
     float C[32];
     if (!by_pairs) {
-      load32_scaled(taddr + c0, inv + c0, C);
+      load32_scaled<SCALED>(taddr + c0, inv + c0, C);
 #pragma unroll
       for (int i = 0; i < 32; i++) C[i] = fmaxf(C[i], -CUDART_INF_F);  // NaN -> -inf
     } else {
       float s[32];
-      load32_scaled(taddr + c0, inv + c0, s);
+      load32_scaled<SCALED>(taddr + c0, inv + c0, s);
 #pragma unroll
       for (int i = 0; i < 16; i++) C[i] = fminf(fmaxf(s[2 * i], -CUDART_INF_F), fmaxf(s[2 * i + 1], -CUDART_INF_F));
-      load32_scaled(taddr + c0 + 32, inv + c0 + 32, s);
+      load32_scaled<SCALED>(taddr + c0 + 32, inv + c0 + 32, s);
 #pragma unroll
       for (int i = 0; i < 16; i++) C[16 + i] = fminf(fmaxf(s[2 * i], -CUDART_INF_F), fmaxf(s[2 * i + 1], -CUDART_INF_F));
     }
@@ -322,11 +332,13 @@ __device__ __noinline__ float k2p_first_tile_threshold(uint32_t taddr, const flo
   return T;
 }
 
-// TF32 = false: bf16 operands (bf16 corpus or bf16 shadow, queries rounded to bf16), UMMA K = 16.
-// TF32 = true : the fp32 corpus and the fp32 queries themselves, rounded to tf32 by TMA on the way into
+// TF32 = false: 16-bit operands, kind::f16, UMMA K = 16: the queries as fp16( q/||q|| ); the rows as the fp16 shadow
+//               of the normalised fp32 rows (SCALED = false: the accumulator IS the cosine estimate), or as the bf16
+//               shadow / the bf16 corpus itself (SCALED = true: times 1/||x|| in the epilogue). P.idesc names the types.
+// TF32 = true : the fp32 corpus and the fp32 queries themselves, converted to tf32 by TMA on the way into
 //               shared memory (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), kind::tf32 UMMA K = 8 — batched scoring
-//               of an fp32 index without the extra memory of a bf16 shadow (HBM streams 4 B/element).
-template <bool TF32>
+//               of an fp32 index without the extra memory of a shadow (HBM streams 4 B/element). SCALED = true.
+template <bool TF32, bool SCALED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KP_THREADS, 1)
 k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const kp_params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -453,7 +465,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                                     kIdescTf32, (kb | ks) != 0 ? 1u : 0u);
             else
               tcgen05_mma_f16_pair(tmem_base + buf * TILE_N, umma_desc_sw128(sa + ks * 32), umma_desc_sw128(sb + ks * 32),
-                                   kIdescBf16, (kb | ks) != 0 ? 1u : 0u);
+                                   P.idesc, (kb | ks) != 0 ? 1u : 0u);
           }
           tcgen05_commit_pair(&empty[stage], 3);  // both CTAs may refill this stage once the MMAs have read it
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -464,7 +476,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         cyc[0] = (unsigned long long)(clk() - t_begin); cyc[1] = (unsigned long long)w_tmem; cyc[2] = (unsigned long long)w_full;
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == 3 && SCALED) {
     // ===== inverse-norm tile loader (NaN marks rows that must never be selected) =====
     uint32_t it = 0;
     for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
@@ -592,7 +604,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (uint32_t p = 0; p < P.pairs; p++) g = min(g, __ldcg(q_pub + (size_t)p * P.Bpub));
         if (g > 1u) thr = fmaxf(thr, rag_unorder_f32(g - 1u));  // admit scores >= the bound
       }
-      mbar_wait(&inv_full[buf], par);
+      if (SCALED) mbar_wait(&inv_full[buf], par);
       mbar_wait(&tmem_full[buf], par);
       if (cyc) c_wait += clk() - tw;
       tcgen05_fence_after();
@@ -602,7 +614,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (P.mode != 2) {
         if (it == 0 && P.mode == 0) {
           const long long tf = cyc ? clk() : 0;
-          const float T = k2p_first_tile_threshold(taddr, inv, kp);
+          const float T = k2p_first_tile_threshold<SCALED>(taddr, inv, kp);
           // admit scores >= T: the threshold is the next float below T
           if (live && T > -CUDART_INF_F) thr = rag_unorder_f32(rag_order_f32(T) - 1u);
           if (cyc) c_first = clk() - tf;
@@ -611,7 +623,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (uint32_t c0 = 0; c0 < TILE_N; c0 += 32) {
           float s[32];
           const long long tl0 = cyc ? clk() : 0;
-          load32_scaled(taddr + c0, inv + c0, s);
+          load32_scaled<SCALED>(taddr + c0, inv + c0, s);
           if (cyc) c_ld += clk() - tl0;
           const uint32_t row = row0 + c0;
           if (P.dbg_scores && live) {
@@ -640,7 +652,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_cluster(buf ? bar_tmem_empty1 : bar_tmem_empty0);  // the leader's barrier (also from the leader itself)
-        mbar_arrive(&inv_empty[buf]);
+        if (SCALED) mbar_arrive(&inv_empty[buf]);
       }
     }
     if (cyc && lane == 0) {
@@ -717,13 +729,17 @@ int kp_init(rag_index* idx) {
   return RAG_OK;
 }
 
-int kp_make_map(kp_state* st, CUtensorMap* m, const void* base, uint64_t rows, uint32_t ld, uint32_t box_rows, bool tf32) {
+// dtype: 0 = tf32 (fp32 memory), 1 = bf16, 2 = fp16 (the two 16-bit types only differ in how TMA would fill out-of-bounds
+// elements, which are zeros either way)
+int kp_make_map(kp_state* st, CUtensorMap* m, const void* base, uint64_t rows, uint32_t ld, uint32_t box_rows, int dtype) {
+  const bool tf32 = dtype == 0;
   const uint32_t es = tf32 ? 4 : 2;
   cuuint64_t dims[2] = {ld, rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * es};
   cuuint32_t box[2] = {ROW_BYTES / es, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = st->encode(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : (dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = st->encode(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return rag_set_error(RAG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -732,7 +748,7 @@ int kp_make_map(kp_state* st, CUtensorMap* m, const void* base, uint64_t rows, u
 
 }  // namespace
 
-// bf16 operand (bf16 corpus / bf16 shadow), or the fp32 corpus read as tf32
+// 16-bit operand (bf16 corpus / fp16 or bf16 shadow), or the fp32 corpus read as tf32
 int k2_available(const rag_index* idx) {
   if (!idx->inv_norm) return 0;
   return idx->shadow != nullptr || idx->desc.dtype == RAG_F32;
@@ -761,7 +777,7 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   RAG_CHECK(kp_init(idx));
   kp_state* st = (kp_state*)idx->k2p_state;
   rag_batch* bt = idx->cur;
-  const bool tf32 = idx->shadow == nullptr;  // fp32 index without a bf16 shadow: score the fp32 rows as tf32
+  const bool tf32 = idx->shadow == nullptr;  // fp32 index without a shadow: score the fp32 rows as tf32
   if (tf32 && idx->desc.dtype != RAG_F32) return rag_set_error(RAG_ERR_STATE, "tensor path: no bf16 operand");
   CUtensorMap map_q, map_x;
   if (!tf32) {
@@ -775,13 +791,13 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
       bt->c_qb = need;
     }
     RAG_CHECK(q_operand_launch(idx, B, Bpad, false));
-    RAG_CHECK(kp_make_map(st, &map_q, bt->d_qb, Bpad, idx->ld, CTA_M, false));
-    RAG_CHECK(kp_make_map(st, &map_x, idx->shadow, idx->rows, idx->ld, HALF_N, false));
+    RAG_CHECK(kp_make_map(st, &map_q, bt->d_qb, Bpad, idx->ld, CTA_M, rag_q16_is_bf16() ? 1 : 2));
+    RAG_CHECK(kp_make_map(st, &map_x, idx->shadow, idx->rows, idx->ld, HALF_N, idx->shadow_f16 ? 2 : 1));
   } else {
     // the fp32 queries as staged ([B][ld], zero padded columns); rows past B read as zeros (TMA OOB fill)
     RAG_CHECK(q_operand_launch(idx, B, B, true));
-    RAG_CHECK(kp_make_map(st, &map_q, bt->d_q, B, idx->ld, CTA_M, true));
-    RAG_CHECK(kp_make_map(st, &map_x, idx->corpus, idx->rows, idx->ld, HALF_N, true));
+    RAG_CHECK(kp_make_map(st, &map_q, bt->d_q, B, idx->ld, CTA_M, 0));
+    RAG_CHECK(kp_make_map(st, &map_x, idx->corpus, idx->rows, idx->ld, HALF_N, 0));
   }
 
   rag_prof_scope ps(idx, RAG_PROF_TENSOR);
@@ -795,6 +811,7 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   P.stages = kp_pick_stages(st, kp);
   P.n_tiles = (uint32_t)((idx->rows + TILE_N - 1) / TILE_N);
   P.inv_norm = idx->inv_norm;
+  P.idesc = idesc_f16(PAIR_M, TILE_N, /*A: fp16 queries*/ rag_q16_is_bf16() ? 1u : 0u, /*B*/ idx->shadow_f16 ? 0u : 1u);
   P.partial = bt->d_partial;
   {
     const uint32_t groups_ = (B + PAIR_M - 1) / PAIR_M;
@@ -829,13 +846,16 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   }
   const size_t smem = kp_smem_bytes(P.stages, kp);
   if (!st->attr_set) {
-    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
+    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
     st->attr_set = true;
   }
   const uint32_t groups = (B + PAIR_M - 1) / PAIR_M;
-  if (tf32) k2_pair_kernel<true><<<dim3(P.pairs * 2, groups), KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
-  else k2_pair_kernel<false><<<dim3(P.pairs * 2, groups), KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
+  const dim3 grid(P.pairs * 2, groups);
+  if (tf32) k2_pair_kernel<true, true><<<grid, KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
+  else if (idx->shadow_f16) k2_pair_kernel<false, false><<<grid, KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
+  else k2_pair_kernel<false, true><<<grid, KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   if (st->prof) {

@@ -132,6 +132,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// kind::f16 with the operand formats chosen independently (0 = fp16, 1 = bf16; cute's MMA traits only ask for two
+// 16-bit types): A format at [7,10), B format at [10,13)
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 // kind::tf32: D=f32 · A=tf32 (2<<7) · B=tf32 (2<<10) · both K-major
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {

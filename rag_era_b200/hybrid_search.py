@@ -105,8 +105,8 @@ class KnowledgeIndex:
     """
 
     def __init__(self, dim: int, capacity_rows: int, embed_model: Optional[Callable[[str], Sequence[float]]] = None,
-                 dtype: int = N.F32, device: int = 0, bf16_shadow: bool = False):
-        self.store = VectorIndex(dim, capacity_rows, dtype=dtype, device=device, bf16_shadow=bf16_shadow)
+                 dtype: int = N.F32, device: int = 0, bf16_shadow: bool = False, shadow: str | None = None):
+        self.store = VectorIndex(dim, capacity_rows, dtype=dtype, device=device, bf16_shadow=bf16_shadow, shadow=shadow)
         self.embed_model = embed_model
         self.nodes: list[Node] = []
         self.keys = KeyInterner()

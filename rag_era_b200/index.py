@@ -93,10 +93,16 @@ class VectorIndex:
     """One shard of the chunk-embedding matrix on one GPU."""
 
     def __init__(self, dim: int, capacity_rows: int, dtype: int = N.F32, device: int = 0,
-                 bf16_shadow: bool = False, id_base: int = 0):
+                 bf16_shadow: bool = False, id_base: int = 0, shadow: str | None = None):
+        """``shadow``: 16-bit tensor-path operand kept next to an fp32 corpus — "f16" (fp16 of the normalised rows,
+        preferred: tight rigorous certification) or "bf16" (``bf16_shadow=True`` is the same); None: no copy (batches are
+        then scored from the fp32 rows as tf32)."""
         self._lib = N.load()
         self.dim, self.capacity_rows, self.dtype, self.device, self.id_base = dim, capacity_rows, dtype, device, id_base
-        desc = N.IndexDesc(capacity_rows, dim, dtype, device, N.INDEX_BF16_SHADOW if bf16_shadow else 0, id_base)
+        if shadow not in (None, "f16", "bf16"):
+            raise ValueError("shadow must be None, 'f16' or 'bf16'")
+        flags = N.INDEX_F16_SHADOW if shadow == "f16" else (N.INDEX_BF16_SHADOW if (shadow == "bf16" or bf16_shadow) else 0)
+        desc = N.IndexDesc(capacity_rows, dim, dtype, device, flags, id_base)
         h = C.c_void_p()
         N.check(self._lib.rag_index_create(C.byref(desc), C.byref(h)))
         self._h = h

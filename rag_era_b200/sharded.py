@@ -83,22 +83,23 @@ def leave_exchange(dist, idx: VectorIndex):
 
 
 def create_sharded_index(dist, total_rows: int, dim: int, dtype: int, device: int, bf16_shadow: bool = False,
-                         rows: tuple[int, int] | None = None, max_batch: int = 1024, max_k: int = 64) -> VectorIndex:
+                         rows: tuple[int, int] | None = None, max_batch: int = 1024, max_k: int = 64,
+                         shadow: str | None = None) -> VectorIndex:
     """Create this rank's shard ([base, base+n) = ``rows`` or the even split) and join the exchange."""
     world, rank = dist.get_world_size(), dist.get_rank()
     base, n = rows if rows is not None else shard_range(total_rows, world, rank)
-    idx = VectorIndex(dim, max(n, 1), dtype=dtype, device=device, bf16_shadow=bf16_shadow, id_base=base)
+    idx = VectorIndex(dim, max(n, 1), dtype=dtype, device=device, bf16_shadow=bf16_shadow, id_base=base, shadow=shadow)
     idx.exchange = join_exchange(dist, idx, device, max_batch, max_k) if world > 1 else "none"
     return idx
 
 
-def open_sharded_cache(dist, cache_path: str, device: int, bf16_shadow: bool = False):
+def open_sharded_cache(dist, cache_path: str, device: int, bf16_shadow: bool = False, shadow: str | None = None):
     """Bring a row-sharded index up from ONE binary sidecar (store_cache.cu): every rank reads the header, creates its
     shard and streams only its own row range (verified block by block) into HBM. Returns (index, all node ids)."""
     from . import _native as N
 
     info = N.cache_info(cache_path)
-    idx = create_sharded_index(dist, info.rows, info.dim, info.dtype, device, bf16_shadow=bf16_shadow)
+    idx = create_sharded_index(dist, info.rows, info.dim, info.dtype, device, bf16_shadow=bf16_shadow, shadow=shadow)
     base, n = shard_range(info.rows, dist.get_world_size(), dist.get_rank())
     ids = idx.load_cache(cache_path, first_row=base, nrows=n) if n else []
     return idx, ids

@@ -684,7 +684,7 @@ def test_c4_memory_rag_three_lists_full_size(rb, native, oracle):
     fresh_limit=0 special case."""
     n, d, B, now = 7_000_000, 1536, 256, 1_760_000_000_000
     go, gn = gen(oracle, native, n, memory_rows=2_000_000, now_ms=now)
-    with rb.VectorIndex(d, n, bf16_shadow=True) as idx:
+    with rb.VectorIndex(d, n, shadow="f16") as idx:
         idx.generate(gn, n)
         Q = idx.generate_queries(gn, 0, B)
         top = idx.query(Q, 10)                                                   # AUTO → tensor path

@@ -17,10 +17,16 @@ def bf16_round(oracle, a):
     return oracle.bf16_to_f32(oracle.f32_to_bf16(a))
 
 
+def f16_unit(Q):
+    """The tensor path's query operand: fp16 of q/||q|| (gen.cu::q_to_f16_kernel), as fp64."""
+    Qd = Q.astype(np.float64)
+    return (Qd / np.linalg.norm(Qd, axis=1, keepdims=True)).astype(np.float32).astype(np.float16).astype(np.float64)
+
+
 @pytest.mark.parametrize("n,d,B", [(256, 256, 1), (300, 64, 5), (1000, 1536, 128), (777, 512, 129), (5000, 256, 256),
                                    (2049, 1024, 300), (70000, 128, 600)])
 def test_tensor_scores_match_numpy(rb, native, oracle, n, d, B):
-    """The raw K2 scores = <bf16(q), x_bf16> / ||x_bf16|| in fp32 accumulation."""
+    """The raw K2 scores on a bf16 corpus = <fp16(q/||q||), x> / ||x|| (kind::f16 with mixed operand types), fp32 accumulation."""
     rng = np.random.default_rng(n + d + B)
     X = oracle.f32_to_bf16(rng.standard_normal((n, d)).astype(np.float32))
     Q = rng.standard_normal((B, d)).astype(np.float32)
@@ -28,13 +34,31 @@ def test_tensor_scores_match_numpy(rb, native, oracle, n, d, B):
         idx.upload(X)
         S = idx.debug_tensor_scores(Q)
     Xf = oracle.bf16_to_f32(X).astype(np.float64)
-    Qf = bf16_round(oracle, Q).astype(np.float64)
-    E = (Qf @ Xf.T) / np.sqrt((Xf * Xf).sum(1))[None, :]
-    scale = np.sqrt((Qf * Qf).sum(1))[:, None]
-    assert np.abs(S - E).max() <= 2e-5 * scale.max(), float(np.abs(S - E).max())
+    E = (f16_unit(Q) @ Xf.T) / np.sqrt((Xf * Xf).sum(1))[None, :]
+    assert np.abs(S - E).max() <= 2e-5, float(np.abs(S - E).max())
 
 
-@pytest.mark.parametrize("dtype_name", ["bf16", "f32+shadow"])
+@pytest.mark.parametrize("n,d,B", [(300, 64, 5), (1000, 1536, 128), (2049, 1024, 300)])
+def test_tensor_scores_match_numpy_f16_shadow(rb, native, oracle, n, d, B):
+    """fp32 corpus + fp16 shadow of the normalised rows: the accumulator IS the cosine estimate (no epilogue scaling)."""
+    rng = np.random.default_rng(n + d + B)
+    X = (rng.standard_normal((n, d)) * rng.uniform(0.01, 300, (n, 1))).astype(np.float32)   # row norms over 4 decades
+    X[7] = 0                                                                                  # a zero row scores NaN
+    Q = (rng.standard_normal((B, d)) * rng.uniform(0.01, 300, (B, 1))).astype(np.float32)
+    with rb.VectorIndex(d, n, shadow="f16") as idx:
+        idx.upload(X)
+        S = idx.debug_tensor_scores(Q)
+    Xd = X.astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        Xh = (Xd / np.linalg.norm(Xd, axis=1, keepdims=True)).astype(np.float32).astype(np.float16).astype(np.float64)
+    E = f16_unit(Q) @ Xh.T
+    ok = np.ones(n, bool)
+    ok[7] = False
+    assert np.isnan(S[:, 7]).all()
+    assert np.abs(S[:, ok] - E[:, ok]).max() <= 2e-5, float(np.abs(S[:, ok] - E[:, ok]).max())
+
+
+@pytest.mark.parametrize("dtype_name", ["bf16", "f32+shadow", "f32+f16"])
 @pytest.mark.parametrize("B,k", [(16, 10), (130, 5), (256, 10), (700, 23)])
 def test_tensor_topk_matches_oracle(rb, native, oracle, dtype_name, B, k):
     n, d = 30000, 512
@@ -42,7 +66,8 @@ def test_tensor_topk_matches_oracle(rb, native, oracle, dtype_name, B, k):
     gn = native.GenDesc.from_buffer_copy(bytes(go))
     bf = dtype_name == "bf16"
     X = oracle.gen_rows(go, 0, n, d, dtype=oracle.BF16 if bf else oracle.F32)
-    with rb.VectorIndex(d, n, dtype=native.BF16 if bf else native.F32, bf16_shadow=not bf) as idx:
+    shadow = None if bf else ("f16" if dtype_name == "f32+f16" else "bf16")
+    with rb.VectorIndex(d, n, dtype=native.BF16 if bf else native.F32, shadow=shadow) as idx:
         idx.generate(gn, n)
         Q = idx.generate_queries(gn, 0, B)
         r = idx.query(Q, k, path=native.PATH_TENSOR)
@@ -69,7 +94,7 @@ def test_tensor_hybrid_batch(rb, native, oracle):
     go = oracle.make_gen(n, n_clusters=32)
     gn = native.GenDesc.from_buffer_copy(bytes(go))
     X = oracle.gen_rows(go, 0, n, d)
-    with rb.VectorIndex(d, n, bf16_shadow=True) as idx:
+    with rb.VectorIndex(d, n, shadow="f16") as idx:
         idx.generate(gn, n)
         Q = idx.generate_queries(gn, 0, B)
         kw = [[int(x) for x in oracle.topk(X, Q[b], 3)[0]] + [n - 1 - b] for b in range(B)]
@@ -98,10 +123,16 @@ def test_bf16_selection_error_is_within_the_stated_tolerance(rb, native, oracle)
         S = idx.debug_tensor_scores(Q).astype(np.float64)
     Qd = Q.astype(np.float64)
     exact = (Qd @ X.T) / (np.sqrt((Qd * Qd).sum(1))[:, None] * np.sqrt((X * X).sum(1))[None, :])
-    err = S / np.sqrt((Qd * Qd).sum(1))[:, None] - exact
+    err = S - exact                                    # the 16-bit path's keys are cosine estimates
     eps = 0.024 / np.sqrt(d)
     assert np.abs(err).max() < 0.6 * eps, (float(np.abs(err).max()), eps)
     assert err.std() < 0.0022 / np.sqrt(d) * 1.25, float(err.std())
+    # the fp16 shadow of the normalised rows: 11 significant bits in both operands, ~6x smaller error
+    with rb.VectorIndex(d, n, shadow="f16") as idx:
+        idx.generate(gn, n)
+        S16 = idx.debug_tensor_scores(Q).astype(np.float64)
+    err16 = S16 - exact
+    assert np.abs(err16).max() < 0.25 * np.abs(err).max() and err16.std() < 0.25 * err.std(), (float(np.abs(err16).max()), float(err16.std()))
 
 
 def test_tf32_path_on_fp32_index_without_shadow(rb, native, oracle):
