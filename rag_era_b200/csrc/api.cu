@@ -151,10 +151,11 @@ int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_
   const bool stat_eps = (flags & RAG_SEARCH_STAT_EPS) != 0;
   uint32_t s = slack;
   // the tensor path selects on 16-bit / tf32 scores: a wider window keeps (nearly) every query certifiable in one
-  // pass — an uncertified query costs a whole extra corpus pass on the stream path. The rigorous bound of an
-  // fp32 index with a BF16 shadow carries bf16's 8-bit rounding of every row (~2e-3 at D=1536): widest window.
-  const bool bf16_shadow = idx->shadow && (const void*)idx->shadow != idx->corpus && !idx->shadow_f16;
-  if (s == 0) s = path == RAG_PATH_TENSOR ? ((!stat_eps && eps <= 0.0 && bf16_shadow) ? 48u : std::max(22u, k)) : 6u;
+  // pass — an uncertified query costs a whole extra corpus pass on the stream path. With bf16 operands (a bf16 corpus
+  // or a bf16 shadow) the rigorous bound carries bf16's 8-bit rounding of the query (~1.7e-3 at D=1536) and, for a
+  // shadow, of every row as well: widest window.
+  const bool bf16_ops = idx->shadow && !idx->shadow_f16;
+  if (s == 0) s = path == RAG_PATH_TENSOR ? ((!stat_eps && eps <= 0.0 && bf16_ops) ? 48u : std::max(22u, k)) : 6u;
   uint32_t kp = std::min<uint32_t>(path == RAG_PATH_TENSOR ? 48u : (uint32_t)RAG_MAX_CANDIDATES, k + s);
   if (kp < k) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path supports k <= 48 (k=%u)", k);
   p->path = path;

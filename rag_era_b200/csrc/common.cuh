@@ -261,7 +261,6 @@ int gen_corpus_launch(rag_index* idx, const rag_gen_desc* g, uint64_t nrows);
 int gen_queries_launch(rag_index* idx, const rag_gen_desc* g, uint64_t b0, uint32_t B, float* d_out);
 int gen_meta_launch(rag_index* idx, const rag_gen_desc* g, uint64_t nrows);
 int aux_build_launch(rag_index* idx, uint64_t row0, uint64_t nrows);  // shadow + inv_norm
-bool rag_q16_is_bf16();  // diagnostic switch RAGERA_K2_QFMT=bf16
 int q_operand_launch(rag_index* idx, uint32_t B, uint32_t Bpad, bool tf32);  // bf16 cast (or none: tf32) + rho_q
 int gather_batch_launch(rag_index* idx, const rag_batch* src, rag_batch* dst, uint32_t n, uint32_t kw_stride);
 int iota_u64_launch(rag_index* idx, uint64_t* d, uint64_t n, uint64_t base);

@@ -73,11 +73,11 @@ __global__ void gen_meta_kernel(uint64_t nrows, uint64_t id_base, rag_gen_desc g
 // ---- tensor-path operands and their rounding residuals (the rigorous certification bound, api.cu::make_plan) ------
 // What K2 multiplies:            queries                       rows
 //   fp32 index + fp16 shadow     fp16( q / ||q|| )             fp16( x / ||x|| )      (pre-normalised: no scaling in the epilogue)
-//   fp32 index + bf16 shadow     fp16( q / ||q|| )             bf16( x ),   scaled by 1/||x|| in the epilogue
-//   bf16 index                   fp16( q / ||q|| )             x itself,    scaled by 1/||x||
+//   fp32 index + bf16 shadow     bf16( q / ||q|| )             bf16( x ),   scaled by 1/||x|| in the epilogue
+//   bf16 index                   bf16( q / ||q|| )             x itself,    scaled by 1/||x||
 //   fp32 index, no shadow        q (tf32, converted by TMA)    x (tf32),    scaled by 1/||x||
-// fp16 keeps 11 significant bits against bf16's 8, at the same tensor-core rate (kind::f16 takes the operand types
-// independently); the normalisation puts every element in [-1, 1], far from fp16's range limits. The residuals
+// fp16 keeps 11 significant bits against bf16's 8, at the same tensor-core rate (kind::f16; both operands must have
+// the same format); the normalisation puts every element in [-1, 1], far from fp16's range limits. The residuals
 //   rho_q[b] = || operand(q) - q/||q|| ||           rho_x = max over rows || operand(x) - x || / ||x||
 // are MEASURED here (fp32 arithmetic, differences of nearby floats are exact), so outliers, subnormals or a value
 // that sits on a rounding midpoint are accounted for as they are — there is no statistical assumption.
@@ -170,7 +170,9 @@ __global__ void aux_build_kernel(const void* __restrict__ X, uint16_t* __restric
 }
 
 // one warp per query: the fp16 operand q / ||q|| of the 16-bit tensor path (rows >= B are zero padding) and the
-// query's residual rho_q[b] = || fp16(q/||q||) - q/||q|| ||. QBF16: bf16 instead (diagnostic, RAGERA_K2_QFMT=bf16).
+// query's residual rho_q[b] = || fp16(q/||q||) - q/||q|| ||. QBF16: bf16 instead — kind::f16 wants both operands in ONE
+// 16-bit format (an fp16 x bf16 instruction descriptor is an illegal instruction on sm_100a, measured), so bf16 rows
+// (a bf16 corpus, a bf16 shadow) take bf16 queries.
 template <bool QBF16>
 __global__ void q_to_f16_kernel(const float* __restrict__ q, uint16_t* __restrict__ qh, float* __restrict__ rho_q,
                                 uint32_t B, uint32_t Bpad, uint32_t ld) {
@@ -240,15 +242,6 @@ __global__ void iota_u64_kernel(uint64_t* d, uint64_t n, uint64_t base) {
   if (i < n) d[i] = base + i;
 }
 
-}  // namespace
-
-// diagnostic: RAGERA_K2_QFMT=bf16 casts the (normalised) queries to bf16 instead of fp16
-bool rag_q16_is_bf16() {
-  static const int v = [] { const char* e = getenv("RAGERA_K2_QFMT"); return (e && e[0] == 'b') ? 1 : 0; }();
-  return v != 0;
-}
-
-namespace {
 uint32_t grid_for(uint64_t work, uint32_t threads, int sm_count) {
   uint64_t blocks = (work + threads - 1) / threads;
   uint64_t cap = (uint64_t)sm_count * 32;
@@ -319,7 +312,7 @@ int q_operand_launch(rag_index* idx, uint32_t B, uint32_t Bpad, bool tf32) {
   const uint32_t rows = tf32 ? B : Bpad;
   const uint32_t grid = grid_for((uint64_t)rows * 32, 256, idx->sm_count);
   if (tf32) q_rho_tf32_kernel<<<grid, 256, 0, idx->stream>>>(bt->d_q, bt->d_rho_q, B, idx->ld);
-  else if (rag_q16_is_bf16()) q_to_f16_kernel<true><<<grid, 256, 0, idx->stream>>>(bt->d_q, reinterpret_cast<uint16_t*>(bt->d_qb), bt->d_rho_q, B, Bpad, idx->ld);
+  else if (!idx->shadow_f16) q_to_f16_kernel<true><<<grid, 256, 0, idx->stream>>>(bt->d_q, reinterpret_cast<uint16_t*>(bt->d_qb), bt->d_rho_q, B, Bpad, idx->ld);
   else q_to_f16_kernel<false><<<grid, 256, 0, idx->stream>>>(bt->d_q, reinterpret_cast<uint16_t*>(bt->d_qb), bt->d_rho_q, B, Bpad, idx->ld);
   RAG_CUDA(cudaGetLastError());
   idx->launches++;

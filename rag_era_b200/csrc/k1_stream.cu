@@ -248,6 +248,92 @@ k1_multi_f32(const float* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsub
       warp_merge_lists(lists + (size_t)b * kp, K1M_WARPS, QB * kp, kp, partial + ((size_t)(b0 + b) * parts + blockIdx.x) * kp, lane);
 }
 
+// ---- bf16 corpus, several queries per corpus pass ------------------------------------------------
+// The bf16 twin of k1_multi_f32 (escalated queries of the tensor path on a bf16 corpus used to cost one whole corpus
+// pass EACH). The fp32 queries are twice as wide as the rows, so shared-memory traffic is QB x the row bytes with two
+// rows in flight: QB = 4 keeps it under the shared-memory bandwidth while HBM streams rows*ld*2 bytes per pass.
+template <int QB, int U>
+__global__ void __launch_bounds__(K1M_THREADS, 1)
+k1_multi_bf16(const __nv_bfloat16* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsub, const float* __restrict__ Q,
+              uint32_t B, uint32_t kp, uint32_t parts, uint64_t* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // per query two planes, so that every 128-bit LDS has a 16-byte lane stride: qa[i] = q[8i..8i+3], qb[i] = q[8i+4..8i+7]
+  float4* qs = reinterpret_cast<float4*>(smem_raw);  // [QB][2][ld/8]
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (size_t)QB * ld * sizeof(float));  // [warps][QB][kp]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b0 = blockIdx.y * QB;
+  const uint32_t ld4 = ld / 4, ld8 = ld / 8;
+  for (uint32_t i = threadIdx.x; i < QB * ld4; i += K1M_THREADS) {
+    const uint32_t b = i / ld4, c = i % ld4;
+    const float4 v = b0 + b < B ? reinterpret_cast<const float4*>(Q + (size_t)(b0 + b) * ld)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    qs[(size_t)b * ld4 + (c & 1) * ld8 + (c >> 1)] = v;
+  }
+  uint64_t* mylists = lists + (size_t)warp * QB * kp;
+  for (uint32_t i = lane; i < QB * kp; i += 32) mylists[i] = 0ull;
+  __syncthreads();
+
+  uint64_t thresh[QB];
+#pragma unroll
+  for (int b = 0; b < QB; b++) thresh[b] = 0ull;
+
+  const uint32_t stride = gridDim.x * K1M_WARPS;
+  for (uint32_t row = blockIdx.x * K1M_WARPS + warp; row < n_rows; row += 2 * stride) {
+    const uint32_t row2 = row + stride;
+    const bool has2 = row2 < n_rows;
+    const uint4* x0 = reinterpret_cast<const uint4*>(X + (size_t)row * ld);
+    const uint4* x1 = reinterpret_cast<const uint4*>(X + (size_t)(has2 ? row2 : row) * ld);
+    float d0[QB], d1[QB], n0 = 0.f, n1 = 0.f;
+#pragma unroll
+    for (int b = 0; b < QB; b++) { d0[b] = 0.f; d1[b] = 0.f; }
+    for (int s = 0; s < nsub; s++) {
+      uint4 v[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = ldg_stream_u4(x0 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) w[u] = ldg_stream_u4(x1 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+        float xv[8], xw[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          xv[2 * j] = __uint_as_float(vv[j] << 16); xv[2 * j + 1] = __uint_as_float(vv[j] & 0xFFFF0000u);
+          xw[2 * j] = __uint_as_float(ww[j] << 16); xw[2 * j + 1] = __uint_as_float(ww[j] & 0xFFFF0000u);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) { n0 = fmaf(xv[j], xv[j], n0); n1 = fmaf(xw[j], xw[j], n1); }
+        const int i = (s * U + u) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < QB; b++) {
+          const float4 a = qs[(size_t)b * ld4 + i], c = qs[(size_t)b * ld4 + ld8 + i];
+          d0[b] = fmaf(xv[0], a.x, d0[b]); d0[b] = fmaf(xv[1], a.y, d0[b]); d0[b] = fmaf(xv[2], a.z, d0[b]); d0[b] = fmaf(xv[3], a.w, d0[b]);
+          d0[b] = fmaf(xv[4], c.x, d0[b]); d0[b] = fmaf(xv[5], c.y, d0[b]); d0[b] = fmaf(xv[6], c.z, d0[b]); d0[b] = fmaf(xv[7], c.w, d0[b]);
+          d1[b] = fmaf(xw[0], a.x, d1[b]); d1[b] = fmaf(xw[1], a.y, d1[b]); d1[b] = fmaf(xw[2], a.z, d1[b]); d1[b] = fmaf(xw[3], a.w, d1[b]);
+          d1[b] = fmaf(xw[4], c.x, d1[b]); d1[b] = fmaf(xw[5], c.y, d1[b]); d1[b] = fmaf(xw[6], c.z, d1[b]); d1[b] = fmaf(xw[7], c.w, d1[b]);
+        }
+      }
+    }
+    const float nrm0 = warp_sum(n0), nrm1 = warp_sum(n1);
+#pragma unroll
+    for (int b = 0; b < QB; b++) {
+      const float dot0 = warp_sum(d0[b]), dot1 = warp_sum(d1[b]);
+      if (b0 + b < B) {  // warp-uniform
+        const uint64_t key0 = rag_pack_key(finish_score(dot0, nrm0), row);
+        if (key0 > thresh[b]) warp_list_insert(mylists + (size_t)b * kp, kp, key0, lane, thresh[b]);
+        if (has2) {
+          const uint64_t key1 = rag_pack_key(finish_score(dot1, nrm1), row2);
+          if (key1 > thresh[b]) warp_list_insert(mylists + (size_t)b * kp, kp, key1, lane, thresh[b]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t b = warp; b < QB; b += K1M_WARPS)
+    if (b0 + b < B)
+      warp_merge_lists(lists + (size_t)b * kp, K1M_WARPS, QB * kp, kp, partial + ((size_t)(b0 + b) * parts + blockIdx.x) * kp, lane);
+}
+
 template <typename F>
 int launch_cfg(F kernel, size_t smem) {
   if (smem > 48 * 1024) {
@@ -310,6 +396,20 @@ int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     if (QB == 8) { if (U == 6) K1M_GO(8, 6); else if (U == 4) K1M_GO(8, 4); else K1M_GO(8, 2); }
     else         { if (U == 6) K1M_GO(4, 6); else if (U == 4) K1M_GO(4, 4); else K1M_GO(4, 2); }
 #undef K1M_GO
+  } else if (idx->desc.dtype == RAG_BF16 && B > 1 && (size_t)4 * ld * sizeof(float) + (size_t)K1M_WARPS * 4 * kp * sizeof(uint64_t) <= 200 * 1024) {
+    const uint32_t per_lane = ld / 256;  // 16-byte loads per lane per row
+    const int U = per_lane % 3 == 0 ? 3 : (per_lane % 2 == 0 ? 2 : 1);
+    const int nsub = (int)(per_lane / U);
+    const size_t msmem = (size_t)4 * ld * sizeof(float) + (size_t)K1M_WARPS * 4 * kp * sizeof(uint64_t);
+    dim3 mgrid(parts, (B + 3) / 4);
+#define K1MB_GO(Uv)                                                                                          \
+  do {                                                                                                        \
+    RAG_CHECK(launch_cfg(k1_multi_bf16<4, Uv>, msmem));                                                       \
+    k1_multi_bf16<4, Uv><<<mgrid, K1M_THREADS, msmem, idx->stream>>>((const __nv_bfloat16*)idx->corpus, n, ld, nsub, \
+                                                                     idx->cur->d_q, B, kp, parts, idx->cur->d_partial); \
+  } while (0)
+    if (U == 3) K1MB_GO(3); else if (U == 2) K1MB_GO(2); else K1MB_GO(1);
+#undef K1MB_GO
   } else if (idx->desc.dtype == RAG_F32) {
     static const int opts[] = {12, 8, 6, 4, 2};
     const uint32_t per_lane = ld / 128;  // float4 per lane per row

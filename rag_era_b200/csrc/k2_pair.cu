@@ -72,7 +72,7 @@ constexpr uint32_t kIdescTf32 = idesc_tf32(PAIR_M, TILE_N);
 
 struct kp_params {
   uint32_t n_rows, ld, B, kp, parts, stages, n_tiles, pairs;
-  uint32_t idesc;      // kind::f16 instruction descriptor: A = fp16 queries, B = fp16 shadow or bf16 rows
+  uint32_t idesc;      // kind::f16 instruction descriptor: fp16 x fp16 (fp16 shadow) or bf16 x bf16
   const float* inv_norm;
   uint64_t* partial;
   uint32_t* pub;       // [pairs][Bpub] ordered score of each (pair, query)'s pub_rank-th best so far (0 = none yet)
@@ -332,15 +332,25 @@ __device__ __noinline__ float k2p_first_tile_threshold(uint32_t taddr, const flo
   return T;
 }
 
-// TF32 = false: 16-bit operands, kind::f16, UMMA K = 16: the queries as fp16( q/||q|| ); the rows as the fp16 shadow
-//               of the normalised fp32 rows (SCALED = false: the accumulator IS the cosine estimate), or as the bf16
-//               shadow / the bf16 corpus itself (SCALED = true: times 1/||x|| in the epilogue). P.idesc names the types.
+// TF32 = false: 16-bit operands, kind::f16, UMMA K = 16: fp16( q/||q|| ) x the fp16 shadow of the normalised fp32 rows
+//               (SCALED = false: the accumulator IS the cosine estimate), or bf16( q/||q|| ) x the bf16 shadow / the
+//               bf16 corpus itself (SCALED = true: times 1/||x|| in the epilogue). P.idesc names the format.
 // TF32 = true : the fp32 corpus and the fp32 queries themselves, converted to tf32 by TMA on the way into
 //               shared memory (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32), kind::tf32 UMMA K = 8 — batched scoring
 //               of an fp32 index without the extra memory of a shadow (HBM streams 4 B/element). SCALED = true.
-template <bool TF32, bool SCALED>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(KP_THREADS, 1)
-k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const kp_params P) {
+// SHARE: how many CTA pairs form one cluster and what they share (launched with the matching cluster shape):
+//   0  cluster = one pair (2,1,1). Every CTA fetches its own 16 KB of queries and 16 KB of rows per k-slice: 64 B per
+//      SM-cycle at the full tensor rate, 9.5 KB/cycle over 148 SMs — ABOVE the ~6.3 KB/cycle the L2 slices deliver
+//      (B300_MICROARCH.md "LTS throughput cap"), so the pair kernel is L2-feed bound at ~2/3 of the tensor peak.
+//   1  cluster = two pairs with DIFFERENT query groups walking the SAME corpus tiles (2,2,1): each CTA fetches half of
+//      its 128 corpus rows and TMA-multicasts it to the CTA of the same parity in the other pair — 24 KB per k-slice.
+//   2  cluster = two pairs of the SAME query group walking DIFFERENT tiles (4,1,1): the queries are the shared operand.
+// Stage hand-back: a producer multicasts into the other pair's shared memory too, so empty[s] counts the commits of
+// BOTH pairs' MMAs (tcgen05.commit multicast to all four CTAs).
+template <bool TF32, bool SCALED, int SHARE>
+__global__ void __launch_bounds__(KP_THREADS, 1)
+k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+               const __grid_constant__ CUtensorMap map_h, const kp_params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout (identical in both CTAs): [stages][A | B] · windows [128][WIN] u64 · best [128][32 or 64] u64 ·
   // inv [2][256] f32 · barriers · tmem ptr
@@ -359,10 +369,17 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(inv_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  constexpr uint32_t CL = SHARE ? 2u : 1u;   // pairs per cluster
+  const uint32_t crank = cluster_ctarank();  // 0..2*CL-1; x is the fastest cluster dimension, so the pair is (crank & ~1, crank | 1)
+  const uint32_t rank = crank & 1u;          // CTA within its pair
+  const uint32_t pic = crank >> 1;           // pair within the cluster
+  const uint32_t lead = crank & ~1u;         // cluster rank of this pair's leader
   const bool leader = rank == 0;
   const uint32_t pair = blockIdx.x >> 1;
   const uint32_t q0 = blockIdx.y * PAIR_M + rank * CTA_M;  // first query of this CTA
+  // pairs of one cluster must run the same number of tiles (they feed each other): a pair that runs out of corpus
+  // walks tiles past the end — TMA fills zeros, the epilogue masks rows >= n_rows
+  const uint32_t n_iter = SHARE == 2 ? (P.n_tiles + P.pairs - 1) / P.pairs : (P.n_tiles > pair ? (P.n_tiles - pair + P.pairs - 1) / P.pairs : 0u);
   constexpr int BK = TF32 ? ROW_BYTES / 4 : ROW_BYTES / 2;  // k elements per stage
   const uint32_t nkb = P.ld / BK;
   unsigned long long* cyc = P.cyc ? P.cyc + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * KP_WARPS + warp) * 8 : nullptr;
@@ -371,7 +388,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     // full[s]: one arrival (the leader's expect_tx of BOTH CTAs' bytes). The peer's TMA completes on the
     // leader's barrier without an arrival of its own; its bytes can only land in the phase they belong
     // to because the peer refills a stage only after the leader's commit has released it.
-    for (uint32_t s = 0; s < P.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (uint32_t s = 0; s < P.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int b = 0; b < 2; b++) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 8);  // 4 epilogue warps x 2 CTAs
@@ -397,16 +414,21 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const long long t_begin = clk();
       // L2 prefetch runs KP_PREFETCH k-slices ahead of the loads: a corpus slice is new to L2 for the first
       // query group that reaches it
-      uint32_t pf_tile = pair, pf_kb = 0;
+      uint32_t pf_it = 0, pf_kb = 0;
+      // what this CTA fetches of the shared operand: rows [own 128-row half] + pic*64 .. +64, multicast to the CTA of
+      // the same parity in both pairs of the cluster
+      const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
       auto prefetch_next = [&]() {
-        if (pf_tile < P.n_tiles) {
-          tma_prefetch_2d(&map_x, (int)(pf_kb * BK), (int)(pf_tile * TILE_N + rank * HALF_N));
-          if (++pf_kb == nkb) { pf_kb = 0; pf_tile += P.pairs; }
+        if (pf_it < n_iter) {
+          const uint32_t t = pair + pf_it * P.pairs;
+          if (SHARE == 1) tma_prefetch_2d(&map_h, (int)(pf_kb * BK), (int)(t * TILE_N + rank * HALF_N + pic * (HALF_N / 2)));
+          else tma_prefetch_2d(&map_x, (int)(pf_kb * BK), (int)(t * TILE_N + rank * HALF_N));
+          if (++pf_kb == nkb) { pf_kb = 0; pf_it++; }
         }
       };
       for (uint32_t i = 0; i < P.prefetch; i++) prefetch_next();
-      uint32_t it = 0;
-      for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
+      for (uint32_t it = 0; it < n_iter; it++) {
+        const uint32_t tile = pair + it * P.pairs;
         // Lockstep of the query groups: the gridDim.y pairs with this pair index read the SAME corpus tiles.
         // Left alone they drift apart until L2 no longer holds a tile for the laggard and every group
         // streams the corpus from HBM by itself (measured: DRAM traffic 1.85x algorithmic at 1M rows, K2
@@ -430,10 +452,17 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           if (cyc) w_empty += clk() - t0;
           unsigned char* sa = stage_base + (size_t)stage * STAGE_BYTES;
-          const uint32_t bar = mapa(smem_u32(&full[stage]), 0);  // the leader's full barrier
+          const uint32_t bar = mapa(smem_u32(&full[stage]), lead);  // the pair leader's full barrier
           if (leader) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
-          tma_load_2d_pair(sa, &map_q, bar, (int)(kb * BK), (int)q0);
-          tma_load_2d_pair(sa + A_BYTES, &map_x, bar, (int)(kb * BK), (int)(tile * TILE_N + rank * HALF_N));
+          if (SHARE == 2)   // the queries are shared: fetch 64 of this CTA's 128 and multicast them
+            tma_load_2d_pair_mc(sa + pic * (A_BYTES / 2), &map_h, smem_u32(&full[stage]), mc_mask, (int)(kb * BK), (int)(q0 + pic * (CTA_M / 2)));
+          else
+            tma_load_2d_pair(sa, &map_q, bar, (int)(kb * BK), (int)q0);
+          if (SHARE == 1)   // the corpus tile is shared: fetch 64 of this CTA's 128 rows and multicast them
+            tma_load_2d_pair_mc(sa + A_BYTES + pic * (B_BYTES / 2), &map_h, smem_u32(&full[stage]), mc_mask, (int)(kb * BK),
+                                (int)(tile * TILE_N + rank * HALF_N + pic * (HALF_N / 2)));
+          else
+            tma_load_2d_pair(sa + A_BYTES, &map_x, bar, (int)(kb * BK), (int)(tile * TILE_N + rank * HALF_N));
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -445,7 +474,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       uint32_t stage = 0, phase = 0, it = 0;
       long long w_tmem = 0, w_full = 0;
       const long long t_begin = clk();
-      for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
+      for (; it < n_iter; it++) {
         const uint32_t buf = it & 1;
         long long t0 = cyc ? clk() : 0;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
@@ -467,10 +496,12 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               tcgen05_mma_f16_pair(tmem_base + buf * TILE_N, umma_desc_sw128(sa + ks * 32), umma_desc_sw128(sb + ks * 32),
                                    P.idesc, (kb | ks) != 0 ? 1u : 0u);
           }
-          tcgen05_commit_pair(&empty[stage], 3);  // both CTAs may refill this stage once the MMAs have read it
+          // every CTA that writes into this pair's stage may refill it once the MMAs have read it: the pair itself,
+          // and with a shared operand the other pair of the cluster too
+          tcgen05_commit_pair(&empty[stage], (uint16_t)(SHARE ? 0xFu : 0x3u));
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit_pair(&tmem_full[buf], 3);  // accumulator complete in both CTAs
+        tcgen05_commit_pair(&tmem_full[buf], (uint16_t)(0x3u << lead));  // accumulator complete in both CTAs of the pair
       }
       if (cyc) {
         cyc[0] = (unsigned long long)(clk() - t_begin); cyc[1] = (unsigned long long)w_tmem; cyc[2] = (unsigned long long)w_full;
@@ -478,8 +509,8 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
   } else if (warp == 3 && SCALED) {
     // ===== inverse-norm tile loader (NaN marks rows that must never be selected) =====
-    uint32_t it = 0;
-    for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
+    for (uint32_t it = 0; it < n_iter; it++) {
+      const uint32_t tile = pair + it * P.pairs;
       const uint32_t buf = it & 1;
       mbar_wait(&inv_empty[buf], ((it >> 1) & 1) ^ 1);
       const uint32_t r0 = tile * TILE_N + lane * 8;
@@ -512,8 +543,8 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const uint32_t win_addr = smem_u32(mywin);  // 256-byte aligned; entry j lives at (j*8) ^ (lane*8)
     const uint32_t lane8 = (uint32_t)lane << 3;
     const uint32_t taddr_q = tmem_base + ((quarter * 32u) << 16);
-    const uint32_t bar_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0);
-    const uint32_t bar_tmem_empty1 = mapa(smem_u32(&tmem_empty[1]), 0);
+    const uint32_t bar_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), lead);
+    const uint32_t bar_tmem_empty1 = mapa(smem_u32(&tmem_empty[1]), lead);
     // Cooperative threshold: the P.pairs CTA pairs that share this query each publish their pub_rank-th best
     // score so far (pairs * pub_rank >= K'). At least K' scored rows are >= the MINIMUM of the published values,
     // so that minimum is a lower bound of the final K'-th best score and nothing below it can be a candidate.
@@ -593,8 +624,8 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (need) fold_lanes(need);
     };
 
-    uint32_t it = 0;
-    for (uint32_t tile = pair; tile < P.n_tiles; tile += P.pairs, it++) {
+    for (uint32_t it = 0; it < n_iter; it++) {
+      const uint32_t tile = pair + it * P.pairs;
       const uint32_t buf = it & 1, par = (it >> 1) & 1;
       const long long tw = cyc ? clk() : 0;
       // refresh the shared bound while the tile is still being accumulated (the loads fly during the wait)
@@ -626,6 +657,11 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           load32_scaled<SCALED>(taddr + c0, inv + c0, s);
           if (cyc) c_ld += clk() - tl0;
           const uint32_t row = row0 + c0;
+          if (row + 32 > P.n_rows) {  // the corpus ends inside (or before) these columns: rows that do not exist never score
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (row + i >= P.n_rows) s[i] = __int_as_float(0x7FC00000);
+          }
           if (P.dbg_scores && live) {
 #pragma unroll
             for (int i = 0; i < 32; i++)
@@ -690,6 +726,8 @@ struct kp_state {
   uint32_t prefetch = KP_PREFETCH;
   uint32_t local_min = 3;
   uint32_t lockstep = 1;
+  int cluster = 0;        // RAGERA_K2_CLUSTER: 0 = pairs only, 1 = share an operand across two pairs when the shape allows
+  int max_clusters[3] = {0, 0, 0};  // co-resident clusters per SHARE variant (cudaOccupancyMaxActiveClusters), lazily
   bool prof = false;
   unsigned long long* d_cyc = nullptr;
   uint32_t* d_pub = nullptr;  // cooperative-threshold board [pairs][Bpub]
@@ -724,6 +762,7 @@ int kp_init(rag_index* idx) {
   if (const char* m = getenv("RAGERA_K2_PREFETCH")) st->prefetch = (uint32_t)atoi(m);
   if (const char* m = getenv("RAGERA_K2_LOCAL_MIN")) st->local_min = (uint32_t)atoi(m);
   if (const char* m = getenv("RAGERA_K2_LOCKSTEP")) st->lockstep = (uint32_t)atoi(m);
+  if (const char* m = getenv("RAGERA_K2_CLUSTER")) st->cluster = atoi(m);
   cudaDeviceGetAttribute(&st->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, idx->device);
   idx->k2p_state = st;
   return RAG_OK;
@@ -746,6 +785,80 @@ int kp_make_map(kp_state* st, CUtensorMap* m, const void* base, uint64_t rows, u
   return RAG_OK;
 }
 
+// the kernel variant of an index: <TF32, SCALED, SHARE>
+typedef void (*kp_kernel_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const kp_params);
+kp_kernel_t kp_kernel(const rag_index* idx, int share) {
+  const bool tf32 = idx->shadow == nullptr;
+#define KP_PICK(T, S) (share == 0 ? k2_pair_kernel<T, S, 0> : share == 1 ? k2_pair_kernel<T, S, 1> : k2_pair_kernel<T, S, 2>)
+  if (tf32) return KP_PICK(true, true);
+  return idx->shadow_f16 ? KP_PICK(false, false) : KP_PICK(false, true);
+#undef KP_PICK
+}
+dim3 kp_cluster_dim(int share) { return share == 1 ? dim3(2, 2, 1) : share == 2 ? dim3(4, 1, 1) : dim3(2, 1, 1); }
+
+int kp_launch_cfg(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, dim3 grid, size_t smem, cudaStream_t stream, int share) {
+  *cfg = cudaLaunchConfig_t();
+  cfg->gridDim = grid;
+  cfg->blockDim = dim3(KP_THREADS);
+  cfg->dynamicSmemBytes = smem;
+  cfg->stream = stream;
+  attr->id = cudaLaunchAttributeClusterDimension;
+  const dim3 c = kp_cluster_dim(share);
+  attr->val.clusterDim.x = c.x;
+  attr->val.clusterDim.y = c.y;
+  attr->val.clusterDim.z = c.z;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+  return RAG_OK;
+}
+
+// Which variant runs a batch of `groups` query groups, and with how many tile walkers (CTA pairs) per group.
+// Sharing needs two pairs per cluster: two query groups on the same tiles (groups even), or — one group only — two
+// walkers. A 4-CTA cluster does not pack the chip as well as a pair does (GPCs of 16/18/20 SMs), so the walkers are
+// sized from the number of clusters that are co-resident.
+int kp_shape(rag_index* idx, uint32_t groups, uint32_t kp, int* share, uint32_t* pairs) {
+  kp_state* st = (kp_state*)idx->k2p_state;
+  const uint32_t all_pairs = (uint32_t)idx->sm_count / 2;
+  const uint64_t n_tiles = (idx->rows + TILE_N - 1) / TILE_N;
+  int sh = 0;
+  if (st->cluster) sh = (groups % 2 == 0) ? 1 : (groups == 1 && n_tiles >= 2 ? 2 : 0);
+  uint64_t p = all_pairs / groups;
+  if (sh) {
+    if (!st->attr_set) return rag_set_error(RAG_ERR_STATE, "k2: kernel attributes not set");
+    if (st->max_clusters[sh] == 0) {
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute attr;
+      const dim3 c = kp_cluster_dim(sh);
+      kp_launch_cfg(&cfg, &attr, dim3(c.x * 64, c.y, 1), kp_smem_bytes(kp_pick_stages(st, kp), kp), idx->stream, sh);
+      int n = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, (const void*)kp_kernel(idx, sh), &cfg);
+      if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+      st->max_clusters[sh] = n;
+    }
+    const int mc = st->max_clusters[sh];
+    if (mc <= 0) sh = 0;
+    else if (sh == 1) p = std::min<uint64_t>(p, (uint64_t)mc / (groups / 2));
+    else p = std::min<uint64_t>(p, (uint64_t)mc * 2) & ~(uint64_t)1;
+    if (p < (sh == 2 ? 2u : 1u)) { sh = 0; p = all_pairs / groups; }
+  }
+  if (p > n_tiles) p = sh == 2 ? (n_tiles & ~(uint64_t)1) : n_tiles;
+  if (p < 1) p = 1;
+  *share = sh;
+  *pairs = (uint32_t)p;
+  return RAG_OK;
+}
+
+int kp_set_attrs(kp_state* st) {
+  if (st->attr_set) return RAG_OK;
+#define KP_ATTR(T, S, H) RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<T, S, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem))
+  KP_ATTR(false, false, 0); KP_ATTR(false, false, 1); KP_ATTR(false, false, 2);
+  KP_ATTR(false, true, 0);  KP_ATTR(false, true, 1);  KP_ATTR(false, true, 2);
+  KP_ATTR(true, true, 0);   KP_ATTR(true, true, 1);   KP_ATTR(true, true, 2);
+#undef KP_ATTR
+  st->attr_set = true;
+  return RAG_OK;
+}
+
 }  // namespace
 
 // 16-bit operand (bf16 corpus / fp16 or bf16 shadow), or the fp32 corpus read as tf32
@@ -763,11 +876,9 @@ int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   const uint32_t all_pairs = (uint32_t)idx->sm_count / 2;
   if (groups > all_pairs)
     return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path: batch %u exceeds %u queries per launch", B, all_pairs * PAIR_M);
-  const uint64_t n_tiles = (idx->rows + TILE_N - 1) / TILE_N;
-  uint64_t pairs = all_pairs / groups;
-  if (pairs > n_tiles) pairs = n_tiles;
-  if (pairs < 1) pairs = 1;
-  *parts = (uint32_t)pairs;
+  RAG_CHECK(kp_set_attrs(st));
+  int share = 0;
+  RAG_CHECK(kp_shape(idx, groups, kp, &share, parts));
   return RAG_OK;
 }
 
@@ -779,7 +890,13 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   rag_batch* bt = idx->cur;
   const bool tf32 = idx->shadow == nullptr;  // fp32 index without a shadow: score the fp32 rows as tf32
   if (tf32 && idx->desc.dtype != RAG_F32) return rag_set_error(RAG_ERR_STATE, "tensor path: no bf16 operand");
-  CUtensorMap map_q, map_x;
+  const uint32_t groups = (B + PAIR_M - 1) / PAIR_M;
+  RAG_CHECK(kp_set_attrs(st));
+  int share = 0;
+  uint32_t pairs_now = 0;
+  RAG_CHECK(kp_shape(idx, groups, kp, &share, &pairs_now));
+  if (pairs_now != parts) return rag_set_error(RAG_ERR_STATE, "k2_launch: parts=%u but the plan says %u", parts, pairs_now);
+  CUtensorMap map_q, map_x, map_h;
   if (!tf32) {
     const uint32_t Bpad = (B + CTA_M - 1) / CTA_M * CTA_M;
     const size_t need = (size_t)Bpad * idx->ld * 2;
@@ -791,13 +908,18 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
       bt->c_qb = need;
     }
     RAG_CHECK(q_operand_launch(idx, B, Bpad, false));
-    RAG_CHECK(kp_make_map(st, &map_q, bt->d_qb, Bpad, idx->ld, CTA_M, rag_q16_is_bf16() ? 1 : 2));
+    RAG_CHECK(kp_make_map(st, &map_q, bt->d_qb, Bpad, idx->ld, CTA_M, idx->shadow_f16 ? 2 : 1));
     RAG_CHECK(kp_make_map(st, &map_x, idx->shadow, idx->rows, idx->ld, HALF_N, idx->shadow_f16 ? 2 : 1));
+    // the shared operand in 64-row boxes (half of what a CTA needs: the other half arrives by multicast)
+    if (share == 2) RAG_CHECK(kp_make_map(st, &map_h, bt->d_qb, Bpad, idx->ld, CTA_M / 2, idx->shadow_f16 ? 2 : 1));
+    else RAG_CHECK(kp_make_map(st, &map_h, idx->shadow, idx->rows, idx->ld, HALF_N / 2, idx->shadow_f16 ? 2 : 1));
   } else {
     // the fp32 queries as staged ([B][ld], zero padded columns); rows past B read as zeros (TMA OOB fill)
     RAG_CHECK(q_operand_launch(idx, B, B, true));
     RAG_CHECK(kp_make_map(st, &map_q, bt->d_q, B, idx->ld, CTA_M, 0));
     RAG_CHECK(kp_make_map(st, &map_x, idx->corpus, idx->rows, idx->ld, HALF_N, 0));
+    if (share == 2) RAG_CHECK(kp_make_map(st, &map_h, bt->d_q, B, idx->ld, CTA_M / 2, 0));
+    else RAG_CHECK(kp_make_map(st, &map_h, idx->corpus, idx->rows, idx->ld, HALF_N / 2, 0));
   }
 
   rag_prof_scope ps(idx, RAG_PROF_TENSOR);
@@ -811,7 +933,9 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   P.stages = kp_pick_stages(st, kp);
   P.n_tiles = (uint32_t)((idx->rows + TILE_N - 1) / TILE_N);
   P.inv_norm = idx->inv_norm;
-  P.idesc = idesc_f16(PAIR_M, TILE_N, /*A: fp16 queries*/ rag_q16_is_bf16() ? 1u : 0u, /*B*/ idx->shadow_f16 ? 0u : 1u);
+  // both operands in one 16-bit format: fp16 x fp16 (fp16 shadow) or bf16 x bf16 (bf16 corpus / bf16 shadow) — a mixed
+  // descriptor raises an illegal-instruction error on sm_100a
+  P.idesc = idesc_f16(PAIR_M, TILE_N, idx->shadow_f16 ? 0u : 1u, idx->shadow_f16 ? 0u : 1u);
   P.partial = bt->d_partial;
   {
     const uint32_t groups_ = (B + PAIR_M - 1) / PAIR_M;
@@ -845,17 +969,10 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     P.cyc = st->d_cyc;
   }
   const size_t smem = kp_smem_bytes(P.stages, kp);
-  if (!st->attr_set) {
-    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-    RAG_CUDA(cudaFuncSetAttribute(k2_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_smem));
-    st->attr_set = true;
-  }
-  const uint32_t groups = (B + PAIR_M - 1) / PAIR_M;
-  const dim3 grid(P.pairs * 2, groups);
-  if (tf32) k2_pair_kernel<true, true><<<grid, KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
-  else if (idx->shadow_f16) k2_pair_kernel<false, false><<<grid, KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
-  else k2_pair_kernel<false, true><<<grid, KP_THREADS, smem, idx->stream>>>(map_q, map_x, P);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr;
+  kp_launch_cfg(&cfg, &attr, dim3(P.pairs * 2, groups), smem, idx->stream, share);
+  RAG_CUDA(cudaLaunchKernelEx(&cfg, kp_kernel(idx, share), map_q, map_x, map_h, P));
   RAG_CUDA(cudaGetLastError());
   idx->launches++;
   if (st->prof) {

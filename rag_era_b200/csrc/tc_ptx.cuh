@@ -91,6 +91,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same, MULTICAST: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each
+// destination's bytes are counted on the barrier at `bar_local_addr`'s offset in the EVEN CTA of that destination's
+// pair (the address is this CTA's own barrier with the peer bit — bit 24 of a shared::cluster address — cleared;
+// the convention of cute's SM100_TMA_2SM_LOAD_MULTICAST)
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* map, uint32_t bar_local_addr,
+                                                    uint16_t cta_mask, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(bar_local_addr & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                      uint32_t accumulate) {
   asm volatile(
@@ -132,8 +144,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-// kind::f16 with the operand formats chosen independently (0 = fp16, 1 = bf16; cute's MMA traits only ask for two
-// 16-bit types): A format at [7,10), B format at [10,13)
+// kind::f16 operand formats (0 = fp16, 1 = bf16): A format at [7,10), B format at [10,13). The descriptor has two
+// fields, but sm_100a raises an illegal-instruction error when they differ (measured): use one format for both.
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt) {
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }

@@ -650,6 +650,23 @@ def test_multi_query_stream_kernel(rb, native, oracle, B, d):
         assert r.certified.all()
 
 
+@pytest.mark.parametrize("B", [2, 4, 5, 9])
+@pytest.mark.parametrize("d", [1536, 512, 72])
+def test_multi_query_stream_kernel_bf16_corpus(rb, native, oracle, B, d):
+    """K1m for a bf16 corpus (4 queries share one corpus pass): what escalated tensor-path queries of a bf16 index run."""
+    n = 9000
+    go, gn = gen(oracle, native, n, n_clusters=16, dup_period=6)
+    X = oracle.gen_rows(go, 0, n, d, dtype=oracle.BF16)
+    with rb.VectorIndex(d, n, dtype=native.BF16) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, B)
+        r = idx.query(Q, 10, path=native.PATH_STREAM)
+        for b in range(B):
+            ei, es = oracle.topk(X, Q[b], 10)
+            assert np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es)
+        assert r.certified.all()
+
+
 def test_c3_full_size_properties(rb, native, oracle):
     """C3: 10M x 1536 fp32 (61 GB), batch 1 — the north-star target config: size-independent properties and an
     exhaustive oracle scan of the whole corpus for every query."""
