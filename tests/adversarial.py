@@ -5,7 +5,7 @@ those dimensions sit just below a bf16 rounding midpoint, the rounding errors of
 and the bf16 copy of the row is SHORTER than the row by ~2^-8 relative — an order of magnitude more than the
 ~11 sigma statistical bound of round 1 (0.024/sqrt(ld)), which assumed independent errors.
 
-The construction (fp32 index + BF16 shadow; the queries go in as fp16 of q/||q||, whose rounding is 8x finer):
+The construction (fp32 index + BF16 shadow; the query goes in as bf16 of q/||q||):
   q      outlier dims = +-8*(1+0.98/256) (bf16 rounds them DOWN to +-8), the rest small bf16-exact values
   star   row `star` = q itself: exact cosine 1.0, the true top-1; its bf16 copy scores (1-delta) ~ 0.9962
   decoys ~80 bf16-exact rows bf16(q) + p_j with exact cosines 0.9970..0.9990: their copies are exact, so all of
@@ -50,11 +50,12 @@ def build(n=6000, d=1536, n_out=16, n_decoy=80, seed=7):
 
 def operands(X, q, rows="bf16"):
     """The tensor path's operands in fp64 (gen.cu's table): (q~, x~ in cosine units, rho_q, rho_x).
-    rows: "bf16" = bf16 shadow of fp32 rows, "f16" = fp16 shadow of the normalised rows, "exact" = a bf16 corpus."""
+    rows: "bf16" = bf16 shadow of fp32 rows, "f16" = fp16 shadow of the normalised rows, "exact" = a bf16 corpus.
+    The query operand has the rows' format (kind::f16 takes one format for both): fp16 with the fp16 shadow, else bf16."""
     Xd, qd = X.astype(np.float64), q.astype(np.float64)
     nx, nq = np.linalg.norm(Xd, axis=1, keepdims=True), np.linalg.norm(qd)
     uq = qd / nq
-    qt = f16_round(uq).astype(np.float64)
+    qt = (f16_round(uq) if rows == "f16" else bf16_round(uq.astype(np.float32))).astype(np.float64)
     ux = Xd / nx
     if rows == "bf16":
         xt = bf16_round(X).astype(np.float64) / nx

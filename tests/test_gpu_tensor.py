@@ -18,15 +18,21 @@ def bf16_round(oracle, a):
 
 
 def f16_unit(Q):
-    """The tensor path's query operand: fp16 of q/||q|| (gen.cu::q_to_f16_kernel), as fp64."""
+    """The tensor path's query operand next to an fp16 shadow: fp16 of q/||q|| (gen.cu::q_to_f16_kernel), as fp64."""
     Qd = Q.astype(np.float64)
     return (Qd / np.linalg.norm(Qd, axis=1, keepdims=True)).astype(np.float32).astype(np.float16).astype(np.float64)
+
+
+def bf16_unit(oracle, Q):
+    """... and next to bf16 rows (a bf16 corpus or a bf16 shadow): bf16 of q/||q|| — kind::f16 takes ONE format."""
+    Qd = Q.astype(np.float64)
+    return bf16_round(oracle, (Qd / np.linalg.norm(Qd, axis=1, keepdims=True)).astype(np.float32)).astype(np.float64)
 
 
 @pytest.mark.parametrize("n,d,B", [(256, 256, 1), (300, 64, 5), (1000, 1536, 128), (777, 512, 129), (5000, 256, 256),
                                    (2049, 1024, 300), (70000, 128, 600)])
 def test_tensor_scores_match_numpy(rb, native, oracle, n, d, B):
-    """The raw K2 scores on a bf16 corpus = <fp16(q/||q||), x> / ||x|| (kind::f16 with mixed operand types), fp32 accumulation."""
+    """The raw K2 scores on a bf16 corpus = <bf16(q/||q||), x> / ||x||, fp32 accumulation."""
     rng = np.random.default_rng(n + d + B)
     X = oracle.f32_to_bf16(rng.standard_normal((n, d)).astype(np.float32))
     Q = rng.standard_normal((B, d)).astype(np.float32)
@@ -34,7 +40,7 @@ def test_tensor_scores_match_numpy(rb, native, oracle, n, d, B):
         idx.upload(X)
         S = idx.debug_tensor_scores(Q)
     Xf = oracle.bf16_to_f32(X).astype(np.float64)
-    E = (f16_unit(Q) @ Xf.T) / np.sqrt((Xf * Xf).sum(1))[None, :]
+    E = (bf16_unit(oracle, Q) @ Xf.T) / np.sqrt((Xf * Xf).sum(1))[None, :]
     assert np.abs(S - E).max() <= 2e-5, float(np.abs(S - E).max())
 
 
