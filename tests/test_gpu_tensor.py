@@ -41,7 +41,9 @@ def test_tensor_scores_match_numpy(rb, native, oracle, n, d, B):
         S = idx.debug_tensor_scores(Q)
     Xf = oracle.bf16_to_f32(X).astype(np.float64)
     E = (bf16_unit(oracle, Q) @ Xf.T) / np.sqrt((Xf * Xf).sum(1))[None, :]
-    assert np.abs(S - E).max() <= 2e-5, float(np.abs(S - E).max())
+    # the device normalises in fp32 (rsqrtf), numpy in fp64: an element of q/||q|| that sits on a bf16 midpoint may round
+    # the other way (2^-8 of ONE element's contribution); a plumbing error would be off by O(0.1)
+    assert np.abs(S - E).max() <= 1e-4, float(np.abs(S - E).max())
 
 
 @pytest.mark.parametrize("n,d,B", [(300, 64, 5), (1000, 1536, 128), (2049, 1024, 300)])
@@ -61,7 +63,7 @@ def test_tensor_scores_match_numpy_f16_shadow(rb, native, oracle, n, d, B):
     ok = np.ones(n, bool)
     ok[7] = False
     assert np.isnan(S[:, 7]).all()
-    assert np.abs(S[:, ok] - E[:, ok]).max() <= 2e-5, float(np.abs(S[:, ok] - E[:, ok]).max())
+    assert np.abs(S[:, ok] - E[:, ok]).max() <= 5e-5, float(np.abs(S[:, ok] - E[:, ok]).max())
 
 
 @pytest.mark.parametrize("dtype_name", ["bf16", "f32+shadow", "f32+f16"])
