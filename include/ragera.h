@@ -215,6 +215,17 @@ int rag_index_load_vector_store(rag_index* idx, const char* vector_store_json, u
 int rag_parse_vector_store_json(const char* path, uint32_t dim, uint64_t slab_rows,
                                 int (*on_rows)(void* user, uint64_t first_row, uint64_t nrows, const float* rows),
                                 void* user, uint64_t* rows_out, char** ids, uint64_t* ids_bytes);
+/* the same parser with a RESUME point: resume_offset = 0 parses the whole file; otherwise it is the *end_offset of an
+ * earlier parse — the byte just after the ']' of the last embedding that parse consumed — and only the embeddings that
+ * follow are parsed (index.insert appends to embeddingDict; src/lib/memory/store.ts:56-67). *end_offset: the resume
+ * point after this parse. stamp_*: size and mtime of the file, taken from the descriptor that was parsed before reading
+ * it. The number text is converted on all host threads (RAGERA_LOADER_THREADS to override). */
+int rag_parse_vector_store_json_ex(const char* path, uint32_t dim, uint64_t slab_rows,
+                                   int (*on_rows)(void* user, uint64_t first_row, uint64_t nrows, const float* rows),
+                                   void* user, uint64_t resume_offset, uint64_t* rows_out, char** ids, uint64_t* ids_bytes,
+                                   uint64_t* end_offset, uint64_t* stamp_size, int64_t* stamp_mtime_ns);
+/* hash of the first nbytes bytes of a file (threaded); *ok = 0 when the file is shorter */
+int rag_file_prefix_hash(const char* path, uint64_t nbytes, uint64_t* hash, int* ok);
 void rag_free(void* p);
 /* second pass over the same file: "metadataDict" (node metadata next to the embeddings). content_type[row] follows
  * vectorSearch's rule (src/lib/hybrid-search.ts:229-234, without the per-call isCodebase flag): metadata.type ===
@@ -236,6 +247,8 @@ typedef struct rag_cache_info {
   uint64_t rows, ids_bytes;
   uint64_t source_size;     /* of the vector_store.json the sidecar was written from (0 = unknown) */
   int64_t  source_mtime_ns;
+  uint64_t source_prefix_bytes; /* where the sidecar's last embedding ended in that JSON (0 = unknown): the resume point */
+  uint64_t source_prefix_hash;  /* rag_file_prefix_hash of the JSON up to there                                          */
 } rag_cache_info;
 /* host-only: header (validated), freshness against the JSON (1 fresh / 0 stale, missing or malformed), whole-file
  * write and read with every checksum verified (any output pointer may be NULL; metadata arrays: all four or none) */
@@ -249,9 +262,15 @@ int rag_cache_read_host(const char* cache_path, uint64_t first_row, uint64_t nro
                         double* confidence, int32_t* access_count, int64_t* last_access_ms, uint64_t* keys, char** ids,
                         uint64_t* ids_bytes);
 /* device side: save this handle's rows (+ metadata / keys if set) with the caller's node ids; append a row range of
- * a sidecar to the handle (nrows = 0: to the end; a shard passes its own range); open a store through its sidecar
- * when fresh, else parse the JSON and rewrite the sidecar (cache_path NULL → "<json>.ragera") */
+ * a sidecar to the handle (nrows = 0: to the end; a shard passes its own range); open a store through its sidecar:
+ * rag_cache_refresh_host, then the binary rows into HBM (*from_cache = the refresh route; cache_path NULL →
+ * "<json>.ragera"; if the sidecar cannot be written the JSON is parsed straight into the index) */
 int rag_index_save_cache(rag_index* idx, const char* cache_path, const char* ids, uint64_t ids_bytes, const char* source_json);
+/* host-only: bring the sidecar of `source_json` up to date. *route: 1 = it was fresh, 2 = the JSON had grown by appended
+ * embeddings (only those were parsed; the sidecar was extended in place), 0 = full parse + rewrite. cache_path NULL →
+ * "<source_json>.ragera". RAG_ERR_STATE if the JSON changes while it is being read (no sidecar is left behind). */
+int rag_cache_refresh_host(const char* cache_path, const char* source_json, uint32_t dtype, uint32_t dim, int* route,
+                           uint64_t* rows_out);
 int rag_index_load_cache(rag_index* idx, const char* cache_path, uint64_t first_row, uint64_t nrows, uint64_t* rows_loaded,
                          char** ids, uint64_t* ids_bytes);
 int rag_index_open_store(rag_index* idx, const char* vector_store_json, const char* cache_path, uint64_t* rows_loaded,

@@ -115,7 +115,7 @@ class CacheInfo(C.Structure):
     """rag_cache_info (include/ragera.h): header of a binary sidecar."""
     _fields_ = [("version", C.c_uint32), ("dtype", C.c_uint32), ("dim", C.c_uint32), ("flags", C.c_uint32),
                 ("rows", C.c_uint64), ("ids_bytes", C.c_uint64), ("source_size", C.c_uint64),
-                ("source_mtime_ns", C.c_int64)]
+                ("source_mtime_ns", C.c_int64), ("source_prefix_bytes", C.c_uint64), ("source_prefix_hash", C.c_uint64)]
 
 
 SYMBOLS = {
@@ -140,6 +140,11 @@ SYMBOLS = {
                                                   C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "rag_cache_info_read": (C.c_int, [C.c_char_p, C.POINTER(CacheInfo)]),
     "rag_cache_is_fresh": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "rag_cache_refresh_host": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "rag_parse_vector_store_json_ex": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint64, _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64),
+                                                 C.POINTER(_vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                                 C.POINTER(C.c_int64)]),
+    "rag_file_prefix_hash": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "rag_cache_write_host": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                        C.c_uint64, C.c_char_p]),
     "rag_cache_read_host": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp),
@@ -224,25 +229,32 @@ def load() -> C.CDLL:
 ON_ROWS = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_float))
 
 
-def parse_vector_store_json(path: str, dim: int, slab_rows: int = 4096):
-    """Host-only parse of a llamaindex vector_store.json → (ids, rows float32 [n, dim]). No GPU needed."""
+def parse_vector_store_json(path: str, dim: int, slab_rows: int = 4096, resume_offset: int | None = None, keep_rows: bool = True):
+    """Host-only parse of a llamaindex vector_store.json → (ids, rows float32 [n, dim]). No GPU needed.
+    With ``resume_offset`` (0 = from the start, else the end offset an earlier parse returned) the result is
+    (ids, rows, end_offset): only the embeddings after that offset are parsed."""
     import numpy as np
 
     lib = load()
     chunks = []
 
     def on_rows(_user, first, n, ptr):
-        chunks.append(np.ctypeslib.as_array(ptr, shape=(n * dim,)).reshape(n, dim).copy())
+        if keep_rows:
+            chunks.append(np.ctypeslib.as_array(ptr, shape=(n * dim,)).reshape(n, dim).copy())
         return OK
 
     cb = ON_ROWS(on_rows)
-    rows, blob, nbytes = C.c_uint64(0), C.c_void_p(), C.c_uint64(0)
-    check(lib.rag_parse_vector_store_json(path.encode(), dim, slab_rows, C.cast(cb, C.c_void_p), None, C.byref(rows),
-                                          C.byref(blob), C.byref(nbytes)))
+    rows, blob, nbytes, end = C.c_uint64(0), C.c_void_p(), C.c_uint64(0), C.c_uint64(0)
+    if resume_offset is None:
+        check(lib.rag_parse_vector_store_json(path.encode(), dim, slab_rows, C.cast(cb, C.c_void_p), None, C.byref(rows),
+                                              C.byref(blob), C.byref(nbytes)))
+    else:
+        check(lib.rag_parse_vector_store_json_ex(path.encode(), dim, slab_rows, C.cast(cb, C.c_void_p), None, resume_offset,
+                                                 C.byref(rows), C.byref(blob), C.byref(nbytes), C.byref(end), None, None))
     ids = C.string_at(blob, nbytes.value).decode("utf-8").split("\0")[:-1] if nbytes.value else []
     lib.rag_free(blob)
     X = np.vstack(chunks) if chunks else np.zeros((0, dim), np.float32)
-    return ids, X
+    return (ids, X) if resume_offset is None else (ids, X, int(end.value))
 
 
 def _ids_blob(ids) -> bytes:
@@ -271,6 +283,15 @@ def cache_info(path: str) -> CacheInfo:
     info = CacheInfo()
     check(load().rag_cache_info_read(path.encode(), C.byref(info)))
     return info
+
+
+def cache_refresh(source_json: str, dtype: int, dim: int, cache_path: str | None = None) -> tuple[int, int]:
+    """rag_cache_refresh_host: bring the sidecar up to date without a GPU. Returns (route, rows): route 1 = fresh,
+    2 = extended in place with the embeddings appended to the JSON, 0 = full parse + rewrite."""
+    route, rows = C.c_int(0), C.c_uint64(0)
+    check(load().rag_cache_refresh_host(cache_path.encode() if cache_path else None, source_json.encode(), dtype, dim,
+                                        C.byref(route), C.byref(rows)))
+    return int(route.value), int(rows.value)
 
 
 def cache_is_fresh(cache_path: str, source_json: str) -> bool:

@@ -168,12 +168,13 @@ class VectorIndex:
         return N._split_blob(blob, nbytes.value)
 
     def open_store(self, vector_store_json: str, cache_path: str | None = None):
-        """loadIndex (index-manager.ts:246-275) for an empty handle: the sidecar when it is fresh, else the JSON
-        (and the sidecar is rewritten). Returns (node ids, from_cache)."""
+        """loadIndex (index-manager.ts:246-275) for an empty handle through the binary sidecar. Returns (node ids, route):
+        route 1 = the sidecar was fresh, 2 = the JSON had grown by appended embeddings (only those were parsed, the sidecar
+        was extended in place), 0 = the JSON was parsed in full (and the sidecar rewritten)."""
         rows, blob, nbytes, hit = C.c_uint64(0), C.c_void_p(), C.c_uint64(0), C.c_int(0)
         N.check(self._lib.rag_index_open_store(self._h, vector_store_json.encode(), cache_path.encode() if cache_path else None,
                                                C.byref(rows), C.byref(blob), C.byref(nbytes), C.byref(hit)))
-        return N._split_blob(blob, nbytes.value), bool(hit.value)
+        return N._split_blob(blob, nbytes.value), int(hit.value)
 
     def generate(self, gen: N.GenDesc, nrows: int):
         N.check(self._lib.rag_index_generate(self._h, C.byref(gen), nrows))

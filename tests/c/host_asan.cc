@@ -39,6 +39,20 @@ int main(int argc, char** argv) {
     rc = rag_cache_read_host(cache, 0, rows, Y.data(), nullptr, nullptr, nullptr, nullptr, nullptr, &ids2, &nb2);
     printf("read rc=%d same=%d\n", rc, (int)(rc == RAG_OK && nb2 == nb && (X.empty() || memcmp(X.data(), Y.data(), X.size() * 4) == 0)));
     rag_free(ids2);
+    {  // the refresh routes: rebuild, fresh, and — after the JSON grew by whitespace — the in-place extension (0 new rows)
+      const std::string c2 = std::string(cache) + ".refresh";
+      int route = -1; uint64_t nr = 0;
+      int r0 = rag_cache_refresh_host(c2.c_str(), json, RAG_BF16, dim, &route, &nr);
+      printf("refresh rc=%d route=%d rows=%llu\n", r0, route, (unsigned long long)nr);
+      r0 = rag_cache_refresh_host(c2.c_str(), json, RAG_BF16, dim, &route, &nr);
+      printf("refresh rc=%d route=%d\n", r0, route);
+      FILE* a = fopen(json, "ab"); fputc('\n', a); fclose(a);
+      r0 = rag_cache_refresh_host(c2.c_str(), json, RAG_BF16, dim, &route, &nr);
+      printf("refresh rc=%d route=%d fresh=%d\n", r0, route, rag_cache_is_fresh(c2.c_str(), json));
+      uint64_t hsh = 0; int hok = 0;
+      rag_file_prefix_hash(json, 1ull << 40, &hsh, &hok);
+      printf("prefix past the end ok=%d\n", hok);
+    }
     // truncate / corrupt at many offsets: must fail cleanly, never crash
     FILE* f = fopen(cache, "rb"); std::string blob; char buf[65536]; size_t n;
     while ((n = fread(buf, 1, sizeof buf, f)) > 0) blob.append(buf, n);

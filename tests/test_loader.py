@@ -244,11 +244,158 @@ def test_open_store_through_the_sidecar(native, oracle, tmp_path):
     with rb.VectorIndex(dim, n, dtype=native.BF16) as idx:                 # dtype mismatch: the sidecar is ignored
         got, hit = idx.open_store(src, cache_path=src + ".ragera")
         assert not hit and np.array_equal(idx.read_rows(0, n), oracle.f32_to_bf16(X))
-    open(src, "a").write("\n")                                             # the JSON changed: stale sidecar
+    open(src, "a").write("\n")                                             # the JSON changed, but only after the embeddings
     with rb.VectorIndex(dim, n) as idx:
         got, hit = idx.open_store(src)
-        assert got == ids and not hit
-    assert native.cache_is_fresh(src + ".ragera", src)                     # ... and it was rewritten
+        assert got == ids and hit == 2                                     # same prefix, nothing appended: re-stamped in place
+        assert np.array_equal(idx.read_rows(0, n), X)
+    assert native.cache_is_fresh(src + ".ragera", src)
+    # index.insert (memory/store.ts:56-67): llamaindex rewrites the JSON with new nodes at the END of embeddingDict
+    X2 = rng.standard_normal((7, dim)).astype(np.float32)
+    ids2 = [f"memory_{k}" for k in range(7)]
+    write_store_with_metadata(src, ids + ids2, np.vstack([X, X2]))
+    with rb.VectorIndex(dim, n + 7) as idx:
+        got, hit = idx.open_store(src)
+        assert got == ids + ids2 and hit == 2 and idx.rows == n + 7        # only the 7 appended embeddings were parsed
+        assert np.array_equal(idx.read_rows(0, n + 7), np.vstack([X, X2]))
+        meta = idx.read_row_meta(0, n + 7)
+        assert np.array_equal(meta["content_type"], expected_ctype(native, n + 7))
+        assert np.array_equal(meta["keys"][:n], want_meta["keys"]) and np.array_equal(meta["confidence"][:n], want_meta["confidence"])
+        gi, gs = idx.query(q, 8).row(0)
+        ei2, es2 = oracle.topk(np.vstack([X, X2]), q, 8)
+        assert np.array_equal(gi, ei2) and np.array_equal(gs, es2)
+    with rb.VectorIndex(dim, n + 7) as idx:
+        assert idx.open_store(src)[1] == 1                                 # and the extended sidecar is fresh
+    write_store_with_metadata(src, ids[1:] + ids2, np.vstack([X[1:], X2]))  # a node was removed: the prefix no longer matches
+    with rb.VectorIndex(dim, n + 7) as idx:
+        got, hit = idx.open_store(src)
+        assert got == ids[1:] + ids2 and hit == 0 and np.array_equal(idx.read_rows(0, n + 6), np.vstack([X[1:], X2]))
+
+
+def test_resume_parses_only_the_appended_embeddings(native, tmp_path):
+    rng = np.random.default_rng(3)
+    dim = 24
+    X = rng.standard_normal((300, dim)).astype(np.float32)
+    ids = [f"n{k}" for k in range(300)]
+    p = str(tmp_path / "vs.json")
+    write_store(p, ids[:200], X[:200], extra_first=False)                    # embeddingDict first, as SimpleVectorStore writes it
+    got_ids, got, end = native.parse_vector_store_json(p, dim, resume_offset=0)
+    assert got_ids == ids[:200] and np.array_equal(got, X[:200]) and end > 0
+    more_ids, more, end2 = native.parse_vector_store_json(p, dim, resume_offset=end)
+    assert more_ids == [] and len(more) == 0 and end2 == end                 # nothing after the last embedding
+    write_store(p, ids, X, extra_first=False)                                # the same store, 100 nodes appended
+    more_ids, more, end3 = native.parse_vector_store_json(p, dim, resume_offset=end, slab_rows=16)
+    assert more_ids == ids[200:] and np.array_equal(more, X[200:]) and end3 > end
+    assert native.parse_vector_store_json(p, dim, resume_offset=end3)[0] == []
+    with pytest.raises(native.RagError):                                     # an offset in the middle of a number
+        native.parse_vector_store_json(p, dim, resume_offset=end - 3)
+    with pytest.raises(native.RagError):
+        native.parse_vector_store_json(p, dim, resume_offset=10**12)
+
+
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_refresh_routes_fresh_extended_rebuilt(native, oracle, tmp_path, dtype_name):
+    """rag_cache_refresh_host: nothing to do / extend in place with the appended embeddings / full rebuild."""
+    rng = np.random.default_rng(5)
+    dim, n = 32, 9000                                                        # more than two 4096-row checksum blocks
+    dt = native.F32 if dtype_name == "f32" else native.BF16
+    conv = (lambda a: a) if dt == native.F32 else oracle.f32_to_bf16
+    X = rng.standard_normal((n + 500, dim)).astype(np.float32)
+    ids = [f"node-{k:05d}" for k in range(n + 500)]
+    src = str(tmp_path / "vector_store.json")
+    cache = src + ".ragera"
+    write_store_with_metadata(src, ids[:n], X[:n])
+    assert native.cache_refresh(src, dt, dim) == (0, n)                      # no sidecar yet: full parse
+    assert native.cache_refresh(src, dt, dim) == (1, n)                      # fresh
+    info = native.cache_info(cache)
+    assert info.rows == n and info.source_prefix_bytes > 0
+    got = native.cache_read_host(cache)
+    assert np.array_equal(got["rows"], conv(X[:n])) and got["ids"] == ids[:n]
+    assert np.array_equal(got["content_type"], expected_ctype(native, n))
+    for step, m in enumerate((n + 1, n + 130, n + 500)):                     # one memory inserted, then more (block boundaries crossed)
+        write_store_with_metadata(src, ids[:m], X[:m])
+        assert native.cache_refresh(src, dt, dim) == (2, m), step
+        assert native.cache_is_fresh(cache, src)
+        got = native.cache_read_host(cache)                                  # every block checksum is verified by the reader
+        assert np.array_equal(got["rows"], conv(X[:m])) and got["ids"] == ids[:m]
+        assert np.array_equal(got["content_type"], expected_ctype(native, m))
+        part = native.cache_read_host(cache, first_row=m - 3, nrows=3)
+        assert np.array_equal(part["rows"], conv(X[m - 3:m]))
+    assert native.cache_refresh(src, dt, dim) == (1, n + 500)
+    # an edit BEFORE the resume point (a node rebuilt): the prefix hash no longer matches → full rebuild
+    Y = X[:n + 500].copy()
+    Y[17, 3] += 1.0
+    write_store_with_metadata(src, ids, Y)
+    assert native.cache_refresh(src, dt, dim) == (0, n + 500)
+    assert np.array_equal(native.cache_read_host(cache)["rows"], conv(Y))
+    # the other dtype: not usable → rebuilt for that dtype
+    other = native.BF16 if dt == native.F32 else native.F32
+    assert native.cache_refresh(src, other, dim)[0] == 0
+    # a malformed appended tail → full parse is attempted and reports the error; no sidecar claims to be fresh
+    assert native.cache_refresh(src, dt, dim)[0] == 0
+    text = open(src).read()
+    cut = text.rindex("]", 0, text.index('"metadataDict"'))
+    open(src, "w").write(text[:cut + 1] + ',"broken":[1,2' + text[cut + 1:])
+    with pytest.raises(native.RagError):
+        native.cache_refresh(src, dt, dim)
+    assert not native.cache_is_fresh(cache, src)
+
+
+def test_append_to_a_100k_row_store_reopens_fast_and_parse_scales(native, tmp_path):
+    """one index.insert used to make the whole sidecar stale (full re-parse at 5.8k rows/s on one core).
+    Now: (a) the full parse runs on all host threads, (b) after one appended row only that row is parsed and the sidecar is
+    extended in place. The store is written by a small C program (tests/c/gen_vector_store.c; Python's json takes minutes)."""
+    import shutil
+    import subprocess
+    import time
+
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "gen_vs")
+    subprocess.run(["gcc", "-O2", "-o", exe, os.path.join(root, "tests", "c", "gen_vector_store.c"), "-lm"], check=True)
+    cores = os.cpu_count() or 1
+    # (a) throughput at D = 1536
+    src = str(tmp_path / "big.json")
+    n, dim = 12_000, 1536
+    subprocess.run([exe, src, str(n), str(dim), "0"], check=True)
+    size_mb = os.path.getsize(src) / 1e6
+    t0 = time.perf_counter()
+    ids, _ = native.parse_vector_store_json(src, dim, slab_rows=4096, keep_rows=False)
+    dt_all = time.perf_counter() - t0
+    os.environ["RAGERA_LOADER_THREADS"] = "1"
+    try:
+        t0 = time.perf_counter()
+        native.parse_vector_store_json(src, dim, slab_rows=4096, keep_rows=False)
+        dt_one = time.perf_counter() - t0
+    finally:
+        del os.environ["RAGERA_LOADER_THREADS"]
+    rate_all, rate_one = n / dt_all, n / dt_one
+    print(f"parse D=1536: {rate_one:.0f} rows/s on 1 thread, {rate_all:.0f} rows/s on {cores} threads "
+          f"({size_mb / dt_all:.0f} MB/s of text)")
+    assert len(ids) == n
+    if cores >= 4:
+        assert rate_all > 2.0 * rate_one, (rate_all, rate_one)               # it scales with the cores
+        assert rate_all > 3_000 * cores, rate_all                            # ≥ 50k rows/s on the 16-core GPU host
+    os.remove(src)
+    # (b) 100k rows (D = 256: 100k x 1536 would be a 2 GB file), then ONE memory inserted
+    src = str(tmp_path / "store.json")
+    n, dim = 100_000, 256
+    subprocess.run([exe, src, str(n), str(dim), "0"], check=True)
+    t0 = time.perf_counter()
+    assert native.cache_refresh(src, native.F32, dim) == (0, n)
+    t_full = time.perf_counter() - t0
+    subprocess.run([exe, src, str(n), str(dim), "1"], check=True)             # the same store + 1 appended node
+    t0 = time.perf_counter()
+    assert native.cache_refresh(src, native.F32, dim) == (2, n + 1)
+    t_append = time.perf_counter() - t0
+    print(f"100k x {dim}: full refresh {t_full:.2f} s, refresh after one appended row {t_append:.3f} s")
+    assert t_append < 1.0 and t_append < 0.5 * t_full
+    got = native.cache_read_host(src + ".ragera", first_row=n - 1, nrows=2)
+    ids_tail, rows_tail, _ = native.parse_vector_store_json(src, dim, resume_offset=native.cache_info(src + ".ragera").source_prefix_bytes)
+    assert ids_tail == [] and got["ids"][-1] == f"memory-{n}" and len(got["ids"]) == n + 1
+    full_ids, full = native.parse_vector_store_json(src, dim)
+    assert np.array_equal(got["rows"], full[n - 1:]) and full_ids == got["ids"]
 
 
 # ---- the parser against Python's json on arbitrary stores (hypothesis) -------------------------------------------
@@ -297,6 +444,13 @@ def test_parser_agrees_with_python_json_on_arbitrary_stores(native, tmp_path, st
         assert mem[r] == want_mem.replace("\0", "�"), (i, m)
 
 
+def rows_of(stdout):
+    import re
+
+    m = re.search(r"parse rc=0 rows=(\d+)", stdout)
+    return int(m.group(1)) if m else 0
+
+
 def test_loader_and_sidecar_under_sanitizers(tmp_path):
     """loader.cu + store_cache.cu are host-only: built as plain C++ with ASAN + UBSAN (tests/c/host_asan.cc) and driven over good,
     truncated, malformed, unicode and deeply nested stores, then over truncated / bit-flipped sidecars. No sanitizer report, every
@@ -342,3 +496,6 @@ def test_loader_and_sidecar_under_sanitizers(tmp_path):
         assert "ACCEPTED CORRUPT DATA" not in r.stdout, (name, r.stdout)
         if ok:
             assert "read rc=0 same=1" in r.stdout and "write rc=0 fresh=1" in r.stdout, (name, r.stdout)
+            assert "refresh rc=0 route=0" in r.stdout and "refresh rc=0 route=1" in r.stdout and "prefix past the end ok=0" in r.stdout, (name, r.stdout)
+            if rows_of(r.stdout) > 0:
+                assert "refresh rc=0 route=2 fresh=1" in r.stdout, (name, r.stdout)
