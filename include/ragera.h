@@ -14,7 +14,10 @@
  *    thread-local message for the last failing call on this thread
  *  - the caller owns every host buffer (outputs are caller-allocated); the
  *    library owns all device memory behind the opaque rag_index handle
- *  - a handle may be used by one thread at a time; distinct handles concurrently
+ *  - calls on ONE handle are serialised by the library (a per-handle mutex held for the whole call): several threads
+ *    may share a handle — concurrent requests of a web server, the micro-batcher's worker next to direct calls — and
+ *    simply take turns; distinct handles run concurrently. The staged form (stage → run → fetch) is a multi-call
+ *    sequence and belongs to one owner at a time
  *  - calls are synchronous w.r.t. the host unless named *_async / *_staged
  *  - there is NO CPU fallback: without a usable sm_100 device calls fail
  *  - ids are uint64 chunk ids = id_base + local row (row order = insertion order

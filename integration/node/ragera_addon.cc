@@ -3,9 +3,12 @@
 // NOT compiled in the build container (no Node toolchain there); the same C ABI is exercised end to end
 // from Python (rag_era_b200/_native.py) and from C (tests/c/abi_demo.c). Build in the reference repo with
 //     cd integration/node && npx node-gyp rebuild
-// Pure C N-API (node_api.h), no C++ wrapper dependency. Every GPU call runs on a libuv worker thread
-// (napi_create_async_work) so the event loop never blocks; a handle is used by one worker at a time
-// because JS callers await each call (or go through the batcher, which has its own worker thread).
+// Pure C N-API (node_api.h), no C++ wrapper dependency. Every search runs on a libuv worker thread
+// (napi_create_async_work) so the event loop never blocks. Several requests may be in flight on ONE handle — parallel
+// HTTP requests, the Promise.all of engine.ts:108, the synchronous mutators below on the main thread: libragera
+// serialises the calls of a handle itself (a per-handle mutex, include/ragera.h), so they take turns on the GPU
+// instead of racing; tests/c/napi_mock.cc queues 2B calls on one handle before draining the loop. For throughput
+// under load route the requests through the batcher, which turns concurrent batch-1 calls into one corpus pass.
 //
 // JS surface (see native-retrieval.ts):
 //   createIndex({rows, dim, dtype:'f32'|'bf16', device, f16Shadow | bf16Shadow}) -> handle (External)

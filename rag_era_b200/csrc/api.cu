@@ -495,6 +495,7 @@ int rag_index_create(const rag_index_desc* d, rag_index** out) {
 
 void rag_index_destroy(rag_index* idx) {
   if (!idx) return;
+  { RAG_LOCK(idx); }  // a call still in flight on another thread finishes first (calls after destroy are the caller's bug)
   cudaSetDevice(idx->device);
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   rag_comm_destroy(idx);
@@ -519,6 +520,7 @@ uint64_t rag_index_rows(const rag_index* idx) { return idx ? idx->rows : 0; }
 
 int rag_index_upload(rag_index* idx, uint64_t row0, uint64_t nrows, const void* host_rows) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (nrows == 0) return RAG_OK;
   if (!host_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_upload: null rows");
   if (row0 > idx->rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_upload: row0=%llu leaves a gap (rows=%llu)",
@@ -546,6 +548,7 @@ int rag_index_upload(rag_index* idx, uint64_t row0, uint64_t nrows, const void* 
 
 int rag_index_generate(rag_index* idx, const rag_gen_desc* gen, uint64_t nrows) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!gen || gen->n_clusters == 0 || gen->total_rows == 0)
     return rag_set_error(RAG_ERR_INVALID, "rag_index_generate: bad generator description");
   if (nrows > idx->desc.capacity_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_generate: nrows exceeds capacity");
@@ -563,6 +566,7 @@ int rag_index_generate(rag_index* idx, const rag_gen_desc* gen, uint64_t nrows) 
 int rag_index_set_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, const uint8_t* content_type,
                            const double* confidence, const int32_t* access_count, const int64_t* last_access_ms) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (row0 + nrows > idx->desc.capacity_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_set_row_meta: range exceeds capacity");
   if (nrows == 0) return RAG_OK;
   RAG_CUDA(cudaSetDevice(idx->device));
@@ -577,6 +581,7 @@ int rag_index_set_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, const 
 
 int rag_index_set_row_keys(rag_index* idx, uint64_t row0, uint64_t nrows, const uint64_t* keys) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (row0 + nrows > idx->desc.capacity_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_set_row_keys: range exceeds capacity");
   if (nrows == 0) return RAG_OK;
   if (!keys) return rag_set_error(RAG_ERR_INVALID, "rag_index_set_row_keys: null keys");
@@ -594,6 +599,7 @@ int rag_index_set_row_keys(rag_index* idx, uint64_t row0, uint64_t nrows, const 
 int rag_index_read_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, uint8_t* content_type, double* confidence,
                             int32_t* access_count, int64_t* last_access_ms, uint64_t* keys) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (row0 + nrows > idx->rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_read_row_meta: range exceeds rows");
   if (nrows == 0) return RAG_OK;
   RAG_CUDA(cudaSetDevice(idx->device));
@@ -619,6 +625,7 @@ int rag_index_read_row_meta(rag_index* idx, uint64_t row0, uint64_t nrows, uint8
 
 int rag_index_read_rows(rag_index* idx, uint64_t row0, uint64_t nrows, void* host_rows) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (row0 + nrows > idx->rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_read_rows: range exceeds rows");
   if (nrows == 0) return RAG_OK;
   if (!host_rows) return rag_set_error(RAG_ERR_INVALID, "rag_index_read_rows: null buffer");
@@ -637,6 +644,7 @@ int rag_index_read_rows(rag_index* idx, uint64_t row0, uint64_t nrows, void* hos
 
 int rag_generate_queries(rag_index* idx, const rag_gen_desc* gen, uint64_t b0, uint32_t B, float* host_out) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!gen || !host_out || B == 0 || gen->total_rows == 0 || gen->n_clusters == 0)
     return rag_set_error(RAG_ERR_INVALID, "rag_generate_queries: bad argument");
   RAG_CUDA(cudaSetDevice(idx->device));
@@ -656,6 +664,7 @@ int rag_generate_queries(rag_index* idx, const rag_gen_desc* gen, uint64_t b0, u
 // ---- search --------------------------------------------------------------------------------
 int rag_search(rag_index* idx, const float* queries, uint32_t B, const rag_search_opts* o, rag_topk_out* out) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!queries || !o || !out || !out->ids || !out->scores || !out->counts || B == 0)
     return rag_set_error(RAG_ERR_INVALID, "rag_search: null argument or empty batch");
   if (o->k == 0 || o->k > RAG_MAX_TOPK) return rag_set_error(RAG_ERR_INVALID, "k must be in 1..%d", RAG_MAX_TOPK);
@@ -764,6 +773,7 @@ static int check_fused_out(const rag_hybrid_opts* o, const rag_fused_out* out, u
 int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const rag_hybrid_opts* o,
                       const uint64_t* kw_keys, const uint32_t* kw_counts, rag_fused_out* out) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!queries || !o || B == 0) return rag_set_error(RAG_ERR_INVALID, "rag_hybrid_search: null argument or empty batch");
   rag_fuse_args fa;
   fresh_cfg fc;
@@ -803,6 +813,7 @@ int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const ra
 int rag_stage_batch(rag_index* idx, const float* queries, uint32_t B, const uint64_t* kw_keys,
                     const uint32_t* kw_counts, uint32_t keyword_limit) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!queries || B == 0) return rag_set_error(RAG_ERR_INVALID, "rag_stage_batch: null queries or empty batch");
   if (keyword_limit > RAG_MAX_KEYWORDS) return rag_set_error(RAG_ERR_INVALID, "keyword_limit must be <= %d", RAG_MAX_KEYWORDS);
   RAG_CUDA(cudaSetDevice(idx->device));
@@ -819,6 +830,7 @@ int rag_stage_batch(rag_index* idx, const float* queries, uint32_t B, const uint
 
 int rag_stage_window(rag_index* idx, uint32_t first, uint32_t count) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   rag_batch* bt = &idx->main;
   if (count == 0 || (uint64_t)first + count > bt->staged_B)
     return rag_set_error(RAG_ERR_INVALID, "rag_stage_window: [%u,%u) is outside the %u staged queries", first, first + count, bt->staged_B);
@@ -829,6 +841,7 @@ int rag_stage_window(rag_index* idx, uint32_t first, uint32_t count) {
 
 int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* o) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!o) return rag_set_error(RAG_ERR_INVALID, "rag_hybrid_search_staged: null options");
   rag_batch* bt = &idx->main;
   if (B == 0 || B != bt->win_count) return rag_set_error(RAG_ERR_STATE, "rag_hybrid_search_staged: B=%u but the staged window holds %u queries", B, bt->win_count);
@@ -863,6 +876,7 @@ int rag_hybrid_search_staged(rag_index* idx, uint32_t B, const rag_hybrid_opts* 
 
 int rag_fetch_fused(rag_index* idx, uint32_t B, const rag_hybrid_opts* o, rag_fused_out* out) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!o) return rag_set_error(RAG_ERR_INVALID, "rag_fetch_fused: null options");
   rag_batch* bt = &idx->main;
   if (B == 0 || B != bt->win_count) return rag_set_error(RAG_ERR_STATE, "rag_fetch_fused: B does not match the staged window");
@@ -878,6 +892,7 @@ int rag_fetch_fused(rag_index* idx, uint32_t B, const rag_hybrid_opts* o, rag_fu
 
 int rag_sync(rag_index* idx) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   RAG_CUDA(cudaSetDevice(idx->device));
   RAG_CUDA(cudaStreamSynchronize(idx->stream));
   return RAG_OK;
@@ -888,6 +903,7 @@ int rag_rrf_fuse(rag_index* idx, uint32_t B, const rag_rrf_config* cfg, const ui
                  const uint8_t* vec_ctype, const uint32_t* vec_counts, uint32_t vec_stride, const uint64_t* kw_keys,
                  const uint32_t* kw_counts, uint32_t kw_stride, rag_fused_out* out) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!cfg || !out || !out->keys || !out->scores || !out->counts || B == 0 || !vec_counts || !kw_counts)
     return rag_set_error(RAG_ERR_INVALID, "rag_rrf_fuse: null argument or empty batch");
   if (vec_stride > RAG_MAX_TOPK || kw_stride > RAG_MAX_KEYWORDS)
@@ -941,6 +957,7 @@ int rag_rrf_fuse(rag_index* idx, uint32_t B, const rag_rrf_config* cfg, const ui
 // ---- memory ------------------------------------------------------------------------------------
 int rag_memory_retrieve(rag_index* idx, const float* queries, uint32_t B, const rag_memory_opts* o, rag_memory_out* out) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!queries || !o || !out || !out->ids || !out->scores || !out->counts || B == 0)
     return rag_set_error(RAG_ERR_INVALID, "rag_memory_retrieve: null argument or empty batch");
   // similarityTopK: limit * 2 — src/lib/memory/store.ts:112 (or the caller's own value)
@@ -992,6 +1009,7 @@ int rag_memory_retrieve(rag_index* idx, const float* queries, uint32_t B, const 
 int rag_freshness_scores(rag_index* idx, uint64_t n, const double* confidence, const int32_t* access_count,
                          const int64_t* last_access_ms, int64_t now_ms, double decay, double bonus, double* out_scores) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (n == 0) return RAG_OK;
   if (!confidence || !access_count || !last_access_ms || !out_scores)
     return rag_set_error(RAG_ERR_INVALID, "rag_freshness_scores: null argument");
@@ -1023,6 +1041,7 @@ int rag_freshness_scores(rag_index* idx, uint64_t n, const double* confidence, c
 // ---- diagnostics -----------------------------------------------------------------------------------
 int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, float* out_scores) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!queries || !out_scores || B == 0) return rag_set_error(RAG_ERR_INVALID, "rag_debug_tensor_scores: null argument");
   if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
   RAG_CUDA(cudaSetDevice(idx->device));
@@ -1058,6 +1077,7 @@ int rag_debug_tensor_scores(rag_index* idx, const float* queries, uint32_t B, fl
 int rag_debug_tensor_candidates(rag_index* idx, const float* queries, uint32_t B, uint32_t kp, float* out_scores,
                                 uint64_t* out_keys) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   if (!queries || !out_scores || !out_keys || B == 0 || kp == 0 || kp > RAG_MAX_CANDIDATES)
     return rag_set_error(RAG_ERR_INVALID, "rag_debug_tensor_candidates: bad argument");
   if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
@@ -1094,6 +1114,7 @@ int rag_debug_tensor_candidates(rag_index* idx, const float* queries, uint32_t B
 
 double rag_index_row_residual(rag_index* idx) {
   if (!idx) return (double)rag_set_error(RAG_ERR_INVALID, "null index handle");
+  RAG_LOCK(idx);
   if (cudaSetDevice(idx->device) != cudaSuccess) return (double)rag_set_error(RAG_ERR_CUDA, "cudaSetDevice failed");
   const int rc = refresh_rho_x(idx);
   return rc != RAG_OK ? (double)rc : (double)idx->rho_x;
@@ -1102,6 +1123,7 @@ double rag_index_row_residual(rag_index* idx) {
 // ---- measurement ---------------------------------------------------------------------------------
 int rag_timer_start(rag_index* idx) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   RAG_CUDA(cudaSetDevice(idx->device));
   RAG_CUDA(cudaEventRecord(idx->ev0, idx->stream));
   return RAG_OK;
@@ -1109,6 +1131,7 @@ int rag_timer_start(rag_index* idx) {
 
 int rag_timer_stop(rag_index* idx, float* elapsed_ms) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   RAG_CUDA(cudaSetDevice(idx->device));
   RAG_CUDA(cudaEventRecord(idx->ev1, idx->stream));
   RAG_CUDA(cudaEventSynchronize(idx->ev1));
@@ -1124,6 +1147,7 @@ uint64_t rag_launch_count(const rag_index* idx) { return idx ? idx->launches : 0
 // were certified by the scoring pass that produced them (escalated re-runs count as their own queries)
 int rag_certified_totals(rag_index* idx, uint64_t* certified, uint64_t* queries) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   RAG_CUDA(cudaSetDevice(idx->device));
   unsigned long long h[2] = {0, 0};
   RAG_CUDA(cudaMemcpyAsync(h, idx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, idx->stream));
@@ -1136,6 +1160,7 @@ int rag_certified_totals(rag_index* idx, uint64_t* certified, uint64_t* queries)
 
 int rag_profile_enable(rag_index* idx, int on) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   RAG_CUDA(cudaSetDevice(idx->device));
   if (on && !idx->prof_spans) {
     idx->prof_spans = new (std::nothrow) rag_prof_span[kProfSpans];
@@ -1154,6 +1179,7 @@ int rag_profile_enable(rag_index* idx, int on) {
 
 int rag_profile_read(rag_index* idx, float ms[RAG_PROF_CLASSES], uint32_t counts[RAG_PROF_CLASSES]) {
   RAG_CHECK(check_handle(idx));
+  RAG_LOCK(idx);
   RAG_CUDA(cudaSetDevice(idx->device));
   prof_drain(idx);
   for (int i = 0; i < RAG_PROF_CLASSES; i++) {

@@ -244,6 +244,7 @@ extern "C" int rag_comm_p2p_export(rag_index* idx, int nranks, int rank, uint32_
   static_assert(sizeof(cudaIpcMemHandle_t) == RAG_COMM_HANDLE_BYTES, "IPC handle size");
   if (!idx || !handle || nranks < 1 || rank < 0 || rank >= nranks || nranks > 8)
     return rag_set_error(RAG_ERR_INVALID, "rag_comm_p2p_export: bad nranks/rank (1..8 ranks supported)");
+  RAG_LOCK(idx);
   if (max_batch == 0 || max_batch > 4096 || max_k == 0 || max_k > RAG_MAX_TOPK)
     return rag_set_error(RAG_ERR_INVALID, "rag_comm_p2p_export: max_batch must be 1..4096, max_k 1..%d", RAG_MAX_TOPK);
   RAG_CUDA(cudaSetDevice(idx->device));
@@ -272,6 +273,7 @@ extern "C" int rag_comm_p2p_export(rag_index* idx, int nranks, int rank, uint32_
 
 extern "C" int rag_comm_p2p_import(rag_index* idx, const uint8_t* handles) {
   if (!idx || !handles) return rag_set_error(RAG_ERR_INVALID, "rag_comm_p2p_import: null argument");
+  RAG_LOCK(idx);
   if (idx->nranks == 1 && !idx->comm) return RAG_OK;
   rag_comm* c = idx->comm;
   if (!c || !c->host_driven || !c->mbox) return rag_set_error(RAG_ERR_STATE, "rag_comm_p2p_import without rag_comm_p2p_export");
@@ -301,6 +303,7 @@ extern "C" int rag_comm_p2p_import(rag_index* idx, const uint8_t* handles) {
 // may any rank free its own mailbox (rag_comm_destroy, rag_index_destroy, a new rag_comm_p2p_export).
 extern "C" int rag_comm_detach(rag_index* idx) {
   if (!idx) return rag_set_error(RAG_ERR_INVALID, "null index handle");
+  RAG_LOCK(idx);
   if (!idx->comm) return RAG_OK;
   RAG_CUDA(cudaSetDevice(idx->device));
   RAG_CUDA(cudaStreamSynchronize(idx->stream));
@@ -322,6 +325,7 @@ extern "C" int rag_comm_unique_id(uint8_t id[RAG_COMM_ID_BYTES]) {
 extern "C" int rag_comm_init(rag_index* idx, int nranks, int rank, const uint8_t id[RAG_COMM_ID_BYTES]) {
   if (!idx || nranks < 1 || rank < 0 || rank >= nranks || nranks > 8)
     return rag_set_error(RAG_ERR_INVALID, "rag_comm_init: bad nranks/rank (1..8 ranks supported)");
+  RAG_LOCK(idx);
   rag_comm_destroy(idx);
   if (nranks == 1) return RAG_OK;
   RAG_CHECK(load_nccl());
@@ -344,6 +348,8 @@ extern "C" int rag_comm_init(rag_index* idx, int nranks, int rank, const uint8_t
 }
 
 extern "C" int rag_comm_destroy(rag_index* idx) {
+  if (!idx) return RAG_OK;
+  RAG_LOCK(idx);
   if (idx && idx->comm) {
     cudaSetDevice(idx->device);
     cudaStreamSynchronize(idx->stream);

@@ -16,6 +16,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/ragera.h"
 
 #define RAG_WARP 32
@@ -144,6 +146,10 @@ struct rag_batch {
 struct rag_prof_span { cudaEvent_t a, b; int cls; };
 
 struct rag_index {
+  // Every public entry point that takes the handle holds this for its whole duration (RAG_LOCK): concurrent callers —
+  // libuv pool threads behind an N-API addon, the micro-batcher's worker next to direct calls — are serialised by the
+  // library instead of racing on the batch buffers. Recursive: entry points call each other (load_cache → upload).
+  std::recursive_mutex mu;
   rag_index_desc desc;
   int device = 0;
   int sm_count = 0;
@@ -195,6 +201,7 @@ int rag_set_error(int code, const char* fmt, ...);
       return rag_set_error(RAG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
                            __FILE__, __LINE__);                                             \
   } while (0)
+#define RAG_LOCK(idx) std::lock_guard<std::recursive_mutex> _rag_lock((idx)->mu)
 #define RAG_CHECK(expr)             \
   do {                              \
     int _r = (expr);                \

@@ -611,6 +611,7 @@ int upload_rows(void* user, uint64_t first, uint64_t n, const float* rows) {
 extern "C" int rag_index_load_vector_store(rag_index* idx, const char* path, uint64_t* rows_loaded, char** ids,
                                            uint64_t* ids_bytes) {
   if (!idx) return rag_set_error(RAG_ERR_INVALID, "null index handle");
+  RAG_LOCK(idx);
   upload_ctx c;
   c.idx = idx;
   c.row0 = idx->rows;

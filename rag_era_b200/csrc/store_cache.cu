@@ -541,6 +541,7 @@ int rag_cache_read_host(const char* cache_path, uint64_t first_row, uint64_t nro
 // not changed since it was read (rag_index_open_store stamps from the descriptor it parsed instead).
 int rag_index_save_cache(rag_index* idx, const char* cache_path, const char* ids, uint64_t ids_bytes, const char* source_json) {
   if (!idx || !cache_path) return rag_set_error(RAG_ERR_INVALID, "rag_index_save_cache: null argument");
+  RAG_LOCK(idx);
   src_stamp st;
   bool have = false;
   if (!stamp_of_path(source_json, &st, &have)) return rag_set_error(RAG_ERR_INVALID, "cannot stat %s: %s", source_json, strerror(errno));
@@ -595,6 +596,7 @@ extern "C" {
 int rag_index_load_cache(rag_index* idx, const char* cache_path, uint64_t first_row, uint64_t nrows, uint64_t* rows_loaded,
                          char** ids, uint64_t* ids_bytes) {
   if (!idx) return rag_set_error(RAG_ERR_INVALID, "null index handle");
+  RAG_LOCK(idx);
   cache_reader r;
   RAG_CHECK(r.open(cache_path, true));
   if (r.h.dtype != idx->desc.dtype || r.h.dim != idx->dim)
@@ -747,6 +749,7 @@ int rag_cache_refresh_host(const char* cache_path, const char* source_json, uint
 int rag_index_open_store(rag_index* idx, const char* vector_store_json, const char* cache_path, uint64_t* rows_loaded,
                          char** ids, uint64_t* ids_bytes, int* from_cache) {
   if (!idx || !vector_store_json) return rag_set_error(RAG_ERR_INVALID, "rag_index_open_store: null argument");
+  RAG_LOCK(idx);
   if (idx->rows != 0) return rag_set_error(RAG_ERR_STATE, "rag_index_open_store needs an empty index (rows=%llu)", (unsigned long long)idx->rows);
   const std::string cp = cache_path ? std::string(cache_path) : std::string(vector_store_json) + ".ragera";
   if (from_cache) *from_cache = 0;

@@ -292,8 +292,8 @@ int main(int argc, char** argv) {
     return object(env, {{"vectorTopK", num(env, k)}, {"keywordLimit", num(env, in.kw_limit)}, {"minVectorScore", num(env, in.min_score)},
                         {"rrf", object(env, {{"k", num(env, 60)}, {"vectorWeight", num(env, 1)}, {"keywordWeight", num(env, 1)}, {"bothBonus", num(env, 0.1)}})}});
   };
-  // every request is its own batch-1 hybridSearch Promise, all in flight at once ... on ONE handle they must not overlap
-  // (ragera.h: one thread per handle), so the loop is drained after each call — as `await` does in hybridSearchNative
+  // every request is its own batch-1 hybridSearch Promise; here the loop is drained after each call — as `await` does in
+  // hybridSearchNative (the concurrent case follows below)
   std::vector<napi_value> promises;
   for (uint32_t b = 0; b < in.B; b++) {
     napi_value p = call(env, exports, "hybridSearch", {h, typed_array(env, napi_float32_array, in.queries.data() + (size_t)b * in.dim, in.dim), num(env, 1), opts(in.k),
@@ -303,6 +303,19 @@ int main(int argc, char** argv) {
     run_event_loop(env);
     promises.push_back(p);
   }
+  // CONCURRENT requests on ONE handle (what a Next.js server does: parallel HTTP requests, the Promise.all of
+  // engine.ts:108): all B hybridSearch calls and B retriever calls are queued before the loop is drained, so their
+  // execute callbacks run on B+B worker threads at once; a synchronous mutator lands in the middle. libragera serialises
+  // them per handle (ragera.h), so every result must equal the one-at-a-time result.
+  std::vector<napi_value> inflight, inflight_topk;
+  for (uint32_t b = 0; b < in.B; b++) {
+    inflight.push_back(call(env, exports, "hybridSearch", {h, typed_array(env, napi_float32_array, in.queries.data() + (size_t)b * in.dim, in.dim), num(env, 1), opts(in.k),
+                                                           typed_array(env, napi_biguint64_array, in.kw_keys.data() + (size_t)b * in.kw_limit, in.kw_limit),
+                                                           typed_array(env, napi_uint32_array, in.kw_counts.data() + b, 1)}));
+    inflight_topk.push_back(call(env, exports, "search", {h, typed_array(env, napi_float32_array, in.queries.data() + (size_t)b * in.dim, in.dim), num(env, 1), num(env, in.k)}));
+    if (b == in.B / 2) call(env, exports, "setRowKeys", {h, num(env, 0), typed_array(env, napi_biguint64_array, in.row_keys.data(), in.n)});  // same keys again
+  }
+  run_event_loop(env);
   // the whole batch in ONE call (B queries)
   napi_value pb = call(env, exports, "hybridSearch", {h, typed_array(env, napi_float32_array, in.queries.data(), in.queries.size()), num(env, in.B), opts(in.k),
                                                       typed_array(env, napi_biguint64_array, in.kw_keys.data(), in.kw_keys.size()),
@@ -338,6 +351,11 @@ int main(int argc, char** argv) {
   for (uint32_t b = 0; b < in.B; b++) {
     if (promises[b]->state != 1) { fprintf(stderr, "promise %u not fulfilled: %s\n", b, promises[b]->settled ? promises[b]->settled->str.c_str() : "pending"); return 4; }
     print_result(promises[b]->settled, b + 1 == in.B);
+  }
+  printf("], \"in_flight\": [\n");
+  for (uint32_t b = 0; b < in.B; b++) {
+    if (inflight[b]->state != 1 || inflight_topk[b]->state != 1) { fprintf(stderr, "concurrent promise %u not fulfilled\n", b); return 4; }
+    print_result(inflight[b]->settled, b + 1 == in.B);
   }
   printf("], \"batched\": [\n");
   for (uint32_t b = 0; b < in.B; b++) {

@@ -88,6 +88,7 @@ def test_addon_results_equal_the_oracle(native, oracle, tmp_path):
         assert g["source"] == [int(s) for s in e["source"]] and g["contentType"] == [int(c) for c in e["ctype"]]
         # the micro-batcher (concurrent submits from worker threads) and the one-call batch give the same answers
         assert out["batched"][b] == g
+        assert out["in_flight"][b] == g          # 2B calls in flight at once on one handle: serialised by the library
         assert out["one_call"][b]["keys"] == g["keys"] and out["one_call"][b]["scores"] == g["scores"]
         # the retriever seam (NativeVectorStore.query) and MemoryStore.retrieve's device half (similarityTopK = limit = k)
         t = out["search"][b]
