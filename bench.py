@@ -57,6 +57,10 @@ WORKLOADS = {
     "c2bb": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                  path="tensor", shadow="bf16",
                  desc="C2 batched with a BF16 shadow: 1M x 1536 fp32 (+bf16 shadow), batch 1024, tcgen05 path (wider candidate window: bf16's rounding bound)"),
+    "c2br": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+                 path="tensor", shadow="f16", replicas=True,
+                 desc="C2 batched, REPLICAS mode: the whole 1M x 1536 fp32 corpus (+fp16 shadow) on every GPU, the 1024-query batch split over "
+                      "the ranks, no exchange — the alternative to row shards for corpora that do not fill the box (SURVEY §8e)"),
     "c4f": dict(rows=7_000_000, dim=1536, dtype="f32", batch=256, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                 path="tensor", shadow=None, memory_rows=2_000_000, fresh_limit=10,
                 desc="C4 memory+RAG unified, fp32 operand: 2M memory + 5M doc rows x 1536 fp32 scored as tf32 (no shadow), vector+keyword+freshness lists fused by RRF, batch 256, tcgen05 kind::tf32"),
@@ -261,6 +265,13 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     from rag_era_b200.sharded import create_sharded_index, leave_exchange, shard_range
 
     rows, d, B = w["rows"], w["dim"], w["batch"]
+    # REPLICAS mode (SURVEY §8e's alternative for corpora that do not fill the box): every rank holds the WHOLE corpus and
+    # answers its own 1/N of the batch; no exchange at all. Below, such a rank behaves like a single-GPU run of B/N queries,
+    # only the clock (barriers, max over ranks) and the final sum are shared.
+    replicas = world if (w.get("replicas") and world > 1) else 1
+    if replicas > 1:
+        B = max(1, B // replicas)
+    sharded = world > 1 and replicas == 1
     dt = N.F32 if w["dtype"] == "f32" else N.BF16
     now_ms = 1_760_000_000_000
     gen = N.GenDesc(SEEDS["seed"], SEEDS["query_seed"], SEEDS["meta_seed"], rows, 4096, 0.6, 0.5, 0,
@@ -268,23 +279,57 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     tensor = w.get("path") == "tensor"
     path = N.PATH_TENSOR if tensor else N.PATH_STREAM
     shadow = w.get("shadow") if dt == N.F32 else None
-    if world > 1:
+    shard_rows = None
+    if sharded:
         idx = create_sharded_index(dist, rows, d, dt, device, shadow=shadow, max_batch=max(B, 32), max_k=w["vector_top_k"])
         base, n_local = shard_range(rows, world, rank)
     else:
         idx = rb.VectorIndex(d, rows, dtype=dt, device=device, shadow=shadow)
         base, n_local = 0, rows
     idx.generate(gen, n_local)
+    if sharded and tensor and os.environ.get("RAGERA_BENCH_BALANCE", "1") != "0":
+        # The batch ends with the SLOWEST shard, and the GPUs of one box differ by several percent under the power cap
+        # (round 1: up to 15% at N=8). Calibrate: a few batches on the even split, every rank's own scoring-kernel time,
+        # then contiguous shards sized by measured speed (boundaries and id_base move, nothing else). Untimed setup.
+        from rag_era_b200.sharded import balanced_ranges
+
+        Qc = idx.generate_queries(gen, 0, B)
+        oc = rb.hybrid_opts(w["vector_top_k"], 0, w["min_score"], path=path)
+        idx.stage_batch(Qc, [[] for _ in range(B)], 0)
+        for _ in range(2):
+            idx.hybrid_staged(B, oc)
+        idx.sync()
+        dist.barrier()
+        idx.profile_enable(True)
+        idx.profile_read()
+        for _ in range(4):
+            idx.hybrid_staged(B, oc)
+        idx.sync()
+        k_ms = idx.profile_read()["tensor"][0] / 4
+        idx.profile_enable(False)
+        per = [None] * world
+        dist.all_gather_object(per, (n_local, k_ms))
+        ranges = balanced_ranges(rows, [p[0] for p in per], [p[1] for p in per])
+        leave_exchange(dist, idx)
+        idx.close()
+        base, n_local = ranges[rank]
+        idx = create_sharded_index(dist, rows, d, dt, device, shadow=shadow, max_batch=max(B, 32), max_k=w["vector_top_k"], rows=ranges[rank])
+        idx.generate(gen, n_local)
+        shard_rows = {"rows": [r[1] for r in ranges], "calibration_kernel_ms": [round(p[1], 3) for p in per],
+                      "note": "contiguous shards sized by measured per-rank scoring speed (untimed calibration on the even split)"}
     total = steps + warmup
     n_pool = min(total, 8) if B >= 64 else total       # big batches cycle through a pool of distinct batches
-    Q = idx.generate_queries(gen, 0, n_pool * B)
+    Q = idx.generate_queries(gen, (rank * n_pool * B) if replicas > 1 else 0, n_pool * B)   # replicas: each rank its own queries
     o = rb.hybrid_opts(w["vector_top_k"], w["keyword_limit"], w["min_score"], path=path, slack=int(os.environ.get("RAGERA_BENCH_SLACK", "0")),
                        fresh_limit=w.get("fresh_limit", 0), fresh_weight=1.0, now_ms=now_ms)
 
     # setup (untimed): true vector top-k of every query → keyword lists with ~30% overlap
-    top = idx.query(Q, w["vector_top_k"], path=path)
-    kw = keyword_lists(top.ids, rows, w["keyword_limit"], np.random.default_rng(KW_SEED))
-    certified_setup = int(top.certified.sum())
+    # (in chunks of one batch — at least 32 queries — so that a sharded index's mailboxes, sized for the batch, hold them)
+    chunk = max(B, 32)
+    tops = [idx.query(Q[lo:lo + chunk], w["vector_top_k"], path=path) for lo in range(0, len(Q), chunk)]
+    top_ids = np.vstack([t.ids for t in tops])
+    kw = keyword_lists(top_ids, rows, w["keyword_limit"], np.random.default_rng(KW_SEED))
+    certified_setup = int(sum(int(t.certified.sum()) for t in tops))
     first_pass = None
     if tensor:
         # first-pass certification of ONE batch by the tensor path alone (no escalation), under both bounds:
@@ -414,8 +459,8 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
             roof["traffic"] = int(tr * bytes_per_launch)
             roof["traffic_source"] = "profiles/traffic.json (ncu --set full dram bytes / algorithmic, scaled to this launch)"
     res = {
-        "value": steps * B / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches), "clocks": clocks,
-        "e2e": {"value": steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        "value": steps * B * replicas / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": {"value": steps * B * replicas / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "latency_ms_p50": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
                 "timing": "host wall clock around the synchronous call (pinned host buffers; escalations included)",
                 "uncertified_after_escalation": uncert},
@@ -429,13 +474,15 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     }
     if first_pass:
         res["first_pass_certification"] = first_pass
+    if shard_rows:
+        res["shard_rows"] = shard_rows
     if world > 1:
         # every rank's own kernel times: the step ends when the SLOWEST rank's scoring kernel does (K5 waits for
         # every rank's records), so the spread between ranks is what the exchange wait in "fuse" is made of
         per_rank = [None] * world
         dist.all_gather_object(per_rank, {k: round(v, 4) for k, v in res["kernel_ms_per_step"].items()})
         res["per_rank_kernel_ms"] = per_rank
-        res["exchange"] = {"p2p": "peer-to-peer mailboxes (CUDA IPC over NVLink), written and awaited inside the fusion kernel; "
+        res["exchange"] = "none: replicas (the whole corpus on every GPU, the batch split over the ranks)" if replicas > 1 else {"p2p": "peer-to-peer mailboxes (CUDA IPC over NVLink), written and awaited inside the fusion kernel; "
                                   "host-driven bootstrap, no NCCL call in the library",
                            "nccl": "ncclAllGather of the local top-k records before the fusion kernel"}[getattr(idx, "exchange", "p2p")]
     if do_cpu and rank == 0:
@@ -446,7 +493,7 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         qps, per_query, sample, info = cpu_reference_leg(w, n_q, 0, 1, sample_rows)   # queries/s (batching does not help a scalar loop)
         res["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                "ms_per_query": per_query * 1e3, "extrapolated": info}
-    if world > 1:
+    if sharded:
         leave_exchange(dist, idx)
     idx.close()
     return res
@@ -485,7 +532,7 @@ def run_ours(args):
     if not args.no_extra:
         # the other BASELINE.json configs in the same line: configs[1] (c2, c2b), configs[0] (c1) and configs[3] (c4) on
         # one GPU; configs[4] (c5, 50M x 1536 bf16 batch 1024, row-sharded) at EVERY N so the scaling run carries its curve
-        plan = [("c2", 200, 5), ("c2b", 30, 5), ("c1", 500, 5), ("c4", 20, 3)] if world == 1 else []
+        plan = [("c2", 200, 5), ("c2b", 30, 5), ("c1", 500, 5), ("c4", 20, 3)] if world == 1 else [("c2b", 30, 5), ("c2br", 30, 5)]
         plan.append(("c5", 10, 3))
         for name, e_steps, e_warm in plan:
             if name == args.workload:

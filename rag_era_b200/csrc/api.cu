@@ -75,6 +75,7 @@ void free_batch(rag_batch* b) {
   cudaFree(b->d_k4s); cudaFree(b->d_ticket);
   if (b->h_in) cudaFreeHost(b->h_in);
   if (b->h_out) cudaFreeHost(b->h_out);
+  if (b->h_q) cudaFreeHost(b->h_q);
   *b = rag_batch();
 }
 
@@ -355,6 +356,139 @@ int escalate(rag_index* idx, std::vector<uint32_t> sel, uint32_t k, plan p, cons
   return rc;
 }
 
+// ---- small-batch latency path as ONE graph launch ---------------------------------------------------------------
+// A batch-1 search over a small corpus (the reference's production size: C1, 10k chunks) is launch-bound: two H2D copies,
+// K1, the fused K3+K4+K5 kernel and the D2H are five API calls and four stream dependencies. The sequence is captured
+// once per call shape and replayed with a single cudaGraphLaunch: the inputs are first copied into pinned buffers with
+// fixed addresses (the caller's pointers change from call to call), every kernel argument is part of the cache key.
+struct graph_key {
+  uint32_t B = 0, k = 0, kp = 0, parts = 0, kw_stride = 0, out_cap = 0, fresh_limit = 0;
+  int path = 0, mode = 0, key_has_qnorm = 0;
+  double eps = 0, min_score = 0, rrf_k = 0, rrf_vw = 0, rrf_kw = 0, rrf_bonus = 0, fresh_weight = 0, mem_min = 0;
+  uint32_t mem_limit = 0;
+  uint64_t rows = 0;
+  const void* ptr[10] = {nullptr};
+  size_t d2h = 0;
+  bool same(const graph_key& o) const {
+    if (B != o.B || k != o.k || kp != o.kp || parts != o.parts || kw_stride != o.kw_stride || out_cap != o.out_cap ||
+        fresh_limit != o.fresh_limit || path != o.path || mode != o.mode || key_has_qnorm != o.key_has_qnorm || eps != o.eps ||
+        min_score != o.min_score || rrf_k != o.rrf_k || rrf_vw != o.rrf_vw || rrf_kw != o.rrf_kw || rrf_bonus != o.rrf_bonus ||
+        fresh_weight != o.fresh_weight || mem_min != o.mem_min || mem_limit != o.mem_limit || rows != o.rows || d2h != o.d2h)
+      return false;
+    for (int i = 0; i < 10; i++)
+      if (ptr[i] != o.ptr[i]) return false;
+    return true;
+  }
+};
+}  // namespace
+struct rag_graph {
+  cudaGraphExec_t exec = nullptr;
+  graph_key key;
+  uint64_t launches = 0;     // kernel launches one replay stands for
+  uint32_t recaptures = 0;   // consecutive misses: a caller that changes shape on every call gets the plain path
+  bool disabled = false;
+};
+namespace {
+bool graphs_enabled() {
+  static const bool on = !(getenv("RAGERA_GRAPH") && atoi(getenv("RAGERA_GRAPH")) == 0);
+  return on;
+}
+
+// Is this call the latency shape? one GPU, batch <= 32 on the stream path with the fused tail, no per-kernel profiling,
+// and nothing in the pipeline that reads the wall clock of the call (freshness needs now_ms, which changes every call).
+bool graph_shape_ok(const rag_index* idx, uint32_t B, const plan& p, const rag_fuse_args& fa) {
+  return graphs_enabled() && idx->nranks == 1 && !idx->prof_on && B <= 32 && p.path == RAG_PATH_STREAM && !p.eps_per_query &&
+         (fa.mode == 2 || (fa.mode == 0 && fa.fresh_limit == 0)) && !(idx->graph && idx->graph->disabled);
+}
+
+// Runs stage→pipeline→fetch for idx->main as one graph launch. queries/kw are the caller's host arrays.
+int run_graphed(rag_index* idx, const float* queries, uint32_t B, uint32_t k, const plan& p, const fresh_cfg& fc, rag_fuse_args fa,
+                const uint64_t* kw_keys, const uint32_t* kw_counts, uint32_t kw_stride, uint32_t out_cap, out_layout* L, bool* ran) {
+  *ran = false;
+  rag_batch* bt = &idx->main;
+  idx->cur = bt;
+  // 1. every allocation up front (none may happen inside a capture), inputs into pinned memory at fixed addresses
+  RAG_CHECK(ensure_queries(idx, bt, B));
+  if (fa.mode == 0) RAG_CHECK(ensure_inputs(idx, bt, B, kw_stride));
+  RAG_CHECK(ensure_work(idx, bt, B, k, out_cap, L));
+  uint32_t parts = 0;
+  RAG_CHECK(k1_plan(idx, B, p.kp, &parts));
+  RAG_CHECK(grow_dev(&bt->d_partial, &bt->c_partial, (size_t)B * parts * p.kp * 8, false));
+  if (!k34_small_ok(idx, B, p.kp, parts)) return RAG_OK;  // not the fused tail: plain path
+  const size_t qbytes = (size_t)B * idx->dim * 4;
+  if (qbytes > bt->c_hq || !bt->h_q) {
+    if (bt->h_q) RAG_CUDA(cudaFreeHost(bt->h_q));
+    bt->h_q = nullptr;
+    bt->c_hq = 0;
+    RAG_CUDA(cudaHostAlloc((void**)&bt->h_q, std::max<size_t>(qbytes, 32 * 8192 * 4 / 8), cudaHostAllocDefault));
+    bt->c_hq = std::max<size_t>(qbytes, 32 * 8192 * 4 / 8);
+  }
+  memcpy(bt->h_q, queries, qbytes);
+  const size_t kwb = ((size_t)B * kw_stride * 8 + 15) & ~(size_t)15;
+  if (fa.mode == 0) {
+    uint32_t* hc = (uint32_t*)(bt->h_in + kwb);
+    if (kw_stride && kw_keys) memcpy(bt->h_in, kw_keys, (size_t)B * kw_stride * 8);
+    for (uint32_t b = 0; b < B; b++) {
+      const uint32_t c = (kw_counts && kw_keys) ? kw_counts[b] : 0u;
+      if (c > kw_stride) return rag_set_error(RAG_ERR_INVALID, "kw_counts[%u]=%u exceeds keyword_limit=%u", b, c, kw_stride);
+      hc[b] = c;
+    }
+    bt->staged_kw_stride = kw_stride;
+  }
+  // 2. the key: everything a captured node bakes in
+  graph_key key;
+  key.B = B; key.k = k; key.kp = p.kp; key.parts = parts; key.kw_stride = fa.mode == 0 ? kw_stride : 0; key.out_cap = out_cap;
+  key.fresh_limit = fa.fresh_limit; key.path = p.path; key.mode = fa.mode; key.key_has_qnorm = p.key_has_qnorm; key.eps = p.eps;
+  key.min_score = fa.min_score; key.rrf_k = fa.rrf.k; key.rrf_vw = fa.rrf.vector_weight; key.rrf_kw = fa.rrf.keyword_weight;
+  key.rrf_bonus = fa.rrf.both_bonus; key.fresh_weight = fa.fresh_weight; key.mem_min = fa.mem_min_relevance; key.mem_limit = fa.mem_limit;
+  key.rows = idx->rows;
+  const void* ptrs[10] = {bt->d_q, bt->d_in, bt->d_out, bt->h_q, bt->h_in, bt->h_out, bt->d_partial, bt->d_cand, bt->d_local, idx->row_keys};
+  for (int i = 0; i < 10; i++) key.ptr[i] = ptrs[i];
+  key.d2h = L->total_no_aux;
+  if (!idx->graph) idx->graph = new (std::nothrow) rag_graph();
+  rag_graph* g = idx->graph;
+  if (!g) return RAG_OK;
+  if (!g->exec || !g->key.same(key)) {
+    if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+    if (++g->recaptures > 8) { g->disabled = true; return RAG_OK; }  // shape changes on every call: capturing costs more than it saves
+    const uint64_t l0 = idx->launches;
+    RAG_CUDA(cudaStreamBeginCapture(idx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = RAG_OK;
+    cudaError_t e = cudaSuccess;
+    if (idx->ld == idx->dim) e = cudaMemcpyAsync(bt->d_q, bt->h_q, qbytes, cudaMemcpyHostToDevice, idx->stream);
+    else e = cudaMemcpy2DAsync(bt->d_q, (size_t)idx->ld * 4, bt->h_q, (size_t)idx->dim * 4, (size_t)idx->dim * 4, B, cudaMemcpyHostToDevice, idx->stream);
+    if (e == cudaSuccess && fa.mode == 0) e = cudaMemcpyAsync(bt->d_in, bt->h_in, kwb + (size_t)B * 4, cudaMemcpyHostToDevice, idx->stream);
+    if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "graph capture (H2D): %s", cudaGetErrorString(e));
+    if (rc == RAG_OK) rc = run_pipeline(idx, B, k, p, fc, fa);
+    if (rc == RAG_OK) {
+      e = cudaMemcpyAsync(bt->h_out, bt->d_out, L->total_no_aux, cudaMemcpyDeviceToHost, idx->stream);
+      if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "graph capture (D2H): %s", cudaGetErrorString(e));
+    }
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(idx->stream, &graph);
+    if (rc == RAG_OK && e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    if (rc == RAG_OK) {
+      e = cudaGraphInstantiate(&g->exec, graph, 0);
+      if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != RAG_OK) { g->exec = nullptr; cudaGetLastError(); return rc; }
+    g->key = key;
+    g->launches = idx->launches - l0;
+    idx->launches = l0;
+  } else {
+    g->recaptures = 0;
+  }
+  bt->staged_B = B;
+  bt->win_first = 0;
+  bt->win_count = B;
+  RAG_CUDA(cudaGraphLaunch(g->exec, idx->stream));
+  idx->launches += g->launches;
+  RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  *ran = true;
+  return RAG_OK;
+}
+
 int check_handle(const rag_index* idx) {
   if (!idx) return rag_set_error(RAG_ERR_INVALID, "null index handle");
   return RAG_OK;
@@ -500,6 +634,10 @@ void rag_index_destroy(rag_index* idx) {
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   rag_comm_destroy(idx);
   k2_destroy(idx);
+  if (idx->graph) {
+    if (idx->graph->exec) cudaGraphExecDestroy(idx->graph->exec);
+    delete idx->graph;
+  }
   free_batch(&idx->main);
   free_batch(&idx->esc);
   if (idx->shadow && (void*)idx->shadow != idx->corpus) cudaFree(idx->shadow);
@@ -676,14 +814,18 @@ int rag_search(rag_index* idx, const float* queries, uint32_t B, const rag_searc
   rag_batch* bt = &idx->main;
   idx->cur = bt;
   out_layout L;
-  RAG_CHECK(stage_queries(idx, bt, queries, B));
-  RAG_CHECK(ensure_work(idx, bt, B, k, k, &L));
   rag_fuse_args fa = {};
   fa.mode = 2;
   fa.out_cap = k;
   const fresh_cfg fc = {0, 0.05, 0.1};
-  RAG_CHECK(run_pipeline(idx, B, k, p, fc, fa));
-  RAG_CHECK(fetch_out(idx, bt, L, false));
+  bool graphed = false;
+  if (graph_shape_ok(idx, B, p, fa)) RAG_CHECK(run_graphed(idx, queries, B, k, p, fc, fa, nullptr, nullptr, 0, k, &L, &graphed));
+  if (!graphed) {
+    RAG_CHECK(stage_queries(idx, bt, queries, B));
+    RAG_CHECK(ensure_work(idx, bt, B, k, k, &L));
+    RAG_CHECK(run_pipeline(idx, B, k, p, fc, fa));
+    RAG_CHECK(fetch_out(idx, bt, L, false));
+  }
 
   writer_fn write = [&](uint32_t ub, const rag_batch* src, const out_layout& SL, uint32_t lb) {
     const uint32_t cnt = ((const uint32_t*)(src->h_out + SL.cnt))[lb];
@@ -787,14 +929,19 @@ int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const ra
   rag_batch* bt = &idx->main;
   idx->cur = bt;
   out_layout L;
-  RAG_CHECK(stage_queries(idx, bt, queries, B));
-  RAG_CHECK(stage_keywords(idx, bt, B, kw_keys, kw_counts, o->keyword_limit));
-  bt->staged_B = B;
-  bt->win_first = 0;
-  bt->win_count = B;
-  RAG_CHECK(ensure_work(idx, bt, B, k, out_cap, &L));
-  RAG_CHECK(run_pipeline(idx, B, k, p, fc, fa));
-  RAG_CHECK(fetch_out(idx, bt, L, false));
+  bool graphed = false;
+  if (graph_shape_ok(idx, B, p, fa))   // the latency shape: one graph launch for H2D + K1 + K3/K4/K5 + D2H
+    RAG_CHECK(run_graphed(idx, queries, B, k, p, fc, fa, kw_keys, kw_counts, o->keyword_limit, out_cap, &L, &graphed));
+  if (!graphed) {
+    RAG_CHECK(stage_queries(idx, bt, queries, B));
+    RAG_CHECK(stage_keywords(idx, bt, B, kw_keys, kw_counts, o->keyword_limit));
+    bt->staged_B = B;
+    bt->win_first = 0;
+    bt->win_count = B;
+    RAG_CHECK(ensure_work(idx, bt, B, k, out_cap, &L));
+    RAG_CHECK(run_pipeline(idx, B, k, p, fc, fa));
+    RAG_CHECK(fetch_out(idx, bt, L, false));
+  }
   writer_fn write = [&](uint32_t ub, const rag_batch* src, const out_layout& SL, uint32_t lb) {
     write_fused(o, out, out_cap, ub, src, SL, lb);
   };

@@ -133,6 +133,7 @@ struct rag_batch {
   // fused outputs: one device block + pinned host mirror, carved per call (out_layout in api.cu)
   uint8_t* d_out = nullptr;         size_t c_out = 0;
   uint8_t* h_out = nullptr;         size_t c_hout = 0;
+  float* h_q = nullptr;             size_t c_hq = 0;       // pinned copy of the caller's queries (graph replay needs a fixed source)
   uint64_t* d_out_keys = nullptr;   double* d_out_scores = nullptr;
   uint8_t* d_out_src = nullptr;     uint8_t* d_out_ct = nullptr;
   uint32_t* d_out_cnt = nullptr;    uint8_t* d_out_rrf = nullptr;
@@ -190,6 +191,8 @@ struct rag_index {
 
   // tensor path (K2) state of the CTA-pair kernel
   void* k2p_state = nullptr;
+  // small-batch latency path: the whole call (H2D, K1, K3+K4+K5, D2H) captured once as a CUDA graph and replayed
+  struct rag_graph* graph = nullptr;
 };
 
 // error plumbing (api.cu)

@@ -24,6 +24,26 @@ def shard_range(total_rows: int, world_size: int, rank: int) -> tuple[int, int]:
     return base, max(0, min(per, total_rows - base))
 
 
+def balanced_ranges(total_rows: int, rows_per_rank: list[int], ms_per_rank: list[float], align: int = 256) -> list[tuple[int, int]]:
+    """Contiguous row shards sized by MEASURED speed: rank i scanned rows_per_rank[i] rows in ms_per_rank[i]; the new
+    shard sizes are proportional to rows/ms (the batch ends with the slowest shard, so equal TIMES, not equal rows, is
+    what minimises it — GPUs of one box differ by several percent under the power cap). Shards stay contiguous, only
+    the boundaries (and with them each rank's id_base) move; sizes are multiples of `align` rows except the last."""
+    world = len(rows_per_rank)
+    speed = [max(r, 1) / max(t, 1e-9) for r, t in zip(rows_per_rank, ms_per_rank)]
+    tot = sum(speed)
+    out, base = [], 0
+    for i in range(world):
+        if i == world - 1:
+            n = total_rows - base
+        else:
+            n = int(round(total_rows * speed[i] / tot / align)) * align
+            n = max(0, min(n, total_rows - base))
+        out.append((base, n))
+        base += n
+    return out
+
+
 def broadcast_unique_id(dist, rank: int, device=None) -> bytes:
     """Rank 0 creates the NCCL unique id; ``dist.broadcast`` hands it to the other ranks."""
     import torch

@@ -214,3 +214,20 @@ def test_tensor_candidate_ties_go_to_the_lower_row(rb, native, oracle, distinct,
     for b in range(0, B, 7):
         e = _expected_candidates(S[b], kp)
         assert np.array_equal(rows[b], e), (b, rows[b], e)
+
+
+def test_shared_operand_cluster_variant(native):
+    """The experimental K2 variant that runs two CTA pairs per cluster and TMA-multicasts the operand they share
+    (RAGERA_K2_CLUSTER=1; measured slower than plain pairs on B200 because a 4-CTA cluster strands SMs — DESIGN.md §4 — so
+    it is off by default): kept verified here by re-running the selection tests of this file with the switch on."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("RAGERA_K2_CLUSTER"):
+        pytest.skip("already inside the variant run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_tensor.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "topk_matches_oracle or hybrid_batch or ties_go_to or tf32_path or f16_shadow"],
+                       env=dict(os.environ, RAGERA_K2_CLUSTER="1"), capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

@@ -64,6 +64,27 @@ def test_shard_ranges_partition_rows():
                 pos += n
 
 
+def test_balanced_ranges_are_contiguous_and_follow_measured_speed():
+    from rag_era_b200.sharded import balanced_ranges
+
+    total = 50_000_000
+    ms = [15.1, 17.4, 16.0, 15.5, 16.2, 15.9, 16.8, 15.3]
+    spans = balanced_ranges(total, [total // 8] * 8, ms)
+    pos = 0
+    for base, n in spans:
+        assert base == pos and n > 0
+        pos += n
+    assert pos == total and all(n % 256 == 0 for _, n in spans[:-1])
+    # predicted time per shard (rows / measured speed) is equal to within one alignment step
+    speed = [total / 8 / t for t in ms]
+    pred = [n / s for (_, n), s in zip(spans, speed)]
+    assert max(pred) / min(pred) < 1.001
+    assert spans[1][1] < spans[0][1]                       # the slowest GPU gets the fewest rows
+    for w in (1, 2, 3):                                    # degenerate inputs still partition the corpus
+        s2 = balanced_ranges(1000, [1000 // w] * w, [1.0] * w)
+        assert sum(n for _, n in s2) == 1000
+
+
 def test_merge_reference_order_ties_by_id():
     ids, sc = merge_reference_order([[5, 9], [2, 7]], [[0.9, 0.5], [0.9, 0.5]], 3)
     assert ids.tolist() == [2, 5, 7] and sc.tolist() == [0.9, 0.9, 0.5]
