@@ -489,6 +489,11 @@ int run_graphed(rag_index* idx, const float* queries, uint32_t B, uint32_t k, co
   return RAG_OK;
 }
 
+bool small_prof_on() {
+  static const bool on = getenv("RAGERA_SMALL_PROF") && atoi(getenv("RAGERA_SMALL_PROF")) != 0;
+  return on;
+}
+
 int check_handle(const rag_index* idx) {
   if (!idx) return rag_set_error(RAG_ERR_INVALID, "null index handle");
   return RAG_OK;
@@ -580,6 +585,7 @@ int rag_index_create(const rag_index_desc* d, rag_index** out) {
   idx->dim = d->dim;
   idx->ld = (d->dim + 255u) & ~255u;
   idx->cur = &idx->main;
+  if (small_prof_on()) { k1_small_prof(1, nullptr); k34_small_prof(1, nullptr); }
   int rc = RAG_OK;
   do {
     cudaError_t e;
@@ -631,6 +637,7 @@ void rag_index_destroy(rag_index* idx) {
   if (!idx) return;
   { RAG_LOCK(idx); }  // a call still in flight on another thread finishes first (calls after destroy are the caller's bug)
   cudaSetDevice(idx->device);
+  if (small_prof_on()) { k1_small_prof(-1, stderr); k34_small_prof(-1, stderr); }
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   rag_comm_destroy(idx);
   k2_destroy(idx);

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <mutex>
 
@@ -236,6 +237,9 @@ int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
 int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 void k2_destroy(rag_index* idx);
 void k2_set_debug(rag_index* idx, float* d_scores);  // diagnostics: dump the scaled score matrix of the next launch
+// diagnostics of the batch-1 latency path (RAGERA_SMALL_PROF=1): enable >= 0 sets / resets, dump != null prints averages
+void k1_small_prof(int enable, FILE* dump);
+void k34_small_prof(int enable, FILE* dump);
 // K3 — merge partial lists → K' candidates per query (k3_merge.cu)
 int k3_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // K4 — exact fp64 rescoring in reference order + local top-k + certification (k4_rescore.cu)

@@ -20,10 +20,16 @@
 // fp32 accumulation decides only WHICH K' rows survive; K4 rescored them exactly.
 #include "common.cuh"
 
+#include <stdio.h>
+
 namespace {
 
 constexpr int K1_THREADS = 512;
 constexpr int K1_WARPS = K1_THREADS / 32;
+
+// diagnostics (RAGERA_SMALL_PROF=1): cycles per phase of the single-query kernel, summed over CTAs
+__device__ int g_k1_prof_on;
+__device__ unsigned long long g_k1_prof[4];  // query staging, row loop (until the CTA's last warp is done), CTA merge, CTAs
 
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
@@ -63,11 +69,14 @@ k1_stream_f32(const float* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsu
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t b = blockIdx.y;
+  const bool prof = g_k1_prof_on != 0;
+  const long long pt0 = prof ? clock64() : 0;
   const float4* q4 = reinterpret_cast<const float4*>(Q + (size_t)b * ld);
   for (uint32_t i = threadIdx.x; i < ld / 4; i += K1_THREADS) qs[i] = q4[i];
   uint64_t* mylist = lists + (size_t)warp * kp;
   for (uint32_t i = lane; i < kp; i += 32) mylist[i] = 0ull;
   __syncthreads();
+  const long long pt1 = prof ? clock64() : 0;
 
   uint64_t thresh = 0ull;
   const uint32_t stride = gridDim.x * K1_WARPS;
@@ -92,8 +101,15 @@ k1_stream_f32(const float* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsu
     if (key > thresh) warp_list_insert(mylist, kp, key, lane, thresh);
   }
   __syncthreads();
+  const long long pt2 = prof ? clock64() : 0;
   if (warp == 0)
     warp_merge_lists(lists, K1_WARPS, kp, kp, partial + ((size_t)b * parts + blockIdx.x) * kp, lane);
+  if (prof && threadIdx.x == 0) {
+    atomicAdd(&g_k1_prof[0], (unsigned long long)(pt1 - pt0));
+    atomicAdd(&g_k1_prof[1], (unsigned long long)(pt2 - pt1));
+    atomicAdd(&g_k1_prof[2], (unsigned long long)(clock64() - pt2));
+    atomicAdd(&g_k1_prof[3], 1ull);
+  }
 }
 
 // ---- bf16 corpus: U 16-byte loads (8 elements) per lane per sub-chunk, 2 rows in flight ----
@@ -351,6 +367,22 @@ int pick_unroll(uint32_t per_lane, const int* opts, int nopts) {
 }
 
 }  // namespace
+
+void k1_small_prof(int enable, FILE* dump) {
+  if (enable >= 0) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_k1_prof_on, &enable, sizeof(int));
+    cudaMemcpyToSymbol(g_k1_prof, z, sizeof(z));
+  }
+  if (dump) {
+    unsigned long long h[4];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_k1_prof, sizeof(h));
+    if (h[3])
+      fprintf(dump, "[k1_stream_f32 prof] avg cycles per CTA over %llu CTAs: query staging %.0f, row loop %.0f, CTA merge + store %.0f\n",
+              h[3], (double)h[0] / h[3], (double)h[1] / h[3], (double)h[2] / h[3]);
+  }
+}
 
 int k1_plan(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   (void)kp;

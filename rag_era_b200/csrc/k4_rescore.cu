@@ -23,6 +23,8 @@
 #include "exact_chain.cuh"
 #include "k5_body.cuh"
 
+#include <stdio.h>
+
 namespace {
 using namespace rag_exact;
 constexpr int K4_WARP_BYTES = WARP_BYTES;
@@ -151,6 +153,10 @@ k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restri
 // instead of one warp of one SM. Every CTA first merges the per-CTA candidate lists of K1/K2
 // itself (sorted lists, k-way merge from shared memory — this is K3, fused); the last CTA of a
 // query to finish (atomic ticket) ranks, certifies and writes the records.
+// diagnostics (RAGERA_SMALL_PROF=1): cycles per phase of the small-batch kernel as seen by the LAST CTA of a query
+__device__ int g_k34_prof_on;
+__device__ unsigned long long g_k34_prof[8];  // stage + K3 merge, exact chains, ticket, (last CTA) finalize, K5, count
+
 constexpr int K4S_CW = 4;                       // candidate warps per CTA
 constexpr int K4S_WARPS = K4S_CW + 1;           // + the ||q||^2 warp
 constexpr int K4S_THREADS = K4S_WARPS * 32;
@@ -243,6 +249,8 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t b = blockIdx.x, slice = blockIdx.y, nslices = gridDim.y;
+  const bool prof = g_k34_prof_on != 0;
+  const long long pt0 = prof ? clock64() : 0;
 
   // ---- K3: merge the sorted per-CTA lists of the scoring kernel (every slice does it: ~1 us) ----
   const uint64_t* in = partial + (size_t)b * parts * kp;
@@ -284,6 +292,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   }
   __syncthreads();
 
+  const long long pt1 = prof ? clock64() : 0;
   // ---- K4: exact sums, one warp per candidate -----------------------------------------------------
   double* my_scratch = scratch + (size_t)b * (2 * RAG_MAX_CANDIDATES + 2);
   const float* q = Q + (size_t)b * ld;
@@ -304,6 +313,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   // ---- the last slice of this query to arrive finishes it ------------------------------------------
   __threadfence();
   __syncthreads();
+  const long long pt2 = prof ? clock64() : 0;
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(&ticket[b], 1u);
     s_last = (t == nslices - 1) ? 1 : 0;
@@ -311,6 +321,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   }
   __syncthreads();
   if (!s_last) return;
+  const long long pt3 = prof ? clock64() : 0;
   __threadfence();
   const volatile double* vs = my_scratch;
   const double nq = vs[2 * RAG_MAX_CANDIDATES];
@@ -328,6 +339,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   //      Sharded (pv.nranks > 1): the same warp first exchanges this query's records with the peer ranks through
   //      the mailboxes; every query's last CTA is resident (the grid is B x K'/4 <= 32 x 32 CTAs), so a rank's
   //      wait for its peers cannot starve them. The product scratch is free by now and hosts K5's working set.
+  const long long pt4 = prof ? clock64() : 0;
   if (fuse_k5) {
     __threadfence();  // the records above are read back through L2
     __syncthreads();
@@ -337,9 +349,34 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
       rag_k5::k5_fuse_body(*reinterpret_cast<rag_k5::fuse_smem*>(&s_prod[0][0]), recs, io, b, lane);
     }
   }
+  if (prof && threadIdx.x == 0) {
+    atomicAdd(&g_k34_prof[0], (unsigned long long)(pt1 - pt0));
+    atomicAdd(&g_k34_prof[1], (unsigned long long)(pt2 - pt1));
+    atomicAdd(&g_k34_prof[2], (unsigned long long)(pt3 - pt2));
+    atomicAdd(&g_k34_prof[3], (unsigned long long)(pt4 - pt3));
+    atomicAdd(&g_k34_prof[4], (unsigned long long)(clock64() - pt4));
+    atomicAdd(&g_k34_prof[5], 1ull);
+  }
 }
 
 }  // namespace
+
+void k34_small_prof(int enable, FILE* dump) {
+  if (enable >= 0) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_k34_prof_on, &enable, sizeof(int));
+    cudaMemcpyToSymbol(g_k34_prof, z, sizeof(z));
+  }
+  if (dump) {
+    unsigned long long h[8];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_k34_prof, sizeof(h));
+    if (h[5])
+      fprintf(dump, "[k34_small prof] avg cycles in the LAST CTA of a query over %llu queries: stage + K3 merge %.0f, exact chains %.0f, "
+              "fence + ticket %.0f, rank + certify + records %.0f, K5 in place %.0f\n",
+              h[5], (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
+  }
+}
 
 int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, rag_eps eps, int key_has_qnorm,
               int64_t now_ms, double decay, double bonus) {

@@ -284,6 +284,7 @@ extern "C" {
 //   end_offset (out): the offset just after the last embedding's ']' (== resume_offset when nothing followed; 0 when
 //     embeddingDict is empty) — what a later resume needs.
 //   stamp (out, optional): size and mtime of the file taken from the descriptor that was parsed, before reading.
+//   on_rows == NULL: structural scan only — ids, row count and resume point at memchr speed, no number is converted.
 int rag_parse_vector_store_json_ex(const char* path, uint32_t dim, uint64_t slab_rows,
                                    int (*on_rows)(void* user, uint64_t first_row, uint64_t nrows, const float* rows),
                                    void* user, uint64_t resume_offset, uint64_t* rows_out, char** ids, uint64_t* ids_bytes,
@@ -307,6 +308,7 @@ int rag_parse_vector_store_json_ex(const char* path, uint32_t dim, uint64_t slab
   };
   auto flush = [&]() {  // convert the collected spans (in parallel) and hand the slab out
     if (spans.empty() || rc != RAG_OK) return;
+    if (!on_rows) { spans.clear(); return; }  // structural scan only (ids, row count, resume point): no number is converted
     if (slab.size() < spans.size() * (size_t)dim) slab.resize(spans.size() * (size_t)dim);
     int err = 0;
     uint32_t cnt = 0;
@@ -316,7 +318,7 @@ int rag_parse_vector_store_json_ex(const char* path, uint32_t dim, uint64_t slab
       if (err == 3) rc = rag_set_error(RAG_ERR_INVALID, "%s: embedding %llu has %u values, index dim is %u", path, (unsigned long long)row, cnt, dim);
       else rc = rag_set_error(RAG_ERR_INVALID, "%s: %s in embedding %llu near byte %llu", path, err == 1 ? "bad number" : "expected ',' in embedding",
                               (unsigned long long)row, (unsigned long long)(spans[bad].b - mf.data));
-    } else if (on_rows) {
+    } else {
       rc = on_rows(user, rows - spans.size(), spans.size(), slab.data());
     }
     spans.clear();

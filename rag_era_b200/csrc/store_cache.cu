@@ -39,6 +39,14 @@
 #include <string>
 #include <vector>
 
+// (loader.cu) the parser with a resume point and the stamp of the descriptor it read; the prefix hash
+extern "C" int rag_parse_vector_store_json_ex(const char* path, uint32_t dim, uint64_t slab_rows,
+                                              int (*on_rows)(void* user, uint64_t first_row, uint64_t nrows, const float* rows),
+                                              void* user, uint64_t resume_offset, uint64_t* rows_out, char** ids,
+                                              uint64_t* ids_bytes, uint64_t* end_offset, uint64_t* stamp_size,
+                                              int64_t* stamp_mtime_ns);
+extern "C" int rag_file_prefix_hash(const char* path, uint64_t nbytes, uint64_t* hash, int* ok);
+
 namespace {
 
 constexpr char kMagic[8] = {'R', 'A', 'G', 'E', 'R', 'A', 'C', '1'};
@@ -336,12 +344,21 @@ void fill_info(const rag_cache_header& h, rag_cache_info* out) {
   out->source_prefix_hash = h.src_prefix_hash;
 }
 
-// stamp from a path (public entry points that take `source_json`): only as good as the caller's promise that the
-// JSON has not changed since the rows were read from it
-bool stamp_of_path(const char* source_json, src_stamp* st, bool* have) {
+// stamp from a path (public entry points that take `source_json`): size + mtime as they are NOW — only as good as the
+// caller's promise that the JSON has not changed since the rows were read from it — and, when the JSON holds exactly
+// `rows` embeddings, the resume point behind the last one (a structural scan at memchr speed), so that a sidecar saved
+// by the host (with its Memory columns and fusion keys) can later be extended in place like one written by the loader
+bool stamp_of_path(const char* source_json, uint64_t rows, src_stamp* st, bool* have) {
   *have = false;
   if (!source_json) return true;
-  if (!stat_source(source_json, &st->size, &st->mtime_ns)) return false;
+  uint64_t n = 0, end = 0;
+  if (rag_parse_vector_store_json_ex(source_json, 1, 65536, nullptr, nullptr, 0, &n, nullptr, nullptr, &end, &st->size, &st->mtime_ns) != RAG_OK) {
+    if (!stat_source(source_json, &st->size, &st->mtime_ns)) return false;  // not a store we can scan: size + mtime only
+    *have = true;
+    return true;
+  }
+  int ok = 0;
+  if (n == rows && end > 0 && rag_file_prefix_hash(source_json, end, &st->prefix_hash, &ok) == RAG_OK && ok) st->prefix_bytes = end;
   *have = true;
   return true;
 }
@@ -459,13 +476,6 @@ int cache_extend(cache_reader& r, const void* new_rows, uint64_t n_new, const ui
 
 }  // namespace
 
-// (loader.cu) the parser with a resume point and the stamp of the descriptor it read; the prefix hash
-extern "C" int rag_parse_vector_store_json_ex(const char* path, uint32_t dim, uint64_t slab_rows,
-                                              int (*on_rows)(void* user, uint64_t first_row, uint64_t nrows, const float* rows),
-                                              void* user, uint64_t resume_offset, uint64_t* rows_out, char** ids,
-                                              uint64_t* ids_bytes, uint64_t* end_offset, uint64_t* stamp_size,
-                                              int64_t* stamp_mtime_ns);
-extern "C" int rag_file_prefix_hash(const char* path, uint64_t nbytes, uint64_t* hash, int* ok);
 extern "C" {
 
 // header of a sidecar (validated: magic, header checksum, version, file size)
@@ -499,7 +509,7 @@ int rag_cache_write_host(const char* cache_path, uint32_t dtype, uint32_t dim, u
   if (nmeta != 0 && nmeta != 4) return rag_set_error(RAG_ERR_INVALID, "rag_cache_write_host: give all four metadata arrays or none");
   src_stamp st;
   bool have = false;
-  if (!stamp_of_path(source_json, &st, &have)) return rag_set_error(RAG_ERR_INVALID, "cannot stat %s: %s", source_json, strerror(errno));
+  if (!stamp_of_path(source_json, rows, &st, &have)) return rag_set_error(RAG_ERR_INVALID, "cannot stat %s: %s", source_json, strerror(errno));
   cache_writer w;
   RAG_CHECK(w.begin(cache_path, dtype, dim, rows));
   RAG_CHECK(w.append_rows(host_rows, rows));
@@ -544,7 +554,7 @@ int rag_index_save_cache(rag_index* idx, const char* cache_path, const char* ids
   RAG_LOCK(idx);
   src_stamp st;
   bool have = false;
-  if (!stamp_of_path(source_json, &st, &have)) return rag_set_error(RAG_ERR_INVALID, "cannot stat %s: %s", source_json, strerror(errno));
+  if (!stamp_of_path(source_json, idx->rows, &st, &have)) return rag_set_error(RAG_ERR_INVALID, "cannot stat %s: %s", source_json, strerror(errno));
   return save_cache_stamped(idx, cache_path, ids, ids_bytes, have ? &st : nullptr);
 }
 }  // extern "C"

@@ -244,6 +244,11 @@ def test_open_store_through_the_sidecar(native, oracle, tmp_path):
     with rb.VectorIndex(dim, n, dtype=native.BF16) as idx:                 # dtype mismatch: the sidecar is ignored
         got, hit = idx.open_store(src, cache_path=src + ".ragera")
         assert not hit and np.array_equal(idx.read_rows(0, n), oracle.f32_to_bf16(X))
+    with rb.VectorIndex(dim, n) as idx:                                    # ... and was rebuilt as bf16; back to fp32 with the
+        assert idx.open_store(src)[1] == 0                                 # Memory columns and fusion keys the host had saved
+        idx.set_row_keys(0, keys)
+        idx.set_row_meta(0, want_meta["content_type"], want_meta["confidence"], want_meta["access_count"], want_meta["last_access_ms"])
+        idx.save_cache(src + ".ragera", ids=ids, source_json=src)
     open(src, "a").write("\n")                                             # the JSON changed, but only after the embeddings
     with rb.VectorIndex(dim, n) as idx:
         got, hit = idx.open_store(src)
