@@ -5,7 +5,10 @@ may import this module; only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do.
 
 PARITY UNPINNED: the reference has no tests or golden vectors for this path and
-cannot run here (TypeScript, no Node.js); see DESIGN.md §Oracle.
+cannot run here (TypeScript, no Node.js); see DESIGN.md §Oracle. Substitute:
+``tests/test_reference_pin.py`` pins the restated lines to the mounted reference
+source (hashes, constants, and the reference's own arithmetic statements executed
+against this oracle).
 """
 from __future__ import annotations
 

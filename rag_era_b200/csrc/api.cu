@@ -72,7 +72,7 @@ int grow_pinned(uint8_t** p, size_t* cap, size_t need) {
 void free_batch(rag_batch* b) {
   cudaFree(b->d_q); cudaFree(b->d_qb); cudaFree(b->d_rho_q); cudaFree(b->d_in); cudaFree(b->d_sel); cudaFree(b->d_partial);
   cudaFree(b->d_cand); cudaFree(b->d_local); cudaFree(b->d_gather); cudaFree(b->d_local_cnt); cudaFree(b->d_out);
-  cudaFree(b->d_k4s); cudaFree(b->d_ticket);
+  cudaFree(b->d_k4s); cudaFree(b->d_ticket); cudaFree(b->d_gin);
   if (b->h_in) cudaFreeHost(b->h_in);
   if (b->h_out) cudaFreeHost(b->h_out);
   if (b->h_q) cudaFreeHost(b->h_q);
@@ -103,20 +103,24 @@ out_layout layout_out(uint32_t B, uint32_t cap, uint32_t k) {
   L.total = o;
   return L;
 }
-void bind_out(rag_batch* b, const out_layout& L) {
-  b->d_out_cnt = (uint32_t*)(b->d_out + L.cnt);
-  b->d_out_rrf = b->d_out + L.rrf;
-  b->d_vec_cnt = (uint32_t*)(b->d_out + L.vcnt);
-  b->d_cert = b->d_out + L.cert;
-  b->d_out_keys = (uint64_t*)(b->d_out + L.keys);
-  b->d_out_scores = (double*)(b->d_out + L.scores);
-  b->d_out_src = b->d_out + L.src;
-  b->d_out_ct = b->d_out + L.ct;
-  b->d_vec_ids = (uint64_t*)(b->d_out + L.vids);
-  b->d_vec_scores = (double*)(b->d_out + L.vscores);
-  b->d_aux0 = (double*)(b->d_out + L.aux0);
-  b->d_aux1 = (double*)(b->d_out + L.aux1);
+// carve the output block at `base`: the device block, or — small batches — its pinned host mirror, which the kernels
+// can write directly (pinned allocations are device-accessible under UVA; a few hundred bytes of posted PCIe writes
+// instead of a D2H copy node)
+void bind_out_at(rag_batch* b, const out_layout& L, uint8_t* base) {
+  b->d_out_cnt = (uint32_t*)(base + L.cnt);
+  b->d_out_rrf = base + L.rrf;
+  b->d_vec_cnt = (uint32_t*)(base + L.vcnt);
+  b->d_cert = base + L.cert;
+  b->d_out_keys = (uint64_t*)(base + L.keys);
+  b->d_out_scores = (double*)(base + L.scores);
+  b->d_out_src = base + L.src;
+  b->d_out_ct = base + L.ct;
+  b->d_vec_ids = (uint64_t*)(base + L.vids);
+  b->d_vec_scores = (double*)(base + L.vscores);
+  b->d_aux0 = (double*)(base + L.aux0);
+  b->d_aux1 = (double*)(base + L.aux1);
 }
+void bind_out(rag_batch* b, const out_layout& L) { bind_out_at(b, L, b->d_out); }
 
 // ---- plan: which kernel scores, how many candidates, what error bound ---------------
 struct plan {
@@ -324,8 +328,8 @@ typedef std::function<void(uint32_t, const rag_batch*, const out_layout&, uint32
 
 // Re-run the queries whose result could not be certified on successively stronger paths.
 int escalate(rag_index* idx, std::vector<uint32_t> sel, uint32_t k, plan p, const fresh_cfg& fc,
-             const rag_fuse_args& fa, uint32_t out_cap, bool with_aux, const writer_fn& write) {
-  rag_batch* src = &idx->main;
+             const rag_fuse_args& fa, uint32_t out_cap, bool with_aux, const writer_fn& write, const rag_batch* src_view = nullptr) {
+  const rag_batch* src = src_view ? src_view : &idx->main;  // where the batch's queries / keyword lists sit on the device
   rag_batch* bt = &idx->esc;
   int rc = RAG_OK;
   while (!sel.empty()) {
@@ -402,49 +406,65 @@ bool graph_shape_ok(const rag_index* idx, uint32_t B, const plan& p, const rag_f
 }
 
 // Runs stage→pipeline→fetch for idx->main as one graph launch. queries/kw are the caller's host arrays.
+// Graph nodes: ONE H2D (queries and keyword lists packed in one pinned block → one device block), K1, the fused
+// K3+K4+K5 kernel. There is no D2H node: the fusion kernel writes the result block straight into pinned host memory.
 int run_graphed(rag_index* idx, const float* queries, uint32_t B, uint32_t k, const plan& p, const fresh_cfg& fc, rag_fuse_args fa,
-                const uint64_t* kw_keys, const uint32_t* kw_counts, uint32_t kw_stride, uint32_t out_cap, out_layout* L, bool* ran) {
+                const uint64_t* kw_keys, const uint32_t* kw_counts, uint32_t kw_stride, uint32_t out_cap, out_layout* L, bool* ran,
+                rag_batch* view_out) {
   *ran = false;
   rag_batch* bt = &idx->main;
   idx->cur = bt;
-  // 1. every allocation up front (none may happen inside a capture), inputs into pinned memory at fixed addresses
-  RAG_CHECK(ensure_queries(idx, bt, B));
-  if (fa.mode == 0) RAG_CHECK(ensure_inputs(idx, bt, B, kw_stride));
+  // 1. every allocation up front (none may happen inside a capture)
   RAG_CHECK(ensure_work(idx, bt, B, k, out_cap, L));
   uint32_t parts = 0;
   RAG_CHECK(k1_plan(idx, B, p.kp, &parts));
   RAG_CHECK(grow_dev(&bt->d_partial, &bt->c_partial, (size_t)B * parts * p.kp * 8, false));
   if (!k34_small_ok(idx, B, p.kp, parts)) return RAG_OK;  // not the fused tail: plain path
-  const size_t qbytes = (size_t)B * idx->dim * 4;
-  if (qbytes > bt->c_hq || !bt->h_q) {
+  const bool with_kw = fa.mode == 0;
+  const size_t qb = (size_t)B * idx->ld * 4;
+  const size_t kwb = with_kw ? (((size_t)B * kw_stride * 8 + 15) & ~(size_t)15) : 0;
+  const size_t in_bytes = qb + kwb + (with_kw ? (size_t)B * 4 : 0);
+  if (in_bytes > bt->c_hq || !bt->h_q) {
     if (bt->h_q) RAG_CUDA(cudaFreeHost(bt->h_q));
     bt->h_q = nullptr;
     bt->c_hq = 0;
-    RAG_CUDA(cudaHostAlloc((void**)&bt->h_q, std::max<size_t>(qbytes, 32 * 8192 * 4 / 8), cudaHostAllocDefault));
-    bt->c_hq = std::max<size_t>(qbytes, 32 * 8192 * 4 / 8);
+    const size_t cap = std::max<size_t>(in_bytes, 64 * 1024);
+    RAG_CUDA(cudaHostAlloc((void**)&bt->h_q, cap, cudaHostAllocDefault));
+    memset(bt->h_q, 0, cap);  // the padding columns of the query rows stay zero
+    bt->c_hq = cap;
   }
-  memcpy(bt->h_q, queries, qbytes);
-  const size_t kwb = ((size_t)B * kw_stride * 8 + 15) & ~(size_t)15;
-  if (fa.mode == 0) {
-    uint32_t* hc = (uint32_t*)(bt->h_in + kwb);
-    if (kw_stride && kw_keys) memcpy(bt->h_in, kw_keys, (size_t)B * kw_stride * 8);
+  RAG_CHECK(grow_dev(&bt->d_gin, &bt->c_gin, std::max<size_t>(in_bytes, 64 * 1024), true));
+  // 2. inputs into the pinned block (fixed address: the caller's pointers change from call to call)
+  uint8_t* hin = reinterpret_cast<uint8_t*>(bt->h_q);
+  if (idx->ld == idx->dim) memcpy(hin, queries, qb);
+  else
+    for (uint32_t b = 0; b < B; b++) memcpy(hin + (size_t)b * idx->ld * 4, queries + (size_t)b * idx->dim, (size_t)idx->dim * 4);
+  if (with_kw) {
+    uint32_t* hc = (uint32_t*)(hin + qb + kwb);
+    if (kw_stride && kw_keys) memcpy(hin + qb, kw_keys, (size_t)B * kw_stride * 8);
     for (uint32_t b = 0; b < B; b++) {
       const uint32_t c = (kw_counts && kw_keys) ? kw_counts[b] : 0u;
       if (c > kw_stride) return rag_set_error(RAG_ERR_INVALID, "kw_counts[%u]=%u exceeds keyword_limit=%u", b, c, kw_stride);
       hc[b] = c;
     }
-    bt->staged_kw_stride = kw_stride;
   }
-  // 2. the key: everything a captured node bakes in
+  // 3. the batch as the kernels see it: inputs in the packed device block, outputs in the pinned mirror
+  rag_batch view = *bt;
+  view.d_q = reinterpret_cast<float*>(bt->d_gin);
+  view.d_kw = reinterpret_cast<uint64_t*>(bt->d_gin + qb);
+  view.d_kwc = reinterpret_cast<uint32_t*>(bt->d_gin + qb + kwb);
+  view.staged_kw_stride = kw_stride;
+  bind_out_at(&view, *L, bt->h_out);
+  // 4. the key: everything a captured node bakes in
   graph_key key;
-  key.B = B; key.k = k; key.kp = p.kp; key.parts = parts; key.kw_stride = fa.mode == 0 ? kw_stride : 0; key.out_cap = out_cap;
+  key.B = B; key.k = k; key.kp = p.kp; key.parts = parts; key.kw_stride = with_kw ? kw_stride : 0; key.out_cap = out_cap;
   key.fresh_limit = fa.fresh_limit; key.path = p.path; key.mode = fa.mode; key.key_has_qnorm = p.key_has_qnorm; key.eps = p.eps;
   key.min_score = fa.min_score; key.rrf_k = fa.rrf.k; key.rrf_vw = fa.rrf.vector_weight; key.rrf_kw = fa.rrf.keyword_weight;
   key.rrf_bonus = fa.rrf.both_bonus; key.fresh_weight = fa.fresh_weight; key.mem_min = fa.mem_min_relevance; key.mem_limit = fa.mem_limit;
   key.rows = idx->rows;
-  const void* ptrs[10] = {bt->d_q, bt->d_in, bt->d_out, bt->h_q, bt->h_in, bt->h_out, bt->d_partial, bt->d_cand, bt->d_local, idx->row_keys};
+  const void* ptrs[10] = {bt->d_gin, bt->h_q, bt->h_out, bt->d_partial, bt->d_cand, bt->d_local, bt->d_k4s, bt->d_ticket, idx->row_keys, idx->ctype};
   for (int i = 0; i < 10; i++) key.ptr[i] = ptrs[i];
-  key.d2h = L->total_no_aux;
+  key.d2h = in_bytes;
   if (!idx->graph) idx->graph = new (std::nothrow) rag_graph();
   rag_graph* g = idx->graph;
   if (!g) return RAG_OK;
@@ -454,16 +474,11 @@ int run_graphed(rag_index* idx, const float* queries, uint32_t B, uint32_t k, co
     const uint64_t l0 = idx->launches;
     RAG_CUDA(cudaStreamBeginCapture(idx->stream, cudaStreamCaptureModeThreadLocal));
     int rc = RAG_OK;
-    cudaError_t e = cudaSuccess;
-    if (idx->ld == idx->dim) e = cudaMemcpyAsync(bt->d_q, bt->h_q, qbytes, cudaMemcpyHostToDevice, idx->stream);
-    else e = cudaMemcpy2DAsync(bt->d_q, (size_t)idx->ld * 4, bt->h_q, (size_t)idx->dim * 4, (size_t)idx->dim * 4, B, cudaMemcpyHostToDevice, idx->stream);
-    if (e == cudaSuccess && fa.mode == 0) e = cudaMemcpyAsync(bt->d_in, bt->h_in, kwb + (size_t)B * 4, cudaMemcpyHostToDevice, idx->stream);
+    cudaError_t e = cudaMemcpyAsync(bt->d_gin, bt->h_q, in_bytes, cudaMemcpyHostToDevice, idx->stream);
     if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "graph capture (H2D): %s", cudaGetErrorString(e));
+    idx->cur = &view;
     if (rc == RAG_OK) rc = run_pipeline(idx, B, k, p, fc, fa);
-    if (rc == RAG_OK) {
-      e = cudaMemcpyAsync(bt->h_out, bt->d_out, L->total_no_aux, cudaMemcpyDeviceToHost, idx->stream);
-      if (e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "graph capture (D2H): %s", cudaGetErrorString(e));
-    }
+    idx->cur = bt;
     cudaGraph_t graph = nullptr;
     e = cudaStreamEndCapture(idx->stream, &graph);
     if (rc == RAG_OK && e != cudaSuccess) rc = rag_set_error(RAG_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
@@ -479,12 +494,12 @@ int run_graphed(rag_index* idx, const float* queries, uint32_t B, uint32_t k, co
   } else {
     g->recaptures = 0;
   }
-  bt->staged_B = B;
-  bt->win_first = 0;
-  bt->win_count = B;
+  bt->staged_B = 0;   // the staged pool (rag_stage_batch) is not what this call used
+  bt->win_count = 0;
   RAG_CUDA(cudaGraphLaunch(g->exec, idx->stream));
   idx->launches += g->launches;
   RAG_CUDA(cudaStreamSynchronize(idx->stream));
+  *view_out = view;  // an escalation of uncertified queries gathers its inputs from here
   *ran = true;
   return RAG_OK;
 }
@@ -826,7 +841,8 @@ int rag_search(rag_index* idx, const float* queries, uint32_t B, const rag_searc
   fa.out_cap = k;
   const fresh_cfg fc = {0, 0.05, 0.1};
   bool graphed = false;
-  if (graph_shape_ok(idx, B, p, fa)) RAG_CHECK(run_graphed(idx, queries, B, k, p, fc, fa, nullptr, nullptr, 0, k, &L, &graphed));
+  rag_batch gview;
+  if (graph_shape_ok(idx, B, p, fa)) RAG_CHECK(run_graphed(idx, queries, B, k, p, fc, fa, nullptr, nullptr, 0, k, &L, &graphed, &gview));
   if (!graphed) {
     RAG_CHECK(stage_queries(idx, bt, queries, B));
     RAG_CHECK(ensure_work(idx, bt, B, k, k, &L));
@@ -851,7 +867,7 @@ int rag_search(rag_index* idx, const float* queries, uint32_t B, const rag_searc
     write(b, bt, L, b);
     if (!cert[b]) sel.push_back(b);
   }
-  if (!sel.empty() && !(o->flags & RAG_SEARCH_NO_ESCALATE)) RAG_CHECK(escalate(idx, sel, k, p, fc, fa, k, false, write));
+  if (!sel.empty() && !(o->flags & RAG_SEARCH_NO_ESCALATE)) RAG_CHECK(escalate(idx, sel, k, p, fc, fa, k, false, write, graphed ? &gview : nullptr));
   return RAG_OK;
 }
 
@@ -937,8 +953,9 @@ int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const ra
   idx->cur = bt;
   out_layout L;
   bool graphed = false;
-  if (graph_shape_ok(idx, B, p, fa))   // the latency shape: one graph launch for H2D + K1 + K3/K4/K5 + D2H
-    RAG_CHECK(run_graphed(idx, queries, B, k, p, fc, fa, kw_keys, kw_counts, o->keyword_limit, out_cap, &L, &graphed));
+  rag_batch gview;
+  if (graph_shape_ok(idx, B, p, fa))   // the latency shape: one graph launch for H2D + K1 + K3/K4/K5 (results land in pinned memory)
+    RAG_CHECK(run_graphed(idx, queries, B, k, p, fc, fa, kw_keys, kw_counts, o->keyword_limit, out_cap, &L, &graphed, &gview));
   if (!graphed) {
     RAG_CHECK(stage_queries(idx, bt, queries, B));
     RAG_CHECK(stage_keywords(idx, bt, B, kw_keys, kw_counts, o->keyword_limit));
@@ -959,7 +976,7 @@ int rag_hybrid_search(rag_index* idx, const float* queries, uint32_t B, const ra
     if (!cert[b]) sel.push_back(b);
   }
   if (!sel.empty() && !(o->flags & RAG_SEARCH_NO_ESCALATE))
-    RAG_CHECK(escalate(idx, sel, k, p, fc, fa, out_cap, false, write));
+    RAG_CHECK(escalate(idx, sel, k, p, fc, fa, out_cap, false, write, graphed ? &gview : nullptr));
   return RAG_OK;
 }
 

@@ -134,7 +134,8 @@ struct rag_batch {
   // fused outputs: one device block + pinned host mirror, carved per call (out_layout in api.cu)
   uint8_t* d_out = nullptr;         size_t c_out = 0;
   uint8_t* h_out = nullptr;         size_t c_hout = 0;
-  float* h_q = nullptr;             size_t c_hq = 0;       // pinned copy of the caller's queries (graph replay needs a fixed source)
+  float* h_q = nullptr;             size_t c_hq = 0;       // graph replay: pinned [queries | keyword keys | counts] at a fixed address
+  uint8_t* d_gin = nullptr;         size_t c_gin = 0;      //   ... and its device block (ONE H2D node)
   uint64_t* d_out_keys = nullptr;   double* d_out_scores = nullptr;
   uint8_t* d_out_src = nullptr;     uint8_t* d_out_ct = nullptr;
   uint32_t* d_out_cnt = nullptr;    uint8_t* d_out_rrf = nullptr;

@@ -46,7 +46,7 @@ struct k4_meta {
 __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k, bool valid, uint32_t row, double score,
                                             double nq, uint64_t last_key, double eps, int key_has_qnorm,
                                             const k4_meta& M, double* s_score, uint32_t* s_row, double* s_kth,
-                                            rag_rec* __restrict__ out, uint32_t* __restrict__ out_cnt) {
+                                            rag_rec* __restrict__ out, uint32_t* __restrict__ out_cnt, rag_rec* s_out = nullptr) {
   // similarity = dot / (norm(q) * norm(x)); NaN (zero norm) is defined as never selected
   const bool good = valid && score == score;
   if (j < kp) {
@@ -95,12 +95,14 @@ __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k,
       r.fresh = fmax(0.0, fmin(1.0, sc));
     }
     out[rank] = r;
+    if (s_out) s_out[rank] = r;
   }
   // empty tail + flags on every slot so the merge sees them even for empty shards
   for (uint32_t i = cnt + j; i < k; i += blockDim.x) {
     rag_rec e;
     e.score = -INFINITY; e.id = ~0ull; e.key = ~0ull; e.fresh = 0.0; e.ctype = 0; e.flags = flags; e.conf_pad = 0.0;
     out[i] = e;
+    if (s_out) s_out[i] = e;
   }
   if (j == 0) *out_cnt = cnt;
 }
@@ -148,85 +150,69 @@ k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restri
 // of a warp compute the products of 32 consecutive elements in parallel (exact: one rounding
 // each, same as the reference's q[i]*x[i]) and then every lane replays the adds in order, fetching
 // product i from lane i%32 with a shuffle — 2 SHFL + 1 DADD per element per sum, no shared
-// memory, nothing but the add latency on the critical path. A query's K' candidates are spread
-// over K'/4 CTAs (4 candidate warps + 1 warp for ||q||^2 each), so a batch-1 search uses 4-8 SMs
-// instead of one warp of one SM. Every CTA first merges the per-CTA candidate lists of K1/K2
+// memory, nothing but the add latency on the critical path. The work items of a query — one per (candidate, sum)
+// pair, dot and ||x||^2 on DIFFERENT warps, plus one for ||q||^2 — are spread over (2K'+1)/5 CTAs: a warp that
+// carries one chain retires an add every ~10.6 cycles, a warp that interleaves two needs 14 per pair
+// (tools/micro/dadd_latency.cu), and a batch-1 search spreads over 5-7 SMs instead of one warp of one SM. Every CTA first merges the per-CTA candidate lists of K1/K2
 // itself (sorted lists, k-way merge from shared memory — this is K3, fused); the last CTA of a
 // query to finish (atomic ticket) ranks, certifies and writes the records.
 // diagnostics (RAGERA_SMALL_PROF=1): cycles per phase of the small-batch kernel as seen by the LAST CTA of a query
 __device__ int g_k34_prof_on;
 __device__ unsigned long long g_k34_prof[8];  // stage + K3 merge, exact chains, ticket, (last CTA) finalize, K5, count
 
-constexpr int K4S_CW = 4;                       // candidate warps per CTA
-constexpr int K4S_WARPS = K4S_CW + 1;           // + the ||q||^2 warp
+constexpr int K4S_WARPS = 5;                    // every warp takes work items (one exact sum each)
 constexpr int K4S_THREADS = K4S_WARPS * 32;
 constexpr size_t K4S_MAX_STAGE = 96 * 1024;     // staged candidate keys (parts * K' * 8 bytes)
 
-template <bool BF16>
-__device__ __forceinline__ void load_block(const void* __restrict__ X, size_t row_off, const float* __restrict__ q,
-                                           int blk, int lane, float (&xr)[8], float (&qr)[8]) {
-#pragma unroll
-  for (int t = 0; t < 8; t++) {
-    const int e = blk * 256 + t * 32 + lane;
-    qr[t] = q ? q[e] : 0.f;
-    if (X) {
-      if (BF16) xr[t] = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(X)[row_off + e] << 16);
-      else xr[t] = reinterpret_cast<const float*>(X)[row_off + e];
-    } else {
-      xr[t] = 0.f;
-    }
-  }
-}
-
-// dot = sum q[i]*x[i], nx = sum x[i]*x[i] in reference order (X != null), or nq = sum q[i]*q[i] (X == null).
-// The 32 lanes compute the (exact) products of a 256-element block in parallel and park them in the
-// warp's shared-memory scratch `sp` [2 buffers][2 sums][256]; the adds are then replayed in order from
-// broadcast 128-bit shared loads, so the only thing on the critical path is the fp64 add latency.
-// Products of block b+1 are computed while the global loads of block b+2 are in flight.
-template <bool BF16>
-__device__ __forceinline__ void warp_chain(const void* __restrict__ X, uint32_t row, uint32_t ld,
-                                           const float* __restrict__ q, int lane, double* sp, double& s0, double& s1) {
-  s0 = 0.0;
-  s1 = 0.0;
+// One exact left-to-right sum over a row, by one warp. WHICH: 0 = sum q[i]*x[i], 1 = sum x[i]*x[i], 2 = sum q[i]*q[i]
+// (the reference's three loops). The 32 lanes compute the (exact) products of a 256-element block in parallel and park
+// them in the warp's shared-memory scratch `sp` [2 buffers][256]; the adds are then replayed in order from broadcast
+// 128-bit shared loads, so the only thing on the critical path is the fp64 add latency. Products of block b+1 are
+// computed while the global loads of block b+2 are in flight.
+template <bool BF16, int WHICH>
+__device__ __forceinline__ double warp_chain1(const void* __restrict__ X, uint32_t row, uint32_t ld,
+                                              const float* __restrict__ q, int lane, double* sp) {
+  double s0 = 0.0;
   const int nblk = (int)(ld / 256);
   const size_t row_off = (size_t)row * ld;
   float xr[8], qr[8];
-  auto park = [&](int buf) {
-    double* p0 = sp + buf * 512;
-    double* p1 = p0 + 256;
+  auto load = [&](int blk) {
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-      const double qd = (double)qr[t], xd = (double)xr[t];
-      p0[t * 32 + lane] = X ? __dmul_rn(qd, xd) : __dmul_rn(qd, qd);
-      if (X) p1[t * 32 + lane] = __dmul_rn(xd, xd);
+      const int e = blk * 256 + t * 32 + lane;
+      if (WHICH != 1) qr[t] = q[e];
+      if (WHICH != 2) {
+        if (BF16) xr[t] = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(X)[row_off + e] << 16);
+        else xr[t] = reinterpret_cast<const float*>(X)[row_off + e];
+      }
     }
   };
-  load_block<BF16>(X, row_off, q, 0, lane, xr, qr);
+  auto park = [&](int buf) {
+    double* p0 = sp + buf * 256;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const double a = WHICH == 1 ? (double)xr[t] : (double)qr[t];
+      const double c = WHICH == 2 ? (double)qr[t] : (double)xr[t];
+      p0[t * 32 + lane] = __dmul_rn(a, c);
+    }
+  };
+  load(0);
   park(0);
   __syncwarp();
   for (int blk = 0; blk < nblk; blk++) {
-    if (blk + 1 < nblk) load_block<BF16>(X, row_off, q, blk + 1, lane, xr, qr);
-    const double2* a0 = reinterpret_cast<const double2*>(sp + (blk & 1) * 512);
-    const double2* a1 = a0 + 128;
-    if (X) {
-#pragma unroll 8
-      for (int i = 0; i < 128; i++) {
-        const double2 u = a0[i], v = a1[i];
-        s0 = __dadd_rn(__dadd_rn(s0, u.x), u.y);
-        s1 = __dadd_rn(__dadd_rn(s1, v.x), v.y);
-      }
-    } else {
-#pragma unroll 8
-      for (int i = 0; i < 128; i++) {
-        const double2 u = a0[i];
-        s0 = __dadd_rn(__dadd_rn(s0, u.x), u.y);
-      }
+    if (blk + 1 < nblk) load(blk + 1);
+    const double2* a0 = reinterpret_cast<const double2*>(sp + (blk & 1) * 256);
+#pragma unroll 16
+    for (int i = 0; i < 128; i++) {
+      const double2 u = a0[i];
+      s0 = __dadd_rn(__dadd_rn(s0, u.x), u.y);
     }
     if (blk + 1 < nblk) {
       park((blk + 1) & 1);
       __syncwarp();
     }
   }
+  return s0;
 }
 
 template <bool BF16>
@@ -240,7 +226,8 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* stg = reinterpret_cast<uint64_t*>(smem);               // [parts][kp] staged lists
   uint64_t* wl = stg + (size_t)parts * kp;                         // [2][K4S_WARPS][kp] per-warp merged lists
-  __shared__ __align__(16) double s_prod[K4S_WARPS][2 * 2 * 256];  // per-warp product scratch of warp_chain
+  __shared__ __align__(16) double s_prod[K4S_WARPS][2 * 2 * 256];  // per-warp product scratch of warp_chain1 (and K5's working set)
+  __shared__ __align__(16) rag_rec s_recs[RAG_MAX_TOPK];            // this query's records for the in-place K5
   __shared__ uint64_t s_cand[RAG_MAX_CANDIDATES];
   __shared__ double s_score[RAG_MAX_CANDIDATES];
   __shared__ uint32_t s_row[RAG_MAX_CANDIDATES];
@@ -256,6 +243,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   const uint64_t* in = partial + (size_t)b * parts * kp;
   for (uint32_t i = threadIdx.x; i < parts * kp; i += K4S_THREADS) stg[i] = in[i];
   __syncthreads();
+  const long long pt0a = prof ? clock64() : 0;
   // warp w merges lists w, w+W, w+2W, ... at most 31 at a time, together with its running result
   // (ping-pong between two per-warp buffers; every warp runs the same number of rounds)
   uint64_t* wl2 = wl + (size_t)K4S_WARPS * kp;
@@ -296,18 +284,18 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   // ---- K4: exact sums, one warp per candidate -----------------------------------------------------
   double* my_scratch = scratch + (size_t)b * (2 * RAG_MAX_CANDIDATES + 2);
   const float* q = Q + (size_t)b * ld;
-  if (warp < K4S_CW) {
-    for (uint32_t j = slice * K4S_CW + warp; j < kp; j += nslices * K4S_CW) {
-      const uint64_t key = s_cand[j];
-      if (key == 0ull) continue;  // warp-uniform
-      double dot, nx;
-      warp_chain<BF16>(X, rag_key_row(key), ld, q, lane, s_prod[warp], dot, nx);
-      if (lane == 0) { my_scratch[2 * j] = dot; my_scratch[2 * j + 1] = nx; }
+  // work item t: t < 2K' → sum (t & 1) of candidate t >> 1 (0 = dot, 1 = ||x||^2);  t == 2K' → ||q||^2
+  for (uint32_t t = slice * K4S_WARPS + warp; t <= 2 * kp; t += nslices * K4S_WARPS) {
+    if (t == 2 * kp) {
+      const double nq = warp_chain1<BF16, 2>(nullptr, 0, ld, q, lane, s_prod[warp]);
+      if (lane == 0) my_scratch[2 * RAG_MAX_CANDIDATES] = nq;
+      continue;
     }
-  } else if (slice == 0) {
-    double nq, unused;
-    warp_chain<BF16>(nullptr, 0, ld, q, lane, s_prod[warp], nq, unused);
-    if (lane == 0) my_scratch[2 * RAG_MAX_CANDIDATES] = nq;
+    const uint64_t key = s_cand[t >> 1];
+    if (key == 0ull) continue;  // warp-uniform
+    const double v = (t & 1) ? warp_chain1<BF16, 1>(X, rag_key_row(key), ld, q, lane, s_prod[warp])
+                             : warp_chain1<BF16, 0>(X, rag_key_row(key), ld, q, lane, s_prod[warp]);
+    if (lane == 0) my_scratch[t] = v;
   }
 
   // ---- the last slice of this query to arrive finishes it ------------------------------------------
@@ -333,7 +321,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
     const uint32_t row = valid ? rag_key_row(key) : 0u;
     const double score = valid ? __ddiv_rn(vs[2 * j], __dmul_rn(__dsqrt_rn(nq), __dsqrt_rn(vs[2 * j + 1]))) : 0.0;
     k4_finalize(j, kp, k, valid, row, score, nq, s_cand[kp - 1], eps, key_has_qnorm, M, s_score, s_row, &s_kth,
-                local + (size_t)b * k, local_cnt + b);
+                local + (size_t)b * k, local_cnt + b, s_recs);
   }
   // ---- K5 in place: filter + fusion of this query by warp 0 — one launch less on the batch-1 latency path.
   //      Sharded (pv.nranks > 1): the same warp first exchanges this query's records with the peer ranks through
@@ -341,16 +329,18 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   //      wait for its peers cannot starve them. The product scratch is free by now and hosts K5's working set.
   const long long pt4 = prof ? clock64() : 0;
   if (fuse_k5) {
-    __threadfence();  // the records above are read back through L2
+    if (pv.nranks > 1) __threadfence();  // sharded: the records above are read back through L2 by the exchange
     __syncthreads();
     static_assert(sizeof(rag_k5::fuse_smem) <= sizeof(s_prod), "K5 working set must fit the product scratch");
     if (warp == 0) {
-      const rag_rec* recs = pv.nranks > 1 ? rag_k5::p2p_exchange(pv, local, io.a.B, b, io.a.k, lane) : local;
-      rag_k5::k5_fuse_body(*reinterpret_cast<rag_k5::fuse_smem*>(&s_prod[0][0]), recs, io, b, lane);
+      rag_k5::fuse_smem& fs = *reinterpret_cast<rag_k5::fuse_smem*>(&s_prod[0][0]);
+      if (pv.nranks > 1) rag_k5::k5_fuse_body<false>(fs, rag_k5::p2p_exchange(pv, local, io.a.B, b, io.a.k, lane), io, b, lane);
+      else rag_k5::k5_fuse_body<true>(fs, s_recs, io, b, lane);   // one GPU: straight from shared memory
     }
   }
   if (prof && threadIdx.x == 0) {
-    atomicAdd(&g_k34_prof[0], (unsigned long long)(pt1 - pt0));
+    atomicAdd(&g_k34_prof[0], (unsigned long long)(pt0a - pt0));
+    atomicAdd(&g_k34_prof[6], (unsigned long long)(pt1 - pt0a));
     atomicAdd(&g_k34_prof[1], (unsigned long long)(pt2 - pt1));
     atomicAdd(&g_k34_prof[2], (unsigned long long)(pt3 - pt2));
     atomicAdd(&g_k34_prof[3], (unsigned long long)(pt4 - pt3));
@@ -372,9 +362,9 @@ void k34_small_prof(int enable, FILE* dump) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(h, g_k34_prof, sizeof(h));
     if (h[5])
-      fprintf(dump, "[k34_small prof] avg cycles in the LAST CTA of a query over %llu queries: stage + K3 merge %.0f, exact chains %.0f, "
+      fprintf(dump, "[k34_small prof] avg cycles in the LAST CTA of a query over %llu queries: staging the lists %.0f, K3 merge %.0f, exact chains %.0f, "
               "fence + ticket %.0f, rank + certify + records %.0f, K5 in place %.0f\n",
-              h[5], (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
+              h[5], (double)h[0] / h[5], (double)h[6] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5]);
   }
 }
 
@@ -412,7 +402,7 @@ int k34_small_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, ui
   const size_t smem = ((size_t)parts * kp + 2 * (size_t)K4S_WARPS * kp) * 8;
   auto kern = bf16 ? k34_small_kernel<true> : k34_small_kernel<false>;
   RAG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K4S_MAX_STAGE + 2 * K4S_WARPS * RAG_MAX_CANDIDATES * 8)));
-  const uint32_t slices = (kp + K4S_CW - 1) / K4S_CW;
+  const uint32_t slices = (2 * kp + 1 + K4S_WARPS - 1) / K4S_WARPS;
   rag_p2p_view pv = rag_p2p_view();
   pv.nranks = 1;
   if (fuse && idx->nranks > 1) RAG_CHECK(comm_p2p_next(idx, B, k, &pv));  // the in-place K5 runs the exchange as well

@@ -26,6 +26,7 @@ struct fuse_smem {
   uint8_t e_src[MAXE];
   uint8_t e_ct[MAXE];
   uint64_t f_key[RAG_MAX_FRESH];
+  uint64_t k_key[RAG_MAX_KEYWORDS];  // the query's keyword list, staged with one coalesced load
 };
 
 // one sequential RRF pass over `n` keys; all lanes execute, lane 0 mutates the map.
@@ -76,13 +77,18 @@ __device__ __forceinline__ void emit_sorted(const fuse_smem& s, uint32_t n, uint
 }
 
 // one record through L2 (ld.global.cg): mailbox records are written by PEER GPUs over NVLink, which this
-// SM's L1 knows nothing about
+// SM's L1 knows nothing about. LOCAL: the records sit in this CTA's shared memory (the fused single-GPU tail).
+template <bool LOCAL>
 __device__ __forceinline__ rag_rec rec_load(const rag_rec* r) {
   union { rag_rec rec; uint4 q[3]; } u;
   const uint4* p = reinterpret_cast<const uint4*>(r);
-  u.q[0] = __ldcg(p);
-  u.q[1] = __ldcg(p + 1);
-  u.q[2] = __ldcg(p + 2);
+  if (LOCAL) {
+    u.q[0] = p[0]; u.q[1] = p[1]; u.q[2] = p[2];
+  } else {
+    u.q[0] = __ldcg(p);
+    u.q[1] = __ldcg(p + 1);
+    u.q[2] = __ldcg(p + 2);
+  }
   return u.rec;
 }
 
@@ -143,7 +149,9 @@ struct k5_io {
   unsigned long long* counters;  // [2] device-side totals since the last rag_certified_totals: certified, queries
 };
 
-// recs: [nranks][B][k] records; executed by one full warp for query b
+// recs: [nranks][B][k] records; executed by one full warp for query b. LOCAL: `recs` points at this query's k records in
+// shared memory (nranks == 1, the fused tail of the small-batch kernel) instead of the global [nranks][B][k] array.
+template <bool LOCAL = false>
 __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, const k5_io io, uint32_t b, int lane) {
   const rag_fuse_args a = io.a;
   const uint32_t k = a.k;
@@ -167,7 +175,7 @@ __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, 
   uint32_t uncert = 0;
   for (uint32_t i = lane; i < m; i += 32) {
     const uint32_t g = i / k, slot = i % k;
-    const rag_rec r = rec_load(recs + ((size_t)g * a.B + b) * k + slot);
+    const rag_rec r = rec_load<LOCAL>(LOCAL ? recs + slot : recs + ((size_t)g * a.B + b) * k + slot);
     s.m_score[i] = r.score; s.m_id[i] = r.id; s.m_src[i] = (uint16_t)i;
     if (slot == 0) uncert |= r.flags & 1u;
   }
@@ -185,7 +193,7 @@ __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, 
     }
     if (rank < k) {
       const uint32_t g = i / k, slot = i % k;
-      const rag_rec r = rec_load(recs + ((size_t)g * a.B + b) * k + slot);
+      const rag_rec r = rec_load<LOCAL>(LOCAL ? recs + slot : recs + ((size_t)g * a.B + b) * k + slot);
       s.v_score[rank] = si; s.v_id[rank] = ii; s.v_key[rank] = r.key;
       s.v_fresh[rank] = r.fresh; s.v_ct[rank] = (uint8_t)r.ctype;
       n_top++;
@@ -252,7 +260,11 @@ __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, 
     return;
   }
 
-  const uint32_t nk = (a.mode == 0 && kwc) ? kwc[b] : 0u;
+  const uint32_t nk = (a.mode == 0 && kwc) ? min(kwc[b], (uint32_t)RAG_MAX_KEYWORDS) : 0u;
+  // the keyword keys in one coalesced load (the fusion pass walks them one by one: from global memory every step
+  // would be a dependent L2 round trip)
+  for (uint32_t i = lane; i < nk; i += 32) s.k_key[i] = kw[(size_t)b * a.kw_stride + i];
+  __syncwarp();
   // ---- 3b. vector-only branch (hybrid-search.ts:346-354) -----------------------------
   if (nk == 0) {
     for (uint32_t i = lane; i < nv; i += 32) {
@@ -266,7 +278,7 @@ __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, 
   uint32_t n = 0;
   rrf_pass(s, n, s.v_key, s.v_ct, nv, a.rrf.vector_weight, a.rrf.k, a.rrf.both_bonus, true,
            RAG_SRC_VECTOR, RAG_CT_DOCUMENT, lane);
-  rrf_pass(s, n, kw + (size_t)b * a.kw_stride, nullptr, nk, a.rrf.keyword_weight, a.rrf.k, a.rrf.both_bonus,
+  rrf_pass(s, n, s.k_key, nullptr, nk, a.rrf.keyword_weight, a.rrf.k, a.rrf.both_bonus,
            false, RAG_SRC_KEYWORD, RAG_CT_DOCUMENT, lane);
   if (a.fresh_limit > 0) {
     // north-star extension (SURVEY N-c4 ii): memory hits of the vector stage ranked by

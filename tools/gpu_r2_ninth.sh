@@ -1,0 +1,7 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_napi.py tests/test_gpu_batcher.py tests/test_loader.py -m gpu -x -q > $OUT/r2i_pytest.log 2>&1; echo "pytest exit $?" | tee -a $OUT/r2i_pytest.log
+tail -4 $OUT/r2i_pytest.log
+for wl in c1 c2; do
+  timeout 300 python bench.py --workload $wl --no-extra --steps 1000 --warmup 20 > $OUT/r2i_bench_${wl}.json 2> $OUT/r2i_bench_${wl}.err; echo "$wl exit $?"
+done
