@@ -35,9 +35,15 @@ __device__ __forceinline__ void rrf_pass(fuse_smem& s, uint32_t& n_entries, cons
                                          const uint8_t* cts, uint32_t n, double weight, double kconst,
                                          double bonus, bool first_pass, uint8_t new_src, uint8_t new_ct,
                                          int lane) {
+  // the per-rank contributions w / (k + rank + 1) for ranks lane and lane + 32, computed side by side (an fp64 division
+  // per step of the sequential walk below would be on its critical path)
+  const double c0 = __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)lane), 1.0));
+  const double c1 = __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)(lane + 32)), 1.0));
   for (uint32_t r = 0; r < n; r++) {
     const uint64_t key = keys[r];
-    const double rrf = __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)r), 1.0));
+    const unsigned long long cb = __double_as_longlong(r < 32 ? c0 : c1);
+    const double rrf = r < 64 ? __longlong_as_double((long long)shfl_u64(cb, (int)(r & 31)))
+                              : __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)r), 1.0));
     int found = -1;
     for (uint32_t base = 0; base < n_entries; base += 32) {
       const uint32_t i = base + lane;
