@@ -472,6 +472,9 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
                               "calls escalate uncertified queries inside the timed call",
                       "setup_queries": certified_setup, "of": n_pool * B, "last_step": int(last.certified.sum()), "last_step_of": B},
     }
+    if timed_certified != timed_queries:
+        res["certified"]["warning"] = (f"{timed_queries - timed_certified} of the {timed_queries} queries behind `value` were NOT certified by the first pass: "
+                                       "the product call (e2e) re-runs them on a stronger path, the device-timed loop does not")
     if first_pass:
         res["first_pass_certification"] = first_pass
     if shard_rows:

@@ -19,6 +19,22 @@ int rag_index_set_row_meta(rag_index*, uint64_t, uint64_t, const uint8_t*, const
 int rag_index_set_row_keys(rag_index*, uint64_t, uint64_t, const uint64_t*) { return RAG_ERR_NO_DEVICE; }
 int rag_index_read_rows(rag_index*, uint64_t, uint64_t, void*) { return RAG_ERR_NO_DEVICE; }
 }
+// the sidecar's header checksum (store_cache.cu::fnv64 restated: the harness forges headers whose checksum is VALID, so
+// the size checks — not the checksum — have to stop them)
+static uint64_t fnv64_test(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  const uint64_t prime = 0x100000001b3ull;
+  uint64_t l0 = h, l1 = h ^ 0x9e3779b97f4a7c15ull, l2 = h ^ 0xc2b2ae3d27d4eb4full, l3 = h ^ 0x165667b19e3779f9ull;
+  for (; n >= 32; n -= 32, p += 32) {
+    uint64_t w[4];
+    memcpy(w, p, 32);
+    l0 = (l0 ^ w[0]) * prime; l1 = (l1 ^ w[1]) * prime; l2 = (l2 ^ w[2]) * prime; l3 = (l3 ^ w[3]) * prime;
+  }
+  h = l0; h = (h ^ l1) * prime; h = (h ^ l2) * prime; h = (h ^ l3) * prime;
+  for (; n >= 8; n -= 8, p += 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * prime; }
+  for (; n; n--, p++) h = (h ^ *p) * prime;
+  return h;
+}
 static int on_rows(void* user, uint64_t, uint64_t n, const float* rows) { *(double*)user += rows[0] * (double)n; return RAG_OK; }
 int main(int argc, char** argv) {
   // argv[1]: a JSON store, argv[2]: dim, argv[3]: a cache path to write/read/corrupt
@@ -76,6 +92,27 @@ int main(int argc, char** argv) {
       }
     }
     printf("corruptions: rejected=%d accepted=%d\n", bad, ok);
+    // forged headers with a VALID checksum and sizes chosen to wrap the section arithmetic (rows*dim*4, rows*8, ids_bytes):
+    // header layout: magic[8] version dtype dim flags (u32 x4) rows ids_bytes (u64 x2) ... head_sum at byte 120
+    if (blob.size() >= 128) {
+      const uint64_t forged[][2] = {{1ull << 61, 0}, {(1ull << 62) + 3, 1ull << 63}, {0xFFFFFFFFFFFFFFF0ull, 16}, {rows, ~0ull - 100}, {1ull << 33, 1ull << 45}};
+      int fr = 0, fa = 0;
+      for (const auto& fz : forged) {
+        std::string b = blob;
+        memcpy(&b[24], &fz[0], 8);
+        memcpy(&b[32], &fz[1], 8);
+        const uint64_t hs = fnv64_test(0xcbf29ce484222325ull, b.data(), 120);
+        memcpy(&b[120], &hs, 8);
+        f = fopen(cache, "wb"); fwrite(b.data(), 1, b.size(), f); fclose(f);
+        rag_cache_info info;
+        char* i4 = nullptr; uint64_t n4 = 0;
+        const int r1 = rag_cache_info_read(cache, &info);
+        const int r2 = rag_cache_read_host(cache, 0, 1, Y.data(), nullptr, nullptr, nullptr, nullptr, nullptr, &i4, &n4);
+        if (r2 == RAG_OK) rag_free(i4);
+        ((r1 != RAG_OK && r2 != RAG_OK) ? fr : fa)++;
+      }
+      printf("forged headers: rejected=%d accepted=%d\n", fr, fa);
+    }
   }
   rag_free(ids);
   return 0;

@@ -499,6 +499,8 @@ def test_loader_and_sidecar_under_sanitizers(tmp_path):
         assert "AddressSanitizer" not in r.stderr and "LeakSanitizer" not in r.stderr and "runtime error" not in r.stderr, (name, r.stderr[-1500:])
         assert ("parse rc=0" in r.stdout) == ok, (name, r.stdout)
         assert "ACCEPTED CORRUPT DATA" not in r.stdout, (name, r.stdout)
+        if "forged headers" in r.stdout:
+            assert "forged headers: rejected=5 accepted=0" in r.stdout, (name, r.stdout)
         if ok:
             assert "read rc=0 same=1" in r.stdout and "write rc=0 fresh=1" in r.stdout, (name, r.stdout)
             assert "refresh rc=0 route=0" in r.stdout and "refresh rc=0 route=1" in r.stdout and "prefix past the end ok=0" in r.stdout, (name, r.stdout)
