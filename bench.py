@@ -287,10 +287,13 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         idx = rb.VectorIndex(d, rows, dtype=dt, device=device, shadow=shadow)
         base, n_local = 0, rows
     idx.generate(gen, n_local)
-    if sharded and tensor and os.environ.get("RAGERA_BENCH_BALANCE", "1") != "0":
-        # The batch ends with the SLOWEST shard, and the GPUs of one box differ by several percent under the power cap
-        # (round 1: up to 15% at N=8). Calibrate: a few batches on the even split, every rank's own scoring-kernel time,
-        # then contiguous shards sized by measured speed (boundaries and id_base move, nothing else). Untimed setup.
+    if sharded and tensor and os.environ.get("RAGERA_BENCH_BALANCE", "0") != "0":
+        # OFF by default (measured: it does not help). The batch ends with the SLOWEST shard, and the GPUs of one box differ by
+        # several percent under the power cap (round 1: up to 15% at N=8). Calibrate: a few batches on the even split, every
+        # rank's own scoring-kernel time, then contiguous shards sized by measured speed (boundaries and id_base move, nothing
+        # else). Result on 4 GPUs (C5): the rank that calibrated fastest (30.9 ms vs 32.7-32.9) got 6% more rows and then ran
+        # 13% SLOWER than the others (34.9 vs 31.0-31.9 ms) — a GPU's speed under the power cap is a thermal state that moves
+        # within seconds, not a property a short calibration can measure. profiles/r02_scaling.md.
         from rag_era_b200.sharded import balanced_ranges
 
         Qc = idx.generate_queries(gen, 0, B)
@@ -369,6 +372,9 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     idx.profile_enable(False)
     timed_certified, timed_queries = idx.certified_totals()   # every query of every timed step, counted on the device
     last = idx.fetch_fused(B, o)
+    parity = None
+    if rank == 0 and os.environ.get("RAGERA_BENCH_PARITY", "1") != "0":
+        parity = parity_check(w, gen, Q[((total - 1) % n_pool) * B:][:B], last, d, dt == N.BF16)   # untimed; the oracle as the checker
     if world > 1:
         import torch
 
@@ -475,6 +481,8 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     if timed_certified != timed_queries:
         res["certified"]["warning"] = (f"{timed_queries - timed_certified} of the {timed_queries} queries behind `value` were NOT certified by the first pass: "
                                        "the product call (e2e) re-runs them on a stronger path, the device-timed loop does not")
+    if parity:
+        res["parity_check"] = parity
     if first_pass:
         res["first_pass_certification"] = first_pass
     if shard_rows:
@@ -500,6 +508,38 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         leave_exchange(dist, idx)
     idx.close()
     return res
+
+
+def parity_check(w, gen, Qlast, last, d, bf16, n_queries=2, window=100_000):
+    """Outside every timed region, on rank 0: the LAST timed step's answer for a few queries against the CPU oracle (the checker,
+    never the thing measured) — (1) every reported cosine is the oracle's fp64 value for that chunk, bit for bit; (2) an oracle
+    scan of a window of the corpus around the best hit finds no chunk that should have been in the answer and is not, and lists
+    the returned chunks of that window in the returned order. Works for any shard count: ids are global."""
+    import oracle
+
+    g = oracle.GenDesc.from_buffer_copy(bytes(gen))
+    odt = oracle.BF16 if bf16 else oracle.F32
+    rows, k = w["rows"], w["vector_top_k"]
+    out = {"queries": 0, "scores_bit_equal": True, "window_rows": min(window, rows), "window_consistent": True}
+    for b in range(min(n_queries, len(Qlast))):
+        r = last.row(b)
+        ids, sc = [int(i) for i in r["vec_ids"]], [float(x) for x in r["vec_scores"]]
+        if not ids:
+            continue
+        out["queries"] += 1
+        for i, x in zip(ids, sc):
+            if oracle.cosine(Qlast[b], oracle.gen_rows(g, i, 1, d, dtype=odt)[0]) != x:
+                out["scores_bit_equal"] = False
+        lo = max(0, min(rows - out["window_rows"], ids[0] - out["window_rows"] // 2))
+        wi, ws = oracle.topk_generated(g, odt, lo, out["window_rows"], d, Qlast[b], k)
+        inside = [i for i in ids if lo <= i < lo + out["window_rows"]]
+        kth = (sc[-1], ids[-1])
+        full = len(ids) == k
+        must = [int(i) for i, x in zip(wi, ws) if x >= w["min_score"] and (not full or (x, -int(i)) > (kth[0], -kth[1]))]
+        if [int(i) for i in wi[:len(inside)]] != inside or any(i not in ids for i in must):
+            out["window_consistent"] = False
+    out["ok"] = bool(out["queries"] > 0 and out["scores_bit_equal"] and out["window_consistent"])
+    return out
 
 
 def idx_ld(d):
@@ -546,7 +586,7 @@ def run_ours(args):
                                "warmup": e_warm, "ms_per_step": r["ms_per_step"], "e2e": r["e2e"], "roofline": r["roofline"],
                                "kernel_ms_per_step": r["kernel_ms_per_step"], "certified": r["certified"], "clocks": r["clocks"],
                                "gpu_launches": r["gpu_launches"]}
-                for key in ("first_pass_certification", "per_rank_kernel_ms", "exchange", "shard_rows"):
+                for key in ("first_pass_certification", "per_rank_kernel_ms", "exchange", "shard_rows", "parity_check"):
                     if key in r:
                         extra[name][key] = r[key]
             except Exception as e:          # e.g. out of memory on a smaller part: say so instead of losing the line
@@ -562,7 +602,7 @@ def run_ours(args):
             # the batched path selects on tcgen05 products of 16-bit (fp16 queries x fp16/bf16 rows) or tf32 operands;
             # ids and scores are still decided in fp64
             line["dtype"] = "tf32" if "operand" in res["roofline"] else ("f16xbf16" if w["dtype"] == "bf16" or w.get("shadow") == "bf16" else "f16")
-        for key in ("per_rank_kernel_ms", "exchange", "e2e_kernel_ms_per_call", "first_pass_certification", "shard_rows"):
+        for key in ("per_rank_kernel_ms", "exchange", "e2e_kernel_ms_per_call", "first_pass_certification", "shard_rows", "parity_check"):
             if key in res:
                 line[key] = res[key]
         if "cpu_baseline" in res:
