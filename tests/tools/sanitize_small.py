@@ -30,5 +30,25 @@ with rb.VectorIndex(d, n, bf16_shadow=True) as idx:
     fr = idx.freshness_scores([0.5, 0.9], [1, 2], [0, 1000], 5000)
     z = idx.rrf_fuse([[1, 2, 3]], [[2, 4]])
     ok &= bool(z.counts[0] == 4)
+# the fp16 shadow of the normalised rows (pre-normalised epilogue), a bf16 corpus (bf16 x bf16 + multi-query bf16 stream
+# kernel), and the small-batch call replayed as a CUDA graph (second call = replay)
+with rb.VectorIndex(d, n, shadow="f16") as idx:
+    idx.generate(gn, n)
+    r = idx.query(Q[:40], 10, path=N.PATH_TENSOR)
+    for b in range(0, 40, 7):
+        ei, es = oracle.topk(X, Q[b], 10)
+        ok &= bool(np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es))
+    for _ in range(2):
+        f = idx.hybrid(Q[:1], rb.hybrid_opts(10, 4, 0.3, path=N.PATH_STREAM), [[1, 2, 3]])
+        e = oracle.hybrid_search(X, Q[0], 10, 0.3, [1, 2, 3])
+        ok &= bool(np.array_equal(f.row(0)["keys"], e["keys"]) and np.array_equal(f.row(0)["scores"], e["scores"]))
+Xb = oracle.gen_rows(go, 0, n, d, dtype=oracle.BF16)
+with rb.VectorIndex(d, n, dtype=N.BF16) as idx:
+    idx.generate(gn, n)
+    for path, B in ((N.PATH_TENSOR, 40), (N.PATH_STREAM, 6)):
+        r = idx.query(Q[:B], 10, path=path)
+        for b in range(0, B, 5):
+            ei, es = oracle.topk(Xb, Q[b], 10)
+            ok &= bool(np.array_equal(r.row(b)[0], ei) and np.array_equal(r.row(b)[1], es))
 print("sanitize_small:", "OK" if ok else "MISMATCH")
 sys.exit(0 if ok else 1)
