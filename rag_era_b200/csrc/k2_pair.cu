@@ -63,7 +63,7 @@ constexpr int B_BYTES = HALF_N * ROW_BYTES;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int KP_THREADS = 256;        // w0 TMA · w1 MMA · w2 TMEM alloc · w3 inv-norm loader · w4..7 epilogue
 constexpr int KP_WARPS = KP_THREADS / 32;
-constexpr int MAX_STAGES = 5;         // 5, 6 and 7 measure the same; shared memory goes to the windows and best lists
+constexpr int MAX_STAGES = 7;         // barrier slots; the product runs what fits beside the windows and best lists (5)
 constexpr int TMEM_COLS = 512;
 constexpr int WIN = 32;                // append window per query (shared memory), entries
 constexpr int KP_PREFETCH = 8;         // k-slices of L2 prefetch ahead of the TMA loads
@@ -83,6 +83,7 @@ struct kp_params {
   uint32_t lockstep;   // a pair starts tile i only when every group's same-index pair has started tile i - lockstep (0 = off)
   float* dbg_scores;
   uint32_t mode;
+  uint32_t nolists;
   unsigned long long* cyc;  // diagnostics (RAGERA_K2_PROF): [ctas][8 warps][8] cycle counters
 };
 __device__ __forceinline__ long long clk() { return clock64(); }
@@ -358,10 +359,13 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   // layout (identical in both CTAs): [stages][A | B] · windows [128][WIN] u64 · best [128][32 or 64] u64 ·
   // inv [2][256] f32 · barriers · tmem ptr
   unsigned char* stage_base = smem;
-  uint64_t* win = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * STAGE_BYTES);
+  // P.nolists (diagnostics, RAGERA_K2_MODE=2 with RAGERA_K2_STAGES): no selection runs, so the windows and best lists
+  // get no memory of their own and the pipeline can be measured with more stages than the product has room for
+  uint64_t* win = reinterpret_cast<uint64_t*>(P.nolists ? smem : smem + (size_t)P.stages * STAGE_BYTES);
   uint64_t* best = win + (size_t)CTA_M * WIN;
   const uint32_t best_stride = P.kp > 32 ? 64u : 32u;  // sorted K' best per query, lane l owns ranks l and 32+l
-  float* s_inv = reinterpret_cast<float*>(best + (size_t)CTA_M * best_stride);
+  float* s_inv = P.nolists ? reinterpret_cast<float*>(smem + (size_t)P.stages * STAGE_BYTES)
+                           : reinterpret_cast<float*>(best + (size_t)CTA_M * best_stride);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 2 * TILE_N);
   uint64_t* full = bars;                        // [stages]  (the leader's are used)
   uint64_t* empty = bars + MAX_STAGES;          // [stages]  (local)
@@ -370,6 +374,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* inv_full = tmem_empty + 2;          // [2]       (local)
   uint64_t* inv_empty = inv_full + 2;           // [2]       (local)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(inv_empty + 2);
+  volatile uint32_t* gate = tmem_ptr + 1;  // [0] tiles the slowest query group has started  [1] this CTA's producer is done
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool SB = SHARE == 1 || SHARE == 3;   // the corpus tile is the shared operand
@@ -386,10 +391,13 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   // walks tiles past the end — TMA fills zeros, the epilogue masks rows >= n_rows
   const uint32_t n_iter = SA ? (P.n_tiles + P.pairs - 1) / P.pairs : (P.n_tiles > pair ? (P.n_tiles - pair + P.pairs - 1) / P.pairs : 0u);
   constexpr int BK = TF32 ? ROW_BYTES / 4 : ROW_BYTES / 2;  // k elements per stage
+  const bool gated = leader && P.lockstep != 0 && gridDim.y > 1;  // lockstep of the query groups (see the producer)
   const uint32_t nkb = P.ld / BK;
   unsigned long long* cyc = P.cyc ? P.cyc + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * KP_WARPS + warp) * 8 : nullptr;
 
   if (threadIdx.x == 0) {
+    gate[0] = 0u;
+    gate[1] = 0u;
     // full[s]: one arrival (the leader's expect_tx of BOTH CTAs' bytes). The peer's TMA completes on the
     // leader's barrier without an arrival of its own; its bytes can only land in the phase they belong
     // to because the peer refills a stage only after the leader's commit has released it.
@@ -440,16 +448,16 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // streams the corpus from HBM by itself (measured: DRAM traffic 1.85x algorithmic at 1M rows, K2
         // 25% slower per flop at 25M rows). A pair may run at most P.lockstep tiles (default 1) ahead of the slowest
         // group; the wait is bounded, so it is a pacing hint and can never deadlock.
-        if (leader && P.lockstep && gridDim.y > 1) {
+        // The progress board is polled by warp 2 (idle once TMEM is allocated), which mirrors the slowest group's count
+        // into shared memory: the L2 round trips of the poll stay off this thread, whose stalls delay the loads
+        // (measured at C2b: polling here cost ~3% of K2 and the MMA thread waited 19% of its cycles for operands; 11% now,
+        // and lockstep on and off time the same).
+        if (gated) {
           __stcg(P.prog + (size_t)blockIdx.y * P.pairs + pair, it + 1);
           if (it >= P.lockstep) {
             const uint32_t need = it + 1 - P.lockstep;
             const long long t0 = clk();
-            for (;;) {
-              uint32_t slowest = 0xFFFFFFFFu;
-              for (uint32_t g = 0; g < gridDim.y; g++) slowest = min(slowest, __ldcg(P.prog + (size_t)g * P.pairs + pair));
-              if (slowest >= need || clk() - t0 > 200000) break;
-            }
+            while (gate[0] < need && clk() - t0 < 200000) {}
           }
         }
         for (uint32_t kb = 0; kb < nkb; kb++) {
@@ -472,7 +480,20 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (gated) gate[1] = 1u;  // the poller may leave
       if (cyc) { cyc[0] = (unsigned long long)(clk() - t_begin); cyc[1] = (unsigned long long)w_empty; }
+    }
+  } else if (warp == 2) {
+    // ===== lockstep poller (leader CTA only): slowest same-index pair over the query groups -> shared memory =====
+    if (gated && lane == 0) {
+      uint32_t shown = 0;
+      while (gate[1] == 0u) {
+        uint32_t slowest = 0xFFFFFFFFu;
+        for (uint32_t g = 0; g < gridDim.y; g++) slowest = min(slowest, __ldcg(P.prog + (size_t)g * P.pairs + pair));
+        if (slowest != shown) gate[0] = shown = slowest;
+        if (slowest >= n_iter) break;
+        __nanosleep(128);
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
@@ -729,6 +750,8 @@ struct kp_state {
   bool attr_set = false;
   float* dbg = nullptr;
   uint32_t mode = 0;
+  uint32_t stage_cap = 5;   // RAGERA_K2_STAGES (diagnostics): 3..7; 6 and 7 only fit without the lists (mode 2)
+  bool nolists = false;
   uint32_t prefetch = KP_PREFETCH;
   uint32_t local_min = 3;
   uint32_t lockstep = 1;
@@ -740,14 +763,14 @@ struct kp_state {
   size_t c_pub = 0;
 };
 
-size_t kp_smem_bytes(uint32_t stages, uint32_t kp) {
-  return (size_t)stages * STAGE_BYTES + (size_t)CTA_M * WIN * 8 + (size_t)CTA_M * (kp > 32 ? 64 : 32) * 8 + 2 * TILE_N * 4 +
-         (2 * MAX_STAGES + 8) * 8 + 16;
+size_t kp_smem_bytes(const kp_state* st, uint32_t stages, uint32_t kp) {
+  const size_t lists = st->nolists ? 0 : (size_t)CTA_M * WIN * 8 + (size_t)CTA_M * (kp > 32 ? 64 : 32) * 8;
+  return (size_t)stages * STAGE_BYTES + lists + 2 * TILE_N * 4 + (2 * MAX_STAGES + 8) * 8 + 16;
 }
 
 uint32_t kp_pick_stages(const kp_state* st, uint32_t kp) {
-  uint32_t s = MAX_STAGES;
-  while (s > 0 && kp_smem_bytes(s, kp) > (size_t)st->max_smem) s--;
+  uint32_t s = st->stage_cap;
+  while (s > 0 && kp_smem_bytes(st, s, kp) > (size_t)st->max_smem) s--;
   return s;
 }
 
@@ -764,6 +787,11 @@ int kp_init(rag_index* idx) {
   }
   st->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   if (const char* m = getenv("RAGERA_K2_MODE")) st->mode = (uint32_t)atoi(m);
+  if (const char* m = getenv("RAGERA_K2_STAGES")) {
+    const int v = atoi(m);
+    if (v >= 3 && v <= MAX_STAGES) st->stage_cap = (uint32_t)v;
+    st->nolists = st->mode == 2 && v > 5;
+  }
   if (const char* m = getenv("RAGERA_K2_PROF")) st->prof = atoi(m) != 0;
   if (const char* m = getenv("RAGERA_K2_PREFETCH")) st->prefetch = (uint32_t)atoi(m);
   if (const char* m = getenv("RAGERA_K2_LOCAL_MIN")) st->local_min = (uint32_t)atoi(m);
@@ -841,7 +869,7 @@ int kp_shape(rag_index* idx, uint32_t groups, uint32_t kp, int* share, uint32_t*
       cudaLaunchConfig_t cfg;
       cudaLaunchAttribute attr;
       const dim3 c = kp_cluster_dim(sh);
-      kp_launch_cfg(&cfg, &attr, dim3(c.x * 64, c.y, 1), kp_smem_bytes(kp_pick_stages(st, kp), kp), idx->stream, sh);
+      kp_launch_cfg(&cfg, &attr, dim3(c.x * 64, c.y, 1), kp_smem_bytes(st, kp_pick_stages(st, kp), kp), idx->stream, sh);
       int n = 0;
       cudaError_t e = cudaOccupancyMaxActiveClusters(&n, (const void*)kp_kernel(idx, sh), &cfg);
       if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
@@ -972,6 +1000,7 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   }
   P.dbg_scores = st->dbg;
   P.mode = st->mode;
+  P.nolists = st->nolists ? 1u : 0u;
   P.prefetch = st->prefetch;
   P.local_min = st->local_min;
   P.cyc = nullptr;
@@ -982,7 +1011,7 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
     RAG_CUDA(cudaMemsetAsync(st->d_cyc, 0, n_cyc * 8, idx->stream));
     P.cyc = st->d_cyc;
   }
-  const size_t smem = kp_smem_bytes(P.stages, kp);
+  const size_t smem = kp_smem_bytes(st, P.stages, kp);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr;
   kp_launch_cfg(&cfg, &attr, dim3(P.pairs * 2, groups), smem, idx->stream, share);
