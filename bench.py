@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — hybrid-search throughput/latency of the retrieval hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c2b|c1|c4|c4f|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c2b|c1|c4|c4f|c5|c3s|c1s] [--impl reference]
 
 One "step" = one hybrid search (cosine scoring of every chunk → top-k → min-cosine filter →
 RRF with the keyword list) of one query batch over the whole corpus.
@@ -16,7 +16,9 @@ RRF with the keyword list) of one query batch over the whole corpus.
 Workloads (BASELINE.json configs): c3 = 10M x 1536 fp32 batch 1 (default; the north-star
 target), c2 = 1M x 1536 fp32 batch 1 (c2b: batch 1024, tcgen05 path), c1 = 10k x 1536 fp32 batch 1
 (L2-resident), c4 = 2M memory + 5M doc rows, three lists, batch 256, c5 = 50M x 1536 bf16 batch 1024.
-The default line carries c2 / c2b / c1 / c4 (one GPU) and c5 (every N) under `extra`.
+c3s / c1s = c3 / c1 with the single query scored by streaming the fp16 shadow of the normalised rows (an EXTRA mode:
+half the bytes, same certified-exact results; the BASELINE config is the fp32 stream).
+The default line carries c2 / c2b / c1 / c4 (one GPU) and c5, c3s (every N) under `extra`.
 For N > 1 the SAME corpus is row-sharded over the ranks (strong scaling): every rank scores
 its shard, the ranks' exact local top-k lists are exchanged inside the final fusion kernel through
 peer-to-peer mailboxes over NVLink (RAGERA_COMM=nccl: one ncclAllGather instead), and the merge +
@@ -51,6 +53,15 @@ WORKLOADS = {
                desc="C3: 10M x 1536 fp32, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1"),
     "c3h": dict(rows=10_000_000, dim=1536, dtype="bf16", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                 desc="C3 with a bf16 corpus: 10M x 1536 bf16, vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1 (stream path)"),
+    "c3s": dict(rows=10_000_000, dim=1536, dtype="f32", batch=1, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
+                path="shadow_stream", shadow="f16",
+                desc="C3 on the fp16 shadow (EXTRA mode, not the BASELINE config): 10M x 1536 fp32 (+fp16 shadow of the normalised rows), "
+                     "batch 1 scored by streaming the shadow (2 B/element), K'=32, certified by the rows' measured rounding residual; "
+                     "vectorTopK=10 keywordLimit=10 RRF(k=60) top-8"),
+    "c1s": dict(rows=10_000, dim=1536, dtype="f32", batch=1, vector_top_k=5, keyword_limit=5, min_score=0.3, show=3,
+                path="shadow_stream", shadow="f16",
+                desc="C1 on the fp16 shadow (EXTRA mode): 10k x 1536 fp32 (+fp16 shadow), batch 1 scored by streaming the shadow; "
+                     "vectorTopK=5 keywordLimit=5 RRF(k=60) top-3"),
     "c2b": dict(rows=1_000_000, dim=1536, dtype="f32", batch=1024, vector_top_k=10, keyword_limit=10, min_score=0.3, show=8,
                 path="tensor", shadow="f16",
                 desc="C2 deep_search batched: 1M x 1536 fp32 (+fp16 shadow of the normalised rows), vectorTopK=10 keywordLimit=10 RRF(k=60) top-8, batch 1024, tcgen05 kind::f16 path"),
@@ -277,7 +288,8 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
     gen = N.GenDesc(SEEDS["seed"], SEEDS["query_seed"], SEEDS["meta_seed"], rows, 4096, 0.6, 0.5, 0,
                     w.get("memory_rows", 0), now_ms)
     tensor = w.get("path") == "tensor"
-    path = N.PATH_TENSOR if tensor else N.PATH_STREAM
+    on_shadow = w.get("path") == "shadow_stream"
+    path = N.PATH_TENSOR if tensor else (N.PATH_SHADOW_STREAM if on_shadow else N.PATH_STREAM)
     shadow = w.get("shadow") if dt == N.F32 else None
     shard_rows = None
     if sharded:
@@ -341,6 +353,11 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
         stat = idx.query(Q[:B], w["vector_top_k"], path=path, flags=N.SEARCH_NO_ESCALATE | N.SEARCH_STAT_EPS)
         first_pass = {"queries": B, "rigorous_bound": int(rig.certified.sum()), "statistical_bound": int(stat.certified.sum()),
                       "row_residual_rho_x": idx.row_residual()}
+    elif on_shadow:
+        nq = min(len(Q), 32)
+        rig = idx.query(Q[:nq], w["vector_top_k"], path=path, flags=N.SEARCH_NO_ESCALATE)
+        first_pass = {"queries": nq, "rigorous_bound": int(rig.certified.sum()), "row_residual_rho_x": idx.row_residual(),
+                      "note": "queries certified by the shadow pass alone; the rest re-run on the fp32 stream inside the product call"}
 
     def barrier():
         idx.sync()
@@ -453,11 +470,12 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
             roof["traffic_source"] = "profiles/traffic.json (ncu --set full dram bytes / algorithmic, scaled to this launch)"
     else:
         k1_ms, k1_n = prof["stream"]
-        bytes_per_launch = n_local * idx_ld(d) * (4 if dt == N.F32 else 2) * B   # K1 streams the shard once per query
+        bytes_per_launch = n_local * idx_ld(d) * (4 if (dt == N.F32 and not on_shadow) else 2) * B   # K1 streams the shard (or its fp16 shadow) once per query
         achieved = bytes_per_launch / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9 if k1_n else None
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src + " hbm_gbs",
-                "kernel": "k1_stream (fused cosine GEMV + top-K')", "algorithmic_bytes_per_launch": int(bytes_per_launch),
+                "kernel": "k1_stream_f16n (fused GEMV over the fp16 shadow of the normalised rows + top-K')" if on_shadow else "k1_stream (fused cosine GEMV + top-K')",
+                "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "avg_launch_ms": k1_ms / max(k1_n, 1), "launches_timed": int(k1_n),
                 "frac_of_nominal_8TBps": (achieved / 8000.0) if achieved else None}
         tr = traffic_ratio("k1_stream", name)
@@ -577,6 +595,7 @@ def run_ours(args):
         # one GPU; configs[4] (c5, 50M x 1536 bf16 batch 1024, row-sharded) at EVERY N so the scaling run carries its curve
         plan = [("c2", 200, 5), ("c2b", 30, 5), ("c1", 500, 5), ("c4", 20, 3)] if world == 1 else [("c2b", 30, 5), ("c2br", 30, 5)]
         plan.append(("c5", 10, 3))
+        plan.append(("c3s", 200, 10))   # labelled extra mode: batch 1 on the fp16 shadow (never the headline)
         for name, e_steps, e_warm in plan:
             if name == args.workload:
                 continue
@@ -598,6 +617,8 @@ def run_ours(args):
                 "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "roofline": res["roofline"],
                 "kernel_ms_per_step": res["kernel_ms_per_step"], "certified": res["certified"],
                 "arithmetic": "fp32 scoring selects K' candidates; fp64 reference-order rescoring decides ids/scores/ties"}
+        if w.get("path") == "shadow_stream":
+            line["dtype"] = "f16"   # selection streams fp16 rows against the fp32 query (fp32 accumulate); ids and scores are decided in fp64
         if res["roofline"].get("bound") == "tensor":
             # the batched path selects on tcgen05 products of 16-bit (fp16 queries x fp16/bf16 rows) or tf32 operands;
             # ids and scores are still decided in fp64

@@ -63,10 +63,14 @@ typedef enum rag_content_type { RAG_CT_DOCUMENT = 0, RAG_CT_MEMORY = 1, RAG_CT_C
 
 /* which scoring kernel produces the candidates (results are identical) */
 typedef enum rag_path {
-  RAG_PATH_AUTO = 0,  /* B < gemm threshold → stream, else tensor (if shadow exists) */
+  RAG_PATH_AUTO = 0,  /* one query on an fp32 index with an fp16 shadow → shadow stream; B < gemm threshold →
+                         stream; else tensor (if an operand exists)                 */
   RAG_PATH_STREAM = 1,/* K1: HBM-bound fused cosine GEMV + top-k, fp32 accumulate   */
   RAG_PATH_TENSOR = 2,/* K2: tcgen05 bf16 GEMM + fused top-k epilogue               */
-  RAG_PATH_EXACT = 3  /* K1x: fp64 reference-order scan of every row (slow, exact)   */
+  RAG_PATH_EXACT = 3, /* K1x: fp64 reference-order scan of every row (slow, exact)   */
+  RAG_PATH_SHADOW_STREAM = 4 /* K1 over the fp16 shadow of the normalised rows (RAG_INDEX_F16_SHADOW): the same HBM-bound
+                         scan at 2 bytes per element; certified by the rows' measured rounding residual, escalates to
+                         RAG_PATH_STREAM                                            */
 } rag_path;
 
 /* 16-bit operand of the tensor path for an fp32 corpus (selection only: reported scores are always recomputed from the

@@ -22,7 +22,7 @@ ERR_TIMEOUT = -8
 F32, BF16 = 0, 1
 SRC_VECTOR, SRC_KEYWORD, SRC_BOTH, SRC_FRESHNESS = 0, 1, 2, 3
 CT_DOCUMENT, CT_MEMORY, CT_CODE = 0, 1, 2
-PATH_AUTO, PATH_STREAM, PATH_TENSOR, PATH_EXACT = 0, 1, 2, 3
+PATH_AUTO, PATH_STREAM, PATH_TENSOR, PATH_EXACT, PATH_SHADOW_STREAM = 0, 1, 2, 3, 4
 INDEX_BF16_SHADOW = 1
 INDEX_F16_SHADOW = 2
 CACHE_META, CACHE_KEYS = 1, 2

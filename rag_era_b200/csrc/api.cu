@@ -28,6 +28,7 @@ constexpr uint32_t kProfSpans = 8192;
 // read as tf32 win from 8 (1.3 vs 1.5 ms). Below that the stream kernels (K1 / K1m) keep fp32 selection.
 constexpr uint32_t kTensorMinBatchBf16 = 4;
 constexpr uint32_t kTensorMinBatchTf32 = 8;
+constexpr uint64_t kShadowStreamMinBytes = 128ull << 20;  // AUTO streams the fp16 shadow for one query once the shadow outgrows L2
 
 size_t elem_size(const rag_index* idx) { return idx->desc.dtype == RAG_BF16 ? 2 : 4; }
 
@@ -146,11 +147,22 @@ int refresh_rho_x(rag_index* idx) {
 int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_t slack, double eps, uint32_t flags,
               plan* p) {
   int path = (int)req_path;
-  if (path == RAG_PATH_AUTO)
+  const bool has_f16_shadow = idx->desc.dtype == RAG_F32 && idx->shadow && idx->shadow_f16 && idx->inv_norm;
+  if (path == RAG_PATH_AUTO) {
+    static const bool shadow_stream_auto = !(getenv("RAGERA_SHADOW_STREAM") && atoi(getenv("RAGERA_SHADOW_STREAM")) == 0);
     path = (k2_available(idx) && B >= (idx->shadow ? kTensorMinBatchBf16 : kTensorMinBatchTf32)) ? RAG_PATH_TENSOR
                                                                                               : RAG_PATH_STREAM;
-  if (path != RAG_PATH_STREAM && path != RAG_PATH_TENSOR && path != RAG_PATH_EXACT)
+    // a single query on an index that carries the fp16 shadow: stream the shadow — half the bytes of the fp32 rows.
+    // Only where bytes are what costs: the shadow pass keeps K' = 32 candidates (its bound is the rows' fp16 residual), and
+    // rescoring 32 instead of 16 rows outweighs the bytes saved while the corpus sits in L2 (measured at C1, 10k rows:
+    // p50 52.6 us on the shadow against 49.0 us on the fp32 rows; at 10M rows 4.45 against 8.52 ms).
+    if (path == RAG_PATH_STREAM && B == 1 && has_f16_shadow && shadow_stream_auto && idx->rows * (uint64_t)idx->ld * 2 >= kShadowStreamMinBytes)
+      path = RAG_PATH_SHADOW_STREAM;
+  }
+  if (path != RAG_PATH_STREAM && path != RAG_PATH_TENSOR && path != RAG_PATH_EXACT && path != RAG_PATH_SHADOW_STREAM)
     return rag_set_error(RAG_ERR_INVALID, "unknown rag_path %d", path);
+  if (path == RAG_PATH_SHADOW_STREAM && !has_f16_shadow)
+    return rag_set_error(RAG_ERR_UNSUPPORTED, "shadow stream path needs an fp32 index created with RAG_INDEX_F16_SHADOW");
   if (path == RAG_PATH_TENSOR && !k2_available(idx))
     return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path (K2) is not available for this index");
   const bool stat_eps = (flags & RAG_SEARCH_STAT_EPS) != 0;
@@ -160,7 +172,8 @@ int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_
   // or a bf16 shadow) the rigorous bound carries bf16's 8-bit rounding of the query (~1.7e-3 at D=1536) and, for a
   // shadow, of every row as well: widest window.
   const bool bf16_ops = idx->shadow && !idx->shadow_f16;
-  if (s == 0) s = path == RAG_PATH_TENSOR ? ((!stat_eps && eps <= 0.0 && bf16_ops) ? 48u : std::max(22u, k)) : 6u;
+  if (s == 0) s = path == RAG_PATH_TENSOR ? ((!stat_eps && eps <= 0.0 && bf16_ops) ? 48u : std::max(22u, k))
+                  : (path == RAG_PATH_SHADOW_STREAM ? std::max(22u, k) : 6u);
   uint32_t kp = std::min<uint32_t>(path == RAG_PATH_TENSOR ? 48u : (uint32_t)RAG_MAX_CANDIDATES, k + s);
   if (kp < k) return rag_set_error(RAG_ERR_UNSUPPORTED, "tensor path supports k <= 48 (k=%u)", k);
   p->path = path;
@@ -171,7 +184,14 @@ int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_
   p->eps_q_mul = 0.0;
   const double u24 = 5.9604644775390625e-08;  // 2^-24
   if (eps > 0.0) p->eps = eps;
-  else if (path == RAG_PATH_STREAM)
+  else if (path == RAG_PATH_SHADOW_STREAM) {
+    // K1 over x~ = fp16(x/||x||): key = fl32(q.x~), in cosine units q.x~/||q||. With u_q = q/||q||, e_x = x~ - x/||x||:
+    //   u_q.x~ - cos = u_q.e_x  =>  |.| <= ||e_x|| <= rho_x  (Cauchy-Schwarz; rho_x measured when the rows were loaded)
+    // + the fp32 accumulation of the dot product (the stream path's bound, relative to ||q|| ||x~|| <= ||q|| (1 + rho_x))
+    RAG_CHECK(refresh_rho_x(idx));
+    const double rx = (double)idx->rho_x * 1.001;
+    p->eps = rx + 2.5 * ((double)idx->ld / 64.0 + 8.0) * u24 * (1.0 + rx);
+  } else if (path == RAG_PATH_STREAM)
     // fp32: <= ld/64 + 8 roundings per sum (2 accumulators per lane, 5 shuffle levels), twice
     // (dot and norm), with a safety factor — 4.8e-6 at D = 1536
     p->eps = 2.5 * ((double)idx->ld / 64.0 + 8.0) * u24;
@@ -204,7 +224,7 @@ int make_plan(rag_index* idx, uint32_t B, uint32_t k, uint32_t req_path, uint32_
 
 bool next_plan(rag_index* idx, uint32_t k, const plan& cur, plan* nxt) {
   *nxt = cur;
-  if (cur.path == RAG_PATH_TENSOR) {
+  if (cur.path == RAG_PATH_TENSOR || cur.path == RAG_PATH_SHADOW_STREAM) {
     make_plan(idx, 1, k, RAG_PATH_STREAM, 0, 0.0, 0, nxt);
     return true;
   }
@@ -287,11 +307,12 @@ int stage_keywords(rag_index* idx, rag_batch* bt, uint32_t B, const uint64_t* kw
 int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fresh_cfg& fc, rag_fuse_args fa) {
   rag_batch* bt = idx->cur;
   uint32_t parts = 0;
-  if (p.path == RAG_PATH_STREAM) RAG_CHECK(k1_plan(idx, B, p.kp, &parts));
+  const bool stream = p.path == RAG_PATH_STREAM || p.path == RAG_PATH_SHADOW_STREAM;
+  if (stream) RAG_CHECK(k1_plan(idx, B, p.kp, &parts));
   else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_plan(idx, B, p.kp, &parts));
   else RAG_CHECK(k1x_plan(idx, B, p.kp, &parts));
   RAG_CHECK(grow_dev(&bt->d_partial, &bt->c_partial, (size_t)B * parts * p.kp * 8, false));
-  if (p.path == RAG_PATH_STREAM) RAG_CHECK(k1_launch(idx, B, p.kp, parts));
+  if (stream) RAG_CHECK(k1_launch(idx, B, p.kp, parts, p.path == RAG_PATH_SHADOW_STREAM));
   else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_launch(idx, B, p.kp, parts));
   else RAG_CHECK(k1x_launch(idx, B, p.kp, parts));
   fa.B = B;
@@ -401,7 +422,7 @@ bool graphs_enabled() {
 // Is this call the latency shape? one GPU, batch <= 32 on the stream path with the fused tail, no per-kernel profiling,
 // and nothing in the pipeline that reads the wall clock of the call (freshness needs now_ms, which changes every call).
 bool graph_shape_ok(const rag_index* idx, uint32_t B, const plan& p, const rag_fuse_args& fa) {
-  return graphs_enabled() && idx->nranks == 1 && !idx->prof_on && B <= 32 && p.path == RAG_PATH_STREAM && !p.eps_per_query &&
+  return graphs_enabled() && idx->nranks == 1 && !idx->prof_on && B <= 32 && (p.path == RAG_PATH_STREAM || p.path == RAG_PATH_SHADOW_STREAM) && !p.eps_per_query &&
          (fa.mode == 2 || (fa.mode == 0 && fa.fresh_limit == 0)) && !(idx->graph && idx->graph->disabled);
 }
 

@@ -227,7 +227,8 @@ struct rag_prof_scope {
 // ---------------------------------------------------------------------------------
 // K1 — stream path: fused cosine GEMV + per-warp top-K' (k1_stream.cu)
 int k1_plan(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
-int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
+// on_shadow: stream the fp16 shadow of the normalised rows instead of the fp32 corpus (RAG_PATH_SHADOW_STREAM)
+int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, bool on_shadow = false);
 // K1x — exact path: fp64 reference-order scan of every row (k1x_exact.cu)
 int k1x_plan(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
 int k1x_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);

@@ -20,6 +20,7 @@
 // fp32 accumulation decides only WHICH K' rows survive; K4 rescored them exactly.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
 #include <stdio.h>
 
 namespace {
@@ -175,6 +176,74 @@ k1_stream_bf16(const __nv_bfloat16* __restrict__ X, uint32_t n_rows, uint32_t ld
     if (keyA > thresh) warp_list_insert(mylist, kp, keyA, lane, thresh);
     if (has2) {
       const uint64_t keyB = rag_pack_key(finish_score(dotB, nrmB), row2);
+      if (keyB > thresh) warp_list_insert(mylist, kp, keyB, lane, thresh);
+    }
+  }
+  __syncthreads();
+  if (warp == 0)
+    warp_merge_lists(lists, K1_WARPS, kp, kp, partial + ((size_t)b * parts + blockIdx.x) * kp, lane);
+}
+
+// ---- fp16 shadow of the NORMALISED rows (RAG_INDEX_F16_SHADOW): batch-1 scoring at half the bytes -------------------
+// The tensor path's row operand — fp16( x / ||x|| ), built by aux_build when rows are loaded — is also the cheapest thing
+// a single query can stream: 2 bytes per element instead of 4, and no ||x||^2 to accumulate (the rows are unit vectors up
+// to their rounding residual, which the certification bound carries: |q.x~/||q|| - cos| <= rho_x + the fp32 accumulation).
+// Same shape as the bf16 kernel: 16-byte loads, two rows in flight per warp, query in two planes. Rows whose norm is zero
+// were stored as NaN and score -inf. K4 rescored the K' survivors from the fp32 rows, so reported values stay bit-exact.
+__device__ __forceinline__ void f16x8_fma(const uint4 v, const float4 qa, const float4 qb, float& d0, float& d1) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+  d0 = fmaf(a.x, qa.x, d0); d1 = fmaf(a.y, qa.y, d1); d0 = fmaf(b.x, qa.z, d0); d1 = fmaf(b.y, qa.w, d1);
+  d0 = fmaf(c.x, qb.x, d0); d1 = fmaf(c.y, qb.y, d1); d0 = fmaf(d.x, qb.z, d0); d1 = fmaf(d.y, qb.w, d1);
+}
+__device__ __forceinline__ float finish_dot(float dot) { return dot == dot ? dot : -INFINITY; }
+
+template <int U>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_stream_f16n(const __half* __restrict__ X, uint32_t n_rows, uint32_t ld, int nsub,
+               const float* __restrict__ Q, uint32_t kp, uint32_t parts, uint64_t* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* qa = reinterpret_cast<float4*>(smem_raw);   // qa[i] = q[8i..8i+3], qb[i] = q[8i+4..8i+7]
+  float4* qb = qa + ld / 8;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ld * sizeof(float));
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t b = blockIdx.y;
+  const float4* q4 = reinterpret_cast<const float4*>(Q + (size_t)b * ld);
+  for (uint32_t i = threadIdx.x; i < ld / 4; i += K1_THREADS) {
+    if (i & 1) qb[i >> 1] = q4[i]; else qa[i >> 1] = q4[i];
+  }
+  uint64_t* mylist = lists + (size_t)warp * kp;
+  for (uint32_t i = lane; i < kp; i += 32) mylist[i] = 0ull;
+  __syncthreads();
+
+  uint64_t thresh = 0ull;
+  const uint32_t stride = gridDim.x * K1_WARPS;
+  for (uint32_t row = blockIdx.x * K1_WARPS + warp; row < n_rows; row += 2 * stride) {
+    const uint32_t row2 = row + stride;
+    const bool has2 = row2 < n_rows;
+    const uint4* xr0 = reinterpret_cast<const uint4*>(X + (size_t)row * ld);
+    const uint4* xr1 = reinterpret_cast<const uint4*>(X + (size_t)(has2 ? row2 : row) * ld);
+    float d0 = 0.f, d1 = 0.f, e0 = 0.f, e1 = 0.f;
+    for (int s = 0; s < nsub; s++) {
+      uint4 v[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = ldg_stream_u4(xr0 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) w[u] = ldg_stream_u4(xr1 + (s * U + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int i = (s * U + u) * 32 + lane;
+        const float4 a = qa[i], c = qb[i];
+        f16x8_fma(v[u], a, c, d0, d1);
+        f16x8_fma(w[u], a, c, e0, e1);
+      }
+    }
+    const float dotA = warp_sum(d0 + d1), dotB = warp_sum(e0 + e1);
+    const uint64_t keyA = rag_pack_key(finish_dot(dotA), row);
+    if (keyA > thresh) warp_list_insert(mylist, kp, keyA, lane, thresh);
+    if (has2) {
+      const uint64_t keyB = rag_pack_key(finish_dot(dotB), row2);
       if (keyB > thresh) warp_list_insert(mylist, kp, keyB, lane, thresh);
     }
   }
@@ -391,7 +460,7 @@ int k1_plan(const rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   return RAG_OK;
 }
 
-int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
+int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, bool on_shadow) {
   rag_prof_scope ps(idx, RAG_PROF_STREAM);
   if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
   if (idx->rows >= 0xFFFFFFFFull) return rag_set_error(RAG_ERR_UNSUPPORTED, "more than 2^32-2 rows per shard");
@@ -406,6 +475,32 @@ int k1_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   } while (0)
   // several queries per corpus pass when they fit in shared memory: 8 (or 4) queries share every row a
   // warp streams; otherwise (very wide rows, very long candidate lists) one query per pass, grid.y = B
+  if (on_shadow) {
+    // the fp16 shadow of the normalised rows as the streamed operand (RAG_PATH_SHADOW_STREAM): one pass per query
+    if (!idx->shadow || !idx->shadow_f16 || idx->desc.dtype != RAG_F32)
+      return rag_set_error(RAG_ERR_UNSUPPORTED, "shadow stream path needs an fp32 index with RAG_INDEX_F16_SHADOW");
+    static const int opts[] = {6, 4, 3, 2, 1};
+    const uint32_t per_lane = ld / 256;  // 16-byte loads per lane per row
+    const int U = pick_unroll(per_lane, opts, 5);
+    const int nsub = (int)(per_lane / U);
+#define K1H_GO(Uv)                                                                                                   \
+  do {                                                                                                               \
+    RAG_CHECK(launch_cfg(k1_stream_f16n<Uv>, smem));                                                                 \
+    k1_stream_f16n<Uv><<<grid, block, smem, idx->stream>>>(reinterpret_cast<const __half*>(idx->shadow), n, ld, nsub, \
+                                                           idx->cur->d_q, kp, parts, idx->cur->d_partial);           \
+  } while (0)
+    switch (U) {
+      case 6: K1H_GO(6); break;
+      case 4: K1H_GO(4); break;
+      case 3: K1H_GO(3); break;
+      case 2: K1H_GO(2); break;
+      default: K1H_GO(1); break;
+    }
+#undef K1H_GO
+    RAG_CUDA(cudaGetLastError());
+    idx->launches++;
+    return RAG_OK;
+  }
   uint32_t QB = 0;
   if (idx->desc.dtype == RAG_F32 && B > 1) {
     const size_t budget = 200 * 1024;

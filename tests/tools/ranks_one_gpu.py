@@ -68,11 +68,11 @@ def main():
         rv.barrier()
         idx.comm_destroy()
 
-    for (total, d, dt, shadow, dup) in [(60_001, 256, N.F32, True, 7), (50_000, 512, N.BF16, False, 0)]:
+    for (total, d, dt, shadow, dup) in [(60_001, 256, N.F32, "f16", 7), (50_000, 512, N.BF16, None, 0)]:
         go = oracle.make_gen(total, n_clusters=32, dup_period=dup, memory_rows=total // 3)   # dup: ties across the shard boundary
         gn = N.GenDesc.from_buffer_copy(bytes(go))
         base, n = shard_range(total, world, rank)
-        idx = rb.VectorIndex(d, n, dtype=dt, device=0, bf16_shadow=shadow, id_base=base)
+        idx = rb.VectorIndex(d, n, dtype=dt, device=0, shadow=shadow, id_base=base)
         idx.generate(gn, n)
         bootstrap(idx, 128, 32, 120_000)     # ranks time-slice ONE GPU and check on the CPU in between: be patient
         B = 72
@@ -94,6 +94,12 @@ def main():
         for b in range(3):
             check_hybrid(idx.hybrid(Q[b:b + 1], rb.hybrid_opts(10, 8, 0.3, path=N.PATH_STREAM), [kw[b]]), [b], "batch-1 stream")
         check_hybrid(idx.hybrid(Q[:9], rb.hybrid_opts(10, 8, 0.3, path=N.PATH_STREAM), kw[:9]), range(9), "batch-9 stream")
+        if shadow == "f16":
+            # one query streamed from the fp16 shadow of every rank's shard (explicitly and as AUTO's choice), same fused tail
+            for b in range(3):
+                check_hybrid(idx.hybrid(Q[b:b + 1], rb.hybrid_opts(10, 8, 0.3, path=N.PATH_SHADOW_STREAM), [kw[b]]), [b], "batch-1 shadow stream")
+                check_hybrid(idx.hybrid(Q[b:b + 1], rb.hybrid_opts(10, 8, 0.3), [kw[b]]), [b], "batch-1 auto")   # small shard: the fp32 stream
+            check_hybrid(idx.hybrid(Q[:5], rb.hybrid_opts(10, 8, 0.3, path=N.PATH_SHADOW_STREAM), kw[:5]), range(5), "batch-5 shadow stream")
         check_hybrid(idx.hybrid(Q[:16], rb.hybrid_opts(10, 8, 0.3, path=N.PATH_TENSOR), kw[:16]), range(16), "batch-16 tensor")
         # larger batches: K3, K4 and K5 (with the exchange) as separate launches
         for path in (N.PATH_STREAM, N.PATH_TENSOR, N.PATH_EXACT):
