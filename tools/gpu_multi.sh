@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU validation: usage  gpurun --gpus N -- 'bash tools/gpu_r2_multi.sh N'
+# multi-GPU validation: usage  gpurun --gpus N -- 'bash tools/gpu_multi.sh N'
 N=${1:-2}; OUT=gpurun_out; mkdir -p $OUT
 export MASTER_ADDR=127.0.0.1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
