@@ -349,11 +349,14 @@ int rag_process_results(const rag_text* contents, const double* scores, const ui
 /* ---- micro-batching front end: concurrent batch-1 callers (one per request thread,
  *      like the reference's per-request hybridSearch) share one corpus pass. One batcher per call-site
  *      class (fixed options). submit() blocks until the caller's own result is ready; results are
- *      identical to a direct batch-1 call. The worker thread is the only user of the index handle. */
+ *      identical to a direct batch-1 call. Callers stage their own inputs into the open batch and copy their own results
+ *      out; two worker threads take turns running batches (the only users of the index handle). */
 typedef struct rag_batcher rag_batcher;
 typedef struct rag_batcher_desc {
   uint32_t max_batch;    /* 1..4096 queries per pass                                    */
-  uint32_t max_wait_us;  /* how long the first request of a batch waits for company     */
+  uint32_t max_wait_us;  /* CAP on how long the first request of a batch waits for company: the batch goes out earlier,
+                            as soon as the arrivals pause (20-50 us without a new request) and no finished batch's callers
+                            are still being woken; ~1000 keeps closed-loop callers in one pass (profiles/r02_batcher_load.md) */
   rag_hybrid_opts opts;  /* HybridSearchOptions of this call site (keyword_limit = row stride) */
 } rag_batcher_desc;
 int rag_batcher_create(rag_index* idx, const rag_batcher_desc* desc, rag_batcher** out);

@@ -5,10 +5,26 @@
 // HBM-bound at batch 1 and tensor-bound at batch >= ~64, so requests that arrive within a few
 // hundred microseconds of each other are worth two orders of magnitude more throughput when
 // they share one pass. The batcher collects concurrent rag_batcher_submit() calls (any threads)
-// for at most `max_wait_us` or until `max_batch` are waiting, runs ONE rag_hybrid_search over
-// them on its own worker thread (the only thread that touches the rag_index, as the handle
-// contract requires), and hands every caller exactly the result it would have got alone:
-// batching never changes a result (tests/test_gpu_batcher.py).
+// into an OPEN batch, runs ONE rag_hybrid_search per batch, and hands every caller exactly the
+// result it would have got alone: batching never changes a result (tests/test_gpu_batcher.py).
+//
+// Pipeline (round 2; the first version did everything on one worker thread and lost 38% of the
+// tensor path's throughput at 1024 request threads — profiles/r02_batcher_load.md):
+//   * the SUBMITTERS stage their own inputs: a request takes a slot of the open batch under the
+//     queue lock, copies its query (6 KB at D=1536) and keyword list into the batch's pinned block
+//     outside the lock, and copies its own result out afterwards — the 6 MB of a 1024-query batch
+//     move on as many cores as there are callers instead of on the worker;
+//   * TWO workers take turns: one holds the turn while it closes the open batch and runs it on the
+//     GPU; the other meanwhile wakes the previous batch's callers. The open batch keeps collecting
+//     for as long as the GPU is busy (that is what sizes the batches under load); when the GPU is
+//     idle it goes out once the arrivals pause (20-50 us without a new request), at the latest `max_wait_us` after
+//     its first request;
+//   * callers sleep on 64 wake groups (16 consecutive slots each), not on one condition variable:
+//     completing a batch is at most 64 short broadcasts instead of 1024 threads fighting for one mutex;
+//   * four batch buffers circulate (open, on the GPU, being read out, spare); a submitter that
+//     finds none free waits (back-pressure).
+// The workers are the only threads that touch the rag_index; calls on the handle are serialised
+// by the library anyway (per-handle mutex).
 //
 // One batcher = one call-site class (fixed HybridSearchOptions: search_knowledge, deep_search, ...),
 // because vectorTopK / keywordLimit / RRF config are per-launch parameters.
@@ -17,6 +33,7 @@
 
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -25,27 +42,19 @@
 #include <thread>
 #include <vector>
 
+namespace {
+constexpr uint32_t kWakeGroups = 64;
+constexpr uint32_t kGroupSlots = 16;   // consecutive slots that share a wake group: a 64-query batch is woken by 4 broadcasts
+constexpr int kBuffers = 4;
+constexpr int kWorkers = 2;
+}  // namespace
+
 struct rag_batcher_req {
-  const float* q;
-  const uint64_t* kw;
-  uint32_t kwc;
-  rag_fused_out* out;
-  int rc = RAG_OK;
-  bool done = false;
-  std::string err;
-  std::chrono::steady_clock::time_point t_enq;
+  bool done = false;  // guarded by the wake group's mutex
 };
 
-struct rag_batcher {
-  rag_index* idx = nullptr;
-  rag_batcher_desc desc;
-  std::mutex mu;
-  std::condition_variable cv_work, cv_done;
-  std::deque<rag_batcher_req*> queue;
-  bool stop = false;
-  std::thread worker;
-  uint64_t n_batches = 0, n_queries = 0, max_seen = 0;
-  // batch staging (worker only)
+// One batch: inputs written by the submitters (slot by slot), outputs written by rag_hybrid_search, read by the submitters.
+struct rag_batch_buf {
   float* h_q = nullptr;  // pinned [max_batch][dim]
   std::vector<uint64_t> kw_keys;
   std::vector<uint32_t> kw_counts;
@@ -53,79 +62,120 @@ struct rag_batcher {
   std::vector<double> scores, vec_scores;
   std::vector<uint8_t> source, ctype, used_rrf, certified;
   std::vector<uint32_t> counts, vec_counts;
+  std::vector<rag_batcher_req*> reqs;
+  uint32_t count = 0;                  // slots handed out (under rag_batcher::mu)
+  std::atomic<uint32_t> staged{0};     // slots whose inputs are in place
+  std::atomic<uint32_t> readers{0};    // callers that have not copied their result out yet
+  std::chrono::steady_clock::time_point t_first, t_last;   // arrival of the first / latest request (under rag_batcher::mu)
+  int rc = RAG_OK;
+  std::string err;
+};
+
+struct rag_wake_group {
+  std::mutex mu;
+  std::condition_variable cv;
+};
+
+struct rag_batcher {
+  rag_index* idx = nullptr;
+  rag_batcher_desc desc;
+  std::mutex mu;                        // open / full / free_bufs / stop / stats
+  std::condition_variable cv_work;      // the worker holding the turn: a first request, a full batch, stop
+  std::condition_variable cv_free;      // submitters waiting for a batch buffer
+  std::mutex turn;                      // one worker at a time closes a batch and runs it
+  rag_batch_buf bufs[kBuffers];
+  rag_batch_buf* open = nullptr;        // the batch that takes new requests
+  std::deque<rag_batch_buf*> full;      // batches that filled up while the GPU was busy
+  std::vector<rag_batch_buf*> free_bufs;
+  rag_wake_group groups[kWakeGroups];
+  bool stop = false;
+  std::atomic<int> waking{0};           // batches whose callers are being woken right now
+  std::thread workers[kWorkers];
+  uint64_t n_batches = 0, n_queries = 0, max_seen = 0;
 };
 
 namespace {
 
-void run_batch(rag_batcher* b, std::vector<rag_batcher_req*>& reqs) {
-  const uint32_t B = (uint32_t)reqs.size(), dim = b->idx->dim;
+void run_batch(rag_batcher* b, rag_batch_buf* bb) {
+  const uint32_t B = bb->count;
   const rag_hybrid_opts& o = b->desc.opts;
-  const uint32_t kl = o.keyword_limit, k = o.vector_top_k, cap = k + kl + o.fresh_limit;
-  for (uint32_t i = 0; i < B; i++) {
-    memcpy(b->h_q + (size_t)i * dim, reqs[i]->q, (size_t)dim * sizeof(float));
-    const uint32_t c = reqs[i]->kw ? std::min(reqs[i]->kwc, kl) : 0u;
-    if (c) memcpy(b->kw_keys.data() + (size_t)i * kl, reqs[i]->kw, (size_t)c * 8);
-    b->kw_counts[i] = c;
-  }
-  rag_fused_out out = {cap, b->keys.data(), b->scores.data(), b->source.data(), b->ctype.data(), b->counts.data(),
-                       b->used_rrf.data(), b->vec_ids.data(), b->vec_scores.data(), b->vec_counts.data(), b->certified.data()};
-  const int rc = rag_hybrid_search(b->idx, b->h_q, B, &o, b->kw_keys.data(), b->kw_counts.data(), &out);
-  const std::string err = rc == RAG_OK ? std::string() : std::string(rag_last_error());
-  for (uint32_t i = 0; i < B; i++) {
-    rag_batcher_req* r = reqs[i];
-    r->rc = rc;
-    r->err = err;
-    if (rc == RAG_OK) {
-      rag_fused_out* d = r->out;
-      const uint32_t n = std::min(d->capacity, cap);
-      memcpy(d->keys, b->keys.data() + (size_t)i * cap, (size_t)n * 8);
-      memcpy(d->scores, b->scores.data() + (size_t)i * cap, (size_t)n * 8);
-      if (d->source) memcpy(d->source, b->source.data() + (size_t)i * cap, n);
-      if (d->content_type) memcpy(d->content_type, b->ctype.data() + (size_t)i * cap, n);
-      d->counts[0] = b->counts[i];
-      if (d->used_rrf) d->used_rrf[0] = b->used_rrf[i];
-      if (d->certified) d->certified[0] = b->certified[i];
-      if (d->vec_ids && d->vec_scores && d->vec_counts) {
-        memcpy(d->vec_ids, b->vec_ids.data() + (size_t)i * k, (size_t)k * 8);
-        memcpy(d->vec_scores, b->vec_scores.data() + (size_t)i * k, (size_t)k * 8);
-        d->vec_counts[0] = b->vec_counts[i];
-      }
+  const uint32_t cap = o.vector_top_k + o.keyword_limit + o.fresh_limit;
+  // every submitter's copy has landed (they are a few microseconds each)
+  while (bb->staged.load(std::memory_order_acquire) != B) std::this_thread::yield();
+  rag_fused_out out = {cap, bb->keys.data(), bb->scores.data(), bb->source.data(), bb->ctype.data(), bb->counts.data(),
+                       bb->used_rrf.data(), bb->vec_ids.data(), bb->vec_scores.data(), bb->vec_counts.data(), bb->certified.data()};
+  bb->rc = rag_hybrid_search(b->idx, bb->h_q, B, &o, bb->kw_keys.data(), bb->kw_counts.data(), &out);
+  bb->err = bb->rc == RAG_OK ? std::string() : std::string(rag_last_error());
+}
+
+// wake the batch's callers: group by group, the flag of every request set under its group's mutex
+void complete_batch(rag_batcher* b, rag_batch_buf* bb) {
+  const uint32_t B = bb->count;
+  bb->readers.store(B, std::memory_order_release);
+  for (uint32_t g = 0; g < kWakeGroups && g * kGroupSlots < B; g++) {
+    {
+      std::lock_guard<std::mutex> lk(b->groups[g].mu);
+      for (uint32_t s0 = g * kGroupSlots; s0 < B; s0 += kWakeGroups * kGroupSlots)
+        for (uint32_t s = s0; s < s0 + kGroupSlots && s < B; s++) bb->reqs[s]->done = true;
     }
+    b->groups[g].cv.notify_all();
   }
 }
 
 void worker_main(rag_batcher* b) {
-  std::vector<rag_batcher_req*> batch;
   for (;;) {
+    rag_batch_buf* mine = nullptr;
     {
-      std::unique_lock<std::mutex> lk(b->mu);
-      b->cv_work.wait(lk, [&] { return b->stop || !b->queue.empty(); });
-      if (b->stop && b->queue.empty()) return;
-      // the OLDEST waiting request opens the collection window (requests that queued up behind a running batch have
-      // already waited: they go out at once); leave early once the batch is full
-      const auto deadline = b->queue.front()->t_enq + std::chrono::microseconds(b->desc.max_wait_us);
-      b->cv_work.wait_until(lk, deadline, [&] { return b->stop || b->queue.size() >= b->desc.max_batch; });
-      batch.clear();
-      while (!b->queue.empty() && batch.size() < b->desc.max_batch) {
-        batch.push_back(b->queue.front());
-        b->queue.pop_front();
+      std::unique_lock<std::mutex> my_turn(b->turn);
+      {
+        std::unique_lock<std::mutex> lk(b->mu);
+        b->cv_work.wait(lk, [&] { return b->stop || !b->full.empty() || (b->open && b->open->count > 0); });
+        if (b->full.empty() && !(b->open && b->open->count > 0)) return;  // stop, and nothing left to run
+        // The open batch's FIRST request opens the collection window (at most max_wait_us; a batch that has been
+        // collecting behind a busy GPU is past it and goes out at once). Inside the window the batch goes out as soon as
+        // the arrivals pause for `gap`: callers that were answered together come back together, within tens of
+        // microseconds of each other, and splitting them over two corpus passes costs a whole pass (a batch below ~256
+        // queries is HBM-bound: the pass costs the same for 30 queries as for 250) — measured with 64 / 256 closed-loop
+        // callers: 39k / 79k requests/s when the window simply expired after 100 us, half-full.
+        const auto gap = std::chrono::microseconds(std::min<uint32_t>(50u, std::max<uint32_t>(20u, b->desc.max_wait_us / 8)));
+        for (;;) {
+          if (b->stop || !b->full.empty() || b->open->count >= b->desc.max_batch) break;
+          const auto now = std::chrono::steady_clock::now();
+          const auto cap = b->open->t_first + std::chrono::microseconds(b->desc.max_wait_us);
+          if (now >= cap) break;
+          // a finished batch's callers are still being woken: they are about to come back, the pause rule waits for them
+          const bool burst = b->waking.load(std::memory_order_acquire) > 0;
+          const auto until = std::min(cap, (burst ? now : b->open->t_last) + gap);
+          if (!burst && now >= until) break;
+          b->cv_work.wait_until(lk, until);
+        }
+        if (!b->full.empty()) {
+          mine = b->full.front();
+          b->full.pop_front();
+        } else {
+          mine = b->open;
+          b->open = nullptr;
+        }
       }
-    }
-    run_batch(b, batch);
+      run_batch(b, mine);
+      b->waking.fetch_add(1, std::memory_order_release);
+    }  // the turn passes on: the other worker closes and launches the next batch while this one wakes its callers
     {
       std::lock_guard<std::mutex> lk(b->mu);
-      for (rag_batcher_req* r : batch) r->done = true;
       b->n_batches++;
-      b->n_queries += batch.size();
-      b->max_seen = std::max<uint64_t>(b->max_seen, batch.size());
+      b->n_queries += mine->count;
+      b->max_seen = std::max<uint64_t>(b->max_seen, mine->count);
     }
-    b->cv_done.notify_all();
+    complete_batch(b, mine);
+    b->waking.fetch_sub(1, std::memory_order_release);
   }
 }
 
 }  // namespace
 
 extern "C" {
+
+void rag_batcher_destroy(rag_batcher* b);
 
 int rag_batcher_create(rag_index* idx, const rag_batcher_desc* d, rag_batcher** out) {
   if (!idx || !d || !out) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_create: null argument");
@@ -139,15 +189,24 @@ int rag_batcher_create(rag_index* idx, const rag_batcher_desc* d, rag_batcher** 
   b->idx = idx;
   b->desc = *d;
   const uint32_t B = d->max_batch, k = o.vector_top_k, cap = k + o.keyword_limit + o.fresh_limit;
-  b->h_q = (float*)rag_host_alloc((uint64_t)B * idx->dim * sizeof(float));
-  if (!b->h_q) { delete b; return RAG_ERR_NOMEM; }
-  b->kw_keys.assign((size_t)B * std::max(1u, o.keyword_limit), 0);
-  b->kw_counts.assign(B, 0);
-  b->keys.resize((size_t)B * cap); b->scores.resize((size_t)B * cap);
-  b->source.resize((size_t)B * cap); b->ctype.resize((size_t)B * cap);
-  b->counts.resize(B); b->used_rrf.resize(B); b->certified.resize(B);
-  b->vec_ids.resize((size_t)B * k); b->vec_scores.resize((size_t)B * k); b->vec_counts.resize(B);
-  b->worker = std::thread(worker_main, b);
+  for (int i = 0; i < kBuffers; i++) {
+    rag_batch_buf& bb = b->bufs[i];
+    bb.h_q = (float*)rag_host_alloc((uint64_t)B * idx->dim * sizeof(float));
+    if (!bb.h_q) {
+      for (int j = 0; j < i; j++) rag_host_free(b->bufs[j].h_q);
+      delete b;
+      return RAG_ERR_NOMEM;
+    }
+    bb.kw_keys.assign((size_t)B * std::max(1u, o.keyword_limit), 0);
+    bb.kw_counts.assign(B, 0);
+    bb.keys.resize((size_t)B * cap); bb.scores.resize((size_t)B * cap);
+    bb.source.resize((size_t)B * cap); bb.ctype.resize((size_t)B * cap);
+    bb.counts.resize(B); bb.used_rrf.resize(B); bb.certified.resize(B);
+    bb.vec_ids.resize((size_t)B * k); bb.vec_scores.resize((size_t)B * k); bb.vec_counts.resize(B);
+    bb.reqs.assign(B, nullptr);
+    b->free_bufs.push_back(&bb);
+  }
+  for (int w = 0; w < kWorkers; w++) b->workers[w] = std::thread(worker_main, b);
   *out = b;
   return RAG_OK;
 }
@@ -159,24 +218,76 @@ int rag_batcher_submit(rag_batcher* b, const float* query, const uint64_t* kw_ke
   if (!b || !query || !out || !out->keys || !out->scores || !out->counts)
     return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: null argument");
   const rag_hybrid_opts& o = b->desc.opts;
-  if (out->capacity < o.vector_top_k + o.keyword_limit + o.fresh_limit)
-    return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: rag_fused_out.capacity too small");
-  if (kw_count > o.keyword_limit) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: kw_count exceeds keyword_limit");
+  const uint32_t kl = o.keyword_limit, k = o.vector_top_k, cap = k + kl + o.fresh_limit, dim = b->idx->dim;
+  if (out->capacity < cap) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: rag_fused_out.capacity too small");
+  if (kw_count > kl) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: kw_count exceeds keyword_limit");
   rag_batcher_req r;
-  r.q = query;
-  r.kw = kw_keys;
-  r.kwc = kw_count;
-  r.out = out;
+  rag_batch_buf* bb = nullptr;
+  uint32_t slot = 0;
   {
     std::unique_lock<std::mutex> lk(b->mu);
-    if (b->stop) return rag_set_error(RAG_ERR_STATE, "rag_batcher_submit: batcher is shutting down");
-    r.t_enq = std::chrono::steady_clock::now();
-    b->queue.push_back(&r);
-    b->cv_work.notify_one();
-    b->cv_done.wait(lk, [&] { return r.done; });
+    for (;;) {
+      if (b->stop) return rag_set_error(RAG_ERR_STATE, "rag_batcher_submit: batcher is shutting down");
+      if (b->open && b->open->count == b->desc.max_batch) {  // filled up behind a busy GPU: queue it whole
+        b->full.push_back(b->open);
+        b->open = nullptr;
+        b->cv_work.notify_all();
+      }
+      if (b->open) break;
+      if (!b->free_bufs.empty()) {
+        b->open = b->free_bufs.back();
+        b->free_bufs.pop_back();
+        break;
+      }
+      b->cv_free.wait(lk);  // every buffer is in flight: back-pressure
+    }
+    bb = b->open;
+    slot = bb->count++;
+    bb->reqs[slot] = &r;
+    bb->t_last = std::chrono::steady_clock::now();
+    if (slot == 0) bb->t_first = bb->t_last;
+    if (slot == 0 || bb->count == b->desc.max_batch) b->cv_work.notify_all();
   }
-  if (r.rc != RAG_OK) return rag_set_error(r.rc, "%s", r.err.c_str());
-  return RAG_OK;
+  // stage this request's inputs in its slot (outside the lock, in parallel with every other caller)
+  memcpy(bb->h_q + (size_t)slot * dim, query, (size_t)dim * sizeof(float));
+  const uint32_t c = kw_keys ? kw_count : 0u;
+  if (c) memcpy(bb->kw_keys.data() + (size_t)slot * kl, kw_keys, (size_t)c * 8);
+  bb->kw_counts[slot] = c;
+  bb->staged.fetch_add(1, std::memory_order_release);
+  {
+    rag_wake_group& g = b->groups[(slot / kGroupSlots) % kWakeGroups];
+    std::unique_lock<std::mutex> lk(g.mu);
+    g.cv.wait(lk, [&] { return r.done; });
+  }
+  const int rc = bb->rc;
+  if (rc == RAG_OK) {
+    const uint32_t n = std::min(out->capacity, cap);
+    memcpy(out->keys, bb->keys.data() + (size_t)slot * cap, (size_t)n * 8);
+    memcpy(out->scores, bb->scores.data() + (size_t)slot * cap, (size_t)n * 8);
+    if (out->source) memcpy(out->source, bb->source.data() + (size_t)slot * cap, n);
+    if (out->content_type) memcpy(out->content_type, bb->ctype.data() + (size_t)slot * cap, n);
+    out->counts[0] = bb->counts[slot];
+    if (out->used_rrf) out->used_rrf[0] = bb->used_rrf[slot];
+    if (out->certified) out->certified[0] = bb->certified[slot];
+    if (out->vec_ids && out->vec_scores && out->vec_counts) {
+      memcpy(out->vec_ids, bb->vec_ids.data() + (size_t)slot * k, (size_t)k * 8);
+      memcpy(out->vec_scores, bb->vec_scores.data() + (size_t)slot * k, (size_t)k * 8);
+      out->vec_counts[0] = bb->vec_counts[slot];
+    }
+  } else {
+    rag_set_error(rc, "%s", bb->err.c_str());
+  }
+  // the last caller to leave hands the buffer back
+  if (bb->readers.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+    bb->staged.store(0, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(b->mu);
+      bb->count = 0;
+      b->free_bufs.push_back(bb);
+    }
+    b->cv_free.notify_one();
+  }
+  return rc;
 }
 
 int rag_batcher_stats(rag_batcher* b, uint64_t* batches, uint64_t* queries, uint64_t* largest_batch) {
@@ -195,8 +306,10 @@ void rag_batcher_destroy(rag_batcher* b) {
     b->stop = true;
   }
   b->cv_work.notify_all();
-  if (b->worker.joinable()) b->worker.join();
-  rag_host_free(b->h_q);
+  b->cv_free.notify_all();
+  for (int w = 0; w < kWorkers; w++)
+    if (b->workers[w].joinable()) b->workers[w].join();
+  for (int i = 0; i < kBuffers; i++) rag_host_free(b->bufs[i].h_q);
   delete b;
 }
 

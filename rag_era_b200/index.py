@@ -426,10 +426,11 @@ class VectorIndex:
 
 class Batcher:
     """Micro-batching front end (``rag_batcher_*``): many threads call ``submit`` with one query each; the
-    library groups what arrives within ``max_wait_us`` into one corpus pass. ctypes releases the GIL during
+    library groups what arrives together into one corpus pass (a batch goes out when the arrivals pause, at the latest
+    ``max_wait_us`` after its first request). ctypes releases the GIL during
     the call, so Python request threads really do overlap."""
 
-    def __init__(self, index: VectorIndex, opts: N.HybridOpts, max_batch: int = 1024, max_wait_us: int = 200):
+    def __init__(self, index: VectorIndex, opts: N.HybridOpts, max_batch: int = 1024, max_wait_us: int = 1000):
         self._lib = N.load()
         self.index, self.opts = index, opts
         d = N.BatcherDesc(max_batch, max_wait_us, opts)

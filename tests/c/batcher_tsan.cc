@@ -1,7 +1,8 @@
 // batcher_tsan.cc — TEST HARNESS: the micro-batcher (batcher.cu, host-only) compiled as plain C++ with -fsanitize=thread and
 // driven by many concurrent submitters against a STUB rag_hybrid_search that derives every output from the query it was
 // given. Checks: every submitter gets exactly its own result back (no cross-talk between slots of a batch), errors of a
-// batch reach every waiter, batches really form (largest batch > 1), shutdown with submitters still arriving is clean, and
+// batch reach every waiter, batches really form (largest batch > 1), callers that outnumber the batch buffers wait and are
+// all served (back-pressure), a lone caller is not left waiting, and
 // ThreadSanitizer reports no race. Run by tests/test_gpu_batcher.py::test_batcher_threads_under_tsan (CPU).
 #include "common.cuh"
 #include <stdarg.h>
@@ -94,6 +95,28 @@ int main() {
   rag_fused_out small = {2, keys, scores, nullptr, nullptr, &cnt, nullptr, nullptr, nullptr, nullptr, nullptr};
   const bool p3 = rag_batcher_submit(bt, q, nullptr, 0, &small) == RAG_ERR_INVALID && rag_batcher_submit(bt, nullptr, nullptr, 0, &small) == RAG_ERR_INVALID;
   rag_batcher_destroy(bt);
-  printf("result: %s\n", (p1 && p2 && p3) ? "OK" : "FAILED");
-  return (p1 && p2 && p3) ? 0 : 1;
+  // phase 4: back-pressure — 96 callers against 4 buffers of 8 slots: submitters wait for a free buffer, full batches queue up
+  // behind the running one, buffers are recycled by the last caller that reads its result
+  g_fail_every = 0;
+  done = 0; wrong = 0; failed = 0;
+  d.max_wait_us = 50;
+  if (rag_batcher_create(&idx, &d, &bt) != RAG_OK) { printf("create failed: %s\n", g_err); return 1; }
+  th.clear();
+  for (int t = 0; t < 96; t++) th.emplace_back(submitter, t, 20);   // tags stay below 2^24: they travel as one float
+  for (auto& t : th) t.join();
+  rag_batcher_stats(bt, &batches, &queries, &largest);
+  printf("phase 4: done=%d wrong=%d failed=%d batches=%llu queries=%llu largest=%llu\n", done.load(), wrong.load(), failed.load(),
+         (unsigned long long)batches, (unsigned long long)queries, (unsigned long long)largest);
+  const bool p4 = done == 96 * 20 && wrong == 0 && failed == 0 && queries == 96 * 20 && largest == 8 && batches < 96 * 20 / 4;
+  // a lone caller is answered after the collection window, not left waiting for company
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    submitter(150, 3);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    printf("lone caller: 3 requests in %.2f ms\n", ms);
+    if (ms > 500.0 || wrong != 0 || failed != 0) { printf("result: FAILED\n"); return 1; }
+  }
+  rag_batcher_destroy(bt);
+  printf("result: %s\n", (p1 && p2 && p3 && p4) ? "OK" : "FAILED");
+  return (p1 && p2 && p3 && p4) ? 0 : 1;
 }
