@@ -442,7 +442,7 @@ napi_value CreateBatcher(napi_env env, napi_callback_info info) {  // createBatc
   rag_batcher_desc d;
   read_opts(env, argv[1], &d.opts);
   d.max_batch = 1024;
-  d.max_wait_us = 200;
+  d.max_wait_us = 1000;   // a cap: a batch goes out earlier, once the arrivals pause
   if (argc > 2) napi_get_value_uint32(env, argv[2], &d.max_batch);
   if (argc > 3) napi_get_value_uint32(env, argv[3], &d.max_wait_us);
   rag_batcher* b = nullptr;
