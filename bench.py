@@ -478,7 +478,7 @@ def measure_workload(rb, N, w, name, steps, warmup, dist, rank, world, device, d
                 "algorithmic_bytes_per_launch": int(bytes_per_launch),
                 "avg_launch_ms": k1_ms / max(k1_n, 1), "launches_timed": int(k1_n),
                 "frac_of_nominal_8TBps": (achieved / 8000.0) if achieved else None}
-        tr = traffic_ratio("k1_stream", name)
+        tr = traffic_ratio("k1_stream_f16n" if on_shadow else "k1_stream", name)
         if tr:
             roof["traffic"] = int(tr * bytes_per_launch)
             roof["traffic_source"] = "profiles/traffic.json (ncu --set full dram bytes / algorithmic, scaled to this launch)"

@@ -285,7 +285,7 @@ int rag_batcher_submit(rag_batcher* b, const float* query, const uint64_t* kw_ke
       bb->count = 0;
       b->free_bufs.push_back(bb);
     }
-    b->cv_free.notify_one();
+    b->cv_free.notify_all();  // every waiting submitter: the buffer becomes the open batch and has room for all of them
   }
   return rc;
 }

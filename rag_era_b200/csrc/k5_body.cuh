@@ -27,45 +27,65 @@ struct fuse_smem {
   uint8_t e_ct[MAXE];
   uint64_t f_key[RAG_MAX_FRESH];
   uint64_t k_key[RAG_MAX_KEYWORDS];  // the query's keyword list, staged with one coalesced load
+  // the lists concatenated in pass order (vector, keyword, freshness): key and RRF contribution of every occurrence
+  uint64_t c_key[MAXE];
+  double c_val[MAXE];
 };
 
-// one sequential RRF pass over `n` keys; all lanes execute, lane 0 mutates the map.
-// first_pass: vector pass semantics (:147-166), else keyword pass semantics (:169-188).
-__device__ __forceinline__ void rrf_pass(fuse_smem& s, uint32_t& n_entries, const uint64_t* keys,
-                                         const uint8_t* cts, uint32_t n, double weight, double kconst,
-                                         double bonus, bool first_pass, uint8_t new_src, uint8_t new_ct,
-                                         int lane) {
-  // the per-rank contributions w / (k + rank + 1) for ranks lane and lane + 32, computed side by side (an fp64 division
-  // per step of the sequential walk below would be on its critical path)
-  const double c0 = __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)lane), 1.0));
-  const double c1 = __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)(lane + 32)), 1.0));
-  for (uint32_t r = 0; r < n; r++) {
-    const uint64_t key = keys[r];
-    const unsigned long long cb = __double_as_longlong(r < 32 ? c0 : c1);
-    const double rrf = r < 64 ? __longlong_as_double((long long)shfl_u64(cb, (int)(r & 31)))
-                              : __ddiv_rn(weight, __dadd_rn(__dadd_rn(kconst, (double)r), 1.0));
-    int found = -1;
-    for (uint32_t base = 0; base < n_entries; base += 32) {
-      const uint32_t i = base + lane;
-      const unsigned hit = __ballot_sync(0xFFFFFFFFu, i < n_entries && s.e_key[i] == key);
-      if (hit) { found = (int)base + __ffs(hit) - 1; break; }
-    }
-    if (lane == 0) {
-      if (found >= 0) {
-        const double e = s.e_score[found];
-        s.e_score[found] = first_pass ? __dadd_rn(e, rrf)
-                                      : __dadd_rn(e, __dadd_rn(rrf, __dmul_rn(bonus, e)));
-        s.e_src[found] = RAG_SRC_BOTH;
-      } else {
-        s.e_key[n_entries] = key;
-        s.e_score[n_entries] = rrf;
-        s.e_src[n_entries] = new_src;
-        s.e_ct[n_entries] = cts ? cts[r] : new_ct;
+// reciprocalRankFusion (src/lib/hybrid-search.ts:129-208) over the vector list (s.v_key / s.v_ct, nv entries), the keyword
+// list (s.k_key, nk) and the optional freshness list (s.f_key, nf), by one warp. The reference walks the lists one key at a
+// time through an insertion-ordered Map; what it computes per key depends only on that key's OWN occurrences, in pass order:
+//   first occurrence      -> new entry {score: w/(k+rank+1), source: its list}                              (:156-166, :178-187)
+//   later, vector list    -> score += rrf; source = 'both'                                                  (:152-155)
+//   later, other lists    -> score += rrf + bothBonus*score (the score BEFORE this add); source = 'both'    (:173-177)
+// and the Map's order is the order of first occurrences. So: every occurrence's contribution is computed side by side (one
+// fp64 division each), every lane takes one element of the concatenation, finds out whether it is its key's first occurrence
+// and, if so, replays that key's occurrences in order with exactly the reference's operations; the entry index is the number
+// of first occurrences before it. ~10 instructions per element of the concatenation instead of a ~130-cycle dependent step
+// per key with one lane mutating the map. Returns the number of entries; fills s.e_key / e_score / e_src / e_ct.
+__device__ __forceinline__ uint32_t rrf_fuse_lists(fuse_smem& s, uint32_t nv, uint32_t nk, uint32_t nf, double w_vec, double w_kw,
+                                                   double w_fresh, double kconst, double bonus, int lane) {
+  const uint32_t T = nv + nk + nf;
+  for (uint32_t j = lane; j < T; j += 32) {
+    const uint32_t list = j < nv ? 0u : (j < nv + nk ? 1u : 2u);
+    const uint32_t r = list == 0 ? j : (list == 1 ? j - nv : j - nv - nk);   // rank within its list
+    const double w = list == 0 ? w_vec : (list == 1 ? w_kw : w_fresh);
+    s.c_key[j] = list == 0 ? s.v_key[r] : (list == 1 ? s.k_key[r] : s.f_key[r]);
+    s.c_val[j] = __ddiv_rn(w, __dadd_rn(__dadd_rn(kconst, (double)r), 1.0));
+  }
+  __syncwarp();
+  uint32_t n = 0;
+  for (uint32_t base = 0; base < T; base += 32) {
+    const uint32_t e = base + lane;
+    const bool live = e < T;
+    const uint64_t key = live ? s.c_key[e] : 0ull;
+    bool first = live, both = false;
+    double score = 0.0;
+    for (uint32_t j = 0; j < T; j++) {
+      const uint64_t kj = s.c_key[j];   // uniform address: one broadcast load
+      const double cj = s.c_val[j];
+      if (live && kj == key) {
+        if (j < e) first = false;
+        else if (j == e) score = cj;
+        else {
+          score = j < nv ? __dadd_rn(score, cj) : __dadd_rn(score, __dadd_rn(cj, __dmul_rn(bonus, score)));
+          both = true;
+        }
       }
     }
-    if (found < 0) n_entries++;
-    __syncwarp();
+    const unsigned fm = __ballot_sync(0xFFFFFFFFu, first);
+    if (first) {
+      const uint32_t at = n + __popc(fm & ((1u << lane) - 1u));
+      const uint32_t list = e < nv ? 0u : (e < nv + nk ? 1u : 2u);
+      s.e_key[at] = key;
+      s.e_score[at] = score;
+      s.e_src[at] = both ? (uint8_t)RAG_SRC_BOTH : (list == 0 ? (uint8_t)RAG_SRC_VECTOR : (list == 1 ? (uint8_t)RAG_SRC_KEYWORD : (uint8_t)RAG_SRC_FRESHNESS));
+      s.e_ct[at] = list == 0 ? s.v_ct[e] : (list == 1 ? (uint8_t)RAG_CT_DOCUMENT : (uint8_t)RAG_CT_MEMORY);
+    }
+    n += __popc(fm);
   }
+  __syncwarp();
+  return n;
 }
 
 // stable sort by score desc over the map (insertion index breaks ties) and emit
@@ -281,15 +301,10 @@ __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, 
   }
 
   // ---- 3c. reciprocalRankFusion (hybrid-search.ts:129-208) ---------------------------
-  uint32_t n = 0;
-  rrf_pass(s, n, s.v_key, s.v_ct, nv, a.rrf.vector_weight, a.rrf.k, a.rrf.both_bonus, true,
-           RAG_SRC_VECTOR, RAG_CT_DOCUMENT, lane);
-  rrf_pass(s, n, s.k_key, nullptr, nk, a.rrf.keyword_weight, a.rrf.k, a.rrf.both_bonus,
-           false, RAG_SRC_KEYWORD, RAG_CT_DOCUMENT, lane);
+  uint32_t nf = 0;
   if (a.fresh_limit > 0) {
     // north-star extension (SURVEY N-c4 ii): memory hits of the vector stage ranked by
     // freshness desc (ties → lower chunk id), fused like a keyword list
-    uint32_t nf = 0;
     for (uint32_t i = lane; i < nv; i += 32) {
       if (s.v_ct[i] != RAG_CT_MEMORY) continue;
       uint32_t rank = 0;
@@ -301,9 +316,8 @@ __device__ __forceinline__ void k5_fuse_body(fuse_smem& s, const rag_rec* recs, 
     }
     nf = __reduce_add_sync(0xFFFFFFFFu, nf);
     __syncwarp();
-    rrf_pass(s, n, s.f_key, nullptr, nf, a.fresh_weight, a.rrf.k, a.rrf.both_bonus, false,
-             RAG_SRC_FRESHNESS, RAG_CT_MEMORY, lane);
   }
+  const uint32_t n = rrf_fuse_lists(s, nv, nk, nf, a.rrf.vector_weight, a.rrf.keyword_weight, a.fresh_weight, a.rrf.k, a.rrf.both_bonus, lane);
   emit_sorted(s, n, ok, os, osrc, oct, lane);
   if (lane == 0) { o_cnt[b] = n; o_rrf[b] = 1; }
 }

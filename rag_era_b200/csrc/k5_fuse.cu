@@ -45,11 +45,14 @@ k5_rrf_only_kernel(rag_rrf_config cfg, const uint64_t* __restrict__ vk, const ui
   __shared__ fuse_smem s;
   const int lane = threadIdx.x;
   const uint32_t b = blockIdx.x;
-  uint32_t n = 0;
-  rrf_pass(s, n, vk + (size_t)b * vstride, vct ? vct + (size_t)b * vstride : nullptr, vc[b], cfg.vector_weight,
-           cfg.k, cfg.both_bonus, true, RAG_SRC_VECTOR, RAG_CT_DOCUMENT, lane);
-  rrf_pass(s, n, kw + (size_t)b * kstride, nullptr, kwc[b], cfg.keyword_weight, cfg.k, cfg.both_bonus, false,
-           RAG_SRC_KEYWORD, RAG_CT_DOCUMENT, lane);
+  const uint32_t nv = min(vc[b], (uint32_t)RAG_MAX_TOPK), nk = min(kwc[b], (uint32_t)RAG_MAX_KEYWORDS);
+  for (uint32_t i = lane; i < nv; i += 32) {
+    s.v_key[i] = vk[(size_t)b * vstride + i];
+    s.v_ct[i] = vct ? vct[(size_t)b * vstride + i] : (uint8_t)RAG_CT_DOCUMENT;
+  }
+  for (uint32_t i = lane; i < nk; i += 32) s.k_key[i] = kw[(size_t)b * kstride + i];
+  __syncwarp();
+  const uint32_t n = rrf_fuse_lists(s, nv, nk, 0, cfg.vector_weight, cfg.keyword_weight, 0.0, cfg.k, cfg.both_bonus, lane);
   emit_sorted(s, n, o_key + (size_t)b * out_cap, o_score + (size_t)b * out_cap, o_src + (size_t)b * out_cap,
               o_ct + (size_t)b * out_cap, lane);
   if (lane == 0) o_cnt[b] = n;
