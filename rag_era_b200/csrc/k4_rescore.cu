@@ -43,10 +43,32 @@ struct k4_meta {
 // Shared tail of both K4 kernels, executed by one thread per candidate (j < blockDim.x, all threads
 // of the CTA must call): exact rank, certification, record write. s_score/s_row/s_tmp are shared
 // arrays of >= kp entries that this function fills.
+// what k4_finalize reads of a candidate's row besides the row itself; the latency variant loads it right after the merge, so
+// that the loads fly under the exact chains instead of sitting (two dependent L2/HBM round trips) on the tail's critical path
+struct k4_row_meta {
+  uint64_t key;
+  uint32_t ctype;
+  double conf;
+  int32_t access;
+  int64_t last_ms;
+};
+__device__ __forceinline__ k4_row_meta k4_load_row_meta(const k4_meta& M, uint32_t row) {
+  k4_row_meta r;
+  r.key = M.row_keys ? M.row_keys[row] : M.id_base + row;
+  r.ctype = M.ctype ? M.ctype[row] : (uint32_t)RAG_CT_DOCUMENT;
+  // the Memory columns are read whatever the row's type turns out to be: independent loads, nobody waits for ctype here
+  const bool mem = M.ctype && M.conf && M.access && M.last_ms;
+  r.conf = mem ? M.conf[row] : 0.0;
+  r.access = mem ? M.access[row] : 0;
+  r.last_ms = mem ? M.last_ms[row] : 0;
+  return r;
+}
+
 __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k, bool valid, uint32_t row, double score,
                                             double nq, uint64_t last_key, double eps, int key_has_qnorm,
                                             const k4_meta& M, double* s_score, uint32_t* s_row, double* s_kth,
-                                            rag_rec* __restrict__ out, uint32_t* __restrict__ out_cnt, rag_rec* s_out = nullptr) {
+                                            rag_rec* __restrict__ out, uint32_t* __restrict__ out_cnt, rag_rec* s_out = nullptr,
+                                            const k4_row_meta* pre = nullptr) {
   // similarity = dot / (norm(q) * norm(x)); NaN (zero norm) is defined as never selected
   const bool good = valid && score == score;
   if (j < kp) {
@@ -78,20 +100,21 @@ __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k,
   const uint32_t flags = certified ? 0u : 1u;
 
   if (good && rank < k) {
+    const k4_row_meta m = pre ? *pre : k4_load_row_meta(M, row);
     rag_rec r;
     r.score = score;
     r.id = M.id_base + row;
-    r.key = M.row_keys ? M.row_keys[row] : r.id;
-    r.ctype = M.ctype ? M.ctype[row] : (uint32_t)RAG_CT_DOCUMENT;
+    r.key = m.key;
+    r.ctype = m.ctype;
     r.flags = flags;
     r.fresh = 0.0;
     r.conf_pad = 0.0;
     if (r.ctype == RAG_CT_MEMORY && M.conf && M.access && M.last_ms) {
       // calculateFreshnessScore — src/lib/memory/freshness.ts:43-55 (exp/log: <=1 ulp libm variance)
-      const double hours = (double)(M.now_ms - M.last_ms[row]) / 3600000.0;
+      const double hours = (double)(M.now_ms - m.last_ms) / 3600000.0;
       const double dec = exp(__dmul_rn(-M.decay, hours));
-      const double fb = __dmul_rn(log((double)M.access[row] + 1.0), M.bonus);
-      const double sc = __dmul_rn(__dmul_rn(M.conf[row], dec), __dadd_rn(1.0, fb));
+      const double fb = __dmul_rn(log((double)m.access + 1.0), M.bonus);
+      const double sc = __dmul_rn(__dmul_rn(m.conf, dec), __dadd_rn(1.0, fb));
       r.fresh = fmax(0.0, fmin(1.0, sc));
     }
     out[rank] = r;
@@ -233,6 +256,8 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   __shared__ uint32_t s_row[RAG_MAX_CANDIDATES];
   __shared__ double s_kth;
   __shared__ int s_last;
+  __shared__ uint64_t s_kw[RAG_MAX_KEYWORDS];
+  __shared__ uint32_t s_kwc;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t b = blockIdx.x, slice = blockIdx.y, nslices = gridDim.y;
@@ -241,7 +266,34 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
 
   // ---- K3: merge the sorted per-CTA lists of the scoring kernel (every slice does it: ~1 us) ----
   const uint64_t* in = partial + (size_t)b * parts * kp;
-  for (uint32_t i = threadIdx.x; i < parts * kp; i += K4S_THREADS) stg[i] = in[i];
+  const uint32_t n_keys = parts * kp;
+  if ((n_keys & 1u) == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+    // 128-bit loads, eight per thread issued before the first store: one L2 round trip for the usual 13-38 KB
+    const uint4* in4 = reinterpret_cast<const uint4*>(in);
+    uint4* st4 = reinterpret_cast<uint4*>(stg);
+    const uint32_t n16 = n_keys / 2;
+    for (uint32_t i0 = threadIdx.x; i0 < n16; i0 += K4S_THREADS * 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t i = i0 + u * K4S_THREADS;
+        v[u] = i < n16 ? __ldg(in4 + i) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t i = i0 + u * K4S_THREADS;
+        if (i < n16) st4[i] = v[u];
+      }
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < n_keys; i += K4S_THREADS) stg[i] = in[i];
+  }
+  // (2) the query's keyword list: fetched now by the idle lanes' loads, read by the in-place K5 from shared memory
+  if (fuse_k5 && io.kwc && io.a.mode == 0 && threadIdx.x < RAG_MAX_KEYWORDS) {
+    const uint32_t nk = min(io.kwc[b], (uint32_t)RAG_MAX_KEYWORDS);
+    if (threadIdx.x == 0) s_kwc = nk;
+    if (threadIdx.x < nk) s_kw[threadIdx.x] = io.kw[(size_t)b * io.a.kw_stride + threadIdx.x];
+  }
   __syncthreads();
   const long long pt0a = prof ? clock64() : 0;
   // warp w merges lists w, w+W, w+2W, ... at most 31 at a time, together with its running result
@@ -280,6 +332,9 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
   }
   __syncthreads();
 
+  // the candidates' row metadata (fusion key, contentType, Memory columns): loaded now, used by the query's last CTA after the chains
+  k4_row_meta pre = k4_row_meta();
+  if (threadIdx.x < kp && s_cand[threadIdx.x] != 0ull) pre = k4_load_row_meta(M, rag_key_row(s_cand[threadIdx.x]));
   const long long pt1 = prof ? clock64() : 0;
   // ---- K4: exact sums, one warp per candidate -----------------------------------------------------
   double* my_scratch = scratch + (size_t)b * (2 * RAG_MAX_CANDIDATES + 2);
@@ -321,7 +376,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
     const uint32_t row = valid ? rag_key_row(key) : 0u;
     const double score = valid ? __ddiv_rn(vs[2 * j], __dmul_rn(__dsqrt_rn(nq), __dsqrt_rn(vs[2 * j + 1]))) : 0.0;
     k4_finalize(j, kp, k, valid, row, score, nq, s_cand[kp - 1], eps, key_has_qnorm, M, s_score, s_row, &s_kth,
-                local + (size_t)b * k, local_cnt + b, s_recs);
+                local + (size_t)b * k, local_cnt + b, s_recs, j0 == 0 ? &pre : nullptr);
   }
   // ---- K5 in place: filter + fusion of this query by warp 0 — one launch less on the batch-1 latency path.
   //      Sharded (pv.nranks > 1): the same warp first exchanges this query's records with the peer ranks through
@@ -334,8 +389,13 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
     static_assert(sizeof(rag_k5::fuse_smem) <= sizeof(s_prod), "K5 working set must fit the product scratch");
     if (warp == 0) {
       rag_k5::fuse_smem& fs = *reinterpret_cast<rag_k5::fuse_smem*>(&s_prod[0][0]);
-      if (pv.nranks > 1) rag_k5::k5_fuse_body<false>(fs, rag_k5::p2p_exchange(pv, local, io.a.B, b, io.a.k, lane), io, b, lane);
-      else rag_k5::k5_fuse_body<true>(fs, s_recs, io, b, lane);   // one GPU: straight from shared memory
+      rag_k5::k5_io io2 = io;
+      if (io.kwc && io.a.mode == 0) {   // the keyword list staged at the top of the kernel: K5 indexes [b * stride + i] / [b]
+        io2.kw = s_kw - (size_t)b * io.a.kw_stride;
+        io2.kwc = &s_kwc - b;
+      }
+      if (pv.nranks > 1) rag_k5::k5_fuse_body<false>(fs, rag_k5::p2p_exchange(pv, local, io.a.B, b, io.a.k, lane), io2, b, lane);
+      else rag_k5::k5_fuse_body<true>(fs, s_recs, io2, b, lane);   // one GPU: straight from shared memory
     }
   }
   if (prof && threadIdx.x == 0) {
