@@ -72,3 +72,13 @@ def emulate(X, q, rows="bf16"):
     exact = (Xd @ qd) / np.linalg.norm(Xd, axis=1) / np.linalg.norm(qd)
     qt, xt, rho_q, rho_x = operands(X, q, rows)
     return exact, xt @ qt, rho_q, rho_x
+
+
+def emulate_shadow_stream(X, q):
+    """(exact cosines, the shadow stream path's scores in cosine units, rho_x): the fp32 query as it is against the fp16
+    shadow of the normalised rows — q.x~ / ||q||, in fp64 (the fp32 accumulation is bounded separately)."""
+    Xd, qd = X.astype(np.float64), q.astype(np.float64)
+    nx, nq = np.linalg.norm(Xd, axis=1, keepdims=True), np.linalg.norm(qd)
+    ux = Xd / nx
+    xt = f16_round(ux).astype(np.float64)
+    return (ux @ qd) / nq, (xt @ qd) / nq, np.linalg.norm(xt - ux, axis=1).max()

@@ -59,6 +59,47 @@ def test_rigorous_bound_holds_on_random_and_scaled_rows():
                 assert np.abs(exact - approx).max() <= rho_q * (1 + rho_x) + rho_x + 1e-12
 
 
+def test_shadow_stream_bound_holds_on_adversarial_and_scaled_rows():
+    """RAG_PATH_SHADOW_STREAM: |q.x~/||q|| - cos| <= rho_x (Cauchy-Schwarz; only the rows are rounded) — on the adversarial
+    corpus, whose outlier dimensions make fp16 rounding errors align, and on rows of very different scales."""
+    X, q, star, _ = adversarial.build()
+    exact, approx, rho_x = adversarial.emulate_shadow_stream(X, q)
+    assert np.abs(exact - approx).max() <= rho_x + 1e-12 and rho_x < 3e-4
+    assert int(np.argmax(approx)) == star                          # 11 significant bits: the best row stays the best
+    rng = np.random.default_rng(4)
+    for d, scale in [(64, 1.0), (1536, 1e-3), (256, 3e4)]:
+        X = (scale * rng.standard_normal((500, d)) * rng.uniform(0.1, 10, (500, 1))).astype(np.float32)
+        X[:50, :4] *= 100
+        for _ in range(20):
+            q = (X[rng.integers(0, 500)] + 0.5 * scale * rng.standard_normal(d)).astype(np.float32)
+            exact, approx, rho_x = adversarial.emulate_shadow_stream(X, q)
+            assert np.abs(exact - approx).max() <= rho_x + 1e-12
+            assert rho_x <= 2.0 ** -11 * 1.01                      # relative fp16 rounding of every element: ||e_x|| <= 2^-11 ||x~||
+
+
+@pytest.mark.gpu
+def test_gpu_shadow_stream_on_the_adversarial_corpus(native, oracle):
+    """The library's shadow stream path on the corpus that defeats the statistical tensor bound: the exact answer, the best
+    row in first place, and whatever the first pass certifies on its own is the oracle's top-k."""
+    import rag_era_b200 as rb
+
+    X, q, star, _ = adversarial.build()
+    n, d = X.shape
+    rng = np.random.default_rng(12)
+    Q = np.stack([q] + [(X[i] + 0.2 * rng.standard_normal(d)).astype(np.float32) for i in rng.integers(0, 2000, 7)])
+    with rb.VectorIndex(d, n, shadow="f16") as idx:
+        idx.upload(X)
+        assert idx.row_residual() < 3e-4
+        for b in range(len(Q)):
+            ei, es = oracle.topk(X, Q[b], 10)
+            r = idx.query(Q[b:b + 1], 10, path=native.PATH_SHADOW_STREAM)
+            assert r.certified[0] == 1 and np.array_equal(r.row(0)[0], ei) and np.array_equal(r.row(0)[1], es), b
+            raw = idx.query(Q[b:b + 1], 10, path=native.PATH_SHADOW_STREAM, flags=native.SEARCH_NO_ESCALATE)
+            if raw.certified[0]:
+                assert np.array_equal(raw.row(0)[0], ei) and np.array_equal(raw.row(0)[1], es), b
+        assert int(idx.query(Q[:1], 10, path=native.PATH_SHADOW_STREAM).row(0)[0][0]) == star
+
+
 @pytest.mark.gpu
 def test_gpu_adversarial_corpus_rigorous_default_is_exact_and_statistical_is_not(native, oracle):
     import rag_era_b200 as rb
