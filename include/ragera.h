@@ -51,7 +51,8 @@ typedef enum rag_status {
   RAG_ERR_UNSUPPORTED = -5, /* e.g. tensor path requested without a bf16 shadow   */
   RAG_ERR_NCCL = -6,
   RAG_ERR_NO_DEVICE = -7,   /* no sm_100 GPU: there is deliberately no fallback   */
-  RAG_ERR_TIMEOUT = -8      /* sharded search: a peer rank never arrived at the exchange */
+  RAG_ERR_TIMEOUT = -8,     /* sharded search: a peer rank never arrived at the exchange */
+  RAG_ERR_BUSY = -9         /* rag_batcher_submit_async: every batch buffer is in flight; nothing was queued */
 } rag_status;
 
 typedef enum rag_dtype { RAG_F32 = 0, RAG_BF16 = 1 } rag_dtype;
@@ -362,7 +363,20 @@ typedef struct rag_batcher_desc {
 int rag_batcher_create(rag_index* idx, const rag_batcher_desc* desc, rag_batcher** out);
 int rag_batcher_submit(rag_batcher* b, const float* query /*[dim]*/, const uint64_t* kw_keys, uint32_t kw_count,
                        rag_fused_out* out /* shaped for one query */);
+/* The same request without parking a thread on it — what a single-threaded host (Node's event loop; libuv's pool has 4
+ * threads by default, so blocking submits could never form a batch above 4) uses to keep thousands of requests in
+ * flight. Takes a slot of the open batch, copies `query` and `kw_keys` into it (the caller may reuse them on return) and
+ * returns. `out` (shaped for one query, as above) must stay valid until `done(user, rc, err)` runs — on a batcher worker
+ * thread, after the result has been copied into `out` (rc == RAG_OK) or with the batch's error text (`err` is valid
+ * during the callback only; it must not call rag_batcher_destroy). RAG_ERR_BUSY: every batch buffer is in flight,
+ * nothing was queued — retry, or fall back to the blocking call. A non-zero return never calls `done`. */
+typedef void (*rag_batcher_done_fn)(void* user, int rc, const char* err);
+int rag_batcher_submit_async(rag_batcher* b, const float* query /*[dim]*/, const uint64_t* kw_keys, uint32_t kw_count,
+                             rag_fused_out* out /* shaped for one query */, rag_batcher_done_fn done, void* user);
 int rag_batcher_stats(rag_batcher* b, uint64_t* batches, uint64_t* queries, uint64_t* largest_batch);
+/* destroy may be called while submit calls are still inside the batcher: requests that hold a slot are run and answered,
+ * (asynchronous ones get their `done`), callers still waiting for a batch buffer fail with RAG_ERR_STATE, and nothing is
+ * freed before the last of them has returned. No submit may START on the handle once destroy has been called. */
 void rag_batcher_destroy(rag_batcher* b);
 
 /* ---- diagnostics: the raw scaled scores (dot_bf16 * 1/||x||, no 1/||q||) the tensor path (K2)

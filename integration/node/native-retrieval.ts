@@ -80,7 +80,30 @@ export class NativeKnowledgeIndex {
   }
   keyString(id: bigint): string { return this.keyStrs[Number(id)]; }
   embedQuery(q: string): Promise<Float32Array> { return this.embed(q); }
+
+  /**
+   * Micro-batcher per call-site class (one per distinct vectorTopK / keywordLimit / minVectorScore / RRF config — they are
+   * per-launch parameters): concurrent requests of the server share ONE corpus pass and each gets exactly its batch-1
+   * result. `native.submit` does not block and does not occupy a libuv pool thread: the Promise is resolved from the
+   * batcher's worker through a thread-safe function, so the event loop can keep thousands of requests in flight.
+   */
+  private batchers = new Map<string, unknown>();
+  batcherFor(opts: { vectorTopK: number; keywordLimit: number; minVectorScore: number; rrf: RRFConfig }): unknown {
+    const key = JSON.stringify(opts);
+    let b = this.batchers.get(key);
+    if (b === undefined) { b = native.createBatcher(this.handle, opts, 1024, 1000); this.batchers.set(key, b); }
+    return b;
+  }
+  /** Closes the handles; calls still in flight are answered first (the addon defers the native destroy to the last of them). */
+  close(): void {
+    this.batchers.forEach(b => native.destroyBatcher(b));
+    this.batchers.clear();
+    native.destroy(this.handle);
+  }
 }
+
+/** RAGERA_BATCH=1: hybridSearchNative goes through the micro-batcher (a busy server); otherwise one direct call per request. */
+const USE_BATCHER = process.env.RAGERA_BATCH === '1';
 
 const docName = (m: any) => (m?.type === 'memory' ? '用户记忆' : m?.documentName || m?.relativePath || m?.filePath || '未知文档'); // :238-240
 
@@ -102,8 +125,12 @@ export async function hybridSearchNative(index: NativeKnowledgeIndex, knowledgeB
       ? meilisearchService.search(knowledgeBaseId, query, keywordLimit) : Promise.resolve([]),
   ]);
   const kwKeys = BigUint64Array.from(hits.map(h => index.keyOf(h.content)));
-  const r = await native.hybridSearch(index.handle, q, 1,
-    { vectorTopK, keywordLimit: hits.length, minVectorScore, rrf }, kwKeys, Uint32Array.of(hits.length));
+  // the batcher's keywordLimit is the call site's (a row stride shared by the whole batch); the direct call sizes it per request
+  const batchOpts = { vectorTopK, keywordLimit, minVectorScore, rrf };   // hits.length <= keywordLimit (Meilisearch's limit)
+  const r = USE_BATCHER
+    ? await native.submit(index.batcherFor(batchOpts), batchOpts, q, kwKeys)
+    : await native.hybridSearch(index.handle, q, 1,
+        { vectorTopK, keywordLimit: hits.length, minVectorScore, rrf }, kwKeys, Uint32Array.of(hits.length));
 
   // re-attach strings: the first occurrence of a key wins, vector hits first, then keyword hits (:147-188)
   const first = new Map<bigint, { n?: NodeRow; h?: (typeof hits)[number] }>();

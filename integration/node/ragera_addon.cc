@@ -8,7 +8,12 @@
 // HTTP requests, the Promise.all of engine.ts:108, the synchronous mutators below on the main thread: libragera
 // serialises the calls of a handle itself (a per-handle mutex, include/ragera.h), so they take turns on the GPU
 // instead of racing; tests/c/napi_mock.cc queues 2B calls on one handle before draining the loop. For throughput
-// under load route the requests through the batcher, which turns concurrent batch-1 calls into one corpus pass.
+// under load route the requests through the batcher, which turns concurrent batch-1 calls into one corpus pass:
+// `submit` does NOT park a pool thread on the request (libuv's pool has 4 threads by default — blocking submits could never
+// form a batch above 4): it hands the request to rag_batcher_submit_async on the main thread and the batcher's worker
+// resolves the Promise through a thread-safe function, so the event loop keeps thousands of requests in flight.
+// Handle lifetime: every queued call holds a reference on its handle; destroy()/destroyBatcher() with calls still in
+// flight marks the handle closed (new calls throw) and the LAST completion destroys it — nothing is freed under a worker.
 //
 // JS surface (see native-retrieval.ts):
 //   createIndex({rows, dim, dtype:'f32'|'bf16', device, f16Shadow | bf16Shadow}) -> handle (External)
@@ -20,7 +25,7 @@
 //   search(handle, Float32Array queries, B, k) -> Promise<{ids, scores, counts, certified}>      (retriever.retrieve / VectorStore.query)
 //   memoryRetrieve(handle, Float32Array queries, B, {limit, minRelevance, nowMs, similarityTopK}) -> Promise<{ids, scores, relevance, freshness, counts}>
 //   createBatcher(handle, opts, maxBatch, maxWaitUs) -> batcher; submit(batcher, opts, Float32Array q, BigUint64Array kwKeys) -> Promise<result>
-//   destroy(handle) / destroyBatcher(batcher)
+//   destroy(handle) / destroyBatcher(batcher)        (deferred until the calls in flight on the handle have completed)
 #include <node_api.h>
 
 #include <stdlib.h>
@@ -45,6 +50,73 @@ napi_value throw_rag(napi_env env, int rc) {
   std::string msg = "libragera error " + std::to_string(rc) + ": " + rag_last_error();
   napi_throw_error(env, nullptr, msg.c_str());
   return nullptr;
+}
+
+// ---- handle lifetime (main thread only) ------------------------------------------------------------------------------
+// What JS holds is an External around one of these. `pending` = queued calls (and live batchers) that still use the
+// native object; destroy() only marks it closing, the last release really destroys it; the External's finalizer frees
+// the wrapper (after the last release if calls are still in flight when the JS object is collected).
+struct IndexHandle {
+  rag_index* idx = nullptr;
+  uint32_t pending = 0;
+  bool closing = false, finalized = false;
+};
+void index_settle(IndexHandle* h) {
+  if (h->pending || !h->closing) return;
+  if (h->idx) { rag_index_destroy(h->idx); h->idx = nullptr; }
+  if (h->finalized) delete h;
+}
+void index_finalize(napi_env, void* data, void*) {
+  auto* h = static_cast<IndexHandle*>(data);
+  h->closing = h->finalized = true;
+  index_settle(h);
+}
+// the live handle behind argv[0], or nullptr with a pending exception
+IndexHandle* index_arg(napi_env env, napi_value v) {
+  IndexHandle* h = nullptr;
+  if (napi_get_value_external(env, v, (void**)&h) != napi_ok || !h) { napi_throw_type_error(env, nullptr, "expected an index handle"); return nullptr; }
+  if (h->closing || !h->idx) { napi_throw_error(env, nullptr, "the index handle was destroyed"); return nullptr; }
+  return h;
+}
+
+struct BatcherHandle {
+  rag_batcher* b = nullptr;
+  IndexHandle* owner = nullptr;              // holds one `pending` on it for the batcher's lifetime
+  napi_threadsafe_function tsfn = nullptr;   // worker thread -> main thread: resolves the Promises of asynchronous submits
+  uint32_t pending = 0;
+  bool closing = false, finalized = false;
+};
+void batcher_settle(napi_env env, BatcherHandle* h) {
+  if (h->pending || !h->closing) return;
+  if (h->b) {
+    rag_batcher_destroy(h->b);   // main thread, nothing in flight: returns at once
+    h->b = nullptr;
+    if (h->tsfn) napi_release_threadsafe_function(h->tsfn, napi_tsfn_release);
+    h->tsfn = nullptr;
+    h->owner->pending--;
+    index_settle(h->owner);
+  }
+  (void)env;
+  if (h->finalized) delete h;
+}
+void batcher_finalize(napi_env env, void* data, void*) {
+  auto* h = static_cast<BatcherHandle*>(data);
+  h->closing = h->finalized = true;
+  batcher_settle(env, h);
+}
+BatcherHandle* batcher_arg(napi_env env, napi_value v) {
+  BatcherHandle* h = nullptr;
+  if (napi_get_value_external(env, v, (void**)&h) != napi_ok || !h) { napi_throw_type_error(env, nullptr, "expected a batcher handle"); return nullptr; }
+  if (h->closing || !h->b) { napi_throw_error(env, nullptr, "the batcher was destroyed"); return nullptr; }
+  return h;
+}
+// a request enters / leaves the batcher: the thread-safe function keeps the event loop alive only while requests are out
+void batcher_enter(napi_env env, BatcherHandle* h) {
+  if (h->pending++ == 0 && h->tsfn) napi_ref_threadsafe_function(env, h->tsfn);
+}
+void batcher_leave(napi_env env, BatcherHandle* h) {
+  if (--h->pending == 0 && h->tsfn) napi_unref_threadsafe_function(env, h->tsfn);
+  batcher_settle(env, h);
 }
 
 bool get_u32(napi_env env, napi_value obj, const char* name, uint32_t* out) {
@@ -94,8 +166,9 @@ bool typed(napi_env env, napi_value v, napi_typedarray_type want, const T** data
 struct SearchWork {
   napi_async_work work = nullptr;
   napi_deferred deferred = nullptr;
-  rag_index* idx = nullptr;
-  rag_batcher* batcher = nullptr;
+  IndexHandle* h = nullptr;        // direct call: the handle it holds a reference on
+  BatcherHandle* bh = nullptr;     // through a batcher
+  rag_fused_out out;
   std::vector<float> q;
   uint32_t B = 1;
   rag_hybrid_opts opts;
@@ -110,20 +183,24 @@ struct SearchWork {
   std::string err;
 };
 
-void search_execute(napi_env, void* data) {  // worker thread: the only place that touches CUDA
-  auto* w = static_cast<SearchWork*>(data);
+// the result arrays of a request, sized on the main thread before anything else can touch them
+void prepare_out(SearchWork* w) {
   const uint32_t k = w->opts.vector_top_k;
   w->cap = k + w->opts.keyword_limit + w->opts.fresh_limit;
   w->keys.resize((size_t)w->B * w->cap); w->scores.resize((size_t)w->B * w->cap);
   w->source.resize((size_t)w->B * w->cap); w->ctype.resize((size_t)w->B * w->cap);
   w->counts.resize(w->B); w->used_rrf.resize(w->B); w->certified.resize(w->B);
   w->vec_ids.resize((size_t)w->B * k); w->vec_scores.resize((size_t)w->B * k); w->vec_counts.resize(w->B);
-  rag_fused_out out = {w->cap, w->keys.data(), w->scores.data(), w->source.data(), w->ctype.data(), w->counts.data(),
-                       w->used_rrf.data(), w->vec_ids.data(), w->vec_scores.data(), w->vec_counts.data(), w->certified.data()};
-  if (w->batcher)
-    w->rc = rag_batcher_submit(w->batcher, w->q.data(), w->kw_keys.data(), w->kw_counts.empty() ? 0 : w->kw_counts[0], &out);
+  w->out = {w->cap, w->keys.data(), w->scores.data(), w->source.data(), w->ctype.data(), w->counts.data(),
+            w->used_rrf.data(), w->vec_ids.data(), w->vec_scores.data(), w->vec_counts.data(), w->certified.data()};
+}
+
+void search_execute(napi_env, void* data) {  // pool thread: the only place that touches CUDA
+  auto* w = static_cast<SearchWork*>(data);
+  if (w->bh)  // the batcher's buffers were all in flight: this request waits for one on a pool thread (back-pressure)
+    w->rc = rag_batcher_submit(w->bh->b, w->q.data(), w->kw_keys.data(), w->kw_counts.empty() ? 0 : w->kw_counts[0], &w->out);
   else
-    w->rc = rag_hybrid_search(w->idx, w->q.data(), w->B, &w->opts, w->kw_keys.data(), w->kw_counts.data(), &out);
+    w->rc = rag_hybrid_search(w->h->idx, w->q.data(), w->B, &w->opts, w->kw_keys.data(), w->kw_counts.data(), &w->out);
   if (w->rc != RAG_OK) w->err = rag_last_error();
 }
 
@@ -161,24 +238,42 @@ void search_complete(napi_env env, napi_status, void* data) {  // main thread: b
     napi_set_named_property(env, r, "vecCounts", make_typed(env, napi_uint32_array, w->vec_counts));
     napi_resolve_deferred(env, w->deferred, r);
   }
-  napi_delete_async_work(env, w->work);
+  if (w->work) napi_delete_async_work(env, w->work);
+  if (w->bh) batcher_leave(env, w->bh);   // the last request of a closing handle destroys it
+  if (w->h) { w->h->pending--; index_settle(w->h); }
   delete w;
 }
 
-napi_value queue_search(napi_env env, SearchWork* w) {
-  napi_value promise, name;
-  NAPI_OK(env, napi_create_promise(env, &w->deferred, &promise));
+// queue the request as pool work; `promise` = the Promise made by the caller, or null to make one here
+napi_value queue_search(napi_env env, SearchWork* w, napi_value promise = nullptr) {
+  napi_value name;
+  if (!promise) NAPI_OK(env, napi_create_promise(env, &w->deferred, &promise));
   NAPI_OK(env, napi_create_string_utf8(env, "ragera.hybridSearch", NAPI_AUTO_LENGTH, &name));
   NAPI_OK(env, napi_create_async_work(env, nullptr, name, search_execute, search_complete, w, &w->work));
   NAPI_OK(env, napi_queue_async_work(env, w->work));
+  if (w->bh) batcher_enter(env, w->bh);
+  if (w->h) w->h->pending++;
   return promise;
+}
+
+// ---- asynchronous submit: batcher worker thread -> thread-safe function -> main thread -------------------------------
+void submit_done(void* user, int rc, const char* err) {   // batcher worker thread; the result is already in w->out's arrays
+  auto* w = static_cast<SearchWork*>(user);
+  w->rc = rc;
+  if (rc != RAG_OK) w->err = err ? err : "";
+  napi_call_threadsafe_function(w->bh->tsfn, w, napi_tsfn_blocking);
+}
+void submit_call_js(napi_env env, napi_value, void*, void* data) {   // main thread
+  auto* w = static_cast<SearchWork*>(data);
+  if (!env) { delete w; return; }   // the environment is going down: nobody is left to resolve for
+  search_complete(env, napi_ok, w);
 }
 
 // ---- retriever.retrieve (SimpleVectorStore.query) and MemoryStore.retrieve as async work -----------------------------
 struct TopkWork {
   napi_async_work work = nullptr;
   napi_deferred deferred = nullptr;
-  rag_index* idx = nullptr;
+  IndexHandle* h = nullptr;
   std::vector<float> q;
   uint32_t B = 1;
   bool memory = false;
@@ -199,11 +294,11 @@ void topk_execute(napi_env, void* data) {
   if (w->memory) {
     w->relevance.resize((size_t)w->B * width); w->freshness.resize((size_t)w->B * width);
     rag_memory_out out = {w->ids.data(), w->scores.data(), w->relevance.data(), w->freshness.data(), w->counts.data()};
-    w->rc = rag_memory_retrieve(w->idx, w->q.data(), w->B, &w->mopts, &out);
+    w->rc = rag_memory_retrieve(w->h->idx, w->q.data(), w->B, &w->mopts, &out);
   } else {
     w->certified.resize(w->B);
     rag_topk_out out = {w->ids.data(), w->scores.data(), w->counts.data(), w->certified.data()};
-    w->rc = rag_search(w->idx, w->q.data(), w->B, &w->sopts, &out);
+    w->rc = rag_search(w->h->idx, w->q.data(), w->B, &w->sopts, &out);
   }
   if (w->rc != RAG_OK) w->err = rag_last_error();
 }
@@ -231,6 +326,8 @@ void topk_complete(napi_env env, napi_status, void* data) {
     napi_resolve_deferred(env, w->deferred, r);
   }
   napi_delete_async_work(env, w->work);
+  w->h->pending--;
+  index_settle(w->h);
   delete w;
 }
 
@@ -240,6 +337,7 @@ napi_value queue_topk(napi_env env, TopkWork* w) {
   NAPI_OK(env, napi_create_string_utf8(env, "ragera.search", NAPI_AUTO_LENGTH, &name));
   NAPI_OK(env, napi_create_async_work(env, nullptr, name, topk_execute, topk_complete, w, &w->work));
   NAPI_OK(env, napi_queue_async_work(env, w->work));
+  w->h->pending++;
   return promise;
 }
 
@@ -263,8 +361,15 @@ napi_value CreateIndex(napi_env env, napi_callback_info info) {
   rag_index* idx = nullptr;
   const int rc = rag_index_create(&d, &idx);
   if (rc != RAG_OK) return throw_rag(env, rc);
+  auto* h = new IndexHandle();
+  h->idx = idx;
   napi_value ext;
-  NAPI_OK(env, napi_create_external(env, idx, nullptr, nullptr, &ext));
+  if (napi_create_external(env, h, index_finalize, nullptr, &ext) != napi_ok) {
+    rag_index_destroy(idx);
+    delete h;
+    napi_throw_error(env, nullptr, "napi_create_external failed");
+    return nullptr;
+  }
   return ext;
 }
 
@@ -272,8 +377,9 @@ napi_value UploadRows(napi_env env, napi_callback_info info) {  // uploadRows(ha
   size_t argc = 4;
   napi_value argv[4];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
+  rag_index* idx = h->idx;
   const float* rows = nullptr;
   size_t n = 0;
   if (!typed(env, argv[1], napi_float32_array, &rows, &n)) { napi_throw_type_error(env, nullptr, "rows must be a Float32Array"); return nullptr; }
@@ -292,8 +398,9 @@ napi_value LoadVectorStore(napi_env env, napi_callback_info info) {  // loadVect
   size_t argc = 2;
   napi_value argv[2];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
+  rag_index* idx = h->idx;
   char path[4096];
   size_t len = 0;
   NAPI_OK(env, napi_get_value_string_utf8(env, argv[1], path, sizeof path, &len));
@@ -321,8 +428,9 @@ napi_value SetRowMeta(napi_env env, napi_callback_info info) {
   size_t argc = 6;
   napi_value argv[6];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
+  rag_index* idx = h->idx;
   uint32_t row0 = 0;
   NAPI_OK(env, napi_get_value_uint32(env, argv[1], &row0));
   const uint8_t* ct = nullptr; const double* conf = nullptr; const int32_t* acc = nullptr; const int64_t* last = nullptr;
@@ -339,8 +447,9 @@ napi_value SetRowKeys(napi_env env, napi_callback_info info) {
   size_t argc = 3;
   napi_value argv[3];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
+  rag_index* idx = h->idx;
   uint32_t row0 = 0;
   NAPI_OK(env, napi_get_value_uint32(env, argv[1], &row0));
   const uint64_t* keys = nullptr;
@@ -354,15 +463,15 @@ napi_value HybridSearch(napi_env env, napi_callback_info info) {
   size_t argc = 6;
   napi_value argv[6];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
   const float* q = nullptr;
   size_t nq = 0;
   if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
   uint32_t B = 0;
   NAPI_OK(env, napi_get_value_uint32(env, argv[2], &B));
   auto* w = new SearchWork();  // owned by the async work from here on (search_complete deletes it)
-  w->idx = idx;
+  w->h = h;
   w->B = B;
   read_opts(env, argv[3], &w->opts);
   if ((size_t)B * w->opts.vector_top_k == 0 || nq % B != 0) { delete w; napi_throw_type_error(env, nullptr, "queries must hold B rows of dim values, B and vectorTopK >= 1"); return nullptr; }
@@ -373,6 +482,7 @@ napi_value HybridSearch(napi_env env, napi_callback_info info) {
   if (argc > 5 && typed(env, argv[5], napi_uint32_array, &kc, &nc)) w->kw_counts.assign(kc, kc + nc);
   w->kw_counts.resize(w->B, 0);
   w->kw_keys.resize((size_t)w->B * w->opts.keyword_limit + 1, 0);
+  prepare_out(w);
   return queue_search(env, w);
 }
 
@@ -382,8 +492,8 @@ napi_value Search(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value argv[4];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
   const float* q = nullptr;
   size_t nq = 0;
   if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
@@ -392,7 +502,7 @@ napi_value Search(napi_env env, napi_callback_info info) {
   NAPI_OK(env, napi_get_value_uint32(env, argv[3], &k));
   if (B == 0 || k == 0 || nq % B != 0) { napi_throw_type_error(env, nullptr, "queries must hold B rows of dim values, B and k >= 1"); return nullptr; }
   auto* w = new TopkWork();
-  w->idx = idx;
+  w->h = h;
   w->B = B;
   w->q.assign(q, q + nq);
   memset(&w->sopts, 0, sizeof w->sopts);
@@ -406,8 +516,8 @@ napi_value MemoryRetrieve(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value argv[4];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
   const float* q = nullptr;
   size_t nq = 0;
   if (!typed(env, argv[1], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "queries must be a Float32Array"); return nullptr; }
@@ -425,7 +535,7 @@ napi_value MemoryRetrieve(napi_env env, napi_callback_info info) {
   mo.now_ms = (int64_t)now_ms;
   if (B == 0 || mo.limit == 0 || nq % B != 0) { napi_throw_type_error(env, nullptr, "queries must hold B rows of dim values, B and limit >= 1"); return nullptr; }
   auto* w = new TopkWork();
-  w->idx = idx;
+  w->h = h;
   w->B = B;
   w->memory = true;
   w->mopts = mo;
@@ -437,33 +547,54 @@ napi_value CreateBatcher(napi_env env, napi_callback_info info) {  // createBatc
   size_t argc = 4;
   napi_value argv[4];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
+  IndexHandle* h = index_arg(env, argv[0]);
+  if (!h) return nullptr;
   rag_batcher_desc d;
   read_opts(env, argv[1], &d.opts);
   d.max_batch = 1024;
   d.max_wait_us = 1000;   // a cap: a batch goes out earlier, once the arrivals pause
   if (argc > 2) napi_get_value_uint32(env, argv[2], &d.max_batch);
   if (argc > 3) napi_get_value_uint32(env, argv[3], &d.max_wait_us);
-  rag_batcher* b = nullptr;
-  const int rc = rag_batcher_create(idx, &d, &b);
-  if (rc != RAG_OK) return throw_rag(env, rc);
-  napi_value ext;
-  NAPI_OK(env, napi_create_external(env, b, nullptr, nullptr, &ext));
+  auto* bh = new BatcherHandle();
+  napi_value name, ext;
+  // the channel from the batcher's worker threads back to the event loop; unreferenced while no request is out, so an idle
+  // batcher does not keep the process alive
+  if (napi_create_string_utf8(env, "ragera.submit", NAPI_AUTO_LENGTH, &name) != napi_ok ||
+      napi_create_threadsafe_function(env, nullptr, nullptr, name, 0, 1, nullptr, nullptr, nullptr, submit_call_js, &bh->tsfn) != napi_ok) {
+    delete bh;
+    napi_throw_error(env, nullptr, "napi_create_threadsafe_function failed");
+    return nullptr;
+  }
+  napi_unref_threadsafe_function(env, bh->tsfn);
+  const int rc = rag_batcher_create(h->idx, &d, &bh->b);
+  if (rc != RAG_OK || napi_create_external(env, bh, batcher_finalize, nullptr, &ext) != napi_ok) {
+    if (bh->b) rag_batcher_destroy(bh->b);
+    napi_release_threadsafe_function(bh->tsfn, napi_tsfn_release);
+    delete bh;
+    if (rc != RAG_OK) return throw_rag(env, rc);
+    napi_throw_error(env, nullptr, "napi_create_external failed");
+    return nullptr;
+  }
+  bh->owner = h;
+  h->pending++;   // the index outlives its batchers
   return ext;
 }
 
-napi_value Submit(napi_env env, napi_callback_info info) {  // submit(batcher, opts, Float32Array q, BigUint64Array kwKeys)
+// submit(batcher, opts, Float32Array q, BigUint64Array kwKeys) -> Promise<result>. Runs on the main thread and does not
+// block: the request takes a slot of the batcher's open batch (rag_batcher_submit_async copies the inputs) and the
+// Promise is resolved from the batcher's worker through the thread-safe function. Only when every batch buffer is in
+// flight (RAG_ERR_BUSY) does the request fall back to a pool thread that waits for one — that is the back-pressure.
+napi_value Submit(napi_env env, napi_callback_info info) {
   size_t argc = 4;
   napi_value argv[4];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_batcher* batcher = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&batcher));
+  BatcherHandle* bh = batcher_arg(env, argv[0]);
+  if (!bh) return nullptr;
   const float* q = nullptr;
   size_t nq = 0;
   if (!typed(env, argv[2], napi_float32_array, &q, &nq)) { napi_throw_type_error(env, nullptr, "query must be a Float32Array"); return nullptr; }
   auto* w = new SearchWork();
-  w->batcher = batcher;
+  w->bh = bh;
   read_opts(env, argv[1], &w->opts);  // must equal the batcher's options (sizes the result arrays)
   w->q.assign(q, q + nq);
   const uint64_t* kk = nullptr;
@@ -472,16 +603,30 @@ napi_value Submit(napi_env env, napi_callback_info info) {  // submit(batcher, o
   w->kw_counts.assign(1, (uint32_t)nk);
   w->kw_keys.resize(nk + 1, 0);
   w->B = 1;
-  return queue_search(env, w);
+  prepare_out(w);
+  napi_value promise;
+  if (napi_create_promise(env, &w->deferred, &promise) != napi_ok) { delete w; napi_throw_error(env, nullptr, "napi_create_promise failed"); return nullptr; }
+  const int rc = rag_batcher_submit_async(bh->b, w->q.data(), w->kw_keys.data(), (uint32_t)nk, &w->out, submit_done, w);
+  // (a completion that is already on its way is delivered by the event loop, i.e. after this function has returned)
+  if (rc == RAG_OK) { batcher_enter(env, bh); return promise; }
+  if (rc == RAG_ERR_BUSY) return queue_search(env, w, promise);
+  w->rc = rc;
+  w->err = rag_last_error();
+  batcher_enter(env, bh);
+  search_complete(env, napi_ok, w);   // rejects the Promise with rag_last_error(), leaves the batcher, deletes w
+  return promise;
 }
 
+// destroy(handle): closes the handle; the native index goes away with the last call still in flight on it (or now)
 napi_value Destroy(napi_env env, napi_callback_info info) {
   size_t argc = 1;
   napi_value argv[1];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_index* idx = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&idx));
-  rag_index_destroy(idx);
+  IndexHandle* h = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&h));
+  if (!h) return nullptr;
+  h->closing = true;
+  index_settle(h);
   return nullptr;
 }
 
@@ -489,9 +634,11 @@ napi_value DestroyBatcher(napi_env env, napi_callback_info info) {
   size_t argc = 1;
   napi_value argv[1];
   NAPI_OK(env, napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
-  rag_batcher* b = nullptr;
-  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&b));
-  rag_batcher_destroy(b);
+  BatcherHandle* bh = nullptr;
+  NAPI_OK(env, napi_get_value_external(env, argv[0], (void**)&bh));
+  if (!bh) return nullptr;
+  bh->closing = true;
+  batcher_settle(env, bh);
   return nullptr;
 }
 

@@ -19,6 +19,7 @@ RAGERA_VERSION = 0x00010000
 MAX_TOPK, MAX_CANDIDATES, MAX_KEYWORDS, MAX_FRESH = 64, 128, 64, 64
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6, -7
 ERR_TIMEOUT = -8
+ERR_BUSY = -9
 F32, BF16 = 0, 1
 SRC_VECTOR, SRC_KEYWORD, SRC_BOTH, SRC_FRESHNESS = 0, 1, 2, 3
 CT_DOCUMENT, CT_MEMORY, CT_CODE = 0, 1, 2
@@ -98,6 +99,10 @@ class BatcherDesc(C.Structure):
     _fields_ = [("max_batch", C.c_uint32), ("max_wait_us", C.c_uint32), ("opts", HybridOpts)]
 
 
+# rag_batcher_done_fn(user, rc, err): called on a batcher worker thread (ctypes takes the GIL for the call)
+BATCHER_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p)
+
+
 class MemoryOpts(C.Structure):
     _fields_ = [("limit", C.c_uint32), ("path", C.c_uint32), ("min_relevance", C.c_double), ("now_ms", C.c_int64),
                 ("time_decay_factor", C.c_double), ("frequency_bonus", C.c_double), ("similarity_top_k", C.c_uint32),
@@ -168,6 +173,7 @@ SYMBOLS = {
     "rag_process_results": (C.c_int, [C.POINTER(Text), _vp, _vp, C.c_uint32, Text, C.POINTER(ProcessOpts), C.POINTER(ProcessedOut)]),
     "rag_batcher_create": (C.c_int, [_vp, C.POINTER(BatcherDesc), C.POINTER(_vp)]),
     "rag_batcher_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.POINTER(FusedOut)]),
+    "rag_batcher_submit_async": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.POINTER(FusedOut), BATCHER_DONE_FN, _vp]),
     "rag_batcher_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rag_batcher_destroy": (None, [_vp]),
     "rag_debug_tensor_scores": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),

@@ -26,6 +26,11 @@
 // The workers are the only threads that touch the rag_index; calls on the handle are serialised
 // by the library anyway (per-handle mutex).
 //
+// Two ways in: rag_batcher_submit blocks its thread until the answer is there (a server with a thread per request);
+// rag_batcher_submit_async takes a slot, stages the inputs and returns — a worker copies the result into the caller's
+// arrays and calls `done` — so ONE thread (Node's event loop) can keep thousands of requests in flight without parking a
+// pool thread per request (libuv's default pool is 4 threads: blocking submits could never form a batch above 4).
+//
 // One batcher = one call-site class (fixed HybridSearchOptions: search_knowledge, deep_search, ...),
 // because vectorTopK / keywordLimit / RRF config are per-launch parameters.
 // Host code only.
@@ -52,6 +57,12 @@ constexpr int kWorkers = 2;
 struct rag_batcher_req {
   bool done = false;  // guarded by the wake group's mutex
 };
+// a request that nobody waits for: where its result goes and whom to tell (rag_batcher_submit_async)
+struct rag_async_req {
+  rag_batcher_done_fn done = nullptr;   // null = the slot belongs to a blocking caller
+  void* user = nullptr;
+  rag_fused_out out;
+};
 
 // One batch: inputs written by the submitters (slot by slot), outputs written by rag_hybrid_search, read by the submitters.
 struct rag_batch_buf {
@@ -63,6 +74,7 @@ struct rag_batch_buf {
   std::vector<uint8_t> source, ctype, used_rrf, certified;
   std::vector<uint32_t> counts, vec_counts;
   std::vector<rag_batcher_req*> reqs;
+  std::vector<rag_async_req> areqs;
   uint32_t count = 0;                  // slots handed out (under rag_batcher::mu)
   std::atomic<uint32_t> staged{0};     // slots whose inputs are in place
   std::atomic<uint32_t> readers{0};    // callers that have not copied their result out yet
@@ -90,11 +102,19 @@ struct rag_batcher {
   rag_wake_group groups[kWakeGroups];
   bool stop = false;
   std::atomic<int> waking{0};           // batches whose callers are being woken right now
+  std::atomic<uint32_t> active{0};      // rag_batcher_submit calls between entry and return: destroy waits for them
   std::thread workers[kWorkers];
   uint64_t n_batches = 0, n_queries = 0, max_seen = 0;
 };
 
 namespace {
+
+// counts a submitter in and out, whichever way it returns
+struct active_call {
+  rag_batcher* b;
+  explicit active_call(rag_batcher* b_) : b(b_) { b->active.fetch_add(1, std::memory_order_acq_rel); }
+  ~active_call() { b->active.fetch_sub(1, std::memory_order_acq_rel); }
+};
 
 void run_batch(rag_batcher* b, rag_batch_buf* bb) {
   const uint32_t B = bb->count;
@@ -108,17 +128,67 @@ void run_batch(rag_batcher* b, rag_batch_buf* bb) {
   bb->err = bb->rc == RAG_OK ? std::string() : std::string(rag_last_error());
 }
 
-// wake the batch's callers: group by group, the flag of every request set under its group's mutex
+// one request's result: from the batch's arrays into the caller's (shaped for ONE query)
+void copy_out(const rag_batcher* b, const rag_batch_buf* bb, uint32_t slot, rag_fused_out* out) {
+  const rag_hybrid_opts& o = b->desc.opts;
+  const uint32_t k = o.vector_top_k, cap = k + o.keyword_limit + o.fresh_limit;
+  const uint32_t n = std::min(out->capacity, cap);
+  memcpy(out->keys, bb->keys.data() + (size_t)slot * cap, (size_t)n * 8);
+  memcpy(out->scores, bb->scores.data() + (size_t)slot * cap, (size_t)n * 8);
+  if (out->source) memcpy(out->source, bb->source.data() + (size_t)slot * cap, n);
+  if (out->content_type) memcpy(out->content_type, bb->ctype.data() + (size_t)slot * cap, n);
+  out->counts[0] = bb->counts[slot];
+  if (out->used_rrf) out->used_rrf[0] = bb->used_rrf[slot];
+  if (out->certified) out->certified[0] = bb->certified[slot];
+  if (out->vec_ids && out->vec_scores && out->vec_counts) {
+    memcpy(out->vec_ids, bb->vec_ids.data() + (size_t)slot * k, (size_t)k * 8);
+    memcpy(out->vec_scores, bb->vec_scores.data() + (size_t)slot * k, (size_t)k * 8);
+    out->vec_counts[0] = bb->vec_counts[slot];
+  }
+}
+
+// a request is through with the batch's arrays; the last one hands the buffer back
+void release_reader(rag_batcher* b, rag_batch_buf* bb) {
+  if (bb->readers.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+  bb->staged.store(0, std::memory_order_relaxed);
+  {
+    std::lock_guard<std::mutex> lk(b->mu);
+    bb->count = 0;
+    b->free_bufs.push_back(bb);
+  }
+  b->cv_free.notify_all();  // every waiting submitter: the buffer becomes the open batch and has room for all of them
+}
+
+// wake the batch's blocking callers group by group (the flag of every request set under its group's mutex), then serve
+// the requests nobody waits for: result into the caller's arrays, `done` called from here (a worker thread)
 void complete_batch(rag_batcher* b, rag_batch_buf* bb) {
   const uint32_t B = bb->count;
   bb->readers.store(B, std::memory_order_release);
+  uint32_t n_async = 0;
   for (uint32_t g = 0; g < kWakeGroups && g * kGroupSlots < B; g++) {
+    bool any = false;
     {
       std::lock_guard<std::mutex> lk(b->groups[g].mu);
       for (uint32_t s0 = g * kGroupSlots; s0 < B; s0 += kWakeGroups * kGroupSlots)
-        for (uint32_t s = s0; s < s0 + kGroupSlots && s < B; s++) bb->reqs[s]->done = true;
+        for (uint32_t s = s0; s < s0 + kGroupSlots && s < B; s++) {
+          if (bb->areqs[s].done) { n_async++; continue; }
+          bb->reqs[s]->done = true;
+          any = true;
+        }
     }
-    b->groups[g].cv.notify_all();
+    if (any) b->groups[g].cv.notify_all();
+  }
+  if (!n_async) return;
+  const int rc = bb->rc;
+  const std::string err = bb->err;   // the buffer may be recycled by the time the last callback runs
+  for (uint32_t s = 0; s < B && n_async; s++) {
+    rag_async_req a = bb->areqs[s];
+    if (!a.done) continue;
+    n_async--;
+    if (rc == RAG_OK) copy_out(b, bb, s, &a.out);
+    bb->areqs[s].done = nullptr;
+    release_reader(b, bb);            // after the last of these `bb` belongs to the submitters again
+    a.done(a.user, rc, rc == RAG_OK ? "" : err.c_str());
   }
 }
 
@@ -204,6 +274,7 @@ int rag_batcher_create(rag_index* idx, const rag_batcher_desc* d, rag_batcher** 
     bb.counts.resize(B); bb.used_rrf.resize(B); bb.certified.resize(B);
     bb.vec_ids.resize((size_t)B * k); bb.vec_scores.resize((size_t)B * k); bb.vec_counts.resize(B);
     bb.reqs.assign(B, nullptr);
+    bb.areqs.assign(B, rag_async_req());
     b->free_bufs.push_back(&bb);
   }
   for (int w = 0; w < kWorkers; w++) b->workers[w] = std::thread(worker_main, b);
@@ -211,83 +282,104 @@ int rag_batcher_create(rag_index* idx, const rag_batcher_desc* d, rag_batcher** 
   return RAG_OK;
 }
 
-// Blocking; callable from any number of threads. `query` is one [dim] fp32 vector, `kw_keys` the
-// request's keyword hits as fusion keys in rank order; `out` is shaped for ONE query (capacity >=
-// vector_top_k + keyword_limit + fresh_limit; counts/used_rrf/certified/vec_counts have 1 entry).
-int rag_batcher_submit(rag_batcher* b, const float* query, const uint64_t* kw_keys, uint32_t kw_count, rag_fused_out* out) {
-  if (!b || !query || !out || !out->keys || !out->scores || !out->counts)
-    return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: null argument");
-  const rag_hybrid_opts& o = b->desc.opts;
-  const uint32_t kl = o.keyword_limit, k = o.vector_top_k, cap = k + kl + o.fresh_limit, dim = b->idx->dim;
-  if (out->capacity < cap) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: rag_fused_out.capacity too small");
-  if (kw_count > kl) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit: kw_count exceeds keyword_limit");
-  rag_batcher_req r;
-  rag_batch_buf* bb = nullptr;
-  uint32_t slot = 0;
-  {
-    std::unique_lock<std::mutex> lk(b->mu);
-    for (;;) {
-      if (b->stop) return rag_set_error(RAG_ERR_STATE, "rag_batcher_submit: batcher is shutting down");
-      if (b->open && b->open->count == b->desc.max_batch) {  // filled up behind a busy GPU: queue it whole
-        b->full.push_back(b->open);
-        b->open = nullptr;
-        b->cv_work.notify_all();
-      }
-      if (b->open) break;
-      if (!b->free_bufs.empty()) {
-        b->open = b->free_bufs.back();
-        b->free_bufs.pop_back();
-        break;
-      }
-      b->cv_free.wait(lk);  // every buffer is in flight: back-pressure
+}  // extern "C"
+
+namespace {
+// Under b->mu: a slot of the open batch (opening one from a free buffer if need be). `wait` = block while every buffer is
+// in flight (back-pressure); otherwise RAG_ERR_BUSY. The slot's owner is recorded before the lock is dropped.
+int take_slot(rag_batcher* b, bool wait, rag_batcher_req* r, const rag_async_req* a, rag_batch_buf** out_bb, uint32_t* out_slot) {
+  std::unique_lock<std::mutex> lk(b->mu);
+  for (;;) {
+    if (b->stop) return rag_set_error(RAG_ERR_STATE, "rag_batcher_submit: batcher is shutting down");
+    if (b->open && b->open->count == b->desc.max_batch) {  // filled up behind a busy GPU: queue it whole
+      b->full.push_back(b->open);
+      b->open = nullptr;
+      b->cv_work.notify_all();
     }
-    bb = b->open;
-    slot = bb->count++;
-    bb->reqs[slot] = &r;
-    bb->t_last = std::chrono::steady_clock::now();
-    if (slot == 0) bb->t_first = bb->t_last;
-    if (slot == 0 || bb->count == b->desc.max_batch) b->cv_work.notify_all();
+    if (b->open) break;
+    if (!b->free_bufs.empty()) {
+      b->open = b->free_bufs.back();
+      b->free_bufs.pop_back();
+      break;
+    }
+    if (!wait) return rag_set_error(RAG_ERR_BUSY, "rag_batcher_submit_async: every batch buffer is in flight");
+    b->cv_free.wait(lk);  // every buffer is in flight: back-pressure
   }
-  // stage this request's inputs in its slot (outside the lock, in parallel with every other caller)
+  rag_batch_buf* bb = b->open;
+  const uint32_t slot = bb->count++;
+  bb->reqs[slot] = r;
+  bb->areqs[slot] = a ? *a : rag_async_req();
+  bb->t_last = std::chrono::steady_clock::now();
+  if (slot == 0) bb->t_first = bb->t_last;
+  if (slot == 0 || bb->count == b->desc.max_batch) b->cv_work.notify_all();
+  *out_bb = bb;
+  *out_slot = slot;
+  return RAG_OK;
+}
+
+// this request's inputs into its slot (outside the lock, in parallel with every other caller)
+void stage_slot(rag_batcher* b, rag_batch_buf* bb, uint32_t slot, const float* query, const uint64_t* kw_keys, uint32_t kw_count) {
+  const uint32_t kl = b->desc.opts.keyword_limit, dim = b->idx->dim;
   memcpy(bb->h_q + (size_t)slot * dim, query, (size_t)dim * sizeof(float));
   const uint32_t c = kw_keys ? kw_count : 0u;
   if (c) memcpy(bb->kw_keys.data() + (size_t)slot * kl, kw_keys, (size_t)c * 8);
   bb->kw_counts[slot] = c;
   bb->staged.fetch_add(1, std::memory_order_release);
+}
+
+int check_submit(const rag_batcher* b, const float* query, uint32_t kw_count, const rag_fused_out* out, const char* who) {
+  if (!b || !query || !out || !out->keys || !out->scores || !out->counts) return rag_set_error(RAG_ERR_INVALID, "%s: null argument", who);
+  const rag_hybrid_opts& o = b->desc.opts;
+  if (out->capacity < o.vector_top_k + o.keyword_limit + o.fresh_limit) return rag_set_error(RAG_ERR_INVALID, "%s: rag_fused_out.capacity too small", who);
+  if (kw_count > o.keyword_limit) return rag_set_error(RAG_ERR_INVALID, "%s: kw_count exceeds keyword_limit", who);
+  return RAG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// Blocking; callable from any number of threads. `query` is one [dim] fp32 vector, `kw_keys` the
+// request's keyword hits as fusion keys in rank order; `out` is shaped for ONE query (capacity >=
+// vector_top_k + keyword_limit + fresh_limit; counts/used_rrf/certified/vec_counts have 1 entry).
+int rag_batcher_submit(rag_batcher* b, const float* query, const uint64_t* kw_keys, uint32_t kw_count, rag_fused_out* out) {
+  RAG_CHECK(check_submit(b, query, kw_count, out, "rag_batcher_submit"));
+  active_call in_flight(b);
+  rag_batcher_req r;
+  rag_batch_buf* bb = nullptr;
+  uint32_t slot = 0;
+  RAG_CHECK(take_slot(b, true, &r, nullptr, &bb, &slot));
+  stage_slot(b, bb, slot, query, kw_keys, kw_count);
   {
     rag_wake_group& g = b->groups[(slot / kGroupSlots) % kWakeGroups];
     std::unique_lock<std::mutex> lk(g.mu);
     g.cv.wait(lk, [&] { return r.done; });
   }
   const int rc = bb->rc;
-  if (rc == RAG_OK) {
-    const uint32_t n = std::min(out->capacity, cap);
-    memcpy(out->keys, bb->keys.data() + (size_t)slot * cap, (size_t)n * 8);
-    memcpy(out->scores, bb->scores.data() + (size_t)slot * cap, (size_t)n * 8);
-    if (out->source) memcpy(out->source, bb->source.data() + (size_t)slot * cap, n);
-    if (out->content_type) memcpy(out->content_type, bb->ctype.data() + (size_t)slot * cap, n);
-    out->counts[0] = bb->counts[slot];
-    if (out->used_rrf) out->used_rrf[0] = bb->used_rrf[slot];
-    if (out->certified) out->certified[0] = bb->certified[slot];
-    if (out->vec_ids && out->vec_scores && out->vec_counts) {
-      memcpy(out->vec_ids, bb->vec_ids.data() + (size_t)slot * k, (size_t)k * 8);
-      memcpy(out->vec_scores, bb->vec_scores.data() + (size_t)slot * k, (size_t)k * 8);
-      out->vec_counts[0] = bb->vec_counts[slot];
-    }
-  } else {
-    rag_set_error(rc, "%s", bb->err.c_str());
-  }
-  // the last caller to leave hands the buffer back
-  if (bb->readers.fetch_sub(1, std::memory_order_acq_rel) == 1) {
-    bb->staged.store(0, std::memory_order_relaxed);
-    {
-      std::lock_guard<std::mutex> lk(b->mu);
-      bb->count = 0;
-      b->free_bufs.push_back(bb);
-    }
-    b->cv_free.notify_all();  // every waiting submitter: the buffer becomes the open batch and has room for all of them
-  }
+  if (rc == RAG_OK) copy_out(b, bb, slot, out);
+  else rag_set_error(rc, "%s", bb->err.c_str());
+  release_reader(b, bb);
   return rc;
+}
+
+// Non-blocking: takes a slot, copies `query` / `kw_keys` into it (the caller may reuse them at once) and returns. `out`
+// (shaped for one query, like rag_batcher_submit's) must stay valid until `done(user, rc, err)` is called — from a
+// batcher worker thread, after the result has been copied into `out` (rc == RAG_OK) or with the batch's error (`err` is
+// valid during the callback only). RAG_ERR_BUSY when every batch buffer is in flight: nothing was queued and `done` will
+// not be called — retry later or fall back to the blocking call. A non-zero return never calls `done`.
+int rag_batcher_submit_async(rag_batcher* b, const float* query, const uint64_t* kw_keys, uint32_t kw_count, rag_fused_out* out,
+                             rag_batcher_done_fn done, void* user) {
+  RAG_CHECK(check_submit(b, query, kw_count, out, "rag_batcher_submit_async"));
+  if (!done) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_submit_async: null completion callback");
+  active_call in_flight(b);
+  rag_async_req a;
+  a.done = done;
+  a.user = user;
+  a.out = *out;
+  rag_batch_buf* bb = nullptr;
+  uint32_t slot = 0;
+  RAG_CHECK(take_slot(b, false, nullptr, &a, &bb, &slot));
+  stage_slot(b, bb, slot, query, kw_keys, kw_count);
+  return RAG_OK;
 }
 
 int rag_batcher_stats(rag_batcher* b, uint64_t* batches, uint64_t* queries, uint64_t* largest_batch) {
@@ -299,6 +391,9 @@ int rag_batcher_stats(rag_batcher* b, uint64_t* batches, uint64_t* queries, uint
   return RAG_OK;
 }
 
+// May be called while submitters are still inside rag_batcher_submit: requests that already hold a slot are run and
+// answered, submitters still waiting for a buffer fail with RAG_ERR_STATE, and the buffers are freed only after the last
+// of them has copied its result out and returned. No submit may START once destroy has been called (the handle dies).
 void rag_batcher_destroy(rag_batcher* b) {
   if (!b) return;
   {
@@ -309,6 +404,10 @@ void rag_batcher_destroy(rag_batcher* b) {
   b->cv_free.notify_all();
   for (int w = 0; w < kWorkers; w++)
     if (b->workers[w].joinable()) b->workers[w].join();
+  while (b->active.load(std::memory_order_acquire) != 0) {  // woken callers copying their results out / leaving
+    b->cv_free.notify_all();
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
   for (int i = 0; i < kBuffers; i++) rag_host_free(b->bufs[i].h_q);
   delete b;
 }

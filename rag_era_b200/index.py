@@ -13,6 +13,8 @@ hold the caller's buffers.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -424,6 +426,20 @@ class VectorIndex:
         N.check(self._lib.rag_comm_destroy(self._h))
 
 
+# asynchronous batcher requests in flight: token (the callback's `user` word) -> (result arrays, on_done). ONE module-level
+# trampoline serves every request, so no ctypes callback object is ever freed while the library may still call it.
+_async_inflight: dict = {}
+_async_lock = threading.Lock()
+_async_tokens = itertools.count(1)
+
+
+@N.BATCHER_DONE_FN
+def _async_done(user, rc, err):
+    with _async_lock:
+        out, on_done = _async_inflight.pop(user)
+    on_done(out.row(0) if rc == N.OK else N.RagError(rc, (err or b"").decode("utf-8", "replace")))
+
+
 class Batcher:
     """Micro-batching front end (``rag_batcher_*``): many threads call ``submit`` with one query each; the
     library groups what arrives together into one corpus pass (a batch goes out when the arrivals pause, at the latest
@@ -445,6 +461,26 @@ class Batcher:
                            self.opts.vector_top_k)
         N.check(self._lib.rag_batcher_submit(self._h, _ptr(q), _ptr(kw), len(kw), C.byref(out._c)))
         return out.row(0)
+
+    def submit_async(self, query, kw_keys, on_done) -> bool:
+        """``rag_batcher_submit_async``: returns at once; ``on_done(result_dict | RagError)`` runs on a batcher worker
+        thread when the request's batch has been answered. False = every batch buffer is in flight (``RAG_ERR_BUSY``):
+        nothing was queued. One thread can keep thousands of requests in flight this way (the N-API addon's route)."""
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        kw = np.ascontiguousarray(kw_keys, dtype=np.uint64)
+        out = _alloc_fused(1, max(1, self.opts.vector_top_k + self.opts.keyword_limit + self.opts.fresh_limit),
+                           self.opts.vector_top_k)
+        token = next(_async_tokens)
+        with _async_lock:
+            _async_inflight[token] = (out, on_done)     # `out` stays alive until the callback has run
+        rc = self._lib.rag_batcher_submit_async(self._h, _ptr(q), _ptr(kw), len(kw), C.byref(out._c), _async_done, token)
+        if rc != N.OK:
+            with _async_lock:
+                _async_inflight.pop(token, None)
+            if rc == N.ERR_BUSY:
+                return False
+            N.check(rc)
+        return True
 
     def stats(self) -> dict:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

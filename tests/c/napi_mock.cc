@@ -13,8 +13,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <deque>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <string>
 #include <thread>
@@ -34,15 +37,28 @@ struct napi_value__ {
   int state = 0;  // Promise: 0 pending, 1 fulfilled, 2 rejected
   napi_value settled = nullptr;
   napi_callback fn = nullptr;
+  napi_finalize finalize = nullptr;   // External: run when the "garbage collector" (end of main) collects it
 };
 struct napi_callback_info__ { std::vector<napi_value> args; };
 struct napi_deferred__ { napi_value promise; };
 struct napi_async_work__ { napi_async_execute_callback execute; napi_async_complete_callback complete; void* data; };
+// thread-safe function: any thread enqueues, the "main" thread (run_event_loop) calls call_js for every item
+struct napi_threadsafe_function__ {
+  napi_env env = nullptr;
+  napi_threadsafe_function_call_js call_js = nullptr;
+  void* context = nullptr;
+  std::deque<void*> items;   // guarded by env->mu
+  bool referenced = true, released = false;
+  uint64_t delivered = 0;
+};
 struct napi_env__ {
   std::vector<std::unique_ptr<napi_value__>> heap;
   bool pending = false;
   std::string exception;
   std::deque<napi_async_work> queue;
+  std::mutex mu;                      // thread-safe function queues
+  std::condition_variable cv;
+  std::vector<napi_threadsafe_function> tsfns;
   napi_value make(napi_value__::Kind k) {
     heap.emplace_back(new napi_value__());
     heap.back()->kind = k;
@@ -88,7 +104,7 @@ napi_status napi_create_string_utf8(napi_env env, const char* str, size_t length
   (*result)->str = length == NAPI_AUTO_LENGTH ? std::string(str) : std::string(str, length);
   return napi_ok;
 }
-napi_status napi_create_external(napi_env env, void* data, napi_finalize, void*, napi_value* result) { *result = env->make(napi_value__::External); (*result)->ext = data; return napi_ok; }
+napi_status napi_create_external(napi_env env, void* data, napi_finalize fin, void*, napi_value* result) { *result = env->make(napi_value__::External); (*result)->ext = data; (*result)->finalize = fin; return napi_ok; }
 napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void** data, napi_value* result) {
   *result = env->make(napi_value__::ArrayBuffer);
   (*result)->bytes.resize(byte_length);
@@ -158,19 +174,78 @@ napi_status napi_create_async_work(napi_env, napi_value, napi_value, napi_async_
 napi_status napi_queue_async_work(napi_env env, napi_async_work w) { env->queue.push_back(w); return napi_ok; }
 napi_status napi_delete_async_work(napi_env, napi_async_work w) { delete w; return napi_ok; }
 
+napi_status napi_create_threadsafe_function(napi_env env, napi_value, napi_value, napi_value, size_t, size_t, void*, napi_finalize, void* context,
+                                            napi_threadsafe_function_call_js call_js, napi_threadsafe_function* result) {
+  auto* f = new napi_threadsafe_function__();
+  f->env = env; f->call_js = call_js; f->context = context;
+  std::lock_guard<std::mutex> lk(env->mu);
+  env->tsfns.push_back(f);
+  *result = f;
+  return napi_ok;
+}
+napi_status napi_call_threadsafe_function(napi_threadsafe_function f, void* data, napi_threadsafe_function_call_mode) {  // any thread
+  {
+    std::lock_guard<std::mutex> lk(f->env->mu);
+    if (f->released) return napi_generic_failure;   // napi_closing in the real thing
+    f->items.push_back(data);
+  }
+  f->env->cv.notify_all();
+  return napi_ok;
+}
+napi_status napi_release_threadsafe_function(napi_threadsafe_function f, napi_threadsafe_function_release_mode) {
+  std::lock_guard<std::mutex> lk(f->env->mu);
+  f->released = true;   // kept in env->tsfns (freed with the environment): items already queued are still delivered
+  return napi_ok;
+}
+napi_status napi_ref_threadsafe_function(napi_env env, napi_threadsafe_function f) { std::lock_guard<std::mutex> lk(env->mu); f->referenced = true; return napi_ok; }
+napi_status napi_unref_threadsafe_function(napi_env env, napi_threadsafe_function f) { std::lock_guard<std::mutex> lk(env->mu); f->referenced = false; return napi_ok; }
+
 napi_value napi_register_module_v1(napi_env env, napi_value exports);  // the addon's NAPI_MODULE_INIT
 }
 
 // ---- the "event loop": every queued work item executes on its own worker thread (concurrently, like the libuv pool),
-//      then its completion runs here on the main thread --------------------------------------------------------------
+//      then its completion runs here on the main thread; items of thread-safe functions are delivered here too. As in
+//      Node, the loop stays alive while work is queued or a REFERENCED thread-safe function exists (the addon references
+//      its function while requests are out) ------------------------------------------------------------------------
+static uint64_t g_tsfn_delivered = 0;
+static bool deliver_tsfn_items(napi_env env) {
+  bool any = false;
+  for (;;) {
+    napi_threadsafe_function f = nullptr;
+    void* item = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(env->mu);
+      for (napi_threadsafe_function c : env->tsfns)
+        if (!c->items.empty()) { f = c; item = c->items.front(); c->items.pop_front(); break; }
+    }
+    if (!f) return any;
+    f->call_js(env, nullptr, f->context, item);
+    f->delivered++;
+    g_tsfn_delivered++;
+    any = true;
+  }
+}
 static void run_event_loop(napi_env env) {
-  while (!env->queue.empty()) {
-    std::vector<napi_async_work> batch(env->queue.begin(), env->queue.end());
-    env->queue.clear();
-    std::vector<std::thread> th;
-    for (napi_async_work w : batch) th.emplace_back([=] { w->execute(env, w->data); });
-    for (auto& t : th) t.join();
-    for (napi_async_work w : batch) w->complete(env, napi_ok, w->data);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    if (!env->queue.empty()) {
+      std::vector<napi_async_work> batch(env->queue.begin(), env->queue.end());
+      env->queue.clear();
+      std::vector<std::thread> th;
+      for (napi_async_work w : batch) th.emplace_back([=] { w->execute(env, w->data); });
+      for (auto& t : th) t.join();   // (a batcher frees its buffers from its own worker threads: pool threads parked in the
+                                     //  blocking submit never wait for this thread)
+      deliver_tsfn_items(env);
+      for (napi_async_work w : batch) w->complete(env, napi_ok, w->data);
+      continue;
+    }
+    if (deliver_tsfn_items(env)) continue;
+    std::unique_lock<std::mutex> lk(env->mu);
+    bool alive = false;
+    for (napi_threadsafe_function f : env->tsfns) alive = alive || (f->referenced && !f->released) || !f->items.empty();
+    if (!alive) return;
+    env->cv.wait_for(lk, std::chrono::milliseconds(20));
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) { fprintf(stderr, "event loop: a referenced thread-safe function never went idle\n"); exit(5); }
   }
 }
 
@@ -328,8 +403,33 @@ int main(int argc, char** argv) {
   for (uint32_t b = 0; b < in.B; b++)
     batched.push_back(call(env, exports, "submit", {bt, opts(in.k), typed_array(env, napi_float32_array, in.queries.data() + (size_t)b * in.dim, in.dim),
                                                     typed_array(env, napi_biguint64_array, in.kw_keys.data() + (size_t)b * in.kw_limit, in.kw_counts[b])}));
+  const uint64_t delivered0 = g_tsfn_delivered;
+  run_event_loop(env);
+  const uint64_t via_tsfn = g_tsfn_delivered - delivered0;   // submits answered without a pool thread (rag_batcher_submit_async)
+  // more requests than the batcher has slots (4 buffers x 4): the overflow falls back to pool threads (RAG_ERR_BUSY) and is
+  // answered all the same; then destroyBatcher with requests still out: they are answered, the batcher goes away with the last
+  napi_value bt_small = call(env, exports, "createBatcher", {h, opts(in.k), num(env, 4), num(env, 20000)});
+  std::vector<napi_value> overflow;
+  for (uint32_t r = 0; r < 3 * in.B; r++) {
+    const uint32_t b = r % in.B;
+    overflow.push_back(call(env, exports, "submit", {bt_small, opts(in.k), typed_array(env, napi_float32_array, in.queries.data() + (size_t)b * in.dim, in.dim),
+                                                     typed_array(env, napi_biguint64_array, in.kw_keys.data() + (size_t)b * in.kw_limit, in.kw_counts[b])}));
+  }
+  call(env, exports, "destroyBatcher", {bt_small});
+  call(env, exports, "submit", {bt_small, opts(in.k), typed_array(env, napi_float32_array, in.queries.data(), in.dim), typed_array(env, napi_biguint64_array, in.kw_keys.data(), 0)});
+  const std::string closed_batcher_error = env->pending ? env->exception : "";
   run_event_loop(env);
   call(env, exports, "destroyBatcher", {bt});
+  // destroy(handle) with searches in flight on it: a second index, B searches queued, destroyed before the loop runs them
+  napi_value h2 = call(env, exports, "createIndex", {object(env, {{"rows", num(env, in.n)}, {"dim", num(env, in.dim)}, {"device", num(env, 0)}})});
+  call(env, exports, "uploadRows", {h2, typed_array(env, napi_float32_array, in.rows.data(), in.rows.size()), num(env, in.n)});
+  std::vector<napi_value> doomed;
+  for (uint32_t b = 0; b < in.B; b++)
+    doomed.push_back(call(env, exports, "search", {h2, typed_array(env, napi_float32_array, in.queries.data() + (size_t)b * in.dim, in.dim), num(env, 1), num(env, in.k)}));
+  call(env, exports, "destroy", {h2});
+  call(env, exports, "search", {h2, typed_array(env, napi_float32_array, in.queries.data(), in.dim), num(env, 1), num(env, in.k)});
+  const std::string closed_index_error = env->pending ? env->exception : "";
+  run_event_loop(env);
   // the retriever seam (NativeVectorStore.query) and MemoryStore.retrieve's device half, one Promise per query
   std::vector<napi_value> topk, mem;
   for (uint32_t b = 0; b < in.B; b++) {
@@ -401,7 +501,27 @@ int main(int argc, char** argv) {
   std::string rej = bad && bad->kind == napi_value__::Promise && bad->state == 2 && bad->settled ? bad->settled->str : "";
   for (std::string* s : {&rej, const_cast<std::string*>(&sync_error)})
     for (char& c : *s) if (c == '"' || c == '\\' || c == '\n') c = ' ';
-  printf("], \"rejected\": \"%s\", \"thrown\": \"%s\"}\n", rej.c_str(), sync_error.c_str());
+  printf("], \"overflow\": [\n");
+  for (size_t r = 0; r < overflow.size(); r++) {
+    if (!overflow[r] || overflow[r]->state != 1) { fprintf(stderr, "overflow promise %zu not fulfilled: %s\n", r, overflow[r] && overflow[r]->settled ? overflow[r]->settled->str.c_str() : "pending"); return 4; }
+    print_result(overflow[r]->settled, r + 1 == overflow.size());
+  }
+  printf("], \"doomed\": [\n");
+  for (uint32_t b = 0; b < in.B; b++) {
+    if (!doomed[b] || doomed[b]->state != 1) { fprintf(stderr, "search %u on the destroyed handle was not answered\n", b); return 4; }
+    napi_value t = doomed[b]->settled;
+    const uint32_t tc = view<uint32_t>(t, "counts", &n)[0];
+    const uint64_t* ti = view<uint64_t>(t, "ids", &n);
+    printf("[");
+    for (uint32_t i = 0; i < tc; i++) printf("%s%llu", i ? ", " : "", (unsigned long long)ti[i]);
+    printf("]%s\n", b + 1 == in.B ? "" : ",");
+  }
+  printf("], \"via_tsfn\": %llu, \"closed_batcher\": \"%s\", \"closed_index\": \"%s\", \"rejected\": \"%s\", \"thrown\": \"%s\"}\n",
+         (unsigned long long)via_tsfn, closed_batcher_error.c_str(), closed_index_error.c_str(), rej.c_str(), sync_error.c_str());
   call(env, exports, "destroy", {h});
+  // "garbage collection" at shutdown: every External's finalizer runs (the wrappers are freed; anything still open is closed)
+  for (auto& v : env->heap)
+    if (v->kind == napi_value__::External && v->finalize) v->finalize(env, v->ext, nullptr);
+  for (napi_threadsafe_function f : env->tsfns) delete f;
   return 0;
 }

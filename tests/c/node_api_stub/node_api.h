@@ -22,6 +22,7 @@ typedef struct napi_value__* napi_value;
 typedef struct napi_callback_info__* napi_callback_info;
 typedef struct napi_deferred__* napi_deferred;
 typedef struct napi_async_work__* napi_async_work;
+typedef struct napi_threadsafe_function__* napi_threadsafe_function;
 
 typedef enum {
   napi_ok,
@@ -60,7 +61,11 @@ typedef enum {
   napi_biguint64_array
 } napi_typedarray_type;
 
+typedef enum { napi_tsfn_release, napi_tsfn_abort } napi_threadsafe_function_release_mode;
+typedef enum { napi_tsfn_nonblocking, napi_tsfn_blocking } napi_threadsafe_function_call_mode;
+
 typedef napi_value (*napi_callback)(napi_env env, napi_callback_info info);
+typedef void (*napi_threadsafe_function_call_js)(napi_env env, napi_value js_callback, void* context, void* data);
 typedef void (*napi_finalize)(napi_env env, void* finalize_data, void* finalize_hint);
 typedef void (*napi_async_execute_callback)(napi_env env, void* data);
 typedef void (*napi_async_complete_callback)(napi_env env, napi_status status, void* data);
@@ -104,6 +109,14 @@ napi_status napi_reject_deferred(napi_env env, napi_deferred deferred, napi_valu
 napi_status napi_create_async_work(napi_env env, napi_value async_resource, napi_value async_resource_name, napi_async_execute_callback execute, napi_async_complete_callback complete, void* data, napi_async_work* result);
 napi_status napi_queue_async_work(napi_env env, napi_async_work work);
 napi_status napi_delete_async_work(napi_env env, napi_async_work work);
+
+napi_status napi_create_threadsafe_function(napi_env env, napi_value func, napi_value async_resource, napi_value async_resource_name, size_t max_queue_size,
+                                            size_t initial_thread_count, void* thread_finalize_data, napi_finalize thread_finalize_cb, void* context,
+                                            napi_threadsafe_function_call_js call_js_cb, napi_threadsafe_function* result);
+napi_status napi_call_threadsafe_function(napi_threadsafe_function func, void* data, napi_threadsafe_function_call_mode is_blocking);
+napi_status napi_release_threadsafe_function(napi_threadsafe_function func, napi_threadsafe_function_release_mode mode);
+napi_status napi_ref_threadsafe_function(napi_env env, napi_threadsafe_function func);
+napi_status napi_unref_threadsafe_function(napi_env env, napi_threadsafe_function func);
 
 typedef napi_value (*napi_addon_register_func)(napi_env env, napi_value exports);
 

@@ -51,3 +51,43 @@ def test_batcher_errors(native):
                 bt.submit(np.ones(64, np.float32), [1, 2, 3])          # more keyword hits than keyword_limit
             r = bt.submit(np.ones(64, np.float32), [1])
             assert len(r["vec_ids"]) == 5
+
+
+def test_batcher_async_submits_from_one_thread(native, oracle):
+    """rag_batcher_submit_async: ONE thread keeps every request in flight (what Node's event loop does — no pool thread
+    parked per request); results arrive through the completion callback and equal the direct batch-1 calls; batches form;
+    RAG_ERR_BUSY (every batch buffer in flight) queues nothing (provoked deterministically in tests/c/batcher_tsan.cc)."""
+    import time
+
+    import rag_era_b200 as rb
+
+    n, d, nq = 40000, 512, 192
+    go = oracle.make_gen(n, n_clusters=64, dup_period=19)
+    gn = native.GenDesc.from_buffer_copy(bytes(go))
+    with rb.VectorIndex(d, n, bf16_shadow=True) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, nq)
+        rng = np.random.default_rng(5)
+        kw = [rng.integers(0, n, int(rng.integers(0, 6))).tolist() for _ in range(nq)]
+        o = rb.hybrid_opts(10, 5, 0.3)
+        direct = [idx.hybrid(Q[i], o, [kw[i]]).row(0) for i in range(nq)]
+        results, busy = [None] * nq, 0
+        done = threading.Semaphore(0)
+        with rb.Batcher(idx, o, max_batch=16, max_wait_us=2000) as bt:       # 4 buffers x 16 slots < 192 requests: BUSY may happen
+            for i in range(nq):
+                def on_done(r, i=i):
+                    results[i] = r
+                    done.release()
+                while not bt.submit_async(Q[i], kw[i], on_done):
+                    busy += 1
+                    time.sleep(0.0005)
+            for _ in range(nq):
+                assert done.acquire(timeout=60)
+            st = bt.stats()
+            with pytest.raises(rb.RagError):
+                bt.submit_async(Q[0], list(range(9)), lambda r: None)          # more keyword hits than keyword_limit
+        assert st["queries"] == nq and st["largest_batch"] > 1 and st["batches"] < nq
+        for i in range(nq):
+            assert not isinstance(results[i], Exception), results[i]
+            for key in ("keys", "scores", "source", "ctype", "vec_ids", "vec_scores", "used_rrf"):
+                assert np.array_equal(results[i][key], direct[i][key]), (i, key)

@@ -1,5 +1,6 @@
 """§8f N2 — the N-API addon (integration/node/ragera_addon.cc) driven WITHOUT Node: tests/c/napi_mock.cc is a minimal
-in-process Node-API host (objects, typed arrays, externals, promises, async work on worker threads) that plays the
+in-process Node-API host (objects, typed arrays, externals + finalizers, promises, async work on worker threads,
+thread-safe functions delivered by its event loop) that plays the
 calls of integration/node/native-retrieval.ts. The addon is compiled unmodified against the stub header and linked with
 libragera.so; its results must equal the oracle's bit for bit — the same bar as the ctypes path."""
 import json
@@ -98,5 +99,13 @@ def test_addon_results_equal_the_oracle(native, oracle, tmp_path):
         oi, osc, ofr = oracle.memory_rank(vs, ctype[vj], conf[vj], acc[vj], last[vj], now, k, min_score)
         assert t["mem_ids"] == [int(vi[i]) for i in oi] and t["mem_relevance"] == [float(vs[i]) for i in oi]
         assert np.allclose(t["mem_scores"], osc, rtol=0, atol=1e-15) and np.allclose(t["mem_freshness"], ofr, rtol=0, atol=1e-15)
+    # submit() does not park a pool thread per request: the batched answers above came back through the thread-safe function
+    assert out["via_tsfn"] == B
+    # 3B submits against a batcher with 16 slots, destroyBatcher called while they are out: every one is answered (overflow
+    # through the RAG_ERR_BUSY fallback), a submit after destroyBatcher throws
+    assert len(out["overflow"]) == 3 * B and all(out["overflow"][r] == out["single"][r % B] for r in range(3 * B))
+    assert "destroyed" in out["closed_batcher"]
+    # destroy(handle) with B searches queued on it: they are answered (the index dies with the last of them), a new call throws
+    assert out["doomed"] == [out["search"][b]["ids"] for b in range(B)] and "destroyed" in out["closed_index"]
     assert "libragera error" in out["rejected"] and "64" in out["rejected"]        # k beyond RAG_MAX_TOPK rejects the Promise
     assert "Float32Array" in out["thrown"]                                         # a bad argument throws synchronously
