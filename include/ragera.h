@@ -360,6 +360,8 @@ typedef struct rag_batcher_desc {
                             are still being woken; ~1000 keeps closed-loop callers in one pass (profiles/r02_batcher_load.md) */
   rag_hybrid_opts opts;  /* HybridSearchOptions of this call site (keyword_limit = row stride) */
 } rag_batcher_desc;
+/* RAG_ERR_UNSUPPORTED on a row-sharded index (nranks > 1): the exchange is collective, every rank must run the same batches —
+ * batch on one front end and hand each batch to all ranks. */
 int rag_batcher_create(rag_index* idx, const rag_batcher_desc* desc, rag_batcher** out);
 int rag_batcher_submit(rag_batcher* b, const float* query /*[dim]*/, const uint64_t* kw_keys, uint32_t kw_count,
                        rag_fused_out* out /* shaped for one query */);
@@ -397,6 +399,8 @@ double rag_index_row_residual(rag_index* idx);
 int rag_timer_start(rag_index* idx);
 int rag_timer_stop(rag_index* idx, float* elapsed_ms);           /* synchronises */
 uint64_t rag_launch_count(const rag_index* idx);                 /* kernels launched so far */
+/* the successor of a sharded-exchange counter value (20 bits, never 0, consecutive values differ in parity across the wrap) */
+uint32_t rag_debug_p2p_next_step(uint32_t step);
 /* queries finished by the fusion kernel since the last call, and how many of them the scoring pass certified
  * (counted on the device: covers the asynchronous *_staged runs, which fetch nothing) */
 int rag_certified_totals(rag_index* idx, uint64_t* certified, uint64_t* queries);

@@ -171,6 +171,7 @@ SYMBOLS = {
     "rag_fetch_fused": (C.c_int, [_vp, C.c_uint32, C.POINTER(HybridOpts), C.POINTER(FusedOut)]),
     "rag_sync": (C.c_int, [_vp]),
     "rag_process_results": (C.c_int, [C.POINTER(Text), _vp, _vp, C.c_uint32, Text, C.POINTER(ProcessOpts), C.POINTER(ProcessedOut)]),
+    "rag_debug_p2p_next_step": (C.c_uint32, [C.c_uint32]),
     "rag_batcher_create": (C.c_int, [_vp, C.POINTER(BatcherDesc), C.POINTER(_vp)]),
     "rag_batcher_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.POINTER(FusedOut)]),
     "rag_batcher_submit_async": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.POINTER(FusedOut), BATCHER_DONE_FN, _vp]),

@@ -251,6 +251,10 @@ int rag_batcher_create(rag_index* idx, const rag_batcher_desc* d, rag_batcher** 
   if (!idx || !d || !out) return rag_set_error(RAG_ERR_INVALID, "rag_batcher_create: null argument");
   *out = nullptr;
   if (d->max_batch == 0 || d->max_batch > 4096) return rag_set_error(RAG_ERR_INVALID, "max_batch must be in 1..4096");
+  // a row-sharded index needs every rank to issue the SAME sequence of calls (the exchange is collective): batches formed
+  // from each rank's own arrivals would differ in size from rank to rank and the exchange would time out
+  if (idx->nranks > 1)
+    return rag_set_error(RAG_ERR_UNSUPPORTED, "rag_batcher_create: the index is one shard of %d; batch on ONE front end and broadcast the batch to the ranks", idx->nranks);
   const rag_hybrid_opts& o = d->opts;
   if (o.vector_top_k == 0 || o.vector_top_k > RAG_MAX_TOPK || o.keyword_limit > RAG_MAX_KEYWORDS || o.fresh_limit > RAG_MAX_FRESH)
     return rag_set_error(RAG_ERR_INVALID, "rag_batcher_create: bad hybrid options");

@@ -94,6 +94,15 @@ void p2p_unmap(rag_index* idx) {
   }
 }
 
+// diagnostics: RAGERA_P2P_STEP0 starts the exchange counter there (every rank alike) so that a test can walk it across
+// the 20-bit wrap in a few searches; even values only, so that the first exchange's parity is what a fresh counter gives
+uint32_t initial_step() {
+  const char* e = getenv("RAGERA_P2P_STEP0");
+  if (!e) return 0;
+  const uint32_t v = (uint32_t)strtoul(e, nullptr, 0);
+  return v <= 0xFFFFEu ? (v & ~1u) : 0;
+}
+
 int comm_common_init(rag_comm* c) {
   double ms = 20000.0;
   if (const char* e = getenv("RAGERA_P2P_TIMEOUT_MS")) ms = atof(e) > 0 ? atof(e) : ms;
@@ -203,7 +212,7 @@ int comm_p2p_ensure(rag_index* idx, uint32_t B, uint32_t k) {
     p2p_unmap(idx);
     c->p2p_failed = true;
   }
-  c->step = 0;  // fresh, zeroed mailboxes on every rank
+  c->step = initial_step();  // fresh, zeroed mailboxes on every rank
   return RAG_OK;
 }
 
@@ -217,8 +226,7 @@ int comm_p2p_next(rag_index* idx, uint32_t B, uint32_t k, rag_p2p_view* v) {
   for (int g = 0; g < idx->nranks; g++) v->base[g] = c->peer[g];
   v->nranks = (uint32_t)idx->nranks;
   v->rank = (uint32_t)idx->rank;
-  c->step = (c->step + 1) & 0xFFFFFu;
-  if (c->step == 0) c->step = 1;  // flag word 0 is the "never written" value
+  c->step = rag_p2p_next_step(c->step);  // never 0, parity alternates across the wrap (common.cuh)
   v->step = c->step;
   v->flag = (c->step << 12) | ((B * 131u + k) & 0xFFFu);
   v->half_bytes = c->half_bytes;
@@ -294,7 +302,7 @@ extern "C" int rag_comm_p2p_import(rag_index* idx, const uint8_t* handles) {
     c->peer[g] = (unsigned char*)p;
   }
   c->imported = true;
-  c->step = 0;
+  c->step = initial_step();
   return RAG_OK;
 }
 
@@ -346,6 +354,8 @@ extern "C" int rag_comm_init(rag_index* idx, int nranks, int rank, const uint8_t
   if (rc != RAG_OK) rag_comm_destroy(idx);
   return rc;
 }
+
+extern "C" uint32_t rag_debug_p2p_next_step(uint32_t step) { return rag_p2p_next_step(step); }
 
 extern "C" int rag_comm_destroy(rag_index* idx) {
   if (!idx) return RAG_OK;

@@ -297,6 +297,11 @@ struct rag_p2p_view {
   long long timeout_cycles;  // a peer that has not arrived by then: give up (status word, no trap)
   uint32_t* status;        // host-mapped word: set to 1 by a query whose exchange timed out
 };
+// The exchange counter: 20 bits (it travels in the flag word above the 12-bit shape hash), never 0 (the value of a flag word
+// nobody has written), and — what the two parity halves of the mailbox rest on — CONSECUTIVE exchanges always differ in
+// parity, across the wrap too: 0xFFFFF (odd) is followed by 2, not by 1. (Wrapping onto 1 would run two exchanges in a row on
+// the same half: a fast rank could refill a mailbox its slower peer is still merging from, once every 2^20 searches.)
+static inline uint32_t rag_p2p_next_step(uint32_t step) { return step >= 0xFFFFFu ? 2u : step + 1u; }
 int comm_p2p_ensure(rag_index* idx, uint32_t B, uint32_t k);            // sizes / checks the mailboxes for this shape
 bool comm_uses_p2p(const rag_index* idx);
 int comm_p2p_next(rag_index* idx, uint32_t B, uint32_t k, rag_p2p_view* v);  // view of the next exchange

@@ -105,3 +105,23 @@ def test_calculate_retrieval_count_matches_reference_table():
     ks = {rb.calculate_retrieval_count(D(queryType=t, priority=p))["vectorTopK"] + 10
           for t in ("semantic", "keyword", "graph", "hybrid") for p in ("high", "medium", "low")}
     assert min(ks) == 12 and max(ks) == 29 and max(ks) <= N.MAX_TOPK
+
+
+def test_exchange_counter_alternates_parity_across_the_wrap(native):
+    """The sharded exchange's two mailbox halves are chosen by the counter's parity: two consecutive exchanges must never
+    share a half (a fast rank would refill a mailbox its slower peer is still merging from). The counter has 20 bits and
+    skips 0 (the value of a flag word nobody has written); its wrap must keep the alternation — 0xFFFFF is followed by 2."""
+    nxt = native.load().rag_debug_p2p_next_step
+    assert nxt(0) == 1 and nxt(1) == 2 and nxt(0xFFFFE) == 0xFFFFF and nxt(0xFFFFF) == 2
+    s = 0xFFFF0
+    for _ in range(64):                      # across the wrap
+        n = nxt(s)
+        assert 0 < n <= 0xFFFFF and (n & 1) != (s & 1), (s, n)
+        s = n
+    s, seen_wrap = 0, 0
+    for _ in range((1 << 20) + 10):          # a whole period from a fresh counter
+        n = nxt(s)
+        assert n != 0 and (n ^ s) & 1
+        seen_wrap += n < s
+        s = n
+    assert seen_wrap == 1

@@ -59,8 +59,9 @@ def main():
         ok = False
         print(f"[rank {rank}] MISMATCH {msg}", flush=True)
 
-    def bootstrap(idx, max_batch, max_k, timeout_ms):
+    def bootstrap(idx, max_batch, max_k, timeout_ms, step0=0):
         os.environ["RAGERA_P2P_TIMEOUT_MS"] = str(timeout_ms)          # read when the communicator is created
+        os.environ["RAGERA_P2P_STEP0"] = str(step0)                     # diagnostics: where the exchange counter starts
         idx.comm_p2p_import(rv.allgather(idx.comm_p2p_export(world, rank, max_batch, max_k)))
 
     def leave(idx):
@@ -74,7 +75,9 @@ def main():
         base, n = shard_range(total, world, rank)
         idx = rb.VectorIndex(d, n, dtype=dt, device=0, shadow=shadow, id_base=base)
         idx.generate(gn, n)
-        bootstrap(idx, 128, 32, 120_000)     # ranks time-slice ONE GPU and check on the CPU in between: be patient
+        # ranks time-slice ONE GPU and check on the CPU in between: be patient. The second corpus starts its exchange counter
+        # 14 exchanges before the 20-bit wrap: everything below then runs across it (the mailbox halves must keep alternating)
+        bootstrap(idx, 128, 32, 120_000, step0=0 if dt == N.F32 else 0xFFFF0)
         B = 72
         Q = idx.generate_queries(gn, 0, B)
         X = oracle.gen_rows(go, 0, total, d, dtype=oracle.F32 if dt == N.F32 else oracle.BF16)
@@ -124,6 +127,13 @@ def main():
             oi, osc, _ = oracle.memory_rank(vs, ct[sel] == 1, cf[sel], ac[sel], la[sel], go.now_ms, 5, 0.3)
             if not (np.array_equal(mem["ids"][b, :len(oi)], vi[oi]) and int(mem["counts"][b]) == len(oi)):
                 bad(f"memory_retrieve rows={total} query={b}")
+        # the micro-batcher forms batches from one process's own arrivals: on a shard it would desynchronise the ranks — refused
+        try:
+            rb.Batcher(idx, rb.hybrid_opts(10, 8, 0.3)).close()
+            bad("a batcher was created on a shard")
+        except N.RagError as e:
+            if e.code != N.ERR_UNSUPPORTED:
+                bad(f"batcher on a shard: error {e.code}")
         # a batch beyond the exported capacity is refused, not silently truncated
         try:
             idx.query(np.tile(Q, (2, 1)), 10, path=N.PATH_STREAM)
