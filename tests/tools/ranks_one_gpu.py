@@ -76,8 +76,8 @@ def main():
         idx = rb.VectorIndex(d, n, dtype=dt, device=0, shadow=shadow, id_base=base)
         idx.generate(gn, n)
         # ranks time-slice ONE GPU and check on the CPU in between: be patient. The second corpus starts its exchange counter
-        # 14 exchanges before the 20-bit wrap: everything below then runs across it (the mailbox halves must keep alternating)
-        bootstrap(idx, 128, 32, 120_000, step0=0 if dt == N.F32 else 0xFFFF0)
+        # 5 exchanges before the 20-bit wrap: everything below then runs across it (the mailbox halves must keep alternating)
+        bootstrap(idx, 128, 32, 120_000, step0=0 if dt == N.F32 else 0xFFFFA)
         B = 72
         Q = idx.generate_queries(gn, 0, B)
         X = oracle.gen_rows(go, 0, total, d, dtype=oracle.F32 if dt == N.F32 else oracle.BF16)
