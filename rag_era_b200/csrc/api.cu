@@ -312,8 +312,23 @@ int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fr
   else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_plan(idx, B, p.kp, &parts));
   else RAG_CHECK(k1x_plan(idx, B, p.kp, &parts));
   RAG_CHECK(grow_dev(&bt->d_partial, &bt->c_partial, (size_t)B * parts * p.kp * 8, false));
+  // The score the caller filters at (hybridSearch keeps r.score >= minVectorScore, hybrid-search.ts:308-314; MemoryStore
+  // keeps relevance >= minRelevance, store.ts:151): rows below it can never reach the result, and filtering commutes with
+  // taking the best k by the same score. K4 uses it to certify (a query whose non-candidates all lie below the filter is
+  // exact whatever its k-th score is — the "nothing relevant" query no longer costs an escalation pass), and the tensor
+  // path (16-bit operands: its keys are cosines) starts its thresholds there instead of at -inf, which removes the
+  // start-up transient of the selection lists. The floor sits a margin below the filter; K4 checks rigorously, per query,
+  // that floor + eps[b] < min — a query for which it does not hold is uncertified and escalates like any other.
+  double min_eff = fa.mode == 0 ? fa.min_score : (fa.mode == 1 ? fa.mem_min_relevance : -INFINITY);
+  if (!(min_eff > -INFINITY) || !(min_eff < INFINITY)) min_eff = -INFINITY;   // NaN / infinite: no filter to lean on
+  double floor = -INFINITY;
+  static const bool k2_floor_on = !(getenv("RAGERA_K2_FLOOR") && atoi(getenv("RAGERA_K2_FLOOR")) == 0);
+  if (k2_floor_on && p.path == RAG_PATH_TENSOR && p.key_has_qnorm && min_eff > -INFINITY) {
+    const double rho_q_typ = (idx->shadow && !idx->shadow_f16) ? 4.0e-3 : 5.0e-4;   // bf16 / fp16 rounding of a unit vector
+    floor = min_eff - 2.0 * (p.eps + (p.eps_per_query ? rho_q_typ * p.eps_q_mul : 0.0)) - 1.0e-6;
+  }
   if (stream) RAG_CHECK(k1_launch(idx, B, p.kp, parts, p.path == RAG_PATH_SHADOW_STREAM));
-  else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_launch(idx, B, p.kp, parts));
+  else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_launch(idx, B, p.kp, parts, (float)floor));
   else RAG_CHECK(k1x_launch(idx, B, p.kp, parts));
   fa.B = B;
   fa.k = k;
@@ -321,7 +336,7 @@ int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fr
   // small batches on one GPU: the last CTA of each query in the K3+K4 kernel runs K5 in place
   static const bool k5_in_place = !(getenv("RAGERA_FUSE_K5") && atoi(getenv("RAGERA_FUSE_K5")) == 0);
   bool fused = false;
-  const rag_eps eps = {p.eps, p.eps_per_query ? idx->cur->d_rho_q : nullptr, p.eps_q_mul};
+  const rag_eps eps = {p.eps, p.eps_per_query ? idx->cur->d_rho_q : nullptr, p.eps_q_mul, floor, min_eff};
   if (k34_small_ok(idx, B, p.kp, parts)) {
     // one GPU, or sharded with the peer-to-peer exchange (which then runs inside the same kernel)
     fused = k5_in_place && (idx->nranks == 1 || k34_small_fuses_exchange(idx));

@@ -236,7 +236,7 @@ int k1x_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // Operand: the bf16 corpus / bf16 shadow, or the fp32 rows read as tf32 when an fp32 index has no shadow.
 int k2_available(const rag_index* idx);
 int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts);
-int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
+int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, float floor = -INFINITY);  // floor: rows scoring <= it are never candidates
 void k2_destroy(rag_index* idx);
 void k2_set_debug(rag_index* idx, float* d_scores);  // diagnostics: dump the scaled score matrix of the next launch
 // diagnostics of the batch-1 latency path (RAGERA_SMALL_PROF=1): enable >= 0 sets / resets, dump != null prints averages
@@ -246,7 +246,11 @@ void k34_small_prof(int enable, FILE* dump);
 int k3_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts);
 // K4 — exact fp64 rescoring in reference order + local top-k + certification (k4_rescore.cu)
 // eps_q (may be null): per-query addend to the selection-error bound, eps[b] = eps + eps_q[b] * eps_q_mul
-struct rag_eps { double eps; const float* eps_q; double eps_q_mul; };
+// What K4's certification needs to know about the selecting pass: its error bound (eps, + eps_q[b] * eps_q_mul per query),
+// `floor` = the selection score at or below which the selecting kernel dropped rows outright (-inf: it dropped nothing),
+// `min_score` = the cosine below which the caller filters results anyway (hybridSearch's minVectorScore, MemoryStore's
+// minRelevance; -inf: a plain top-k). All in cosine units.
+struct rag_eps { double eps; const float* eps_q; double eps_q_mul; double floor; double min_score; };
 int k4_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t k, rag_eps eps, int key_has_qnorm,
               int64_t now_ms, double decay, double bonus);
 // K3+K4 fused, latency variant for small batches (k4_rescore.cu)

@@ -74,6 +74,7 @@ struct kp_params {
   uint32_t n_rows, ld, B, kp, parts, stages, n_tiles, pairs;
   uint32_t idesc;      // kind::f16 instruction descriptor: fp16 x fp16 (fp16 shadow) or bf16 x bf16
   const float* inv_norm;
+  float floor;             // a row must score ABOVE it to be a candidate (-inf: none; see rag_eps::floor)
   uint64_t* partial;
   uint32_t* pub;       // [pairs][Bpub] ordered score of each (pair, query)'s pub_rank-th best so far (0 = none yet)
   uint32_t Bpub, pub_rank, pub_every;
@@ -564,7 +565,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     uint64_t* warp_win = win + (size_t)quarter * 32 * WIN;
     uint64_t* mywin = warp_win + (size_t)lane * WIN;
     uint64_t* warp_best = best + (size_t)quarter * 32 * best_stride;
-    float thr = live ? -CUDART_INF_F : CUDART_INF_F;  // a score must beat it to be a candidate
+    float thr = live ? P.floor : CUDART_INF_F;  // a score must beat it to be a candidate (the floor: what the caller filters out anyway)
     uint32_t off = 0;  // bytes used in this lane's window (8 per entry)
     int nbest = 0;     // keys in this lane's sorted best list
     const uint32_t win_addr = smem_u32(mywin);  // 256-byte aligned; entry j lives at (j*8) ^ (lane*8)
@@ -674,7 +675,7 @@ k2_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           const long long tf = cyc ? clk() : 0;
           const float T = k2p_first_tile_threshold<SCALED>(taddr, inv, kp);
           // admit scores >= T: the threshold is the next float below T
-          if (live && T > -CUDART_INF_F) thr = rag_unorder_f32(rag_order_f32(T) - 1u);
+          if (live && T > -CUDART_INF_F) thr = fmaxf(thr, rag_unorder_f32(rag_order_f32(T) - 1u));
           if (cyc) c_first = clk() - tf;
         }
 #pragma unroll 1
@@ -922,7 +923,7 @@ int k2_plan(rag_index* idx, uint32_t B, uint32_t kp, uint32_t* parts) {
   return RAG_OK;
 }
 
-int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
+int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts, float floor) {
   if (idx->rows == 0) return rag_set_error(RAG_ERR_STATE, "search on an empty index");
   if (idx->rows >= 0xFFFFFF00ull) return rag_set_error(RAG_ERR_UNSUPPORTED, "more than 2^32-257 rows per shard");
   RAG_CHECK(kp_init(idx));
@@ -975,6 +976,7 @@ int k2_launch(rag_index* idx, uint32_t B, uint32_t kp, uint32_t parts) {
   P.stages = kp_pick_stages(st, kp);
   P.n_tiles = (uint32_t)((idx->rows + TILE_N - 1) / TILE_N);
   P.inv_norm = idx->inv_norm;
+  P.floor = floor;
   // both operands in one 16-bit format: fp16 x fp16 (fp16 shadow) or bf16 x bf16 (bf16 corpus / bf16 shadow) — a mixed
   // descriptor raises an illegal-instruction error on sm_100a
   P.idesc = idesc_f16(PAIR_M, TILE_N, idx->shadow_f16 ? 0u : 1u, idx->shadow_f16 ? 0u : 1u);

@@ -65,8 +65,8 @@ __device__ __forceinline__ k4_row_meta k4_load_row_meta(const k4_meta& M, uint32
 }
 
 __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k, bool valid, uint32_t row, double score,
-                                            double nq, uint64_t last_key, double eps, int key_has_qnorm,
-                                            const k4_meta& M, double* s_score, uint32_t* s_row, double* s_kth,
+                                            double nq, uint64_t last_key, double eps, double floor_u, double min_eff,
+                                            int key_has_qnorm, const k4_meta& M, double* s_score, uint32_t* s_row, double* s_kth,
                                             rag_rec* __restrict__ out, uint32_t* __restrict__ out_cnt, rag_rec* s_out = nullptr,
                                             const k4_row_meta* pre = nullptr) {
   // similarity = dot / (norm(q) * norm(x)); NaN (zero norm) is defined as never selected
@@ -91,12 +91,22 @@ __device__ __forceinline__ void k4_finalize(uint32_t j, uint32_t kp, uint32_t k,
   // certification of the local top-k against rows that were never candidates
   if (good && rank + 1 == cnt) *s_kth = score;
   __syncthreads();
+  // U = what the exact score of a row OUTSIDE the candidate set can be at most: the selection score of the K'-th candidate
+  // when the list is full, else the floor below which the selecting kernel dropped rows (-inf: every scored row is a
+  // candidate), plus the selection-error bound. The local top-k is the exact scan's if its k-th score clears U — or,
+  // whatever the candidates are, if U lies below the score the caller filters at (hybridSearch's minVectorScore,
+  // hybrid-search.ts:308-314; MemoryStore's minRelevance, store.ts:151): a row that is not a candidate could then never
+  // survive the filter, and filtering commutes with taking the best k by the same score.
   bool certified = true;
+  double U = -INFINITY;
   if (last_key != 0ull && cnt > 0) {  // list full: rows outside the candidate set exist
     // K1/K2 keys hold dot/||x|| (||q|| cannot change the order); K1x keys hold the cosine itself
     const double t = key_has_qnorm ? (double)rag_key_score(last_key) : (double)rag_key_score(last_key) / sqrt(nq);
-    certified = cnt == k && *s_kth > t + eps;
+    U = t + eps;
+  } else if (floor_u > -INFINITY) {
+    U = floor_u + eps;
   }
+  if (U > -INFINITY) certified = U < min_eff || (cnt == k && *s_kth > U);
   const uint32_t flags = certified ? 0u : 1u;
 
   if (good && rank < k) {
@@ -163,7 +173,7 @@ k4_rescore_kernel(const void* __restrict__ X, uint32_t ld, const float* __restri
   __syncthreads();
   c.nq = s_nq;
   const double eps = E.eps_q ? E.eps + (double)E.eps_q[b] * E.eps_q_mul : E.eps;
-  k4_finalize(j, kp, k, valid, row, finish(c), s_nq, cand[(size_t)b * RAG_MAX_CANDIDATES + kp - 1], eps, key_has_qnorm, M,
+  k4_finalize(j, kp, k, valid, row, finish(c), s_nq, cand[(size_t)b * RAG_MAX_CANDIDATES + kp - 1], eps, E.floor, E.min_score, key_has_qnorm, M,
               s_score, s_row, &s_kth, local + (size_t)b * k, local_cnt + b);
 }
 
@@ -375,7 +385,7 @@ k34_small_kernel(const void* __restrict__ X, uint32_t ld, const float* __restric
     const bool valid = key != 0ull;
     const uint32_t row = valid ? rag_key_row(key) : 0u;
     const double score = valid ? __ddiv_rn(vs[2 * j], __dmul_rn(__dsqrt_rn(nq), __dsqrt_rn(vs[2 * j + 1]))) : 0.0;
-    k4_finalize(j, kp, k, valid, row, score, nq, s_cand[kp - 1], eps, key_has_qnorm, M, s_score, s_row, &s_kth,
+    k4_finalize(j, kp, k, valid, row, score, nq, s_cand[kp - 1], eps, E.floor, E.min_score, key_has_qnorm, M, s_score, s_row, &s_kth,
                 local + (size_t)b * k, local_cnt + b, s_recs, j0 == 0 ? &pre : nullptr);
   }
   // ---- K5 in place: filter + fusion of this query by warp 0 — one launch less on the batch-1 latency path.

@@ -178,3 +178,81 @@ def test_gpu_selected_scores_stay_within_the_rigorous_bound(native, oracle, kind
     for b in range(0, B, 7):
         bi, bs = oracle.topk(Xs, Q[b], 10)
         assert np.array_equal(r.row(b)[0], bi) and np.array_equal(r.row(b)[1], bs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shadow,dtype_name", [("f16", "f32"), ("bf16", "f32"), (None, "bf16")])
+def test_gpu_min_score_filter_pushed_into_selection_and_certification(native, oracle, shadow, dtype_name):
+    """hybridSearch keeps r.score >= minVectorScore (hybrid-search.ts:308-314), and filtering commutes with taking the best k.
+    The library leans on that twice: the tensor path never makes a row below (min - margin) a candidate, and K4 certifies
+    a query whose non-candidates provably lie below the filter whatever its k-th score is. Neither may change a result:
+      * min placed EXACTLY on the exact score of the j-th best row (>= keeps it, the next row goes), per query, tensor path;
+      * min above every score ("nothing relevant"): empty result, certified in the FIRST pass (no escalation) on the tensor,
+        stream and exact paths alike — before, such a query cost an extra corpus pass;
+      * one batch, one min: ids / scores / fused order equal the oracle's, every query certified in the first pass."""
+    import rag_era_b200 as rb
+
+    n, d, B, k = 30000, 256, 160, 10
+    go = oracle.make_gen(n, n_clusters=40, dup_period=0)
+    gn = native.GenDesc.from_buffer_copy(bytes(go))
+    dt = native.F32 if dtype_name == "f32" else native.BF16
+    X = oracle.gen_rows(go, 0, n, d, dtype=oracle.F32 if dt == native.F32 else oracle.BF16)
+    with rb.VectorIndex(d, n, dtype=dt, shadow=shadow) as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, B)
+        rng = np.random.default_rng(8)
+        kw = [rng.integers(0, n, 4).tolist() for _ in range(B)]
+        first_pass = native.SEARCH_NO_ESCALATE
+        # the filter exactly on a score
+        for b in range(12):
+            ei, es = oracle.topk(X, Q[b], k)
+            j = int(rng.integers(1, k))
+            m = float(es[j])
+            e = oracle.hybrid_search(X, Q[b], k, m, kw[b])
+            assert len(e["vec_ids"]) >= j + 1                               # rows with the same score as row j stay too
+            g = idx.hybrid(Q[b:b + 1], rb.hybrid_opts(k, 4, m, path=native.PATH_TENSOR), [kw[b]]).row(0)
+            assert g["certified"] and np.array_equal(g["vec_ids"], e["vec_ids"]) and np.array_equal(g["vec_scores"], e["vec_scores"]), (b, j)
+            assert np.array_equal(g["keys"], e["keys"]) and np.array_equal(g["scores"], e["scores"]) and np.array_equal(g["source"], e["source"])
+            m_up = float(np.nextafter(es[j], 2.0))                          # one ulp higher: row j goes
+            e = oracle.hybrid_search(X, Q[b], k, m_up, kw[b])
+            g = idx.hybrid(Q[b:b + 1], rb.hybrid_opts(k, 4, m_up, path=native.PATH_TENSOR), [kw[b]]).row(0)
+            assert g["certified"] and np.array_equal(g["vec_ids"], e["vec_ids"]) and len(g["vec_ids"]) < len(ei), (b, j)
+        # nothing relevant: certified at once on every path
+        for path in (native.PATH_TENSOR, native.PATH_STREAM, native.PATH_EXACT):
+            r = idx.hybrid(Q[:32], rb.hybrid_opts(k, 4, 0.999, path=path, flags=first_pass), kw[:32])
+            for b in range(32):
+                g = r.row(b)
+                e = oracle.hybrid_search(X, Q[b], k, 0.999, kw[b])
+                assert g["certified"] and len(g["vec_ids"]) == 0, (path, b)
+                assert np.array_equal(g["keys"], e["keys"]) and np.array_equal(g["scores"], e["scores"]), (path, b)
+        # one batch on the tensor path, min = 0.3 and a min in the middle of the scores: first pass certifies, results exact
+        for m in (0.3, float(np.median([oracle.topk(X, Q[b], k)[1][k // 2] for b in range(8)]))):
+            r = idx.hybrid(Q, rb.hybrid_opts(k, 4, m, path=native.PATH_TENSOR, flags=first_pass), kw)
+            n_cert = 0
+            for b in range(B):
+                g = r.row(b)
+                n_cert += int(g["certified"])
+                if not g["certified"]:
+                    continue                                                # first pass only: an uncertified query promises nothing
+                e = oracle.hybrid_search(X, Q[b], k, m, kw[b])
+                assert np.array_equal(g["vec_ids"], e["vec_ids"]) and np.array_equal(g["vec_scores"], e["vec_scores"]), (m, b)
+                assert np.array_equal(g["keys"], e["keys"]) and np.array_equal(g["scores"], e["scores"]), (m, b)
+            assert n_cert >= B - 2, (m, n_cert)
+            full = idx.hybrid(Q, rb.hybrid_opts(k, 4, m, path=native.PATH_TENSOR), kw)       # with escalation: all exact
+            for b in range(B):
+                e = oracle.hybrid_search(X, Q[b], k, m, kw[b])
+                g = full.row(b)
+                assert g["certified"] and np.array_equal(g["vec_ids"], e["vec_ids"]) and np.array_equal(g["keys"], e["keys"]) and np.array_equal(g["scores"], e["scores"]), (m, b)
+        # queries that resemble nothing in the corpus: (almost) no row clears the floor, the candidate lists stay short or
+        # empty — certified in the first pass because whatever was dropped lies below the filter
+        Qr = rng.standard_normal((24, d)).astype(np.float32)
+        r = idx.hybrid(Qr, rb.hybrid_opts(k, 4, 0.3, path=native.PATH_TENSOR, flags=first_pass), kw[:24])
+        for b in range(24):
+            g = r.row(b)
+            e = oracle.hybrid_search(X, Qr[b], k, 0.3, kw[b])
+            assert g["certified"] and np.array_equal(g["vec_ids"], e["vec_ids"]) and np.array_equal(g["vec_scores"], e["vec_scores"]), b
+            assert np.array_equal(g["keys"], e["keys"]) and np.array_equal(g["scores"], e["scores"]), b
+        # MemoryStore.retrieve's minRelevance is the same kind of filter
+        ct, cf, ac, la = oracle.gen_meta(go, 0, n)
+        mem = idx.memory_retrieve(Q[:16], 5, 0.999, now_ms=go.now_ms, path=native.PATH_TENSOR)
+        assert int(mem["counts"].sum()) == 0
