@@ -200,8 +200,8 @@ constexpr size_t K4S_MAX_STAGE = 96 * 1024;     // staged candidate keys (parts 
 // One exact left-to-right sum over a row, by one warp. WHICH: 0 = sum q[i]*x[i], 1 = sum x[i]*x[i], 2 = sum q[i]*q[i]
 // (the reference's three loops). The 32 lanes compute the (exact) products of a 256-element block in parallel and park
 // them in the warp's shared-memory scratch `sp` [2 buffers][256]; the adds are then replayed in order from broadcast
-// 128-bit shared loads, so the only thing on the critical path is the fp64 add latency. Products of block b+1 are
-// computed while the global loads of block b+2 are in flight.
+// 128-bit shared loads, so the only thing on the critical path is the fp64 add latency. The global loads of block b+1 fly
+// under the first half of block b's adds, its products are formed in the issue slots between the second half's adds.
 template <bool BF16, int WHICH>
 __device__ __forceinline__ double warp_chain1(const void* __restrict__ X, uint32_t row, uint32_t ld,
                                               const float* __restrict__ q, int lane, double* sp) {
@@ -229,21 +229,36 @@ __device__ __forceinline__ double warp_chain1(const void* __restrict__ X, uint32
       p0[t * 32 + lane] = __dmul_rn(a, c);
     }
   };
+  auto park_one = [&](int buf, int t) {
+    const double a = WHICH == 1 ? (double)xr[t] : (double)qr[t];
+    const double c = WHICH == 2 ? (double)qr[t] : (double)xr[t];
+    sp[buf * 256 + t * 32 + lane] = __dmul_rn(a, c);
+  };
   load(0);
   park(0);
   __syncwarp();
   for (int blk = 0; blk < nblk; blk++) {
-    if (blk + 1 < nblk) load(blk + 1);
+    const bool more = blk + 1 < nblk;
+    if (more) load(blk + 1);
     const double2* a0 = reinterpret_cast<const double2*>(sp + (blk & 1) * 256);
+    // first half of the block's adds: the loads of the next block are in flight under them
 #pragma unroll 16
-    for (int i = 0; i < 128; i++) {
+    for (int i = 0; i < 64; i++) {
       const double2 u = a0[i];
       s0 = __dadd_rn(__dadd_rn(s0, u.x), u.y);
     }
-    if (blk + 1 < nblk) {
-      park((blk + 1) & 1);
-      __syncwarp();
+    // second half: the next block's products (conversions, multiply, store — independent of the chain) are slotted between
+    // the dependent adds, one of this lane's eight per 8 adds, instead of standing between two blocks' chains
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      if (more) park_one((blk + 1) & 1, t);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const double2 u = a0[64 + t * 8 + i];
+        s0 = __dadd_rn(__dadd_rn(s0, u.x), u.y);
+      }
     }
+    if (more) __syncwarp();
   }
   return s0;
 }
