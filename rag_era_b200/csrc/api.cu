@@ -326,6 +326,7 @@ int run_pipeline(rag_index* idx, uint32_t B, uint32_t k, const plan& p, const fr
   if (k2_floor_on && p.path == RAG_PATH_TENSOR && p.key_has_qnorm && min_eff > -INFINITY) {
     const double rho_q_typ = (idx->shadow && !idx->shadow_f16) ? 4.0e-3 : 5.0e-4;   // bf16 / fp16 rounding of a unit vector
     floor = min_eff - 2.0 * (p.eps + (p.eps_per_query ? rho_q_typ * p.eps_q_mul : 0.0)) - 1.0e-6;
+    floor = (double)(float)floor;   // K2 compares in fp32: K4 must reason about the very value K2 used
   }
   if (stream) RAG_CHECK(k1_launch(idx, B, p.kp, parts, p.path == RAG_PATH_SHADOW_STREAM));
   else if (p.path == RAG_PATH_TENSOR) RAG_CHECK(k2_launch(idx, B, p.kp, parts, (float)floor));
