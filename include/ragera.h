@@ -156,7 +156,11 @@ typedef struct rag_fused_out {
   uint64_t* vec_ids;      /* [B][vector_top_k]                                      */
   double*   vec_scores;   /* [B][vector_top_k]                                      */
   uint32_t* vec_counts;   /* [B]                                                    */
-  uint8_t*  certified;    /* [B] optional                                           */
+  uint8_t*  certified;    /* [B] optional: 1 = proven equal to the reference's result. The score filter is part of the
+                             proof: rows that provably lie below min_vector_score (below min_relevance for
+                             rag_memory_retrieve) can never reach the result, so a query whose non-candidates all
+                             lie there is certified whatever its k-th score is, and the tensor path never makes such
+                             rows candidates (filtering commutes with taking the best k) */
 } rag_fused_out;
 
 /* MemoryStore.retrieve(query, limit, minRelevance) — src/lib/memory/store.ts:102-180 */
