@@ -55,3 +55,30 @@ def test_topk_is_a_stable_descending_prefix(oracle, n, d, k, seed, dup):
     allsc = np.array([oracle.cosine(q, X[i]) for i in range(n)])
     order = sorted(range(n), key=lambda i: (-allsc[i], i))[:k]                 # stable desc, earlier row first
     assert [int(i) for i in ids] == order and np.array_equal(sc, allsc[order])
+
+
+@settings(max_examples=80, deadline=None)
+@given(n=st.integers(1, 250), d=st.sampled_from([8, 64]), k=st.integers(1, 20), seed=st.integers(0, 2**31),
+       pick=st.integers(0, 400), dup=st.booleans())
+def test_score_filter_commutes_with_topk(oracle, n, d, k, seed, pick, dup):
+    """What the library's filter pushdown rests on: hybridSearch takes the best k rows and THEN keeps
+    r.score >= minVectorScore (src/lib/hybrid-search.ts:306-317). Dropping the rows below the filter FIRST and taking the
+    best k of what is left gives the same list — for a filter placed anywhere, in particular exactly on a row's score and
+    one ulp above it — so a row that provably scores below the filter can be ignored by the selection."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    if dup and n > 2:
+        X[n - 1] = X[0]
+    q = rng.standard_normal(d).astype(np.float32)
+    allsc = np.array([oracle.cosine(q, X[i]) for i in range(n)])
+    base = float(allsc[pick % n])
+    for m in (base, float(np.nextafter(base, 2.0)), float(np.nextafter(base, -2.0)), -1.5, 1.5):
+        ids, sc = oracle.topk(X, q, k)
+        a_ids, a_sc = oracle.filter_min_score(ids, sc, m)                       # the reference's order: top-k, then filter
+        keep = np.flatnonzero(allsc >= m)                                        # the other order: filter, then top-k
+        if len(keep):
+            b_ids, b_sc = oracle.topk(np.ascontiguousarray(X[keep]), q, k)
+            b_ids = keep[b_ids.astype(np.int64)]
+        else:
+            b_ids, b_sc = np.zeros(0, np.int64), np.zeros(0)
+        assert [int(i) for i in a_ids] == [int(i) for i in b_ids] and np.array_equal(a_sc, b_sc), m
