@@ -198,10 +198,18 @@ export class NativeVectorStore {
   /** getTopKEmbeddings: score all rows, stable sort, first k — ties to the earlier row. Exact fp64 cosines. */
   async query(q: { queryEmbedding?: number[]; similarityTopK: number }): Promise<{ ids: string[]; similarities: number[] }> {
     if (!q.queryEmbedding) throw new Error('NativeVectorStore.query needs queryEmbedding');
-    const r = await native.search(this.index.handle, Float32Array.from(q.queryEmbedding), 1, q.similarityTopK);
-    const n: number = r.counts[0];
     const ids: string[] = [];
     const similarities: number[] = [];
+    if (USE_BATCHER) {
+      // a plain top-k through the micro-batcher = the vector-only branch with no keyword list and a filter below every
+      // cosine: concurrent retrievers (hybridSearch, MemoryStore, summarize_topic) share one corpus pass
+      const opts = { vectorTopK: q.similarityTopK, keywordLimit: 0, minVectorScore: -2, rrf: PRESETS.document.rrf };
+      const r = await native.submit(this.index.batcherFor(opts), opts, Float32Array.from(q.queryEmbedding), new BigUint64Array(0));
+      for (let i = 0; i < r.vecCounts[0]; i++) { ids.push(this.index.nodes[Number(r.vecIds[i])].id); similarities.push(r.vecScores[i]); }
+      return { ids, similarities };
+    }
+    const r = await native.search(this.index.handle, Float32Array.from(q.queryEmbedding), 1, q.similarityTopK);
+    const n: number = r.counts[0];
     for (let i = 0; i < n; i++) { ids.push(this.index.nodes[Number(r.ids[i])].id); similarities.push(r.scores[i]); }
     return { ids, similarities };
   }

@@ -91,3 +91,39 @@ def test_batcher_async_submits_from_one_thread(native, oracle):
             assert not isinstance(results[i], Exception), results[i]
             for key in ("keys", "scores", "source", "ctype", "vec_ids", "vec_scores", "used_rrf"):
                 assert np.array_equal(results[i][key], direct[i][key]), (i, key)
+
+
+def test_batcher_serves_the_retriever_seam(native, oracle):
+    """`index.asRetriever({similarityTopK}).retrieve(q)` (hybrid-search.ts:223-224, memory/store.ts:111-116, the summarize tool)
+    is a plain top-k. Through the batcher it is the vector-only branch with no keyword list and a filter below every cosine
+    (keywordLimit 0, minVectorScore -2): ids and raw cosines equal rag_search's — what NativeVectorStore.query sends when
+    RAGERA_BATCH=1."""
+    import rag_era_b200 as rb
+
+    n, d, nq, k = 20000, 256, 48, 7
+    go = oracle.make_gen(n, n_clusters=32)
+    gn = native.GenDesc.from_buffer_copy(bytes(go))
+    with rb.VectorIndex(d, n, shadow="f16") as idx:
+        idx.generate(gn, n)
+        Q = idx.generate_queries(gn, 0, nq)
+        direct = idx.query(Q, k)
+        results = [None] * nq
+        done = threading.Semaphore(0)
+        with rb.Batcher(idx, rb.hybrid_opts(k, 0, -2.0), max_batch=64, max_wait_us=2000) as bt:
+            for i in range(nq):
+                def on_done(r, i=i):
+                    results[i] = r
+                    done.release()
+                assert bt.submit_async(Q[i], [], on_done)
+            for _ in range(nq):
+                assert done.acquire(timeout=60)
+        X = oracle.gen_rows(go, 0, n, d)
+        for i in range(nq):
+            r = results[i]
+            assert not isinstance(r, Exception), r
+            assert not r["used_rrf"] and r["certified"]
+            assert np.array_equal(r["vec_ids"], direct.row(i)[0]) and np.array_equal(r["vec_scores"], direct.row(i)[1]), i
+            assert np.array_equal(r["keys"], direct.row(i)[0]) and np.array_equal(r["scores"], direct.row(i)[1]), i
+            if i < 4:
+                ei, es = oracle.topk(X, Q[i], k)
+                assert np.array_equal(r["vec_ids"], ei) and np.array_equal(r["vec_scores"], es)
