@@ -12,6 +12,7 @@
 // 0 is the empty sentinel (every real score, even -inf, packs to a non-zero key).
 #pragma once
 
+#include <math.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
