@@ -1,11 +1,26 @@
 /* abi_demo.c — the C ABI from plain C (no Python, no C++): what an FFI / N-API shim does.
  * Build: gcc -std=c11 -I include tests/c/abi_demo.c -o abi_demo -L rag_era_b200 -lragera -Wl,-rpath,$PWD/rag_era_b200
  * Generates a small synthetic index on the device, runs deep_search-shaped hybrid searches through
- * rag_hybrid_search and prints one line per query:  <b> <used_rrf> <count> <key0> <score0 as hex float> */
+ * rag_hybrid_search and prints one line per query:  <b> <used_rrf> <count> <key0> <score0 as hex float> <certified>;
+ * then sends the same queries through rag_batcher_submit_async (completion callback on a worker thread) and prints them again */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include "ragera.h"
+
+/* completion of an asynchronous batcher request: called on a batcher worker thread */
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
+static int g_done = 0, g_failed = 0;
+static void on_done(void* user, int rc, const char* err) {
+  (void)user; (void)err;
+  pthread_mutex_lock(&g_mu);
+  g_done++;
+  if (rc != RAG_OK) g_failed++;
+  pthread_cond_signal(&g_cv);
+  pthread_mutex_unlock(&g_mu);
+}
 
 #define CHECK(x) do { int rc_ = (x); if (rc_ != RAG_OK) { fprintf(stderr, "%s failed (%d): %s\n", #x, rc_, rag_last_error()); return 2; } } while (0)
 
@@ -36,6 +51,27 @@ int main(int argc, char** argv) {
   CHECK(rag_hybrid_search(idx, q, B, &o, kw, kwc, &out));
   for (uint32_t b = 0; b < B; b++)
     printf("%u %u %u %llu %a %u\n", b, rrf[b], counts[b], (unsigned long long)keys[b * cap], scores[b * cap], cert[b]);
+  /* the same three requests through the micro-batcher's non-blocking entry point: submit all, then wait for the callbacks;
+   * one more line per query, which must repeat the line above */
+  rag_batcher_desc bd;
+  memset(&bd, 0, sizeof bd);
+  bd.max_batch = 8; bd.max_wait_us = 500; bd.opts = o;
+  rag_batcher* bt = NULL;
+  CHECK(rag_batcher_create(idx, &bd, &bt));
+  uint64_t akeys[3 * 14]; double ascores[3 * 14]; uint8_t arrf[3], acert[3]; uint32_t acounts[3];
+  rag_fused_out aout[3];
+  for (uint32_t b = 0; b < B; b++) {
+    rag_fused_out one = { cap, akeys + b * cap, ascores + b * cap, NULL, NULL, acounts + b, arrf + b, NULL, NULL, NULL, acert + b };
+    aout[b] = one;
+    CHECK(rag_batcher_submit_async(bt, q + (size_t)b * dim, kw + b * kl, kwc[b], &aout[b], on_done, NULL));
+  }
+  pthread_mutex_lock(&g_mu);
+  while (g_done < (int)B) pthread_cond_wait(&g_cv, &g_mu);
+  pthread_mutex_unlock(&g_mu);
+  if (g_failed) { fprintf(stderr, "an asynchronous request failed\n"); return 3; }
+  for (uint32_t b = 0; b < B; b++)
+    printf("%u %u %u %llu %a %u\n", b, arrf[b], acounts[b], (unsigned long long)akeys[b * cap], ascores[b * cap], acert[b]);
+  rag_batcher_destroy(bt);
   rag_host_free(q);
   rag_index_destroy(idx);
   return 0;

@@ -790,9 +790,11 @@ def test_c_abi_from_plain_c(rb, native, oracle, tmp_path):
     exe = str(tmp_path / "abi_demo")
     lib_dir = os.path.join(ROOT, "rag_era_b200")
     subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_demo.c"), "-o", exe,
-                    "-L", lib_dir, "-lragera", f"-Wl,-rpath,{lib_dir}"], check=True)
+                    "-L", lib_dir, "-lragera", f"-Wl,-rpath,{lib_dir}", "-lpthread"], check=True)
     n = 20000
-    lines = subprocess.run([exe, str(n)], capture_output=True, text=True, check=True).stdout.split("\n")[:3]
+    out = subprocess.run([exe, str(n)], capture_output=True, text=True, check=True).stdout.split("\n")
+    lines = out[:3]
+    assert out[3:6] == lines                      # the same requests through rag_batcher_submit_async + callback
     go = oracle.make_gen(n, n_clusters=32)
     X = oracle.gen_rows(go, 0, n, 256)
     Q = oracle.gen_queries(go, 0, 3, 256)
