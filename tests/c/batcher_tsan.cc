@@ -128,7 +128,7 @@ int main() {
   th.clear();
   for (int t = 0; t < 40; t++) th.emplace_back([&, t] { entering++; submitter(100 + t, 1); });   // tags below 2^24
   while (entering.load() != 40) std::this_thread::yield();
-  std::this_thread::sleep_for(std::chrono::milliseconds(100));   // every caller is inside submit by now (the stub is shut)
+  std::this_thread::sleep_for(std::chrono::milliseconds(600));   // every caller is inside submit by now (the stub is shut; generous for a loaded box)
   std::thread closer([&] { rag_batcher_destroy(bt); });
   std::this_thread::sleep_for(std::chrono::milliseconds(20));
   g_gate_closed = 0;
