@@ -261,7 +261,8 @@ void submit_done(void* user, int rc, const char* err) {   // batcher worker thre
   auto* w = static_cast<SearchWork*>(user);
   w->rc = rc;
   if (rc != RAG_OK) w->err = err ? err : "";
-  napi_call_threadsafe_function(w->bh->tsfn, w, napi_tsfn_blocking);
+  // (napi_closing: the environment is being torn down and nobody is left to resolve for — the request is simply dropped)
+  if (napi_call_threadsafe_function(w->bh->tsfn, w, napi_tsfn_blocking) != napi_ok) delete w;
 }
 void submit_call_js(napi_env env, napi_value, void*, void* data) {   // main thread
   auto* w = static_cast<SearchWork*>(data);
